@@ -1,0 +1,378 @@
+// C-ABI entry points for the convolution family (forward, data gradient, weight gradient, weight packing).
+#include "conv_gemm.cuh"
+#include "host_common.cuh"
+#include "wgrad_gemm.cuh"
+
+#include <algorithm>
+
+namespace yb {
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+template <int BN, int BK>
+static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid, int stages,
+                            cudaStream_t st) {
+  using Cfg = ConvGemmCfg<BN, BK>;
+  static int max_set = 0;
+  const int smem = stages * Cfg::kStageBytes + 1024;
+  if (smem > max_set) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    max_set = smem;
+  }
+  conv_gemm_kernel<BN, BK><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p, stages);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_conv(int bn, int bk, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid,
+                       int stages, cudaStream_t st) {
+#define YB_CASE(BN, BK) \
+  if (bn == BN && bk == BK) return launch_conv_inst<BN, BK>(tmA, tmB, p, grid, stages, st);
+  YB_CASE(16, 16) YB_CASE(16, 32) YB_CASE(16, 64)
+  YB_CASE(32, 16) YB_CASE(32, 32) YB_CASE(32, 64)
+  YB_CASE(64, 16) YB_CASE(64, 32) YB_CASE(64, 64)
+  YB_CASE(128, 16) YB_CASE(128, 32) YB_CASE(128, 64)
+#undef YB_CASE
+  return fail(YB200_ERR_UNSUPPORTED, "no conv_gemm instantiation for BLOCK_N=%d BLOCK_K=%d", bn, bk);
+}
+
+static int pick_block_k(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
+static int pick_block_n(int c) { return c > 64 ? 128 : (c > 32 ? 64 : (c > 16 ? 32 : 16)); }
+
+static int check_act(const yb200_act* a, const char* name) {
+  YB_REQUIRE(a != nullptr && a->ptr != nullptr, YB200_ERR_INVALID, "%s: null view", name);
+  YB_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0 && a->c > 0, YB200_ERR_INVALID, "%s: empty extent", name);
+  YB_REQUIRE(a->c % 8 == 0 && a->c_pitch % 8 == 0 && a->c_off % 8 == 0 && a->c_off + a->c <= a->c_pitch, YB200_ERR_INVALID,
+             "%s: channels (c=%d pitch=%d off=%d) must be multiples of 8 with off+c<=pitch", name, a->c, a->c_pitch, a->c_off);
+  return 0;
+}
+
+// fill the forward-style tap table (reads input pixel  stride*o + k - pad)
+static int fill_fwd_taps(ConvTap* taps, const yb200_act& x, int ksize, int stride, int k_per_tap) {
+  int nt = 0;
+  if (ksize == 1) {
+    taps[nt++] = ConvTap{x.c_off, 0, 0, 0, 0};
+  } else {
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        ConvTap t;
+        if (stride == 1) {
+          t.c0 = x.c_off; t.dw = kw - 1; t.p = 0; t.dh = kh - 1;
+        } else {  // input row 2*o + kh - 1: kh=0 -> (parity 1, o-1), kh=1 -> (0, o), kh=2 -> (1, o)
+          t.p = (kh == 1) ? 0 : 1; t.dh = (kh == 0) ? -1 : 0;
+          const int pw = (kw == 1) ? 0 : 1;
+          t.dw = (kw == 0) ? -1 : 0;
+          t.c0 = pw * x.c_pitch + x.c_off;
+        }
+        t.kb = (kh * 3 + kw) * k_per_tap;
+        taps[nt++] = t;
+      }
+  }
+  return nt;
+}
+
+static void set_out_view(ConvGemmParams& p, const yb200_act& o) {
+  p.out = static_cast<__nv_bfloat16*>(o.ptr) + o.c_off;
+  p.out_sw = o.c_pitch;
+  p.out_sh = 1LL * o.c_pitch * o.w;
+  p.out_sn = 1LL * o.c_pitch * o.w * o.h;
+  p.out_sc = 1;
+  p.out_mh = 1; p.out_ph = 0; p.out_mw = 1; p.out_pw = 0;
+}
+
+static void set_tiles(ConvGemmParams& p, int n, int h, int w) {
+  choose_tile(n, h, w, 128, &p.log_tw, &p.log_th);
+  const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
+  p.tiles_w = ceil_div(w, tw); p.tiles_h = ceil_div(h, th); p.tiles_n = ceil_div(n, tn);
+  p.n_valid = n; p.h_valid = h; p.w_valid = w;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad, int cin_pad,
+                                        __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const long long total = 1LL * cout_pad * taps * cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = static_cast<int>(i % cin_pad);
+    const int t = static_cast<int>((i / cin_pad) % taps);
+    const int co = static_cast<int>(i / (1LL * cin_pad * taps));
+    const float v = (co < cout && ci < cin) ? w[(1LL * co * cin + ci) * taps + t] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    if (wf) wf[i] = b;
+    if (wd) wd[(1LL * ci * taps + t) * cout_pad + co] = b;
+  }
+}
+
+extern "C" int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, void* w_fwd,
+                                      void* w_dgrad, void* stream) {
+  YB_REQUIRE(w_oihw && (w_fwd || w_dgrad), YB200_ERR_INVALID, "pack_conv_weight: null pointer");
+  YB_REQUIRE(cout > 0 && cin > 0 && (ksize == 1 || ksize == 3) && cout_pad >= cout && cin_pad >= cin, YB200_ERR_INVALID,
+             "pack_conv_weight: bad sizes cout=%d cin=%d k=%d pads=%d,%d", cout, cin, ksize, cout_pad, cin_pad);
+  const long long total = 1LL * cout_pad * ksize * ksize * cin_pad;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
+  pack_conv_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, cout_pad, cin_pad,
+                                                                 static_cast<__nv_bfloat16*>(w_fwd),
+                                                                 static_cast<__nv_bfloat16*>(w_dgrad));
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int ksize, int stride, ConvGemmParams& p,
+                           cudaStream_t st) {
+  YB_REQUIRE(w_fwd != nullptr, YB200_ERR_INVALID, "conv fwd: null weights");
+  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
+             "conv fwd: ksize=%d stride=%d not implemented", ksize, stride);
+  const int bk = pick_block_k(x->c);
+  YB_REQUIRE(bk != 0, YB200_ERR_UNSUPPORTED, "conv fwd: input channels %d must be a multiple of 16", x->c);
+  const int bn = pick_block_n(cout);
+  const int oh = x->h / stride, ow = x->w / stride;
+  set_tiles(p, x->n, oh, ow);
+  p.num_taps = fill_fwd_taps(p.taps, *x, ksize, stride, x->c);
+  p.cin_blocks = x->c / bk;
+  p.cout = cout;
+  const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
+  CUtensorMap tmA, tmB;
+  int rc = make_act_map(&tmA, *x, stride == 2, bk, tw, th, tn);
+  if (rc) return rc;
+  rc = make_mat_map(&tmB, w_fwd, cout, 1LL * p.num_taps * x->c, bn, bk);
+  if (rc) return rc;
+  const int num_kb = p.num_taps * p.cin_blocks;
+  const int stages = num_kb < kMaxStages ? num_kb : kMaxStages;
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cout, bn));
+  return launch_conv(bn, bk, tmA, tmB, p, grid, stages, st);
+}
+
+extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride,
+                                double* stat_sum, double* stat_sqsum, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv2d_fwd x"))) return rc;
+  if ((rc = check_act(z, "conv2d_fwd z"))) return rc;
+  YB_REQUIRE(stride == 1 || stride == 2, YB200_ERR_UNSUPPORTED, "conv2d_fwd: stride %d", stride);
+  YB_REQUIRE(z->n == x->n && z->h * stride == x->h && z->w * stride == x->w, YB200_ERR_INVALID,
+             "conv2d_fwd: output %dx%dx%d does not match input %dx%dx%d / stride %d", z->n, z->h, z->w, x->n, x->h, x->w, stride);
+  YB_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), YB200_ERR_INVALID, "conv2d_fwd: pass both or neither stat buffer");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_out_view(p, *z);
+  p.epi_mode = stat_sum ? EPI_BF16_STATS : EPI_BF16;
+  p.stat_sum = stat_sum;
+  p.stat_sq = stat_sqsum;
+  return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream));
+}
+
+extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, const float* bias, int cout, float* out,
+                                      int a_total, int a_off, int c_total, int c_off, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv1x1_bias_f32 x"))) return rc;
+  YB_REQUIRE(bias && out && cout > 0 && cout <= 128, YB200_ERR_INVALID, "conv1x1_bias_f32: bad arguments (cout=%d)", cout);
+  YB_REQUIRE(a_off >= 0 && a_off + x->h * x->w <= a_total && c_off >= 0 && c_off + cout <= c_total, YB200_ERR_INVALID,
+             "conv1x1_bias_f32: slice [%d+%d, %d+%d] outside [%d, %d]", a_off, x->h * x->w, c_off, cout, a_total, c_total);
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = out + 1LL * a_off * c_total + c_off;
+  p.out_sn = 1LL * a_total * c_total;
+  p.out_sh = 1LL * x->w * c_total;
+  p.out_sw = c_total;
+  p.out_sc = 1;
+  p.out_mh = 1; p.out_mw = 1;
+  p.bias = bias;
+  p.epi_mode = EPI_F32_BIAS;
+  return conv_fwd_common(x, w_fwd, cout, 1, 1, p, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// data gradient
+// ------------------------------------------------------------------------------------------------
+extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend,
+                                  int ksize, int stride, void* stream) {
+  int rc;
+  if ((rc = check_act(dz, "conv2d_dgrad dz"))) return rc;
+  if ((rc = check_act(dx, "conv2d_dgrad dx"))) return rc;
+  if (addend && (rc = check_act(addend, "conv2d_dgrad addend"))) return rc;
+  YB_REQUIRE(w_dgrad != nullptr, YB200_ERR_INVALID, "conv2d_dgrad: null weights");
+  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
+             "conv2d_dgrad: ksize=%d stride=%d not implemented", ksize, stride);
+  YB_REQUIRE(dz->n == dx->n && dz->h * stride == dx->h && dz->w * stride == dx->w, YB200_ERR_INVALID,
+             "conv2d_dgrad: dz %dx%dx%d vs dx %dx%dx%d stride %d", dz->n, dz->h, dz->w, dx->n, dx->h, dx->w, stride);
+  YB_REQUIRE(!addend || (addend->n == dx->n && addend->h == dx->h && addend->w == dx->w && addend->c == dx->c), YB200_ERR_INVALID,
+             "conv2d_dgrad: addend shape mismatch");
+  const int bk = pick_block_k(dz->c);
+  YB_REQUIRE(bk != 0, YB200_ERR_UNSUPPORTED, "conv2d_dgrad: dz channels %d must be a multiple of 16", dz->c);
+  const int cin = dx->c;
+  const int bn = pick_block_n(cin);
+  const int taps_total = ksize * ksize;
+  cudaStream_t st = as_stream(stream);
+
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_out_view(p, *dx);
+  p.epi_mode = EPI_BF16;
+  p.cout = cin;
+  p.cin_blocks = dz->c / bk;
+  if (addend) {
+    p.addend = static_cast<const __nv_bfloat16*>(addend->ptr) + addend->c_off;
+    p.add_sw = addend->c_pitch;
+    p.add_sh = 1LL * addend->c_pitch * addend->w;
+    p.add_sn = 1LL * addend->c_pitch * addend->w * addend->h;
+  }
+  set_tiles(p, dz->n, dz->h, dz->w);  // pixel grid = dz grid (for stride 2: one output-parity class at a time)
+  const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
+  CUtensorMap tmA, tmB;
+  if ((rc = make_act_map(&tmA, *dz, false, bk, tw, th, tn))) return rc;
+  if ((rc = make_mat_map(&tmB, w_dgrad, cin, 1LL * taps_total * dz->c, bn, bk))) return rc;
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cin, bn));
+
+  if (stride == 1) {
+    int nt = 0;
+    if (ksize == 1) {
+      p.taps[nt++] = ConvTap{dz->c_off, 0, 0, 0, 0};
+    } else {
+      // dx[y,x] = sum_k dz[y + 1 - kh, x + 1 - kw] * W[kh,kw]
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) p.taps[nt++] = ConvTap{dz->c_off, 1 - kw, 0, 1 - kh, (kh * 3 + kw) * dz->c};
+    }
+    p.num_taps = nt;
+    const int num_kb = nt * p.cin_blocks;
+    return launch_conv(bn, bk, tmA, tmB, p, grid, num_kb < kMaxStages ? num_kb : kMaxStages, st);
+  }
+  // stride 2: input pixel (2i+ph, 2j+pw) receives  kh with (ph + 1 - kh) even:  ph=0 -> kh=1 (row i);  ph=1 -> kh=0 (row i+1), kh=2 (row i)
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      int nt = 0;
+      for (int kh = 0; kh < 3; ++kh) {
+        if (((ph + 1 - kh) & 1) != 0) continue;
+        const int dh = (ph + 1 - kh) / 2;
+        for (int kw = 0; kw < 3; ++kw) {
+          if (((pw + 1 - kw) & 1) != 0) continue;
+          const int dw = (pw + 1 - kw) / 2;
+          p.taps[nt++] = ConvTap{dz->c_off, dw, 0, dh, (kh * 3 + kw) * dz->c};
+        }
+      }
+      p.num_taps = nt;
+      p.out_mh = 2; p.out_ph = ph; p.out_mw = 2; p.out_pw = pw;
+      const int num_kb = nt * p.cin_blocks;
+      if ((rc = launch_conv(bn, bk, tmA, tmB, p, grid, num_kb < kMaxStages ? num_kb : kMaxStages, st))) return rc;
+    }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct WgradPlan {
+  WgradParams p;
+  int tmem_cols;
+  int splits;
+  int smem;
+  int tw, th, tn;
+};
+
+int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, WgradPlan* pl) {
+  int rc;
+  if ((rc = check_act(x, "conv2d_wgrad x"))) return rc;
+  if ((rc = check_act(dz, "conv2d_wgrad dz"))) return rc;
+  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
+             "conv2d_wgrad: ksize=%d stride=%d not implemented", ksize, stride);
+  YB_REQUIRE(dz->n == x->n && dz->h * stride == x->h && dz->w * stride == x->w, YB200_ERR_INVALID,
+             "conv2d_wgrad: dz %dx%dx%d vs x %dx%dx%d stride %d", dz->n, dz->h, dz->w, x->n, x->h, x->w, stride);
+  YB_REQUIRE(x->c % 16 == 0, YB200_ERR_UNSUPPORTED, "conv2d_wgrad: input channels %d must be a multiple of 16", x->c);
+  YB_REQUIRE(dz->c % 16 == 0, YB200_ERR_UNSUPPORTED, "conv2d_wgrad: output channels %d must be a multiple of 16", dz->c);
+  WgradParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.cout = dz->c;
+  p.cin = x->c;
+  p.kc_a = dz->c >= 64 ? 64 : (dz->c >= 32 ? 32 : 16);
+  YB_REQUIRE(dz->c % p.kc_a == 0 || dz->c == dz->c_pitch, YB200_ERR_UNSUPPORTED,
+             "conv2d_wgrad: dz channel slice %d not a multiple of %d", dz->c, p.kc_a);
+  p.ma = dz->c >= 128 ? 2 : 1;
+  if (dz->c > 64 && dz->c < 128) p.ma = 2;  // e.g. 80 classes: second box is partly out of bounds (zero filled)
+  p.cout_tiles = ceil_div(dz->c, 128);
+  p.kc_b = x->c % 64 == 0 ? 64 : (x->c % 32 == 0 ? 32 : 16);
+  p.bn = x->c % 128 == 0 ? 128 : (x->c % 64 == 0 ? 64 : p.kc_b);
+  p.nb = p.bn / p.kc_b;
+  p.cin_tiles = x->c / p.bn;
+  p.num_taps = fill_fwd_taps(p.taps, *x, ksize, stride, 0);
+  p.tpc = p.num_taps == 1 ? 1 : kWgMaxTpc;
+  p.tap_groups = ceil_div(p.num_taps, p.tpc);
+  p.dz_c0 = dz->c_off;
+  choose_tile(dz->n, dz->h, dz->w, kWgPix, &p.log_tw, &p.log_th);
+  pl->tw = 1 << p.log_tw; pl->th = 1 << p.log_th; pl->tn = kWgPix >> (p.log_tw + p.log_th);
+  p.tiles_w = ceil_div(dz->w, pl->tw); p.tiles_h = ceil_div(dz->h, pl->th); p.tiles_n = ceil_div(dz->n, pl->tn);
+  p.num_blocks = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int base = p.cout_tiles * p.cin_tiles * p.tap_groups;
+  int splits = ceil_div(2 * sm_count(), base);
+  if (splits > p.num_blocks) splits = p.num_blocks;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  p.blocks_per_split = ceil_div(p.num_blocks, splits);
+  pl->splits = ceil_div(p.num_blocks, p.blocks_per_split);
+  int cols = p.tpc * p.bn;
+  int tc = 32;
+  while (tc < cols) tc <<= 1;
+  pl->tmem_cols = tc;
+  const int stage = kWgPix * 2 * (p.kc_a * p.ma + p.kc_b * p.nb * p.tpc);
+  pl->smem = stage * kWgStages + 1024;
+  return 0;
+}
+}  // namespace
+
+extern "C" int64_t yb200_conv2d_wgrad_workspace(const yb200_act* x, const yb200_act* dz, int ksize, int stride) {
+  WgradPlan pl;
+  int rc = plan_wgrad(x, dz, ksize, stride, &pl);
+  if (rc) return rc;
+  return 4LL * pl.splits * pl.p.cout * pl.p.num_taps * pl.p.cin;
+}
+
+template <int TC>
+static int launch_wgrad_inst(const CUtensorMap& tmDz, const CUtensorMap& tmX, const WgradPlan& pl, dim3 grid, cudaStream_t st) {
+  static int max_set = 0;
+  if (pl.smem > max_set) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+    max_set = pl.smem;
+  }
+  wgrad_gemm_kernel<TC><<<grid, kConvThreads, pl.smem, st>>>(tmDz, tmX, pl.p);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_conv2d_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real, float* grad_oihw,
+                                  int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+  WgradPlan pl;
+  int rc = plan_wgrad(x, dz, ksize, stride, &pl);
+  if (rc) return rc;
+  YB_REQUIRE(grad_oihw && workspace, YB200_ERR_INVALID, "conv2d_wgrad: null pointer");
+  YB_REQUIRE(cin_real > 0 && cin_real <= x->c, YB200_ERR_INVALID, "conv2d_wgrad: cin_real %d vs padded %d", cin_real, x->c);
+  const int64_t need = 4LL * pl.splits * pl.p.cout * pl.p.num_taps * pl.p.cin;
+  YB_REQUIRE(workspace_bytes >= need, YB200_ERR_INVALID, "conv2d_wgrad: workspace %lld < %lld bytes", (long long)workspace_bytes,
+             (long long)need);
+  pl.p.ws = static_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap tmDz, tmX;
+  if ((rc = make_act_map(&tmDz, *dz, false, pl.p.kc_a, pl.tw, pl.th, pl.tn))) return rc;
+  if ((rc = make_act_map(&tmX, *x, stride == 2, pl.p.kc_b, pl.tw, pl.th, pl.tn))) return rc;
+  dim3 grid(pl.p.cout_tiles * pl.p.cin_tiles * pl.p.tap_groups, pl.splits);
+  switch (pl.tmem_cols) {
+    case 32: rc = launch_wgrad_inst<32>(tmDz, tmX, pl, grid, st); break;
+    case 64: rc = launch_wgrad_inst<64>(tmDz, tmX, pl, grid, st); break;
+    case 128: rc = launch_wgrad_inst<128>(tmDz, tmX, pl, grid, st); break;
+    case 256: rc = launch_wgrad_inst<256>(tmDz, tmX, pl, grid, st); break;
+    case 512: rc = launch_wgrad_inst<512>(tmDz, tmX, pl, grid, st); break;
+    default: return fail(YB200_ERR_UNSUPPORTED, "conv2d_wgrad: %d TMEM columns", pl.tmem_cols);
+  }
+  if (rc) return rc;
+  const long long total = 1LL * pl.p.cout * pl.p.num_taps * pl.p.cin;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8 * sm_count()));
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(pl.p.ws, grad_oihw, pl.splits, pl.p.cout, pl.p.num_taps, pl.p.cin, cin_real, accumulate);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

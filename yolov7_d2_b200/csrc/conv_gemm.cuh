@@ -1,0 +1,257 @@
+// Implicit-GEMM convolution on tcgen05 (sm_100a).
+//
+//   D[128 pixels, BLOCK_N channels] = sum over (tap, cin-block)  A_tap[128 px, BLOCK_K] * B_tap[BLOCK_N, BLOCK_K]^T
+//
+// A is the NHWC bf16 activation tensor seen through a 5-D TMA map (c, w, p, h, n): a "tap" is a
+// coordinate offset of the 128-pixel box (TW x TH x TN), so zero padding is TMA out-of-bounds fill and
+// stride-2 convolutions are taps on the space-to-depth view (p = row parity, column parity folded into c).
+// B is the packed weight matrix [rows][taps*K] (K-major).  Accumulators live in TMEM; one CTA computes
+// one 128 x BLOCK_N output tile with a TMA->smem->UMMA mbarrier ring.
+//
+// Used for: conv forward (F3/F2/F8 of SURVEY.md par.8a), data-gradient (same kernel, transposed tap table)
+// and the 1x1 prediction convolutions (fp32 + bias epilogue).
+#pragma once
+#include "sm100.cuh"
+
+namespace yb {
+
+constexpr int kConvThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
+constexpr int kMaxTaps = 9;
+constexpr int kMaxStages = 4;
+
+enum EpiMode : int {
+  EPI_BF16 = 0,        // out = bf16(acc [+ addend])
+  EPI_BF16_STATS = 1,  // out = bf16(acc); per-channel sum / sum-of-squares of the stored values (fp64 atomics)
+  EPI_F32_BIAS = 2,    // out = acc + bias[c]   (fp32, arbitrary element strides)
+};
+
+struct ConvTap {
+  int c0;  // coordinate offset in the innermost (channel) dimension of the A map
+  int dw;  // offset in w
+  int p;   // coordinate in the parity dimension
+  int dh;  // offset in h
+  int kb;  // column offset of this tap inside the B matrix
+};
+
+struct ConvGemmParams {
+  int tiles_w, tiles_h, tiles_n;
+  int log_tw, log_th;          // tile = (1<<log_tw) x (1<<log_th) x (128 >> (log_tw+log_th)) pixels
+  int num_taps, cin_blocks;    // K loop = num_taps * cin_blocks blocks of BLOCK_K
+  int n_valid, h_valid, w_valid;  // pixel-grid extents (tile-space); pixels outside are neither stored nor counted
+  int cout;                    // valid output channels (columns >= cout are dropped)
+  int epi_mode;
+  // output element (n, y, x, c) lives at out[n*out_sn + (y*out_mh+out_ph)*out_sh + (x*out_mw+out_pw)*out_sw + c*out_sc]
+  long long out_sn, out_sh, out_sw;
+  int out_sc, out_mh, out_ph, out_mw, out_pw;
+  void* out;
+  const __nv_bfloat16* addend;  // optional, bf16, same (n,y,x) -> offset mapping with its own strides, channel stride 1
+  long long add_sn, add_sh, add_sw;
+  const float* bias;
+  double* stat_sum;
+  double* stat_sq;
+  ConvTap taps[kMaxTaps];
+};
+
+template <int BLOCK_N, int BLOCK_K>
+struct ConvGemmCfg {
+  static constexpr int kSwizzle = BLOCK_K * 2;  // bytes of one K-row: 32 / 64 / 128
+  static constexpr int kABytes = 128 * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;  // epilogue column chunk
+  static_assert(BLOCK_K == 16 || BLOCK_K == 32 || BLOCK_K == 64, "BLOCK_K");
+  static_assert(BLOCK_N == 16 || BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128, "BLOCK_N");
+  static_assert(kABytes % (8 * kSwizzle) == 0 && kStageBytes % (8 * kSwizzle) == 0, "tiles must start on a swizzle-pattern boundary");
+};
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(kConvThreads)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvGemmParams p, int num_stages) {
+  using Cfg = ConvGemmCfg<BLOCK_N, BLOCK_K>;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2 * kMaxStages + 1];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_sum[BLOCK_N];
+  __shared__ float s_sq[BLOCK_N];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // swizzled tiles need 1024B alignment
+  const uint32_t bar_full = smem_u32(&s_bar[0]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kMaxStages]);
+  const uint32_t bar_acc = smem_u32(&s_bar[2 * kMaxStages]);
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  const int log_tw = p.log_tw, log_th = p.log_th;
+  const int w0 = tw << log_tw, h0 = th << log_th, n0 = tn << (7 - log_tw - log_th);
+  const int col0 = blockIdx.y * BLOCK_N;
+  const int num_kb = p.num_taps * p.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_fence_init();
+  }
+  if (threadIdx.x < BLOCK_N) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(&s_tmem));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t full = bar_full + 8 * stage;
+        mbar_expect_tx(full, Cfg::kStageBytes);
+        const ConvTap& tp = p.taps[tap];
+        tma_load_5d(sa, &tmA, full, tp.c0 + cb * BLOCK_K, w0 + tp.dw, tp.p, h0 + tp.dh, n0);
+        tma_load_2d(sb, &tmB, full, tp.kb + cb * BLOCK_K, col0);
+        if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected thread) =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t lcode = umma_layout_code(Cfg::kSwizzle);
+      constexpr uint32_t sbo = 8 * Cfg::kSwizzle;  // 8 rows of one swizzle atom
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
+          const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
+          umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(bar_acc);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;
+    const int xl = m & ((1 << log_tw) - 1);
+    const int yl = (m >> log_tw) & ((1 << log_th) - 1);
+    const int nl = m >> (log_tw + log_th);
+    const int x = w0 + xl, y = h0 + yl, n = n0 + nl;
+    const bool valid = (x < p.w_valid) && (y < p.h_valid) && (n < p.n_valid);
+    const long long pix_off = (long long)n * p.out_sn + (long long)(y * p.out_mh + p.out_ph) * p.out_sh +
+                              (long long)(x * p.out_mw + p.out_pw) * p.out_sw;
+    const long long add_off = (long long)n * p.add_sn + (long long)(y * p.out_mh + p.out_ph) * p.add_sh +
+                              (long long)(x * p.out_mw + p.out_pw) * p.add_sw;
+
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+
+    constexpr int CH = Cfg::kChunk;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += CH) {
+      uint32_t r[CH];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c;
+      if constexpr (CH == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
+      tmem_ld_wait();
+      float v[CH];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+      const int cbase = col0 + c;
+
+      if (p.epi_mode == EPI_F32_BIAS) {
+        if (valid) {
+          float* o = reinterpret_cast<float*>(p.out) + pix_off;
+#pragma unroll
+          for (int i = 0; i < CH; ++i)
+            if (cbase + i < p.cout) o[(long long)(cbase + i) * p.out_sc] = v[i] + p.bias[cbase + i];
+        }
+      } else {
+        if (p.addend != nullptr && valid) {
+          const __nv_bfloat16* a = p.addend + add_off + cbase;
+#pragma unroll
+          for (int i = 0; i < CH; i += 8) {
+            if (cbase + i < p.cout) {
+              const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+              v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
+              v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
+              v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
+              v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
+            }
+          }
+        }
+        // round once; statistics describe exactly the values that are stored
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = valid ? bf16_round(v[i]) : 0.f;
+        if (valid) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
+#pragma unroll
+          for (int i = 0; i < CH; i += 8)
+            if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+        }
+        if (p.epi_mode == EPI_BF16_STATS) {
+          float sq[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
+          float cs, cq;
+          if constexpr (CH == 32) { cs = warp_colsum32(v, lane); cq = warp_colsum32(sq, lane); }
+          else { cs = warp_colsum16(v, lane); cq = warp_colsum16(sq, lane); }
+          if (lane < CH) {
+            atomicAdd(&s_sum[c + lane], cs);
+            atomicAdd(&s_sq[c + lane], cq);
+          }
+        }
+      }
+    }
+    if (p.epi_mode == EPI_BF16_STATS) {
+      named_bar_sync(1, 128);  // the four epilogue warps
+      const int e = threadIdx.x - 64;
+      if (e < BLOCK_N && col0 + e < p.cout) {
+        atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s_sum[e]));
+        atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s_sq[e]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+}  // namespace yb

@@ -1,0 +1,43 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, TMA descriptor encoding,
+// tile selection.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/yb200.h"
+
+namespace yb {
+
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+int sm_count();
+
+#define YB_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return yb::fail(YB200_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define YB_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) return yb::fail(code, __VA_ARGS__); \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// 5-D TMA view (c, w, p, h, n) of an NHWC bf16 activation.  space_to_depth=false: p is a dummy dimension of
+// extent 1.  space_to_depth=true (stride-2 taps): rows split into (h/2, p=row parity) and the column parity is
+// folded into the channel coordinate (c' = col_parity*c_pitch + c).
+int make_act_map(CUtensorMap* m, const yb200_act& a, bool space_to_depth, int box_c, int tw, int th, int tn);
+// 2-D K-major bf16 matrix [rows][cols], box [box_rows][box_cols]
+int make_mat_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, int box_rows, int box_cols);
+
+// pick (tw, th, tn) with tw*th*tn == npix (power of two) minimising padded pixels for an (n,h,w) grid
+void choose_tile(int n, int h, int w, int npix, int* log_tw, int* log_th);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+}  // namespace yb
