@@ -71,6 +71,78 @@ int64_t yb200_conv2d_wgrad_workspace(const yb200_act* x, const yb200_act* dz, in
 int yb200_conv2d_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real,
                        float* grad_oihw, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- preprocessing ------------------------------------------------------------------------------- */
+/* uint8 NCHW images -> Focus (space-to-depth) NHWC bf16 [n, h/2, w/2, 16]: channel = patch*3 + rgb with patch order
+ * (top-left, bottom-left, top-right, bottom-right) as wrappers.py:210-220, channels 12..15 zero.  No mean/std
+ * normalisation (yolox.py:98).  hw_valid (device int32 [n][2], may be NULL) gives each image's true (h, w); pixels
+ * beyond it read as pad_value = MODEL.PADDED_VALUE 114 (yolox.py:100-101, detectron2 ImageList.from_tensors).   */
+int yb200_preprocess_focus(const uint8_t* images_nchw, int n, int h, int w, const int32_t* hw_valid, float pad_value,
+                           const yb200_act* out, void* stream);
+
+/* ---- BatchNorm + SiLU (nn.BatchNorm2d + nn.SiLU of BaseConv, wrappers.py:76-80; eps/momentum yolox.py:85-90) ---- */
+/* Training statistics -> per-channel affine: scale = gamma*invstd, shift = beta - mean*scale (biased variance);
+ * updates running_mean / running_var (unbiased variance, momentum) and num_batches_tracked in place when given;
+ * zeroes stat_sum / stat_sqsum for the next step.                                                          */
+int yb200_bn_finalize(double* stat_sum, double* stat_sqsum, int c, int64_t count, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+/* Eval mode: scale/shift from running statistics (the folding of utils/checkpoint.py:11-43 as an epilogue).   */
+int yb200_bn_eval_affine(int c, const float* gamma, const float* beta, const float* running_mean,
+                         const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* out = SiLU(z*scale + shift) [+ residual]  (Bottleneck shortcut, wrappers.py:119-123); when out_up2x is given the
+ * result is also written nearest-upsampled x2 into that view (nn.Upsample + torch.cat of yolo_pafpn.py:96-102). */
+int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const float* shift, const yb200_act* residual,
+                        const yb200_act* out, const yb200_act* out_up2x, void* stream);
+/* Backward of SiLU(BN(z)) in training mode.  The incoming gradient is da [+ da2] [+ 2x2 sum-pool of da_up2x]
+ * (fan-out of the activation / backward of the upsample).  Writes dz (bf16) and dgamma / dbeta (fp32, optionally
+ * accumulated).  acc_dgamma / acc_dbeta: fp64 scratch [c], must be zero on entry, are zero on exit.          */
+int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const yb200_act* da2, const yb200_act* da_up2x,
+                      const float* scale, const float* shift, const float* save_mean, const float* save_invstd,
+                      double* acc_dgamma, double* acc_dbeta, const yb200_act* dz, float* dgamma, float* dbeta,
+                      int accumulate, void* stream);
+
+/* ---- SPP / concat helpers ------------------------------------------------------------------------ */
+/* nn.MaxPool2d(k, 1, k//2) for k = 5, 9, 13 written into three channel slices (SPPBottleneck, wrappers.py:150-160).
+ * argmax (may be NULL): uint8 [3][n][h][w][c] window offsets for the backward.                                */
+int yb200_spp_pool(const yb200_act* x, const yb200_act* o5, const yb200_act* o9, const yb200_act* o13, uint8_t* argmax,
+                   void* stream);
+/* dx = d0 + maxpool-backward(d5, d9, d13);  scratch: fp32 [n*h*w*c].                                           */
+int yb200_spp_pool_bwd(const yb200_act* d0, const yb200_act* d5, const yb200_act* d9, const yb200_act* d13,
+                       const uint8_t* argmax, float* scratch, const yb200_act* dx, void* stream);
+int yb200_copy_view(const yb200_act* src, const yb200_act* dst, void* stream);
+
+/* ---- YOLOX head tail: decode, SimOTA, losses ----------------------------------------------------- */
+/* level_hw_stride: HOST int32 [num_levels][3] = (h, w, stride) of each FPN level, anchors ordered level by level,
+ * row-major (yolox_head.py:226-245).  outputs: [batch][num_anchors][5+C] fp32 = (x, y, w, h, obj, cls...).     */
+/* In place: xy = (xy + grid)*stride, wh = exp(wh)*stride (yolox_head.py:238-244); eval_mode also applies sigmoid to
+ * obj / cls (yolox_head.py:209-211, 247-272).                                                                  */
+int yb200_yolox_decode(float* outputs, int batch, int num_anchors, int channels, const int32_t* level_hw_stride,
+                       int num_levels, int eval_mode, void* stream);
+/* SimOTA dynamic-k assignment for the whole batch (get_assignments + get_in_boxes_info + dynamic_k_matching,
+ * yolox_head.py:450-669) on DECODED outputs and labels [batch][max_gt][5] = (cls, cx, cy, w, h), zero padded.
+ * Per anchor: fg_mask (u8), matched_gt (-1 when background), matched_iou, matched_cls; per image num_gt / num_fg;
+ * totals[0] = number of foreground anchors in the batch, totals[1] = number of gts.                            */
+int64_t yb200_simota_workspace(int batch, int num_anchors);
+int yb200_simota_assign(const float* outputs, const float* labels, int batch, int num_anchors, int channels, int max_gt,
+                        const int32_t* level_hw_stride, int num_levels, void* workspace, int32_t* num_gt,
+                        uint8_t* fg_mask, int32_t* matched_gt, float* matched_iou, int32_t* matched_cls,
+                        int32_t* num_fg_img, int32_t* totals, void* stream);
+/* Losses of get_losses (yolox_head.py:412-441) and/or their gradient w.r.t. the RAW (pre-decode) head outputs.
+ *   losses6 (device float[6], may be NULL): total, 5*iou, obj, cls, l1 (= 0), num_fg/num_gt.
+ *   weights3 (device float[3], NULL = no gradient): d objective / d (loss_iou, loss_obj, loss_cls)  (5, 1, 1 for `total`).
+ *   d_cls[l] / d_regobj[l] (HOST arrays of device pointers, one per level): bf16 NHWC [batch][h][w][C] / [..][16]
+ *   (reg 0-3, obj 4, zero padding) -- the dz tensors of the prediction convs.  d_dense: optional fp32 [batch][A][5+C].
+ *   bias_acc: optional fp64 [num_levels][5+C] accumulators (zeroed by the caller) of the summed gradients.
+ *   loss_acc3: fp64 scratch [3], zero on entry and exit.                                                        */
+int yb200_yolox_loss(const float* outputs, const float* labels, int batch, int num_anchors, int channels, int max_gt,
+                     const int32_t* level_hw_stride, int num_levels, const uint8_t* fg_mask, const int32_t* matched_gt,
+                     const float* matched_iou, const int32_t* matched_cls, const int32_t* totals, const float* weights3,
+                     double* loss_acc3, float* losses6, void* const* d_cls, void* const* d_regobj, float* d_dense,
+                     double* bias_acc, void* stream);
+/* bias gradients of reg_preds / obj_preds / cls_preds of one level out of bias_acc (which is re-zeroed).          */
+int yb200_head_bias_grad(double* bias_acc, int num_levels, int channels, int level, float* grad_reg_bias4,
+                         float* grad_obj_bias1, float* grad_cls_bias, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,10 @@ SHAPES = [
     (5, 12, 20, 128, 128, 3, 2),   # ragged stride 2
     (2, 80, 80, 128, 128, 3, 1),   # 80x80 head level
     (1, 320, 320, 16, 32, 3, 1),   # full-size stem row tiles
+    (1, 32, 32, 16, 32, 3, 1),     # single image
+    (16, 64, 64, 16, 32, 3, 1),    # 512 CTAs: several CTAs resident per SM, more than one wave
+    (16, 64, 64, 64, 64, 1, 1),    # 512 single-k-block CTAs (memory-bound 1x1)
+    (8, 80, 80, 128, 128, 3, 1),   # 400 CTAs x 18 k-blocks
 ]
 
 

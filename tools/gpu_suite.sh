@@ -1,0 +1,22 @@
+#!/bin/bash
+# Runs the GPU test groups in separate processes (a trapped kernel kills its CUDA context, not the whole suite).
+# usage: tools/gpu_suite.sh [group ...]   logs -> gpurun_out/suite_<group>.log
+mkdir -p gpurun_out
+groups=("$@")
+[ ${#groups[@]} -eq 0 ] && groups=(conv_fwd conv_misc conv_dgrad conv_wgrad elementwise simota engine)
+for g in "${groups[@]}"; do
+  case $g in
+    conv_fwd)    sel="tests/test_conv_gpu.py -k test_conv_fwd_stats" ;;
+    conv_misc)   sel="tests/test_conv_gpu.py -k 'slices or bias'" ;;
+    conv_dgrad)  sel="tests/test_conv_gpu.py -k test_conv_dgrad" ;;
+    conv_wgrad)  sel="tests/test_conv_gpu.py -k test_conv_wgrad" ;;
+    elementwise) sel="tests/test_elementwise_gpu.py" ;;
+    simota)      sel="tests/test_simota_gpu.py" ;;
+    engine)      sel="tests/test_engine_gpu.py" ;;
+    nms)         sel="tests/test_nms_gpu.py" ;;
+    *)           sel="$g" ;;
+  esac
+  echo "=== $g"
+  eval timeout 300 python -m pytest $sel -m gpu -q -x --timeout=120 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -60 | cut -c1-400 > gpurun_out/suite_$g.log
+  tail -4 gpurun_out/suite_$g.log
+done

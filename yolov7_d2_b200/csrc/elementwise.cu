@@ -1,0 +1,518 @@
+// HBM-bound kernels around the convolutions: image preprocessing (Focus layout), BatchNorm finalize / apply+SiLU /
+// backward, SPP max-pooling, nearest upsampling.  All activations are NHWC bf16 views (see include/yb200.h); every
+// thread moves 8 channels (16 bytes) per access so warps read and write whole 128-byte lines.
+#include <algorithm>
+
+#include "host_common.cuh"
+#include "sm100.cuh"
+
+using namespace yb;
+
+namespace {
+
+struct View {  // device-side copy of yb200_act with element strides resolved
+  __nv_bfloat16* p;  // already offset by c_off
+  int n, h, w, c, pitch;
+};
+
+View mk(const yb200_act* a) {
+  View v;
+  v.p = static_cast<__nv_bfloat16*>(a->ptr) + a->c_off;
+  v.n = a->n; v.h = a->h; v.w = a->w; v.c = a->c; v.pitch = a->c_pitch;
+  return v;
+}
+
+int check_view(const yb200_act* a, const char* name) {
+  YB_REQUIRE(a && a->ptr, YB200_ERR_INVALID, "%s: null view", name);
+  YB_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0 && a->c > 0 && a->c % 8 == 0 && a->c_pitch % 8 == 0 && a->c_off % 8 == 0 &&
+                 a->c_off + a->c <= a->c_pitch,
+             YB200_ERR_INVALID, "%s: bad view n=%d h=%d w=%d c=%d pitch=%d off=%d", name, a->n, a->h, a->w, a->c, a->c_pitch, a->c_off);
+  return 0;
+}
+
+bool same_shape(const yb200_act* a, const yb200_act* b) { return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c; }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+
+int grid_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  long long cap = 32LL * sm_count();
+  return static_cast<int>(std::max<long long>(1, std::min(b, cap)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// preprocess: uint8 NCHW image batch -> Focus (space-to-depth) NHWC bf16 with 16 channels
+//   channel = patch*3 + rgb, patch order (top-left, bottom-left, top-right, bottom-right)   wrappers.py:210-220
+//   channels 12..15 are zero (pads K to the UMMA granule); pixels beyond (h_valid[n], w_valid[n]) read as pad_value
+//   (detectron2 ImageList.from_tensors with MODEL.PADDED_VALUE = 114, yolox.py:100-101).
+// ------------------------------------------------------------------------------------------------
+__global__ void preprocess_focus_kernel(const uint8_t* __restrict__ img, int n, int h, int w, const int* __restrict__ hw_valid,
+                                        float pad_value, __nv_bfloat16* __restrict__ out) {
+  const int oh = h / 2, ow = w / 2;
+  const long long total = 1LL * n * oh * ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % ow);
+    const int y = static_cast<int>((i / ow) % oh);
+    const int b = static_cast<int>(i / (1LL * ow * oh));
+    const int hv = hw_valid ? hw_valid[2 * b] : h;
+    const int wv = hw_valid ? hw_valid[2 * b + 1] : w;
+    float f[16];
+#pragma unroll
+    for (int patch = 0; patch < 4; ++patch) {
+      const int yy = 2 * y + (patch & 1);   // patches 1 and 3 are the odd rows
+      const int xx = 2 * x + (patch >> 1);  // patches 2 and 3 are the odd columns
+      const bool in = yy < hv && xx < wv;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        f[patch * 3 + c] = in ? static_cast<float>(img[((1LL * b * 3 + c) * h + yy) * w + xx]) : pad_value;
+    }
+    f[12] = f[13] = f[14] = f[15] = 0.f;
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = pack8(f);
+    o[1] = pack8(f + 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (training): finalize statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(double* __restrict__ ssum, double* __restrict__ ssq, int c, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && num_batches) *num_batches += 1;
+  if (i >= c) return;
+  const double mean = ssum[i] / count;
+  double var = ssq[i] / count - mean * mean;  // biased variance, used for normalisation (ATen batch_norm)
+  if (var < 0) var = 0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma[i];
+  scale[i] = g * invstd;
+  shift[i] = beta[i] - static_cast<float>(mean) * g * invstd;
+  mean_out[i] = static_cast<float>(mean);
+  invstd_out[i] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * static_cast<float>(mean);
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * static_cast<float>(unbiased);
+  }
+  ssum[i] = 0.0;  // ready for the next step
+  ssq[i] = 0.0;
+}
+
+// eval mode: scale/shift from the running statistics (the fold of utils/checkpoint.py:11-43 applied as an epilogue)
+__global__ void bn_eval_affine_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
+                                      const float* __restrict__ rv, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float s = gamma[i] / sqrtf(rv[i] + eps);
+  scale[i] = s;
+  shift[i] = beta[i] - rm[i] * s;
+}
+
+// a = SiLU(z*scale + shift) [+ residual];  optionally also written 2x nearest-upsampled into a second view
+__global__ void bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     int has_res, int has_up) {
+  const int cv = z.c / 8;
+  const long long total = 1LL * z.n * z.h * z.w * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv) * 8;
+    const long long pix = i / cv;
+    float f[8], s[8], t[8];
+    unpack8(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), f);
+    *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale + c8);
+    *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale + c8 + 4);
+    *reinterpret_cast<float4*>(t) = *reinterpret_cast<const float4*>(shift + c8);
+    *reinterpret_cast<float4*>(t + 4) = *reinterpret_cast<const float4*>(shift + c8 + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], s[k], t[k]));
+    if (has_res) {
+      // residual is added to the *rounded* activation, as in the reference where y = conv2(...) is materialised first
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(res.p + pix * res.pitch + c8), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k]) + r[k];
+    }
+    const uint4 o = pack8(f);
+    *reinterpret_cast<uint4*>(a.p + pix * a.pitch + c8) = o;
+    if (has_up) {
+      const int x = static_cast<int>(pix % z.w);
+      const int y = static_cast<int>((pix / z.w) % z.h);
+      const long long b = pix / (1LL * z.w * z.h);
+      __nv_bfloat16* u = up.p + ((b * up.h + 2 * y) * up.w + 2 * x) * up.pitch + c8;
+      *reinterpret_cast<uint4*>(u) = o;
+      *reinterpret_cast<uint4*>(u + up.pitch) = o;
+      *reinterpret_cast<uint4*>(u + (long long)up.w * up.pitch) = o;
+      *reinterpret_cast<uint4*>(u + (long long)(up.w + 1) * up.pitch) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + SiLU backward
+//   u = z*scale + shift, a = silu(u);   du = da * sig(u) * (1 + u*(1-sig(u)))
+//   pass 1: dbeta = sum du, dgamma = sum du * zhat        (zhat = (z-mean)*invstd)
+//   pass 2: dz = gamma*invstd * (du - dbeta/M - zhat*dgamma/M)
+// `da` may be the sum of up to two views (fan-out of the activation) and, for upsampled consumers, a third view that
+// is 2x larger and gets 2x2 sum-pooled (backward of nn.Upsample(nearest), yolo_pafpn.py:28).
+// ------------------------------------------------------------------------------------------------
+struct DaSrc {
+  View a, b, up;
+  int has_b, has_up;
+};
+
+__device__ __forceinline__ void load_da(const DaSrc& s, long long pix, int x, int y, long long bimg, int c8, float* d) {
+  unpack8(*reinterpret_cast<const uint4*>(s.a.p + pix * s.a.pitch + c8), d);
+  if (s.has_b) {
+    float e[8];
+    unpack8(*reinterpret_cast<const uint4*>(s.b.p + pix * s.b.pitch + c8), e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] += e[k];
+  }
+  if (s.has_up) {
+    const __nv_bfloat16* u = s.up.p + ((bimg * s.up.h + 2 * y) * s.up.w + 2 * x) * s.up.pitch + c8;
+    float e[8];
+    const long long offs[4] = {0, s.up.pitch, (long long)s.up.w * s.up.pitch, (long long)(s.up.w + 1) * s.up.pitch};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      unpack8(*reinterpret_cast<const uint4*>(u + offs[q]), e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] += e[k];
+    }
+  }
+}
+
+constexpr int kBnBwdThreads = 256;
+
+// grid.x covers pixel chunks, each block reduces its chunk for all channels into fp64 atomics
+__global__ void __launch_bounds__(kBnBwdThreads)
+bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, int pix_per_block) {
+  extern __shared__ float sm[];  // [2][c]
+  const int cv = z.c / 8;
+  for (int i = threadIdx.x; i < 2 * z.c; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const long long npix = 1LL * z.n * z.h * z.w;
+  const long long p0 = 1LL * blockIdx.x * pix_per_block;
+  const long long p1 = min(npix, p0 + pix_per_block);
+  // thread t owns channel vector (t % cv) and walks pixels with stride blockDim/cv -> per-thread partial sums in registers
+  const int lanes_per_pix = cv;
+  const int my_cv = threadIdx.x % lanes_per_pix;
+  const int pix_stride = blockDim.x / lanes_per_pix;
+  const int c8 = my_cv * 8;
+  float gs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (threadIdx.x < pix_stride * lanes_per_pix) {
+    float s[8], t[8], mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; mu[k] = mean[c8 + k]; is[k] = invstd[c8 + k]; }
+    for (long long pix = p0 + threadIdx.x / lanes_per_pix; pix < p1; pix += pix_stride) {
+      const int x = static_cast<int>(pix % z.w);
+      const int y = static_cast<int>((pix / z.w) % z.h);
+      const long long b = pix / (1LL * z.w * z.h);
+      float zf[8], d[8];
+      unpack8(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
+      load_da(da, pix, x, y, b, c8, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float u = fmaf(zf[k], s[k], t[k]);
+        const float sg = 1.f / (1.f + __expf(-u));
+        const float du = d[k] * sg * (1.f + u * (1.f - sg));
+        bs[k] += du;
+        gs[k] += du * (zf[k] - mu[k]) * is[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sm[c8 + k], gs[k]);
+      atomicAdd(&sm[z.c + c8 + k], bs[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < z.c; i += blockDim.x) {
+    atomicAdd(dgamma_acc + i, static_cast<double>(sm[i]));
+    atomicAdd(dbeta_acc + i, static_cast<double>(sm[z.c + i]));
+  }
+}
+
+__global__ void bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
+                                         const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
+                                         const double* __restrict__ dbeta_acc, double inv_count) {
+  const int cv = z.c / 8;
+  const long long total = 1LL * z.n * z.h * z.w * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv) * 8;
+    const long long pix = i / cv;
+    const int x = static_cast<int>(pix % z.w);
+    const int y = static_cast<int>((pix / z.w) % z.h);
+    const long long b = pix / (1LL * z.w * z.h);
+    float zf[8], d[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
+    load_da(da, pix, x, y, b, c8, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 + k;
+      const float s = scale[c], is = invstd[c];
+      const float u = fmaf(zf[k], s, shift[c]);
+      const float sg = 1.f / (1.f + __expf(-u));
+      const float du = d[k] * sg * (1.f + u * (1.f - sg));
+      const float zh = (zf[k] - mean[c]) * is;
+      const float mg = static_cast<float>(dgamma_acc[c] * inv_count);
+      const float mb = static_cast<float>(dbeta_acc[c] * inv_count);
+      o[k] = s * (du - mb - zh * mg);  // s = gamma*invstd
+    }
+    *reinterpret_cast<uint4*>(dz.p + pix * dz.pitch + c8) = pack8(o);
+  }
+}
+
+// parameter gradients out of the fp64 accumulators, then re-zero them
+__global__ void bn_param_grad_kernel(double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, int c, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float g = static_cast<float>(dgamma_acc[i]), b = static_cast<float>(dbeta_acc[i]);
+  dgamma[i] = accumulate ? dgamma[i] + g : g;
+  dbeta[i] = accumulate ? dbeta[i] + b : b;
+  dgamma_acc[i] = 0.0;
+  dbeta_acc[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPP: max-pool k = 5, 9, 13 (stride 1, pad k/2, -inf padding) of x into three channel slices; argmax offsets kept
+// for the backward (first maximum in row-major window order, as ATen max_pool2d_with_indices).
+// ------------------------------------------------------------------------------------------------
+__global__ void spp_pool_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ arg) {
+  const int cv = x.c / 8;
+  const long long total = 1LL * x.n * x.h * x.w * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv) * 8;
+    const long long pix = i / cv;
+    const int px = static_cast<int>(pix % x.w);
+    const int py = static_cast<int>((pix / x.w) % x.h);
+    const long long b = pix / (1LL * x.w * x.h);
+    float m[3][8];
+    int am[3][8];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { m[j][k] = -INFINITY; am[j][k] = 0; }
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int yy = py + dy;
+      if (yy < 0 || yy >= x.h) continue;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int xx = px + dx;
+        if (xx < 0 || xx >= x.w) continue;
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(x.p + ((b * x.h + yy) * x.w + xx) * x.pitch + c8), v);
+        const int ady = dy < 0 ? -dy : dy, adx = dx < 0 ? -dx : dx;
+        const int r = ady > adx ? ady : adx;  // Chebyshev radius: window k covers r <= k/2
+        const int code = (dy + 6) * 13 + (dx + 6);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (v[k] > m[2][k]) { m[2][k] = v[k]; am[2][k] = code; }
+          if (r <= 4 && v[k] > m[1][k]) { m[1][k] = v[k]; am[1][k] = code; }
+          if (r <= 2 && v[k] > m[0][k]) { m[0][k] = v[k]; am[0][k] = code; }
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(o5.p + pix * o5.pitch + c8) = pack8(m[0]);
+    *reinterpret_cast<uint4*>(o9.p + pix * o9.pitch + c8) = pack8(m[1]);
+    *reinterpret_cast<uint4*>(o13.p + pix * o13.pitch + c8) = pack8(m[2]);
+    if (arg) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        uint8_t* a = arg + ((1LL * j * x.n * x.h * x.w + pix) * x.c + c8);
+        uint2 pk;
+        pk.x = am[j][0] | (am[j][1] << 8) | (am[j][2] << 16) | (am[j][3] << 24);
+        pk.y = am[j][4] | (am[j][5] << 8) | (am[j][6] << 16) | (am[j][7] << 24);
+        *reinterpret_cast<uint2*>(a) = pk;
+      }
+    }
+  }
+}
+
+// backward: scatter the three pooled gradients to their argmax positions (fp32 atomics into a zeroed scratch), ...
+__global__ void spp_pool_bwd_scatter_kernel(View d5, View d9, View d13, const uint8_t* __restrict__ arg, float* __restrict__ scratch, int n,
+                                            int h, int w, int c) {
+  const long long total = 3LL * n * h * w * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const long long pix = (i / c) % (1LL * n * h * w);
+    const int j = static_cast<int>(i / (1LL * c * n * h * w));
+    const View& d = j == 0 ? d5 : (j == 1 ? d9 : d13);
+    const float g = __bfloat162float(d.p[pix * d.pitch + ch]);
+    const int code = arg[i];
+    const int dy = code / 13 - 6, dx = code % 13 - 6;
+    const int px = static_cast<int>(pix % w), py = static_cast<int>((pix / w) % h);
+    const long long b = pix / (1LL * w * h);
+    atomicAdd(scratch + ((b * h + py + dy) * w + px + dx) * c + ch, g);
+  }
+}
+// ... then dx = identity-branch gradient + scattered sums
+__global__ void spp_pool_bwd_finish_kernel(View d0, const float* __restrict__ scratch, View dx) {
+  const int cv = dx.c / 8;
+  const long long total = 1LL * dx.n * dx.h * dx.w * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv) * 8;
+    const long long pix = i / cv;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(d0.p + pix * d0.pitch + c8), f);
+    const float* s = scratch + pix * dx.c + c8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += s[k];
+    *reinterpret_cast<uint4*>(dx.p + pix * dx.pitch + c8) = pack8(f);
+  }
+}
+
+// plain copy between views (used to place an activation into a concat slice when it cannot be produced there)
+__global__ void copy_view_kernel(View s, View d) {
+  const int cv = s.c / 8;
+  const long long total = 1LL * s.n * s.h * s.w * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv) * 8;
+    const long long pix = i / cv;
+    *reinterpret_cast<uint4*>(d.p + pix * d.pitch + c8) = *reinterpret_cast<const uint4*>(s.p + pix * s.pitch + c8);
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int yb200_preprocess_focus(const uint8_t* images_nchw, int n, int h, int w, const int32_t* hw_valid, float pad_value,
+                                      const yb200_act* out, void* stream) {
+  YB_REQUIRE(images_nchw && out && out->ptr, YB200_ERR_INVALID, "preprocess_focus: null pointer");
+  YB_REQUIRE(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, YB200_ERR_INVALID, "preprocess_focus: image %dx%dx%d", n, h, w);
+  YB_REQUIRE(out->n == n && out->h == h / 2 && out->w == w / 2 && out->c == 16 && out->c_pitch == 16 && out->c_off == 0, YB200_ERR_INVALID,
+             "preprocess_focus: output must be a dense [n,h/2,w/2,16] view");
+  const long long total = 1LL * n * (h / 2) * (w / 2);
+  preprocess_focus_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(images_nchw, n, h, w, hw_valid, pad_value,
+                                                                              static_cast<__nv_bfloat16*>(out->ptr));
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_bn_finalize(double* stat_sum, double* stat_sqsum, int c, int64_t count, const float* gamma, const float* beta, float eps,
+                                 float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
+                                 float* shift, float* save_mean, float* save_invstd, void* stream) {
+  YB_REQUIRE(stat_sum && stat_sqsum && gamma && beta && scale && shift && save_mean && save_invstd, YB200_ERR_INVALID, "bn_finalize: null pointer");
+  YB_REQUIRE(c > 0 && count > 0, YB200_ERR_INVALID, "bn_finalize: c=%d count=%lld", c, (long long)count);
+  YB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), YB200_ERR_INVALID, "bn_finalize: running stats must come in pairs");
+  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, as_stream(stream)>>>(stat_sum, stat_sqsum, c, static_cast<double>(count), gamma, beta, eps,
+                                                                      momentum, running_mean, running_var,
+                                                                      reinterpret_cast<long long*>(num_batches_tracked), scale, shift,
+                                                                      save_mean, save_invstd);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_bn_eval_affine(int c, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                                    float* scale, float* shift, void* stream) {
+  YB_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && c > 0, YB200_ERR_INVALID, "bn_eval_affine: bad arguments");
+  bn_eval_affine_kernel<<<ceil_div(c, 128), 128, 0, as_stream(stream)>>>(c, gamma, beta, running_mean, running_var, eps, scale, shift);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const float* shift, const yb200_act* residual, const yb200_act* out,
+                                   const yb200_act* out_up2x, void* stream) {
+  int rc;
+  if ((rc = check_view(z, "bn_apply_silu z")) || (rc = check_view(out, "bn_apply_silu out"))) return rc;
+  if (residual && (rc = check_view(residual, "bn_apply_silu residual"))) return rc;
+  if (out_up2x && (rc = check_view(out_up2x, "bn_apply_silu out_up2x"))) return rc;
+  YB_REQUIRE(scale && shift, YB200_ERR_INVALID, "bn_apply_silu: null scale/shift");
+  YB_REQUIRE(same_shape(z, out) && (!residual || same_shape(z, residual)), YB200_ERR_INVALID, "bn_apply_silu: shape mismatch");
+  YB_REQUIRE(!out_up2x || (out_up2x->n == z->n && out_up2x->h == 2 * z->h && out_up2x->w == 2 * z->w && out_up2x->c == z->c), YB200_ERR_INVALID,
+             "bn_apply_silu: upsampled view must be [n,2h,2w,c]");
+  View vz = mk(z), vo = mk(out), vr = residual ? mk(residual) : vz, vu = out_up2x ? mk(out_up2x) : vz;
+  const long long total = 1LL * z->n * z->h * z->w * (z->c / 8);
+  bn_apply_silu_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(vz, vo, vr, vu, scale, shift, residual != nullptr, out_up2x != nullptr);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const yb200_act* da2, const yb200_act* da_up2x, const float* scale,
+                                 const float* shift, const float* save_mean, const float* save_invstd, double* acc_dgamma, double* acc_dbeta,
+                                 const yb200_act* dz, float* dgamma, float* dbeta, int accumulate, void* stream) {
+  int rc;
+  if ((rc = check_view(z, "bn_silu_bwd z")) || (rc = check_view(da, "bn_silu_bwd da")) || (rc = check_view(dz, "bn_silu_bwd dz"))) return rc;
+  if (da2 && (rc = check_view(da2, "bn_silu_bwd da2"))) return rc;
+  if (da_up2x && (rc = check_view(da_up2x, "bn_silu_bwd da_up2x"))) return rc;
+  YB_REQUIRE(scale && shift && save_mean && save_invstd && acc_dgamma && acc_dbeta && dgamma && dbeta, YB200_ERR_INVALID, "bn_silu_bwd: null pointer");
+  YB_REQUIRE(same_shape(z, da) && same_shape(z, dz) && (!da2 || same_shape(z, da2)), YB200_ERR_INVALID, "bn_silu_bwd: shape mismatch");
+  YB_REQUIRE(!da_up2x || (da_up2x->n == z->n && da_up2x->h == 2 * z->h && da_up2x->w == 2 * z->w && da_up2x->c == z->c), YB200_ERR_INVALID,
+             "bn_silu_bwd: upsampled gradient view must be [n,2h,2w,c]");
+  YB_REQUIRE(z->c / 8 <= kBnBwdThreads, YB200_ERR_UNSUPPORTED, "bn_silu_bwd: %d channels", z->c);
+  cudaStream_t st = as_stream(stream);
+  DaSrc src;
+  src.a = mk(da);
+  src.b = da2 ? mk(da2) : src.a;
+  src.up = da_up2x ? mk(da_up2x) : src.a;
+  src.has_b = da2 != nullptr;
+  src.has_up = da_up2x != nullptr;
+  View vz = mk(z), vdz = mk(dz);
+  const long long npix = 1LL * z->n * z->h * z->w;
+  const int pix_stride = kBnBwdThreads / (z->c / 8);
+  // enough blocks to fill the machine, each walking >= 8 pixel rows per thread
+  int blocks = static_cast<int>(std::min<long long>(8LL * sm_count(), std::max<long long>(1, npix / (8LL * pix_stride))));
+  const int ppb = static_cast<int>((npix + blocks - 1) / blocks);
+  blocks = static_cast<int>((npix + ppb - 1) / ppb);
+  bn_silu_bwd_reduce_kernel<<<blocks, kBnBwdThreads, 2 * z->c * sizeof(float), st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma,
+                                                                                      acc_dbeta, ppb);
+  YB_CHECK_CUDA(cudaGetLastError());
+  const long long total = npix * (z->c / 8);
+  bn_silu_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                                  1.0 / static_cast<double>(npix));
+  YB_CHECK_CUDA(cudaGetLastError());
+  bn_param_grad_kernel<<<ceil_div(z->c, 128), 128, 0, st>>>(acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_spp_pool(const yb200_act* x, const yb200_act* o5, const yb200_act* o9, const yb200_act* o13, uint8_t* argmax, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "spp_pool x")) || (rc = check_view(o5, "spp_pool o5")) || (rc = check_view(o9, "spp_pool o9")) ||
+      (rc = check_view(o13, "spp_pool o13")))
+    return rc;
+  YB_REQUIRE(same_shape(x, o5) && same_shape(x, o9) && same_shape(x, o13), YB200_ERR_INVALID, "spp_pool: shape mismatch");
+  const long long total = 1LL * x->n * x->h * x->w * (x->c / 8);
+  spp_pool_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(mk(x), mk(o5), mk(o9), mk(o13), argmax);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_spp_pool_bwd(const yb200_act* d0, const yb200_act* d5, const yb200_act* d9, const yb200_act* d13, const uint8_t* argmax,
+                                  float* scratch, const yb200_act* dx, void* stream) {
+  int rc;
+  if ((rc = check_view(d0, "spp_pool_bwd d0")) || (rc = check_view(d5, "spp_pool_bwd d5")) || (rc = check_view(d9, "spp_pool_bwd d9")) ||
+      (rc = check_view(d13, "spp_pool_bwd d13")) || (rc = check_view(dx, "spp_pool_bwd dx")))
+    return rc;
+  YB_REQUIRE(argmax && scratch, YB200_ERR_INVALID, "spp_pool_bwd: null pointer");
+  YB_REQUIRE(same_shape(dx, d0) && same_shape(dx, d5) && same_shape(dx, d9) && same_shape(dx, d13), YB200_ERR_INVALID, "spp_pool_bwd: shape mismatch");
+  cudaStream_t st = as_stream(stream);
+  const long long elems = 1LL * dx->n * dx->h * dx->w * dx->c;
+  YB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, elems * sizeof(float), st));
+  spp_pool_bwd_scatter_kernel<<<grid_for(3 * elems, 256), 256, 0, st>>>(mk(d5), mk(d9), mk(d13), argmax, scratch, dx->n, dx->h, dx->w, dx->c);
+  YB_CHECK_CUDA(cudaGetLastError());
+  spp_pool_bwd_finish_kernel<<<grid_for(elems / 8, 256), 256, 0, st>>>(mk(d0), scratch, mk(dx));
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_copy_view(const yb200_act* src, const yb200_act* dst, void* stream) {
+  int rc;
+  if ((rc = check_view(src, "copy_view src")) || (rc = check_view(dst, "copy_view dst"))) return rc;
+  YB_REQUIRE(same_shape(src, dst), YB200_ERR_INVALID, "copy_view: shape mismatch");
+  const long long total = 1LL * src->n * src->h * src->w * (src->c / 8);
+  copy_view_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(mk(src), mk(dst));
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

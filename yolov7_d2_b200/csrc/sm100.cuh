@@ -53,13 +53,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kills the context) instead of hanging the GPU box.
+// Bounded wait (about one second of SM clock): a protocol bug traps and kills the context instead of hanging the
+// GPU box until the job limit.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("yb200: mbarrier wait timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-             blockIdx.y, threadIdx.x, bar, parity);
+    if (clock64() - t0 > 2000000000LL) {
+      printf("yb200: mbarrier wait timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, bar, parity);
       __trap();
     }
   }

@@ -1,0 +1,550 @@
+"""Static execution plan of the YOLOX hot path on one B200: every tensor of the forward and backward pass is
+allocated once (NHWC bf16 activations, concat buffers addressed through channel-slice views, fp32 flat parameter /
+gradient buffers) and a step is a fixed sequence of C-ABI kernel launches -- capturable in a CUDA graph.
+
+Structure follows the reference (CSPDarknet darknetx.py:103-177, YOLOPAFPN yolo_pafpn.py:79-114, YOLOXHead
+yolox_head.py:151-245) with three fusions the reference cannot express:
+  * the two 1x1 convolutions of every CSPLayer (conv1, conv2: wrappers.py:194-195) and the first cls/reg 3x3
+    convolutions of the head (yolox_head.py:160-168) read the same input and run as ONE GEMM;
+  * torch.cat / nn.Upsample / Focus never materialise: producers write into channel slices of the consumer's buffer;
+  * the three prediction convolutions write the [B, A, 85] head output directly.
+There is no PyTorch fallback: every op is a libyb200.so call.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import capi
+
+BN_EPS = 1e-3       # yolox.py:85-90
+BN_MOMENTUM = 0.03
+STRIDES = (8, 16, 32)
+
+
+def _ceil(a, b):
+    return (a + b - 1) // b * b
+
+
+class Buf:
+    """NHWC bf16 activation buffer (+ lazily allocated gradient of the same shape)"""
+
+    def __init__(self, name, n, h, w, c, device):
+        self.name, self.n, self.h, self.w, self.c = name, n, h, w, c
+        self.t = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=device)
+        self.g = None
+        self.written = []  # channel ranges of .g already produced in the current backward pass
+
+    def view(self, off=0, c=None):
+        return View(self, off, self.c - off if c is None else c)
+
+    def grad(self):
+        if self.g is None:
+            self.g = torch.zeros_like(self.t)
+        return self.g
+
+
+class View:
+    def __init__(self, buf, off, c):
+        self.buf, self.off, self.c = buf, off, c
+        self._act = None
+        self._gact = None
+
+    def act(self):
+        if self._act is None:
+            self._act = capi.act(self.buf.t, self.off, self.c)
+        return ctypes.byref(self._act)
+
+    def gact(self):
+        if self._gact is None:
+            self._gact = capi.act(self.buf.grad(), self.off, self.c)
+        return ctypes.byref(self._gact)
+
+    @property
+    def shape(self):
+        return (self.buf.n, self.buf.h, self.buf.w, self.c)
+
+    def tensor(self):
+        return self.buf.t[..., self.off:self.off + self.c]
+
+    def grad_tensor(self):
+        return self.buf.grad()[..., self.off:self.off + self.c]
+
+
+class BnHead:
+    """one BatchNorm+SiLU of a (possibly merged) convolution: channel range [c0, c0+c) of the GEMM output"""
+
+    def __init__(self, prefix, c0, c, out, residual=None, up=None):
+        self.prefix, self.c0, self.c, self.out, self.residual, self.up = prefix, c0, c, out, residual, up
+
+
+class ConvOp:
+    def __init__(self, prefixes, x, z, heads, ksize, stride, cin_real):
+        self.prefixes, self.x, self.z, self.heads = prefixes, x, z, heads
+        self.ksize, self.stride, self.cin_real = ksize, stride, cin_real
+        self.cin_pad, self.cout = x.c, z.c
+        self.first = False  # no data gradient needed (network input)
+
+
+class PredOp:
+    """prediction 1x1 convolutions of one level: cls (C) and reg+obj (5), bias, fp32 output into [B, A, 5+C]"""
+
+    def __init__(self, level, cls_feat, reg_feat):
+        self.level, self.cls_feat, self.reg_feat = level, cls_feat, reg_feat
+
+
+class SppOp:
+    def __init__(self, views, arg):
+        self.views, self.arg = views, arg
+
+
+class YoloxEngine:
+    def __init__(self, batch, height, width, num_classes=80, width_mul=0.5, depth_mul=0.33, max_gt=100, device="cuda"):
+        assert height % 32 == 0 and width % 32 == 0, "input must be padded to a multiple of 32 (yolox.py:100-101)"
+        self.L = capi.lib()
+        self.dev = torch.device(device)
+        self.n, self.h, self.w, self.nc, self.max_gt = batch, height, width, num_classes, max_gt
+        self.wm, self.dm = width_mul, depth_mul
+        self.ops = []
+        self.bufs = {}
+        self.param_specs = []   # (name, shape) in flat order
+        self._build()
+        self._alloc_params()
+        self._alloc_runtime()
+
+    # ------------------------------------------------------------------ graph construction
+    def _buf(self, name, h, w, c):
+        b = Buf(name, self.n, h, w, c, self.dev)
+        self.bufs[name] = b
+        return b
+
+    def _conv(self, prefixes, x, couts, k, s, outs=None, residuals=None, ups=None, cin_real=None):
+        n, h, w, _ = x.shape
+        oh, ow = h // s, w // s
+        ctot = sum(couts)
+        z = self._buf(prefixes[0] + ".z", oh, ow, ctot)
+        heads, res = [], []
+        c0 = 0
+        for i, (p, c) in enumerate(zip(prefixes, couts)):
+            out = outs[i] if outs and outs[i] is not None else self._buf(p + ".a", oh, ow, c).view()
+            assert out.shape == (n, oh, ow, c), (p, out.shape, (n, oh, ow, c))
+            heads.append(BnHead(p, c0, c, out, residuals[i] if residuals else None, ups[i] if ups else None))
+            res.append(out)
+            c0 += c
+        op = ConvOp(prefixes, x, z.view(), heads, k, s, cin_real or x.c)
+        self.ops.append(op)
+        cin = op.cin_real
+        for p, c in zip(prefixes, couts):
+            self.param_specs.append((p + ".conv.weight", (c, cin, k, k)))
+        return res
+
+    def _csp(self, prefix, x, cout, n, shortcut, out=None):
+        hdn = cout // 2
+        _, h, w, _ = x.shape
+        cat = self._buf(prefix + ".cat", h, w, 2 * hdn)
+        y, _ = self._conv([prefix + ".conv1", prefix + ".conv2"], x, [hdn, hdn], 1, 1, outs=[None, cat.view(hdn, hdn)])
+        for i in range(n):
+            (t,) = self._conv([f"{prefix}.m.{i}.conv1"], y, [hdn], 1, 1)
+            (y,) = self._conv([f"{prefix}.m.{i}.conv2"], t, [hdn], 3, 1, outs=[cat.view(0, hdn) if i == n - 1 else None],
+                              residuals=[y if shortcut else None])
+        (o,) = self._conv([prefix + ".conv3"], cat.view(), [cout], 1, 1, outs=[out])
+        return o
+
+    def _build(self):
+        bc = int(self.wm * 64)
+        bd = max(round(self.dm * 3), 1)
+        nn_ = round(3 * self.dm)
+        H, W = self.h, self.w
+        c3, c4, c5 = bc * 4, bc * 8, bc * 16
+        focus = self._buf("focus", H // 2, W // 2, 16)
+        self.focus = focus
+        # concat buffers of the neck; backbone / neck producers write straight into their slices
+        cat_p4 = self._buf("neck.cat_p4", H // 16, W // 16, 2 * c4)   # [up(fpn_out0) | dark4]
+        cat_p3 = self._buf("neck.cat_p3", H // 8, W // 8, 2 * c3)     # [up(fpn_out1) | dark3]
+        cat_n3 = self._buf("neck.cat_n3", H // 16, W // 16, 2 * c3)   # [bu_conv2     | fpn_out1]
+        cat_n4 = self._buf("neck.cat_n4", H // 32, W // 32, 2 * c4)   # [bu_conv1     | fpn_out0]
+        (x,) = self._conv(["backbone.stem.conv"], focus.view(), [bc], 3, 1, cin_real=12)
+        self.ops[-1].first = True
+        (x,) = self._conv(["backbone.dark2.0"], x, [bc * 2], 3, 2)
+        x = self._csp("backbone.dark2.1", x, bc * 2, bd, True)
+        (x,) = self._conv(["backbone.dark3.0"], x, [c3], 3, 2)
+        d3 = self._csp("backbone.dark3.1", x, c3, bd * 3, True, out=cat_p3.view(c3, c3))
+        (x,) = self._conv(["backbone.dark4.0"], d3, [c4], 3, 2)
+        d4 = self._csp("backbone.dark4.1", x, c4, bd * 3, True, out=cat_p4.view(c4, c4))
+        (x,) = self._conv(["backbone.dark5.0"], d4, [c5], 3, 2)
+        spp_cat = self._buf("backbone.dark5.1.cat", H // 32, W // 32, 4 * c4)
+        self._conv(["backbone.dark5.1.conv1"], x, [c4], 1, 1, outs=[spp_cat.view(0, c4)])
+        arg = torch.empty(3, self.n, H // 32, W // 32, c4, dtype=torch.uint8, device=self.dev)
+        self.ops.append(SppOp([spp_cat.view(i * c4, c4) for i in range(4)], arg))
+        (x,) = self._conv(["backbone.dark5.1.conv2"], spp_cat.view(), [c5], 1, 1)
+        d5 = self._csp("backbone.dark5.2", x, c5, bd, False)
+        # neck (yolo_pafpn.py:79-114)
+        self._conv(["neck.lateral_conv0"], d5, [c4], 1, 1, outs=[cat_n4.view(c4, c4)], ups=[cat_p4.view(0, c4)])
+        f_out0 = self._csp("neck.C3_p4", cat_p4.view(), c4, nn_, False)
+        self._conv(["neck.reduce_conv1"], f_out0, [c3], 1, 1, outs=[cat_n3.view(c3, c3)], ups=[cat_p3.view(0, c3)])
+        pan2 = self._csp("neck.C3_p3", cat_p3.view(), c3, nn_, False)
+        self._conv(["neck.bu_conv2"], pan2, [c3], 3, 2, outs=[cat_n3.view(0, c3)])
+        pan1 = self._csp("neck.C3_n3", cat_n3.view(), c4, nn_, False)
+        self._conv(["neck.bu_conv1"], pan1, [c4], 3, 2, outs=[cat_n4.view(0, c4)])
+        pan0 = self._csp("neck.C3_n4", cat_n4.view(), c5, nn_, False)
+        # head (yolox_head.py:151-175)
+        hc = int(256 * self.wm)
+        self.levels = []
+        a_off = 0
+        for k, f in enumerate((pan2, pan1, pan0)):
+            _, fh, fw, _ = f.shape
+            (x,) = self._conv([f"head.stems.{k}"], f, [hc], 1, 1)
+            cr = self._buf(f"head.cr0.{k}", fh, fw, 2 * hc)
+            self._conv([f"head.cls_convs.{k}.0", f"head.reg_convs.{k}.0"], x, [hc, hc], 3, 1, outs=[cr.view(0, hc), cr.view(hc, hc)])
+            (cf,) = self._conv([f"head.cls_convs.{k}.1"], cr.view(0, hc), [hc], 3, 1)
+            (rf,) = self._conv([f"head.reg_convs.{k}.1"], cr.view(hc, hc), [hc], 3, 1)
+            self.ops.append(PredOp(k, cf, rf))
+            self.param_specs += [(f"head.cls_preds.{k}.weight", (self.nc, hc, 1, 1)), (f"head.reg_preds.{k}.weight", (4, hc, 1, 1)),
+                                 (f"head.obj_preds.{k}.weight", (1, hc, 1, 1))]
+            self.levels.append((fh, fw, STRIDES[k], a_off))
+            a_off += fh * fw
+        self.num_anchors = a_off
+        self.hc = hc
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_params(self):
+        """flat fp32 parameter / gradient buffers; the tensors in self.params / self.grads are views into them.
+        Layout: [conv + pred weights in op order][pad][bn gamma | bn beta per op][pred biases]; merged convolutions
+        are adjacent so one packing / one weight-gradient launch covers them."""
+        dev = self.dev
+        specs = list(self.param_specs)
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                for hd in op.heads:
+                    specs.append((hd.prefix + ".bn.weight", (hd.c,)))
+                for hd in op.heads:
+                    specs.append((hd.prefix + ".bn.bias", (hd.c,)))
+        for k in range(len(self.levels)):
+            specs += [(f"head.cls_preds.{k}.bias", (self.nc,)), (f"head.reg_preds.{k}.bias", (4,)), (f"head.obj_preds.{k}.bias", (1,))]
+        offs, total = {}, 0
+        for name, shape in specs:
+            if name.startswith("head.reg_preds") and name.endswith(".weight"):
+                total = _ceil(total, 4)
+            offs[name] = total
+            total += math.prod(shape)
+            if name.startswith("head.obj_preds") and name.endswith(".weight"):
+                total += 11 * shape[1]  # room for the 16-row (padded) weight-gradient tile of reg+obj
+            total = _ceil(total, 4)  # 16-byte alignment of every tensor
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params, self.grads = {}, {}
+        for name, shape in specs:
+            n = math.prod(shape)
+            self.params[name] = self.flat_param[offs[name]:offs[name] + n].view(shape)
+            self.grads[name] = self.flat_grad[offs[name]:offs[name] + n].view(shape)
+        self.param_names = [n for n, _ in specs]
+        # BatchNorm buffers
+        nbn = sum(hd.c for op in self.ops if isinstance(op, ConvOp) for hd in op.heads)
+        self.flat_rm = torch.zeros(nbn, device=dev)
+        self.flat_rv = torch.ones(nbn, device=dev)
+        self.flat_scale = torch.empty(nbn, device=dev)
+        self.flat_shift = torch.empty(nbn, device=dev)
+        self.flat_mean = torch.empty(nbn, device=dev)
+        self.flat_invstd = torch.empty(nbn, device=dev)
+        self.flat_stats = torch.zeros(4 * nbn, dtype=torch.float64, device=dev)  # sum | sqsum | dgamma acc | dbeta acc
+        self.buffers = {}
+        nbt = []
+        o = 0
+        for op in self.ops:
+            if not isinstance(op, ConvOp):
+                continue
+            op.bn_off = o
+            for hd in op.heads:
+                self.buffers[hd.prefix + ".bn.running_mean"] = self.flat_rm[o:o + hd.c]
+                self.buffers[hd.prefix + ".bn.running_var"] = self.flat_rv[o:o + hd.c]
+                nbt.append(hd.prefix + ".bn.num_batches_tracked")
+                hd.bn_off = o
+                o += hd.c
+        self.nbn = nbn
+        self.flat_nbt = torch.zeros(len(nbt), dtype=torch.int64, device=dev)
+        for i, name in enumerate(nbt):
+            self.buffers[name] = self.flat_nbt[i]
+        # packed bf16 operands
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                kk = op.ksize * op.ksize
+                op.w_fwd = torch.empty(op.cout, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
+                op.w_dgrad = None if op.first else torch.empty(op.cin_pad, kk, op.cout, dtype=torch.bfloat16, device=dev)
+                op.w_src = self.params[op.prefixes[0] + ".conv.weight"]
+                op.g_dst = self.grads[op.prefixes[0] + ".conv.weight"]
+            elif isinstance(op, PredOp):
+                k, hc = op.level, self.hc
+                op.wc_fwd = torch.empty(self.nc, 1, hc, dtype=torch.bfloat16, device=dev)
+                op.wc_dgrad = torch.empty(hc, 1, self.nc, dtype=torch.bfloat16, device=dev)
+                op.wr_fwd = torch.empty(16, 1, hc, dtype=torch.bfloat16, device=dev)
+                op.wr_dgrad = torch.empty(hc, 1, 16, dtype=torch.bfloat16, device=dev)
+                op.wc_src, op.wr_src = self.params[f"head.cls_preds.{k}.weight"], self.params[f"head.reg_preds.{k}.weight"]
+                op.gc_dst, op.gr_dst = self.grads[f"head.cls_preds.{k}.weight"], self.grads[f"head.reg_preds.{k}.weight"]
+                op.bc, op.br = self.params[f"head.cls_preds.{k}.bias"], self.params[f"head.reg_preds.{k}.bias"]
+                assert self.params[f"head.obj_preds.{k}.weight"].data_ptr() == op.wr_src.data_ptr() + 4 * 4 * hc
+                assert self.params[f"head.obj_preds.{k}.bias"].data_ptr() == op.br.data_ptr() + 16
+
+    def init_weights(self, seed=0):
+        """reference default initialisation (nn.Conv2d kaiming-uniform a=sqrt(5); BN 1/0; prior biases, yolox_head.py:140-149)"""
+        g = torch.Generator().manual_seed(seed)
+        for name, p in self.params.items():
+            if name.endswith(".bn.weight"):
+                p.fill_(1.0)
+            elif name.endswith(".bias") and "preds" in name:
+                p.fill_(-math.log((1 - 1e-2) / 1e-2) if ("cls_preds" in name or "obj_preds" in name) else 0.0)
+            elif name.endswith(".bn.bias"):
+                p.zero_()
+            else:
+                fan_in = p.shape[1] * p.shape[2] * p.shape[3]
+                p.copy_(((torch.rand(p.shape, generator=g) * 2 - 1) / math.sqrt(fan_in)).to(self.dev))
+        self.flat_rm.zero_()
+        self.flat_rv.fill_(1.0)
+        self.flat_nbt.zero_()
+
+    def load_state_dict(self, sd):
+        """copy a reference-layout state_dict (fp32 OIHW weights, BN tensors, prediction biases) into the flat buffers"""
+        missing = []
+        for name, dst in list(self.params.items()) + list(self.buffers.items()):
+            if name not in sd:
+                missing.append(name)
+                continue
+            dst.copy_(sd[name].to(self.dev).reshape(dst.shape))
+        if missing:
+            raise KeyError(f"state_dict lacks {len(missing)} tensors, e.g. {missing[:3]}")
+
+    def state_dict(self):
+        out = {k: v.detach().clone() for k, v in self.params.items()}
+        out.update({k: v.detach().clone() for k, v in self.buffers.items()})
+        return out
+
+    # ------------------------------------------------------------------ runtime buffers
+    def _alloc_runtime(self):
+        dev, n, a, ch = self.dev, self.n, self.num_anchors, 5 + self.nc
+        self.outputs = torch.zeros(n, a, ch, device=dev)
+        self.labels = torch.zeros(n, self.max_gt, 5, device=dev)
+        self.lv = (ctypes.c_int32 * (3 * len(self.levels)))(*[v for (h, w, s, _) in self.levels for v in (h, w, s)])
+        self.simota_ws = torch.empty(self.L.yb200_simota_workspace(n, a), dtype=torch.uint8, device=dev)
+        self.num_gt = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.fg_mask = torch.zeros(n, a, dtype=torch.uint8, device=dev)
+        self.matched_gt = torch.zeros(n, a, dtype=torch.int32, device=dev)
+        self.matched_iou = torch.zeros(n, a, device=dev)
+        self.matched_cls = torch.zeros(n, a, dtype=torch.int32, device=dev)
+        self.num_fg_img = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.totals = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.loss_acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.losses = torch.zeros(6, device=dev)
+        self.loss_weights = torch.tensor([5.0, 1.0, 1.0], device=dev)
+        self.bias_acc = torch.zeros(len(self.levels), ch, dtype=torch.float64, device=dev)
+        self.d_cls = [torch.zeros(n, h, w, self.nc, dtype=torch.bfloat16, device=dev) for (h, w, _, _) in self.levels]
+        self.d_ro = [torch.zeros(n, h, w, 16, dtype=torch.bfloat16, device=dev) for (h, w, _, _) in self.levels]
+        self.p_dcls = (ctypes.c_void_p * len(self.levels))(*[t.data_ptr() for t in self.d_cls])
+        self.p_dro = (ctypes.c_void_p * len(self.levels))(*[t.data_ptr() for t in self.d_ro])
+        self.images_u8 = torch.zeros(n, 3, self.h, self.w, dtype=torch.uint8, device=dev)
+        self.hw_valid = torch.tensor([[self.h, self.w]] * n, dtype=torch.int32, device=dev)
+        self.ws_bytes = 0
+        self.ws = None
+        self.spp_scratch = None
+        self._dz = {}
+        self.kernel_launches = 0
+
+    def _count(self, k=1):
+        self.kernel_launches += k
+
+    def _ensure_ws(self, nbytes):
+        if nbytes > self.ws_bytes:
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            self.ws_bytes = nbytes
+
+    # ------------------------------------------------------------------ forward
+    def pack_weights(self):
+        L, sp = self.L, capi.stream_ptr()
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                capi.check(L.yb200_pack_conv_weight(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad, capi.ptr(op.w_fwd),
+                                                    capi.ptr(op.w_dgrad), sp), "pack")
+                self._count()
+            elif isinstance(op, PredOp):
+                capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wc_src), self.nc, self.hc, 1, self.nc, self.hc, capi.ptr(op.wc_fwd),
+                                                    capi.ptr(op.wc_dgrad), sp), "pack cls")
+                capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, capi.ptr(op.wr_fwd), capi.ptr(op.wr_dgrad),
+                                                    sp), "pack reg+obj")
+                self._count(2)
+
+    def preprocess(self):
+        """images_u8 [N,3,H,W] (device) -> focus buffer"""
+        capi.check(self.L.yb200_preprocess_focus(capi.ptr(self.images_u8), self.n, self.h, self.w, capi.ptr(self.hw_valid), ctypes.c_float(114.0),
+                                                 self.focus.view().act(), capi.stream_ptr()), "preprocess_focus")
+        self._count()
+
+    def forward_features(self, training=True):
+        L, sp = self.L, capi.stream_ptr()
+        nb = self.nbn
+        f8 = self.flat_stats
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                o = op.bn_off
+                ssum = ctypes.c_void_p(f8.data_ptr() + 8 * o) if training else None
+                ssq = ctypes.c_void_p(f8.data_ptr() + 8 * (nb + o)) if training else None
+                capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, ssum, ssq, sp), op.prefixes[0])
+                gamma = self.params[op.prefixes[0] + ".bn.weight"]
+                beta = self.params[op.heads[0].prefix + ".bn.bias"]
+                pf = lambda t, off=o: ctypes.c_void_p(t.data_ptr() + 4 * off)
+                if training:
+                    cnt = op.z.buf.n * op.z.buf.h * op.z.buf.w
+                    capi.check(L.yb200_bn_finalize(ssum, ssq, op.cout, ctypes.c_int64(cnt), capi.ptr(gamma), capi.ptr(beta), ctypes.c_float(BN_EPS),
+                                                   ctypes.c_float(BN_MOMENTUM), pf(self.flat_rm), pf(self.flat_rv), None, pf(self.flat_scale),
+                                                   pf(self.flat_shift), pf(self.flat_mean), pf(self.flat_invstd), sp), "bn_finalize")
+                else:
+                    capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm), pf(self.flat_rv),
+                                                      ctypes.c_float(BN_EPS), pf(self.flat_scale), pf(self.flat_shift), sp), "bn_eval_affine")
+                self._count(2)
+                for hd in op.heads:
+                    zv = op.z.buf.view(hd.c0, hd.c)
+                    capi.check(L.yb200_bn_apply_silu(zv.act(), pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
+                                                     hd.residual.act() if hd.residual else None, hd.out.act(), hd.up.act() if hd.up else None, sp),
+                               "bn_apply_silu " + hd.prefix)
+                    self._count()
+            elif isinstance(op, SppOp):
+                v = op.views
+                capi.check(L.yb200_spp_pool(v[0].act(), v[1].act(), v[2].act(), v[3].act(), capi.ptr(op.arg) if training else None, sp), "spp_pool")
+                self._count()
+            else:
+                h, w, s, a_off = self.levels[op.level]
+                ch = 5 + self.nc
+                capi.check(L.yb200_conv1x1_bias_f32(op.cls_feat.act(), capi.ptr(op.wc_fwd), capi.ptr(op.bc), self.nc, capi.ptr(self.outputs),
+                                                    self.num_anchors, a_off, ch, 5, sp), "cls_pred")
+                capi.check(L.yb200_conv1x1_bias_f32(op.reg_feat.act(), capi.ptr(op.wr_fwd), capi.ptr(op.br), 5, capi.ptr(self.outputs),
+                                                    self.num_anchors, a_off, ch, 0, sp), "reg_obj_pred")
+                self._count(2)
+        if training:
+            self.flat_nbt += 1
+        capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
+                                        0 if training else 1, sp), "decode")
+        self._count()
+
+    def assign_and_loss(self, with_grad=True):
+        L, sp = self.L, capi.stream_ptr()
+        n, a, ch = self.n, self.num_anchors, 5 + self.nc
+        capi.check(L.yb200_simota_assign(capi.ptr(self.outputs), capi.ptr(self.labels), n, a, ch, self.max_gt, self.lv, len(self.levels),
+                                         capi.ptr(self.simota_ws), capi.ptr(self.num_gt), capi.ptr(self.fg_mask), capi.ptr(self.matched_gt),
+                                         capi.ptr(self.matched_iou), capi.ptr(self.matched_cls), capi.ptr(self.num_fg_img), capi.ptr(self.totals), sp),
+                   "simota_assign")
+        self._count(5)
+        capi.check(L.yb200_yolox_loss(capi.ptr(self.outputs), capi.ptr(self.labels), n, a, ch, self.max_gt, self.lv, len(self.levels),
+                                      capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls),
+                                      capi.ptr(self.totals), capi.ptr(self.loss_weights) if with_grad else None, capi.ptr(self.loss_acc),
+                                      capi.ptr(self.losses), self.p_dcls if with_grad else None, self.p_dro if with_grad else None, None,
+                                      capi.ptr(self.bias_acc) if with_grad else None, sp), "yolox_loss")
+        self._count(2)
+
+    def loss_grad_only(self):
+        """recompute d loss / d head outputs with the current loss_weights (autograd path: upstream gradients arrive late)"""
+        L, sp = self.L, capi.stream_ptr()
+        n, a, ch = self.n, self.num_anchors, 5 + self.nc
+        capi.check(L.yb200_yolox_loss(capi.ptr(self.outputs), capi.ptr(self.labels), n, a, ch, self.max_gt, self.lv, len(self.levels),
+                                      capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls),
+                                      capi.ptr(self.totals), capi.ptr(self.loss_weights), capi.ptr(self.loss_acc), None, self.p_dcls, self.p_dro, None,
+                                      capi.ptr(self.bias_acc), sp), "yolox_loss grad")
+        self._count()
+
+    # ------------------------------------------------------------------ backward
+    def _dz_buf(self, op):
+        b = self._dz.get(id(op))
+        if b is None:
+            zb = op.z.buf
+            b = Buf(zb.name + ".dz", zb.n, zb.h, zb.w, zb.c, self.dev)
+            self._dz[id(op)] = b
+        return b
+
+    def _grad_target(self, view):
+        """returns (addend or None) for a data-gradient that lands in view's gradient: first producer writes, later ones accumulate"""
+        buf = view.buf
+        lo, hi = view.off, view.off + view.c
+        covered = any(a <= lo and hi <= b for a, b in buf.written)
+        overlap = any(not (hi <= a or b <= lo) for a, b in buf.written)
+        if covered:
+            return view
+        assert not overlap, f"partial overlap of gradient writes on {buf.name}"
+        buf.written.append((lo, hi))
+        return None
+
+    def backward(self, accumulate=False):
+        L, sp = self.L, capi.stream_ptr()
+        nb = self.nbn
+        f8 = self.flat_stats
+        acc = 1 if accumulate else 0
+        for b in self.bufs.values():
+            b.written = []
+        pending_res = {}  # id(view.buf), off -> gradient view of the residual sum
+        for op in reversed(self.ops):
+            if isinstance(op, PredOp):
+                k = op.level
+                h, w, s, a_off = self.levels[k]
+                dcls = capi.act(self.d_cls[k])
+                dro = capi.act(self.d_ro[k])
+                capi.check(L.yb200_head_bias_grad(capi.ptr(self.bias_acc), len(self.levels), 5 + self.nc, k, capi.ptr(self.grads[f"head.reg_preds.{k}.bias"]),
+                                                  capi.ptr(self.grads[f"head.obj_preds.{k}.bias"]), capi.ptr(self.grads[f"head.cls_preds.{k}.bias"]),
+                                                  acc, sp), "head_bias_grad")
+                for feat, dz, gdst, wd, cr in ((op.cls_feat, dcls, op.gc_dst, op.wc_dgrad, self.nc), (op.reg_feat, dro, op.gr_dst, op.wr_dgrad, 16)):
+                    need = L.yb200_conv2d_wgrad_workspace(feat.act(), ctypes.byref(dz), 1, 1)
+                    assert need > 0, L.yb200_last_error()
+                    self._ensure_ws(need)
+                    capi.check(L.yb200_conv2d_wgrad(feat.act(), ctypes.byref(dz), 1, 1, self.hc, capi.ptr(gdst), acc, capi.ptr(self.ws),
+                                                    ctypes.c_int64(self.ws_bytes), sp), "pred wgrad")
+                    add = self._grad_target(feat)
+                    capi.check(L.yb200_conv2d_dgrad(ctypes.byref(dz), capi.ptr(wd), feat.gact(), add.gact() if add else None, 1, 1, sp), "pred dgrad")
+                self._count(7)
+            elif isinstance(op, SppOp):
+                v = op.views
+                if self.spp_scratch is None:
+                    self.spp_scratch = torch.empty(v[0].buf.n * v[0].buf.h * v[0].buf.w * v[0].c, device=self.dev)
+                # in place: the identity slice of the concat gradient receives the pooled gradients
+                capi.check(L.yb200_spp_pool_bwd(v[0].gact(), v[1].gact(), v[2].gact(), v[3].gact(), capi.ptr(op.arg), capi.ptr(self.spp_scratch),
+                                                v[0].gact(), sp), "spp_pool_bwd")
+                self._count(3)
+            else:
+                dzb = self._dz_buf(op)
+                pf = lambda t, off: ctypes.c_void_p(t.data_ptr() + 4 * off)
+                for hd in op.heads:
+                    zv = op.z.buf.view(hd.c0, hd.c)
+                    dzv = dzb.view(hd.c0, hd.c)
+                    o = hd.bn_off
+                    capi.check(L.yb200_bn_silu_bwd(zv.act(), hd.out.gact(), None, hd.up.gact() if hd.up else None, pf(self.flat_scale, o),
+                                                   pf(self.flat_shift, o), pf(self.flat_mean, o), pf(self.flat_invstd, o),
+                                                   ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)), ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)),
+                                                   dzv.act(), capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
+                                                   acc, sp), "bn_silu_bwd " + hd.prefix)
+                    self._count(3)
+                    if hd.residual is not None:
+                        pending_res[(id(hd.residual.buf), hd.residual.off)] = hd.out
+                dz = dzb.view()
+                need = L.yb200_conv2d_wgrad_workspace(op.x.act(), dz.act(), op.ksize, op.stride)
+                assert need > 0, L.yb200_last_error()
+                self._ensure_ws(need)
+                capi.check(L.yb200_conv2d_wgrad(op.x.act(), dz.act(), op.ksize, op.stride, op.cin_real, capi.ptr(op.g_dst), acc, capi.ptr(self.ws),
+                                                ctypes.c_int64(self.ws_bytes), sp), "wgrad " + op.prefixes[0])
+                self._count(2)
+                if not op.first:
+                    res = pending_res.pop((id(op.x.buf), op.x.off), None)
+                    add = self._grad_target(op.x)
+                    assert not (res is not None and add is not None), "residual + fan-out on the same activation"
+                    addend = res.gact() if res is not None else (add.gact() if add is not None else None)
+                    capi.check(L.yb200_conv2d_dgrad(dz.act(), capi.ptr(op.w_dgrad), op.x.gact(), addend, op.ksize, op.stride, sp),
+                               "dgrad " + op.prefixes[0])
+                    self._count(4 if op.stride == 2 else 1)
+
+    # ------------------------------------------------------------------ whole steps
+    def train_step(self, accumulate=False):
+        """forward + backward on the resident batch (images_u8 / labels already on the device)"""
+        self.pack_weights()
+        self.preprocess()
+        self.forward_features(True)
+        self.assign_and_loss(True)
+        self.backward(accumulate)
+        return self.losses
+
+    def eval_forward(self):
+        self.pack_weights()
+        self.preprocess()
+        self.forward_features(False)
+        return self.outputs
