@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Headline benchmark: YOLOX-s 640x640 forward+backward images/s on N B200s (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libyb200.so kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A "step" = one pass of the hot path over one synthetic COCO-shaped batch per GPU: uint8->Focus preprocessing, CSPDarknet,
+YOLOPAFPN, YOLOX head, SimOTA assignment, IoU/BCE losses and the full backward (data + weight + BN gradients); for N > 1
+followed by ONE NCCL all-reduce of the flat gradient buffer.  No optimizer step (the metric is fwd+bwd).
+`value`  : inputs resident in HBM, engine called directly, CUDA-event time, max over ranks.
+`e2e`    : the public API a detectron2 trainer calls -- YOLOX.forward(batched_inputs) on pinned HOST uint8 images +
+           sum(losses).backward() + loss.item() -- with the H2D / D2H copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (640x640) YOLOX-s fwd+bwd"
+WORKLOAD = "YOLOX-s 640x640 bs=64 per GPU, fwd+bwd, synthetic COCO-shaped input (BASELINE.json configs[1])"
+FLOP_PER_IMAGE = 79.35e9  # 26.69 fwd + 52.66 bwd GFLOP
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0), tf_sust=d.get("bf16_tflops_sustained", 1400.0),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def ns(**kw):
+    return types.SimpleNamespace(**kw)
+
+
+def yolox_s_cfg(device="cuda"):
+    """the attributes YOLOX.__init__ reads from configs/coco/yolox_s.yaml + yolov7/config.py defaults (yolox.py:38-58)"""
+    return ns(MODEL=ns(DEVICE=device, NMS_TYPE="normal", PADDED_VALUE=114.0, PIXEL_MEAN=[0.485, 0.456, 0.406], PIXEL_STD=[0.229, 0.224, 0.225],
+                       BACKBONE=ns(NAME="build_cspdarknetx_backbone"), DARKNET=ns(DEPTH_WISE=False, OUT_FEATURES=["dark3", "dark4", "dark5"]),
+                       YOLO=ns(CLASSES=80, CONF_THRESHOLD=0.001, NMS_THRESHOLD=0.65, WIDTH_MUL=0.50, DEPTH_MUL=0.33, LOSS_TYPE="v7",
+                               MAX_BOXES_NUM=100, IN_FEATURES=["dark3", "dark4", "dark5"])),
+              SOLVER=ns(MAX_ITER=230000), INPUT=ns(MOSAIC_AND_MIXUP=ns(DISABLE_AT_ITER=120000)))
+
+
+class _GtBoxes:
+    def __init__(self, t):
+        self.tensor = t
+
+
+def batched_inputs_from(images_u8, labels):
+    """list[dict] in detectron2's format: uint8 CHW host image + Instances-like (gt_boxes XYXY, gt_classes)"""
+    out = []
+    for b in range(images_u8.shape[0]):
+        lab = labels[b]
+        lab = lab[lab.sum(1) > 0]
+        xyxy = __import__("torch").stack([lab[:, 1] - lab[:, 3] / 2, lab[:, 2] - lab[:, 4] / 2, lab[:, 1] + lab[:, 3] / 2, lab[:, 2] + lab[:, 4] / 2], 1)
+        out.append({"image": images_u8[b], "instances": ns(gt_boxes=_GtBoxes(xyxy), gt_classes=lab[:, 0].long()), "height": 640, "width": 640})
+    return out
+
+
+def run_reference(args, rank, world):
+    """the reference's own CPU implementation of the path (oracle port: plain torch fp32, all host threads)"""
+    import torch
+    from oracle import yolox_oracle as orc
+
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bs = args.ref_batch
+    sd = orc.yolox_state_dict(0)
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and "running" not in k:
+            v.requires_grad_(True)
+    images, labels = orc.synthetic_batch(bs, 640, 0)
+    x = images.float()
+
+    def step():
+        for v in sd.values():
+            if v.requires_grad and v.grad is not None:
+                v.grad = None
+        out = orc.yolox_forward_train(x, labels, sd)
+        out[0].backward()
+        return float(out[0])
+
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = bs * args.steps / dt
+    line = {"metric": METRIC, "value": val, "unit": "images/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"bs={bs} per step on the host CPU"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} steps of bs={bs} YOLOX-s 640x640 fwd+bwd (oracle/yolox_oracle.py, torch CPU fp32)"},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="yb200", choices=["yb200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU (BASELINE.json configs[1]: 64)")
+    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from oracle import yolox_oracle as orc  # cpu_baseline leg + synthetic data generator only
+    from yolov7_d2_b200 import capi
+    from yolov7_d2_b200.engine import YoloxEngine
+    from yolov7_d2_b200.modeling import YOLOX, postprocess
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    capi.lib()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    model = YOLOX(yolox_s_cfg("cuda"))
+    sd = orc.yolox_state_dict(0)
+    model.load_state_dict({k: v for k, v in sd.items()}, strict=True)
+    model.train()
+    eng = model._plan(B, 640, 640)
+    images, labels = orc.synthetic_batch(B, 640, seed=100 + rank)
+    eng.images_u8.copy_(images.to(dev))
+    eng.labels.copy_(labels.to(dev))
+    flat_grad = eng.flat_grad
+
+    def step_eager():
+        eng.train_step()
+        if world > 1:
+            dist.all_reduce(flat_grad)  # the single gradient all-reduce (sum; /world folded into the optimizer's lr in DDP terms)
+
+    # probe: CUDA events around the dominant kernel (head 3x3 128->128 @80x80, merged cls|reg: 128->256) on the launch stream
+    probe = {"ev": [], "op": None}
+    for op in eng.ops:
+        if getattr(op, "prefixes", [""])[0] == "head.cls_convs.0.0":
+            probe["op"] = op
+
+    for _ in range(max(args.warmup, 3)):
+        step_eager()
+    torch.cuda.synchronize()
+    launches_per_step = eng.kernel_launches // max(args.warmup, 3)
+
+    graph = None
+    if not args.no_graph and world == 1:
+        try:
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                eng.train_step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                eng.train_step()
+            graph = g
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); timing eager launches\n")
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_eager()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    clocks = sampler.stop() if sampler else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream (eager launches of the same step) ----
+    pk = peaks()
+    roof = None
+    op = probe["op"]
+    if op is not None:
+        L = eng.L
+        evs = []
+        for _ in range(max(3, min(args.steps, 10))):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eng.train_step()  # keeps the cache state of a real step around the probed launch
+            a.record()
+            capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, None, None, capi.stream_ptr()), "probe")
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        t_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+        n, oh, ow, cout = op.z.shape
+        flops = 2.0 * n * oh * ow * cout * op.cin_pad * op.ksize * op.ksize
+        ach = flops / (t_ms * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as fh:
+                traffic = json.load(fh).get("conv_gemm_head3x3_bytes_per_launch")
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<128,64> (head 3x3 128->256 @80x80, implicit GEMM M=%d N=%d K=%d)" % (n * oh * ow, cout, op.cin_pad * 9),
+                "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
+                "peak_source": pk["source"] + " bf16_tflops (burst: kernel timed alone between events)", "us_per_launch": 1e3 * t_ms,
+                "step_frac_of_sustained_peak": value / world * FLOP_PER_IMAGE / 1e12 / pk["tf_sust"]}
+
+    # ---- end to end through the public API: pinned host uint8 images -> loss.item() ----
+    e2e = None
+    if not args.no_e2e:
+        host_imgs = images.pin_memory()
+        bi = batched_inputs_from(host_imgs, labels)
+        h2d = host_imgs.numel() + labels.numel() * 4 + B * 8
+        for _ in range(2):
+            losses = model(bi)
+            sum(losses.values()).backward()
+            if world > 1:
+                dist.all_reduce(flat_grad)
+            _ = float(losses["total_loss"])
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            losses = model(bi)
+            sum(losses.values()).backward()
+            if world > 1:
+                dist.all_reduce(flat_grad)
+            _ = float(losses["total_loss"])  # device -> host read of the step's result
+        e1.record()
+        barrier()
+        ms2 = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms2], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t)
+        e2e = {"value": world * B * args.steps / (ms2 / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+               "api": "YOLOX.forward(batched_inputs) + sum(loss_dict.values()).backward() + loss.item()"}
+
+    # ---- NMS boxes/s (second half of the BASELINE metric) ----
+    nms = None
+    if rank == 0:
+        from oracle.gen_golden import clustered_predictions
+        pred = clustered_predictions(4, 8400, 80, 7).repeat(B // 4, 1, 1).to(dev)
+        cand = int(((pred[..., 4] * pred[..., 5:].max(-1).values) >= 0.001).sum())
+        for _ in range(3):
+            postprocess(pred.clone(), 80, 0.001, 0.65)
+        clones = [pred.clone() for _ in range(5)]
+        torch.cuda.synchronize()
+        e0.record()
+        for c in clones:
+            postprocess(c, 80, 0.001, 0.65)
+        e1.record()
+        torch.cuda.synchronize()
+        nms = {"value": cand * len(clones) / (e0.elapsed_time(e1) / 1e3), "unit": "boxes/s", "candidates_per_call": cand,
+               "workload": "postprocess on [%d,8400,85] clustered stress set, conf 0.001, IoU 0.65" % B}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        csd = orc.yolox_state_dict(0)
+        for k, v in csd.items():
+            if v.dtype == torch.float32 and "running" not in k:
+                v.requires_grad_(True)
+        ci, cl = orc.synthetic_batch(2, 640, 0)
+        cx = ci.float()
+
+        def cstep():
+            for v in csd.values():
+                if v.requires_grad:
+                    v.grad = None
+            orc.yolox_forward_train(cx, cl, csd)[0].backward()
+
+        cstep()
+        t0 = time.perf_counter()
+        iters = 0
+        while iters < 3 or (time.perf_counter() - t0 < 10 and iters < 20):
+            cstep()
+            iters += 1
+        cdt = time.perf_counter() - t0
+        cpu = {"value": 2 * iters / cdt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{iters} iterations of bs=2 YOLOX-s 640x640 fwd+bwd (BASELINE.json configs[0]) with oracle/yolox_oracle.py, torch CPU fp32"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": graph is not None,
+                           "l2": "per-step working set (~%.0f GB of activations and gradients) exceeds the 126 MB L2; no explicit flush" % (0.245 * B)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu, "nms": nms,
+                "loss": float(eng.losses[0])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,17 @@ int yb200_yolox_loss(const float* outputs, const float* labels, int batch, int n
 int yb200_head_bias_grad(double* bias_acc, int num_levels, int channels, int level, float* grad_reg_bias4,
                          float* grad_obj_bias1, float* grad_cls_bias, int accumulate, void* stream);
 
+/* ---- post-processing ----------------------------------------------------------------------------- */
+/* `postprocess` (boxes.py:171-210) for the whole batch: prediction [batch][A][5+C] = (cx, cy, w, h, obj, cls...) with
+ * probabilities already applied.  Per image: class_conf / class_pred = max / first argmax over classes; candidates have
+ * obj*class_conf >= conf_thre; per-class NMS (torchvision batched_nms, "vanilla" semantics: stable descending score
+ * order, suppress when IoU > nms_thre on un-offset fp32 xyxy boxes); survivors ordered by descending score.
+ * detections [batch][A][7] = (x1, y1, x2, y2, obj_conf, class_conf, class_pred), det_count[batch] rows are valid.
+ * mutate_prediction != 0 also rewrites prediction[..., :4] to xyxy in place, as the reference does (boxes.py:177).     */
+int64_t yb200_nms_workspace(int batch, int num_anchors);
+int yb200_postprocess_nms(float* prediction, int batch, int num_anchors, int num_classes, float conf_thre, float nms_thre,
+                          int mutate_prediction, void* workspace, float* detections, int32_t* det_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

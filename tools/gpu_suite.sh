@@ -6,7 +6,12 @@ groups=("$@")
 [ ${#groups[@]} -eq 0 ] && groups=(conv_fwd conv_misc conv_dgrad conv_wgrad elementwise simota engine)
 for g in "${groups[@]}"; do
   case $g in
-    conv_fwd)    sel="tests/test_conv_gpu.py -k test_conv_fwd_stats" ;;
+    conv_fwd)    sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and not 1x320 and not 16x64 and not 8x80x80'" ;;
+    fwd_a)       sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and 1x32x32'" ;;
+    fwd_b)       sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and 16x64x64x16'" ;;
+    fwd_c)       sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and 16x64x64x64'" ;;
+    fwd_d)       sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and 8x80x80'" ;;
+    fwd_e)       sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and 1x320'" ;;
     conv_misc)   sel="tests/test_conv_gpu.py -k 'slices or bias'" ;;
     conv_dgrad)  sel="tests/test_conv_gpu.py -k test_conv_dgrad" ;;
     conv_wgrad)  sel="tests/test_conv_gpu.py -k test_conv_wgrad" ;;

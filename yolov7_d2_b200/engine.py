@@ -99,7 +99,7 @@ class SppOp:
 
 
 class YoloxEngine:
-    def __init__(self, batch, height, width, num_classes=80, width_mul=0.5, depth_mul=0.33, max_gt=100, device="cuda"):
+    def __init__(self, batch, height, width, num_classes=80, width_mul=0.5, depth_mul=0.33, max_gt=100, device="cuda", share_params_of=None):
         assert height % 32 == 0 and width % 32 == 0, "input must be padded to a multiple of 32 (yolox.py:100-101)"
         self.L = capi.lib()
         self.dev = torch.device(device)
@@ -109,7 +109,7 @@ class YoloxEngine:
         self.bufs = {}
         self.param_specs = []   # (name, shape) in flat order
         self._build()
-        self._alloc_params()
+        self._alloc_params(share_params_of)
         self._alloc_runtime()
 
     # ------------------------------------------------------------------ graph construction
@@ -207,8 +207,10 @@ class YoloxEngine:
         self.hc = hc
 
     # ------------------------------------------------------------------ parameters
-    def _alloc_params(self):
-        """flat fp32 parameter / gradient buffers; the tensors in self.params / self.grads are views into them.
+    def _alloc_params(self, share=None):
+        """flat fp32 parameter / gradient buffers; the tensors in self.params / self.grads are views into them
+        (`share`: another engine of the same architecture whose parameter storage is reused -- one set of weights, one
+        plan per input shape).
         Layout: [conv + pred weights in op order][pad][bn gamma | bn beta per op][pred biases]; merged convolutions
         are adjacent so one packing / one weight-gradient launch covers them."""
         dev = self.dev
@@ -230,8 +232,10 @@ class YoloxEngine:
             if name.startswith("head.obj_preds") and name.endswith(".weight"):
                 total += 11 * shape[1]  # room for the 16-row (padded) weight-gradient tile of reg+obj
             total = _ceil(total, 4)  # 16-byte alignment of every tensor
-        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        if share is not None:
+            assert share.flat_param.numel() == total and share.param_names == [n for n, _ in specs], "architectures differ"
+        self.flat_param = share.flat_param if share is not None else torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = share.flat_grad if share is not None else torch.zeros(total, dtype=torch.float32, device=dev)
         self.params, self.grads = {}, {}
         for name, shape in specs:
             n = math.prod(shape)
@@ -240,8 +244,8 @@ class YoloxEngine:
         self.param_names = [n for n, _ in specs]
         # BatchNorm buffers
         nbn = sum(hd.c for op in self.ops if isinstance(op, ConvOp) for hd in op.heads)
-        self.flat_rm = torch.zeros(nbn, device=dev)
-        self.flat_rv = torch.ones(nbn, device=dev)
+        self.flat_rm = share.flat_rm if share is not None else torch.zeros(nbn, device=dev)
+        self.flat_rv = share.flat_rv if share is not None else torch.ones(nbn, device=dev)
         self.flat_scale = torch.empty(nbn, device=dev)
         self.flat_shift = torch.empty(nbn, device=dev)
         self.flat_mean = torch.empty(nbn, device=dev)
@@ -261,7 +265,7 @@ class YoloxEngine:
                 hd.bn_off = o
                 o += hd.c
         self.nbn = nbn
-        self.flat_nbt = torch.zeros(len(nbt), dtype=torch.int64, device=dev)
+        self.flat_nbt = share.flat_nbt if share is not None else torch.zeros(len(nbt), dtype=torch.int64, device=dev)
         for i, name in enumerate(nbt):
             self.buffers[name] = self.flat_nbt[i]
         # packed bf16 operands

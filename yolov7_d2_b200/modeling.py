@@ -1,0 +1,344 @@
+"""Drop-in surface: the reference's registry / module contracts for the YOLOX path, backed by the B200 engine.
+
+Mirrors (same names, constructor arguments, attributes, state_dict keys and return types):
+  * `@META_ARCH_REGISTRY.register() class YOLOX(nn.Module)`            yolov7/modeling/meta_arch/yolox.py:35-252
+  * `@BACKBONE_REGISTRY.register() build_cspdarknetx_backbone(cfg, _)`   yolov7/modeling/backbone/darknetx.py:194-213
+  * `CSPDarknet`, `YOLOPAFPN`, `YOLOXHead`                               darknetx.py:103, yolo_pafpn.py:13, yolox_head.py:24
+  * `postprocess(prediction, num_classes, conf_thre, nms_thre)`          yolov7/utils/boxes.py:171-210
+When detectron2 is importable the classes register into ITS registries (so train_det.py / configs/*.yaml drive them);
+otherwise a bundled registry with the same interface is used.  All arithmetic happens in libyb200.so: the modules only
+own parameters (views into the engine's flat fp32 buffers) and marshal tensors.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import capi
+from .engine import YoloxEngine
+
+try:  # pragma: no cover - detectron2 is not installed in the build container
+    from detectron2.modeling import META_ARCH_REGISTRY
+    from detectron2.modeling.backbone import BACKBONE_REGISTRY, Backbone
+    from detectron2.layers import ShapeSpec
+    from detectron2.structures import Boxes, ImageList, Instances
+    from detectron2.modeling.postprocessing import detector_postprocess
+    HAVE_D2 = True
+except Exception:  # noqa: BLE001
+    HAVE_D2 = False
+
+    class _Registry(dict):
+        """detectron2.utils.registry.Registry look-alike"""
+
+        def __init__(self, name):
+            super().__init__()
+            self._name = name
+
+        def register(self, obj=None):
+            if obj is None:
+                return lambda o: self.register(o)
+            assert obj.__name__ not in self, f"{obj.__name__} already registered in {self._name}"
+            self[obj.__name__] = obj
+            return obj
+
+        def get(self, name):
+            if name not in self:
+                raise KeyError(f"No object named '{name}' found in '{self._name}' registry!")
+            return self[name]
+
+    META_ARCH_REGISTRY = _Registry("META_ARCH")
+    BACKBONE_REGISTRY = _Registry("BACKBONE")
+
+    class Backbone(nn.Module):
+        @property
+        def size_divisibility(self):
+            return 0
+
+    class ShapeSpec:
+        def __init__(self, channels=None, height=None, width=None, stride=None):
+            self.channels, self.height, self.width, self.stride = channels, height, width, stride
+
+    class Boxes:
+        def __init__(self, tensor):
+            self.tensor = tensor
+
+    class Instances:
+        def __init__(self, image_size, **kw):
+            self.image_size = image_size
+            self.__dict__.update(kw)
+
+    def detector_postprocess(results, output_height, output_width):
+        sx, sy = output_width / results.image_size[1], output_height / results.image_size[0]
+        b = results.pred_boxes.tensor.clone()
+        b[:, 0::2] = (b[:, 0::2] * sx).clamp(0, output_width)
+        b[:, 1::2] = (b[:, 1::2] * sy).clamp(0, output_height)
+        keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+        out = Instances((output_height, output_width))
+        out.pred_boxes, out.scores, out.pred_classes = Boxes(b[keep]), results.scores[keep], results.pred_classes[keep]
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# postprocess
+# ------------------------------------------------------------------------------------------------
+_nms_ws = {}
+
+
+def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45):
+    """boxes.py:171-210: returns a list with one [n_i, 7] tensor (x1,y1,x2,y2,obj,cls_conf,cls) or None per image and, like
+    the reference, rewrites prediction[:, :, :4] to corner format in place."""
+    if not (prediction.is_cuda and prediction.dtype == torch.float32 and prediction.dim() == 3):
+        raise capi.Yb200Error("postprocess: expects a CUDA fp32 [B, A, 5+C] tensor (no CPU fallback)")
+    pred = prediction if prediction.is_contiguous() else prediction.contiguous()
+    b, a, ch = pred.shape
+    if ch != 5 + num_classes:
+        raise IndexError(f"prediction has {ch} channels, expected {5 + num_classes}")
+    L = capi.lib()
+    key = (pred.device.index, b, a)
+    if key not in _nms_ws:
+        _nms_ws[key] = (torch.empty(L.yb200_nms_workspace(b, a), dtype=torch.uint8, device=pred.device),
+                        torch.empty(b, a, 7, device=pred.device), torch.empty(b, dtype=torch.int32, device=pred.device))
+    ws, det, cnt = _nms_ws[key]
+    capi.check(L.yb200_postprocess_nms(capi.ptr(pred), b, a, num_classes, ctypes.c_float(conf_thre), ctypes.c_float(nms_thre), 1, capi.ptr(ws),
+                                       capi.ptr(det), capi.ptr(cnt), capi.stream_ptr()), "postprocess_nms")
+    if pred is not prediction:
+        prediction.copy_(pred)
+    counts = cnt.tolist()  # the one host synchronisation: the output is a ragged Python list
+    return [det[i, :n].clone() if n > 0 else None for i, n in enumerate(counts)]
+
+
+# ------------------------------------------------------------------------------------------------
+# modules
+# ------------------------------------------------------------------------------------------------
+class _ParamTree(nn.Module):
+    """nn.Module tree whose Parameters / buffers are views of an engine's flat storage, under the reference's names"""
+
+    def __init__(self):
+        super().__init__()
+
+    def _adopt(self, engine, prefix):
+        for name, t in engine.params.items():
+            if name.startswith(prefix):
+                self._place(name[len(prefix):], nn.Parameter(t, requires_grad=True), False)
+        for name, t in engine.buffers.items():
+            if name.startswith(prefix):
+                self._place(name[len(prefix):], t, True)
+
+    def _place(self, dotted, value, is_buffer):
+        mod = self
+        parts = dotted.split(".")
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, nn.Module())
+            mod = mod._modules[p]
+        if is_buffer:
+            mod.register_buffer(parts[-1], value)
+        else:
+            mod.register_parameter(parts[-1], value)
+
+
+class CSPDarknet(Backbone, _ParamTree):
+    """YOLOX CSPDarknet (darknetx.py:103-191).  Parameters live in the engine of the owning YOLOX model."""
+
+    def __init__(self, dep_mul, wid_mul, out_features=("dark3", "dark4", "dark5"), depthwise=False, act="silu"):
+        Backbone.__init__(self)
+        if depthwise:
+            raise capi.Yb200Error("depthwise CSPDarknet is not implemented by the B200 path")
+        if act != "silu":
+            raise AttributeError("Unsupported act type: {}".format(act))
+        assert out_features, "please provide output features of Darknet"
+        self.dep_mul, self.wid_mul, self.out_features = dep_mul, wid_mul, out_features
+        bc = int(wid_mul * 64)
+        self.output_shape_dict = {f"dark{i + 2}": ShapeSpec(channels=bc * 2 ** (i + 1)) for i in range(4)}
+        self._engine = None
+
+    def output_shape(self):
+        return self.output_shape_dict
+
+    @property
+    def size_divisibility(self):
+        return 32
+
+    def forward(self, x):
+        raise capi.Yb200Error("CSPDarknet runs fused inside YOLOX.forward; standalone execution is not exposed in this build")
+
+
+class YOLOPAFPN(_ParamTree):
+    def __init__(self, depth=1.0, width=1.0, in_features=("dark3", "dark4", "dark5"), in_channels=[256, 512, 1024], depthwise=False, act="silu"):
+        super().__init__()
+        if depthwise:
+            raise capi.Yb200Error("depthwise YOLOPAFPN is not implemented by the B200 path")
+        self.in_features, self.in_channels = in_features, in_channels
+
+    def forward(self, out_features):
+        raise capi.Yb200Error("YOLOPAFPN runs fused inside YOLOX.forward; standalone execution is not exposed in this build")
+
+
+class YOLOXHead(_ParamTree):
+    def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu", depthwise=False):
+        super().__init__()
+        if depthwise:
+            raise capi.Yb200Error("depthwise YOLOXHead is not implemented by the B200 path")
+        self.n_anchors, self.num_classes = 1, num_classes
+        self.decode_in_inference = True
+        self.use_l1 = False
+        self.strides = strides
+        self.onnx_export = False
+        self.hw = None
+
+    def initialize_biases(self, prior_prob):
+        """yolox_head.py:140-149"""
+        v = -math.log((1 - prior_prob) / prior_prob)
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if name.endswith(".bias") and (name.startswith("cls_preds") or name.startswith("obj_preds")):
+                    p.fill_(v)
+
+    def forward(self, xin, labels=None, imgs=None):
+        raise capi.Yb200Error("YOLOXHead runs fused inside YOLOX.forward; standalone execution is not exposed in this build")
+
+
+@BACKBONE_REGISTRY.register()
+def build_cspdarknetx_backbone(cfg, input_shape=None):
+    """darknetx.py:194-213"""
+    return CSPDarknet(dep_mul=cfg.MODEL.YOLO.DEPTH_MUL, wid_mul=cfg.MODEL.YOLO.WIDTH_MUL, depthwise=cfg.MODEL.DARKNET.DEPTH_WISE,
+                      out_features=cfg.MODEL.DARKNET.OUT_FEATURES, act="silu")
+
+
+class _TrainStep(torch.autograd.Function):
+    """forward = engine forward + SimOTA + losses; backward = the whole engine backward.  Inputs are the model's
+    parameters so that autograd / DDP / optimizers see ordinary per-parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, engine, *params):
+        engine.pack_weights()
+        engine.preprocess()
+        engine.forward_features(True)
+        engine.assign_and_loss(with_grad=False)
+        ctx.engine = engine
+        l = engine.losses
+        return l[0].clone(), l[1].clone(), l[2].clone(), l[3].clone()
+
+    @staticmethod
+    def backward(ctx, g_total, g_iou, g_obj, g_cls):
+        eng = ctx.engine
+        # outputs: total = 5*iou + obj + cls, iou_loss = 5*iou, conf_loss = obj, cls_loss = cls   (yolox.py:201-206)
+        eng.loss_weights.copy_(torch.stack([5.0 * (g_total + g_iou), g_total + g_obj, g_total + g_cls]).float())
+        eng.loss_grad_only()
+        eng.backward()
+        return (None,) + tuple(eng.grads[n].clone() for n in eng.param_names)
+
+
+@META_ARCH_REGISTRY.register()
+class YOLOX(nn.Module):
+    """yolox.py:35-252.  `forward(batched_inputs)` -> loss dict (training) or list of {"instances": Instances} (eval)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.device = torch.device(cfg.MODEL.DEVICE)
+        if self.device.type != "cuda":
+            raise capi.Yb200Error("the B200 YOLOX path needs MODEL.DEVICE = cuda")
+        self.conf_threshold = cfg.MODEL.YOLO.CONF_THRESHOLD
+        self.nms_threshold = cfg.MODEL.YOLO.NMS_THRESHOLD
+        self.nms_type = cfg.MODEL.NMS_TYPE
+        self.loss_type = cfg.MODEL.YOLO.LOSS_TYPE
+        self.use_l1 = False
+        self.depth_mul, self.width_mul = cfg.MODEL.YOLO.DEPTH_MUL, cfg.MODEL.YOLO.WIDTH_MUL
+        self.iter = 0
+        self.max_iter = cfg.SOLVER.MAX_ITER
+        self.enable_l1_loss_at = cfg.INPUT.MOSAIC_AND_MIXUP.DISABLE_AT_ITER
+        self.num_classes = cfg.MODEL.YOLO.CLASSES
+        self.max_boxes_num = cfg.MODEL.YOLO.MAX_BOXES_NUM
+        self.in_features = cfg.MODEL.YOLO.IN_FEATURES
+        self.padded_value = cfg.MODEL.PADDED_VALUE
+        self.size_divisibility = 32
+        self.onnx_export = False
+
+        # parameter storage lives in a tiny "root" plan; execution plans per (batch, H, W) share it
+        self._root = YoloxEngine(1, 32, 32, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device)
+        self._root.init_weights(0)
+        self._plans = {}
+        self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, None)
+        self.neck = YOLOPAFPN(depth=self.depth_mul, width=self.width_mul, in_features=self.in_features)
+        self.head = YOLOXHead(self.num_classes, width=self.width_mul)
+        self.backbone._adopt(self._root, "backbone.")
+        self.neck._adopt(self._root, "neck.")
+        self.head._adopt(self._root, "head.")
+        self.head.initialize_biases(1e-2)
+        self._param_list = None
+
+    def update_iter(self, i):
+        self.iter = i
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _plan(self, batch, h, w):
+        key = (batch, h, w)
+        if key not in self._plans:
+            self._plans[key] = YoloxEngine(batch, h, w, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device,
+                                           share_params_of=self._root)
+        return self._plans[key]
+
+    def _params_in_engine_order(self):
+        if self._param_list is None:
+            by_name = dict(self.named_parameters())
+            self._param_list = [by_name[n] for n in self._root.param_names]
+        return self._param_list
+
+    def preprocess_image(self, batched_inputs, training):
+        """yolox.py:95-162: stack uint8 CHW images (padded bottom/right to a multiple of 32; pad pixels = PADDED_VALUE on the
+        device), build [B, max_boxes, 5] = (cls, cx, cy, w, h) labels from XYXY gt boxes."""
+        imgs = [x["image"] for x in batched_inputs]
+        hmax = max(i.shape[-2] for i in imgs)
+        wmax = max(i.shape[-1] for i in imgs)
+        hp, wp = (hmax + 31) // 32 * 32, (wmax + 31) // 32 * 32
+        eng = self._plan(len(imgs), hp, wp)
+        same = all(i.shape[-2:] == (hp, wp) for i in imgs)
+        if same and all(i.dtype == torch.uint8 for i in imgs):
+            host = torch.stack([i for i in imgs]) if not imgs[0].is_cuda else None
+            if host is not None:
+                eng.images_u8.copy_(host.pin_memory() if not host.is_pinned() else host, non_blocking=True)
+            else:
+                eng.images_u8.copy_(torch.stack(imgs))
+        else:
+            for k, im in enumerate(imgs):
+                eng.images_u8[k, :, :im.shape[-2], :im.shape[-1]].copy_(im.to(torch.uint8), non_blocking=True)
+        eng.hw_valid.copy_(torch.tensor([[i.shape[-2], i.shape[-1]] for i in imgs], dtype=torch.int32), non_blocking=True)
+        image_sizes = [(i.shape[-2], i.shape[-1]) for i in imgs]
+        if training:
+            labels = torch.zeros(len(imgs), self.max_boxes_num, 5)
+            for k, x in enumerate(batched_inputs):
+                inst = x.get("instances", x.get("targets"))
+                if inst is None:
+                    continue
+                boxes = inst.gt_boxes.tensor.detach().float().cpu()[: self.max_boxes_num]
+                cls = inst.gt_classes.detach().float().cpu()[: self.max_boxes_num]
+                n = boxes.shape[0]
+                labels[k, :n, 0] = cls
+                labels[k, :n, 1] = (boxes[:, 0] + boxes[:, 2]) / 2  # BoxModeMy XYXY_ABS -> (cx, cy, w, h)   boxes.py:547-551
+                labels[k, :n, 2] = (boxes[:, 1] + boxes[:, 3]) / 2
+                labels[k, :n, 3] = boxes[:, 2] - boxes[:, 0]
+                labels[k, :n, 4] = boxes[:, 3] - boxes[:, 1]
+            eng.labels.copy_(labels, non_blocking=True)
+        return eng, image_sizes
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, batched_inputs):
+        eng, image_sizes = self.preprocess_image(batched_inputs, self.training)
+        if self.training:
+            total, iou, conf, cls = _TrainStep.apply(eng, *self._params_in_engine_order())
+            return {"total_loss": total, "iou_loss": iou, "conf_loss": conf, "cls_loss": cls}
+        with torch.no_grad():
+            outputs = eng.eval_forward()
+            detections = postprocess(outputs, self.num_classes, self.conf_threshold, self.nms_threshold)
+        results = []
+        for idx, (out, inp) in enumerate(zip(detections, batched_inputs)):
+            if out is None:
+                out = outputs.new_zeros((0, 7))
+            res = Instances(image_sizes[idx])
+            res.pred_boxes = Boxes(out[:, :4])
+            res.scores = out[:, 5] * out[:, 4]
+            res.pred_classes = out[:, -1]
+            h, w = inp.get("height", image_sizes[idx][0]), inp.get("width", image_sizes[idx][1])
+            results.append({"instances": detector_postprocess(res, h, w)})
+        return results
