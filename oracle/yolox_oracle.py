@@ -26,15 +26,29 @@ def silu(x):
     return x * torch.sigmoid(x)
 
 
+# Optional instrumentation (tests only): TRACE collects every BaseConv output by parameter prefix; ROUND_BF16 rounds the
+# stored tensors (pre-BN conv output, activation, residual sum) to bf16 exactly where the CUDA engine stores bf16, so the
+# engine can be checked against an oracle that differs from it only by fp32 summation order.
+TRACE = None
+ROUND_BF16 = False
+
+
+def _q(t):
+    return t.to(torch.bfloat16).float() if ROUND_BF16 else t
+
+
 def base_conv(x, sd, prefix, stride=1, training=True):
     """BaseConv = Conv2d(bias=False, pad=(k-1)//2) -> BatchNorm2d -> SiLU   (wrappers.py:60-80)"""
     w = sd[prefix + ".conv.weight"]
-    z = F.conv2d(x, w, None, stride, (w.shape[-1] - 1) // 2)
+    z = _q(F.conv2d(x, w, None, stride, (w.shape[-1] - 1) // 2))
     z = F.batch_norm(z, sd[prefix + ".bn.running_mean"], sd[prefix + ".bn.running_var"], sd[prefix + ".bn.weight"],
                      sd[prefix + ".bn.bias"], training, BN_MOMENTUM, BN_EPS)
     if training and (prefix + ".bn.num_batches_tracked") in sd:
         sd[prefix + ".bn.num_batches_tracked"] += 1
-    return silu(z)
+    a = _q(silu(z))
+    if TRACE is not None:
+        TRACE[prefix] = a.detach()
+    return a
 
 
 def focus(x):
@@ -45,7 +59,11 @@ def focus(x):
 def bottleneck(x, sd, prefix, shortcut, training):
     """1x1 -> 3x3, residual when shortcut and cin == cout   (wrappers.py:105-123)"""
     y = base_conv(base_conv(x, sd, prefix + ".conv1", 1, training), sd, prefix + ".conv2", 1, training)
-    return y + x if (shortcut and y.shape[1] == x.shape[1]) else y
+    if shortcut and y.shape[1] == x.shape[1]:
+        y = _q(y + x)
+        if TRACE is not None:
+            TRACE[prefix + ".conv2"] = y.detach()  # what the engine stores for this op: the residual sum
+    return y
 
 
 def csp_layer(x, sd, prefix, shortcut, training):

@@ -22,7 +22,8 @@ def test_preprocess_focus(cuda):
     hwv = torch.tensor([[64, 96], [50, 70], [64, 40]], dtype=torch.int32)
     out = torch.empty(3, 32, 48, 16, dtype=torch.bfloat16, device=cuda)
     oa = capi.act(out)
-    capi.check(capi.lib().yb200_preprocess_focus(capi.ptr(img.to(cuda)), 3, 64, 96, capi.ptr(hwv.to(cuda)), ctypes.c_float(114.0),
+    img_d, hwv_d = img.to(cuda), hwv.to(cuda)  # keep the device tensors alive across the asynchronous launch
+    capi.check(capi.lib().yb200_preprocess_focus(capi.ptr(img_d), 3, 64, 96, capi.ptr(hwv_d), ctypes.c_float(114.0),
                                                  ctypes.byref(oa), capi.stream_ptr()), "preprocess")
     ref_in = orc.preprocess([img[i, :, :int(hwv[i, 0]), :int(hwv[i, 1])] for i in range(3)])
     ref = nhwc(orc.focus(ref_in))
@@ -68,7 +69,8 @@ def test_bn_finalize_apply_and_backward(cuda, c, hw, res, up):
     out = torch.zeros(n, hw, hw, 2 * c, dtype=torch.bfloat16, device=cuda)  # write into the upper channel slice of a wider buffer
     outu = torch.zeros(n, 2 * hw, 2 * hw, c, dtype=torch.bfloat16, device=cuda) if up else None
     za, oa = capi.act(zd), capi.act(out, c, c)
-    ra = capi.act(nhwc(resid).to(cuda)) if res else None
+    resid_d = nhwc(resid).to(cuda) if res else None
+    ra = capi.act(resid_d) if res else None
     ua = capi.act(outu) if up else None
     capi.check(L.yb200_bn_apply_silu(ctypes.byref(za), capi.ptr(scale), capi.ptr(shift), ctypes.byref(ra) if res else None, ctypes.byref(oa),
                                      ctypes.byref(ua) if up else None, capi.stream_ptr()), "bn_apply_silu")
@@ -83,7 +85,8 @@ def test_bn_finalize_apply_and_backward(cuda, c, hw, res, up):
     dgam, dbet = torch.empty(c, device=cuda), torch.empty(c, device=cuda)
     acc1, acc2 = torch.zeros(c, dtype=torch.float64, device=cuda), torch.zeros(c, dtype=torch.float64, device=cuda)
     daa, dza = capi.act(dad), capi.act(dz)
-    dua = capi.act(nhwc(da_up).to(cuda)) if up else None
+    da_up_d = nhwc(da_up).to(cuda) if up else None
+    dua = capi.act(da_up_d) if up else None
     capi.check(L.yb200_bn_silu_bwd(ctypes.byref(za), ctypes.byref(daa), None, ctypes.byref(dua) if up else None, capi.ptr(scale), capi.ptr(shift),
                                    capi.ptr(mean), capi.ptr(invstd), capi.ptr(acc1), capi.ptr(acc2), ctypes.byref(dza), capi.ptr(dgam),
                                    capi.ptr(dbet), 0, capi.stream_ptr()), "bn_silu_bwd")
