@@ -47,7 +47,8 @@ int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, in
 
 /* ---- convolution (implicit GEMM on tcgen05) ------------------------------------------------------ */
 /* z = conv2d(x, w) without bias, padding (k-1)/2 -- BaseConv.conv, wrappers.py:67-80.
- * ksize in {1,3}, stride in {1,2} (stride 2 only with ksize 3).  z is the bf16 pre-BatchNorm output.
+ * ksize in {1,3}, stride in {1,2} (stride 2 only with ksize 3).  z is the pre-BatchNorm output, stored as **fp16**
+ * (same 2-byte NHWC view; BatchNorm's mean subtraction makes this tensor the precision-critical one).
  * If stat_sum/stat_sqsum are non-NULL the per-channel sum and sum of squares of the *stored* z are
  * accumulated into them (fp64, must be zeroed by the caller) -- the batch statistics nn.BatchNorm2d
  * (wrappers.py:76) computes in training mode.                                                          */
@@ -89,7 +90,8 @@ int yb200_bn_finalize(double* stat_sum, double* stat_sqsum, int c, int64_t count
 /* Eval mode: scale/shift from running statistics (the folding of utils/checkpoint.py:11-43 as an epilogue).   */
 int yb200_bn_eval_affine(int c, const float* gamma, const float* beta, const float* running_mean,
                          const float* running_var, float eps, float* scale, float* shift, void* stream);
-/* out = SiLU(z*scale + shift) [+ residual]  (Bottleneck shortcut, wrappers.py:119-123); when out_up2x is given the
+/* z is the fp16 tensor written by yb200_conv2d_fwd; every other activation / gradient view is bf16.
+ * out = SiLU(z*scale + shift) [+ residual]  (Bottleneck shortcut, wrappers.py:119-123); when out_up2x is given the
  * result is also written nearest-upsampled x2 into that view (nn.Upsample + torch.cat of yolo_pafpn.py:96-102). */
 int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const float* shift, const yb200_act* residual,
                         const yb200_act* out, const yb200_act* out_up2x, void* stream);

@@ -18,12 +18,12 @@ eng.load_state_dict(sd)
 eng.images_u8.copy_(images.to(dev)); eng.labels.copy_(labels.to(dev))
 eng.train_step(); torch.cuda.synchronize()
 for mode in (True, False):
-    orc.ROUND_BF16 = mode
+    orc.EMULATE_STORAGE = mode
     orc.TRACE = {}
     ref_sd = {k: v.clone() for k, v in sd.items()}
     with torch.no_grad():
         res = orc.yolox_forward_train(images.float(), labels, ref_sd)
-    print("=== oracle ROUND_BF16 =", mode, "losses", [float(x) for x in res[:4]], "engine", eng.losses.tolist())
+    print("=== oracle EMULATE_STORAGE =", mode, "losses", [float(x) for x in res[:4]], "engine", eng.losses.tolist())
     for op in eng.ops:
         if not isinstance(op, ConvOp): continue
         for hd in op.heads:

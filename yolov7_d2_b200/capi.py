@@ -83,6 +83,6 @@ def ptr(t):
 
 def act(t, c_off=0, c=None):
     """View of an NHWC bf16 tensor [N,H,W,Cpitch] (contiguous) restricted to channels [c_off, c_off+c)."""
-    assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    assert t.dtype in (torch.bfloat16, torch.float16) and t.dim() == 4 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
     n, h, w, cp = t.shape
     return Act(t.data_ptr(), n, h, w, cp - c_off if c is None else c, cp, c_off)

@@ -163,7 +163,7 @@ extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb2
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   set_out_view(p, *z);
-  p.epi_mode = stat_sum ? EPI_BF16_STATS : EPI_BF16;
+  p.epi_mode = stat_sum ? EPI_F16_STATS : EPI_F16;
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sqsum;
   return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream));

@@ -11,6 +11,8 @@
 // Used for: conv forward (F3/F2/F8 of SURVEY.md par.8a), data-gradient (same kernel, transposed tap table)
 // and the 1x1 prediction convolutions (fp32 + bias epilogue).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "sm100.cuh"
 
 namespace yb {
@@ -20,10 +22,15 @@ constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 4;
 
 enum EpiMode : int {
-  EPI_BF16 = 0,        // out = bf16(acc [+ addend])
-  EPI_BF16_STATS = 1,  // out = bf16(acc); per-channel sum / sum-of-squares of the stored values (fp64 atomics)
-  EPI_F32_BIAS = 2,    // out = acc + bias[c]   (fp32, arbitrary element strides)
+  EPI_BF16 = 0,       // out = bf16(acc [+ addend])                          (data gradients)
+  EPI_F16 = 1,        // out = fp16(acc)                                     (pre-BatchNorm conv output, eval mode)
+  EPI_F16_STATS = 2,  // out = fp16(acc) + per-channel sum / sum-of-squares of the stored values (fp64 atomics)
+  EPI_F32_BIAS = 3,   // out = acc + bias[c]   (fp32, arbitrary element strides)
 };
+// The pre-BatchNorm tensor is stored in fp16, not bf16: BatchNorm subtracts the channel mean, which turns the
+// *relative* rounding error of the stored value into an error relative to the (often much smaller) channel
+// standard deviation.  fp16 has 3 more mantissa bits; its range (65504) is ample for a convolution of normalised
+// activations (same exposure as the reference's AMP fp16 path).
 
 struct ConvTap {
   int c0;  // coordinate offset in the innermost (channel) dimension of the A map
@@ -65,6 +72,18 @@ struct ConvGemmCfg {
   static_assert(kABytes % (8 * kSwizzle) == 0 && kStageBytes % (8 * kSwizzle) == 0, "tiles must start on a swizzle-pattern boundary");
 };
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void store_f16x8(__half* dst, const float* v) {
+  uint4 u;
+  u.x = pack_f16x2(v[0], v[1]);
+  u.y = pack_f16x2(v[2], v[3]);
+  u.z = pack_f16x2(v[4], v[5]);
+  u.w = pack_f16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]);
@@ -82,8 +101,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[2 * kMaxStages + 1];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_sum[BLOCK_N];
-  __shared__ float s_sq[BLOCK_N];
+  __shared__ float s_part[4][2][BLOCK_N];  // per epilogue warp: column sums / sums of squares of its 32 rows
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,10 +128,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(bar_acc, 1);
     mbar_fence_init();
-  }
-  if (threadIdx.x < BLOCK_N) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(&s_tmem));
   tc_fence_before();
@@ -217,34 +231,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // round once; statistics describe exactly the values that are stored
+        const bool f16 = p.epi_mode != EPI_BF16;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = valid ? bf16_round(v[i]) : 0.f;
+        for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
         if (valid) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
+          if (f16) {
+            __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
 #pragma unroll
-          for (int i = 0; i < CH; i += 8)
-            if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+            for (int i = 0; i < CH; i += 8)
+              if (cbase + i < p.cout) store_f16x8(o + i, v + i);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8)
+              if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+          }
         }
-        if (p.epi_mode == EPI_BF16_STATS) {
+        if (p.epi_mode == EPI_F16_STATS) {
           float sq[CH];
 #pragma unroll
           for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
           float cs, cq;
           if constexpr (CH == 32) { cs = warp_colsum32(v, lane); cq = warp_colsum32(sq, lane); }
           else { cs = warp_colsum16(v, lane); cq = warp_colsum16(sq, lane); }
-          if (lane < CH) {
-            atomicAdd(&s_sum[c + lane], cs);
-            atomicAdd(&s_sq[c + lane], cq);
+          if (lane < CH) {  // plain stores: each (warp, column) slot has exactly one writer
+            s_part[q][0][c + lane] = cs;
+            s_part[q][1][c + lane] = cq;
           }
         }
-      }
-    }
-    if (p.epi_mode == EPI_BF16_STATS) {
-      named_bar_sync(1, 128);  // the four epilogue warps
-      const int e = threadIdx.x - 64;
-      if (e < BLOCK_N && col0 + e < p.cout) {
-        atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s_sum[e]));
-        atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s_sq[e]));
       }
     }
   }
@@ -252,6 +266,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (p.epi_mode == EPI_F16_STATS) {
+    // one fp64 atomic per channel and CTA (after the block-wide barrier above: no named barrier, no shared atomics)
+    const int e = threadIdx.x;
+    if (e < BLOCK_N && col0 + e < p.cout) {
+      const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
+      const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
+      atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
+      atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+    }
+  }
 }
 
 }  // namespace yb

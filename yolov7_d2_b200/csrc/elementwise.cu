@@ -3,6 +3,8 @@
 // thread moves 8 channels (16 bytes) per access so warps read and write whole 128-byte lines.
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "host_common.cuh"
 #include "sm100.cuh"
 
@@ -35,6 +37,16 @@ bool same_shape(const yb200_act* a, const yb200_act* b) { return a->n == b->n &&
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+// the pre-BatchNorm tensor z is stored in fp16 (see conv_gemm.cuh); the view type only carries the 2-byte element size
+__device__ __forceinline__ void unpack8_f16(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __half22float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -127,7 +139,7 @@ __global__ void bn_apply_silu_kernel(View z, View a, View res, View up, const fl
     const int c8 = static_cast<int>(i % cv) * 8;
     const long long pix = i / cv;
     float f[8], s[8], t[8];
-    unpack8(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), f);
+    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), f);
     *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale + c8);
     *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale + c8 + 4);
     *reinterpret_cast<float4*>(t) = *reinterpret_cast<const float4*>(shift + c8);
@@ -218,7 +230,7 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
       const int y = static_cast<int>((pix / z.w) % z.h);
       const long long b = pix / (1LL * z.w * z.h);
       float zf[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
+      unpack8_f16(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
       load_da(da, pix, x, y, b, c8, d);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -254,7 +266,7 @@ __global__ void bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float*
     const int y = static_cast<int>((pix / z.w) % z.h);
     const long long b = pix / (1LL * z.w * z.h);
     float zf[8], d[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
+    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
     load_da(da, pix, x, y, b, c8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {

@@ -29,9 +29,9 @@ def _ceil(a, b):
 class Buf:
     """NHWC bf16 activation buffer (+ lazily allocated gradient of the same shape)"""
 
-    def __init__(self, name, n, h, w, c, device):
+    def __init__(self, name, n, h, w, c, device, dtype=torch.bfloat16):
         self.name, self.n, self.h, self.w, self.c = name, n, h, w, c
-        self.t = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=device)
+        self.t = torch.zeros(n, h, w, c, dtype=dtype, device=device)
         self.g = None
         self.written = []  # channel ranges of .g already produced in the current backward pass
 
@@ -113,8 +113,8 @@ class YoloxEngine:
         self._alloc_runtime()
 
     # ------------------------------------------------------------------ graph construction
-    def _buf(self, name, h, w, c):
-        b = Buf(name, self.n, h, w, c, self.dev)
+    def _buf(self, name, h, w, c, dtype=torch.bfloat16):
+        b = Buf(name, self.n, h, w, c, self.dev, dtype)
         self.bufs[name] = b
         return b
 
@@ -122,7 +122,7 @@ class YoloxEngine:
         n, h, w, _ = x.shape
         oh, ow = h // s, w // s
         ctot = sum(couts)
-        z = self._buf(prefixes[0] + ".z", oh, ow, ctot)
+        z = self._buf(prefixes[0] + ".z", oh, ow, ctot, torch.float16)  # pre-BN conv output: fp16 (conv_gemm.cuh)
         heads, res = [], []
         c0 = 0
         for i, (p, c) in enumerate(zip(prefixes, couts)):
