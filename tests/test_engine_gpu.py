@@ -105,23 +105,56 @@ def test_bn_running_stats(step):
         assert int(eng.buffers[name + ".num_batches_tracked"]) == 1
 
 
-def test_parameter_gradients(step):
-    eng, ref_sd, emu_sd = step["eng"], step["ref"]["sd"], step["emu"]["sd"]
+def _linear_functional_grads(sd, images, g_raw, emulate):
+    """d/d params of  sum(G * raw head outputs)  -- no discrete decision (SimOTA) between parameters and objective"""
+    orc.EMULATE_STORAGE = emulate
+    try:
+        sd = {k: v.clone() for k, v in sd.items()}
+        for k, v in sd.items():
+            if v.dtype == torch.float32 and "running" not in k:
+                v.requires_grad_(True)
+        raw = orc.head_raw(orc.pafpn(orc.csp_darknet(images.float(), sd, True), sd, True), sd, True)
+        flat = torch.cat([r.permute(0, 2, 3, 1).reshape(r.shape[0], -1, r.shape[1]) for r in raw], 1)
+        (flat * g_raw).sum().backward()
+    finally:
+        orc.EMULATE_STORAGE = False
+    return {k: v.grad for k, v in sd.items() if v.requires_grad}
+
+
+def test_backward_against_oracle(step, cuda):
+    """conv / BatchNorm / SPP / upsample / residual backward of the whole network for a fixed upstream gradient G on the raw
+    head outputs (the loss kernel's own gradient is verified bit-level against the reference in test_simota_gpu.py)."""
+    eng, images, sd0 = step["eng"], step["images"], step["sd0"]
+    gen = torch.Generator().manual_seed(77)
+    n, a, ch = eng.outputs.shape
+    g_raw = (torch.randn(n, a, ch, generator=gen) * 1e-2).to(torch.bfloat16).float()
+    eng.load_state_dict(sd0)
+    eng.pack_weights()
+    eng.preprocess()
+    eng.forward_features(True)
+    for k, (h, w, s, a_off) in enumerate(eng.levels):
+        gl = g_raw[:, a_off:a_off + h * w]
+        eng.d_cls[k].copy_(gl[..., 5:].reshape(n, h, w, ch - 5).to(cuda))
+        eng.d_ro[k].zero_()
+        eng.d_ro[k][..., :5].copy_(gl[..., :5].reshape(n, h, w, 5).to(cuda))
+        eng.bias_acc[k].copy_(gl.double().sum((0, 1)).to(cuda))
+    eng.backward()
+    torch.cuda.synchronize()
+    ref = _linear_functional_grads(sd0, images, g_raw, False)
+    emu = _linear_functional_grads(sd0, images, g_raw, True)
     rows = []
     for name in eng.param_names:
         g = eng.grads[name].cpu().flatten().double()
-        r = ref_sd[name].grad.flatten().double()
-        e = emu_sd[name].grad.flatten().double()
+        r, e = ref[name].flatten().double(), emu[name].flatten().double()
         cos = float((g @ r) / (g.norm() * r.norm() + 1e-30))
         cos_e = float((e @ r) / (e.norm() * r.norm() + 1e-30))
-        ratio = float(g.norm() / (r.norm() + 1e-30))
-        rows.append((cos, cos_e, ratio, name))
+        rows.append((cos, cos_e, float(g.norm() / (r.norm() + 1e-30)), name))
     rows.sort()
-    print("lowest cosine similarities (engine, emulating oracle, norm ratio):")
-    for r in rows[:8]:
+    print("lowest cosine similarity to the fp32 oracle (engine, emulating oracle, norm ratio):")
+    for r in rows[:10]:
         print("   %.4f %.4f %.3f %s" % r)
     for cos, cos_e, ratio, name in rows:
-        assert cos >= min(0.9, cos_e - 0.05) and cos >= cos_e - 0.05 and 0.8 <= ratio <= 1.25, (name, cos, cos_e, ratio)
+        assert cos >= cos_e - 0.03 and cos >= 0.9 and 0.85 <= ratio <= 1.18, (name, cos, cos_e, ratio)
 
 
 def test_second_step_is_reproducible(step):

@@ -130,40 +130,57 @@ __global__ void bn_eval_affine_kernel(int c, const float* __restrict__ gamma, co
   shift[i] = beta[i] - rm[i] * s;
 }
 
+// Thread mapping of the BatchNorm kernels: blockDim = (channel vectors of 8, pixels), so a thread's channels are fixed
+// (per-channel constants live in registers) and no integer division is needed to decode an element index; consecutive
+// linear thread ids touch consecutive 16-byte chunks, i.e. warps read and write whole 128-byte lines.
+constexpr int kEwThreads = 256;
+constexpr int kEwIters = 8;  // pixels per thread
+
+struct PixXY {
+  int x, y, b;
+};
+__device__ __forceinline__ PixXY decode_pix(unsigned pix, int w, int h) {
+  PixXY r;
+  const unsigned row = pix / static_cast<unsigned>(w);
+  r.x = static_cast<int>(pix - row * w);
+  r.b = static_cast<int>(row / static_cast<unsigned>(h));
+  r.y = static_cast<int>(row - static_cast<unsigned>(r.b) * h);
+  return r;
+}
+
 // a = SiLU(z*scale + shift) [+ residual];  optionally also written 2x nearest-upsampled into a second view
-__global__ void bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift,
-                                     int has_res, int has_up) {
-  const int cv = z.c / 8;
-  const long long total = 1LL * z.n * z.h * z.w * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = static_cast<int>(i % cv) * 8;
-    const long long pix = i / cv;
-    float f[8], s[8], t[8];
-    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), f);
-    *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale + c8);
-    *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale + c8 + 4);
-    *reinterpret_cast<float4*>(t) = *reinterpret_cast<const float4*>(shift + c8);
-    *reinterpret_cast<float4*>(t + 4) = *reinterpret_cast<const float4*>(shift + c8 + 4);
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift, int has_res,
+                     int has_up, unsigned npix) {
+  const int c8 = threadIdx.x * 8;
+  float s[8], t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
+  const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
+#pragma unroll 4
+  for (int it = 0; it < kEwIters; ++it) {
+    const unsigned pix = p0 + it * blockDim.y;
+    if (pix >= npix) break;
+    float f[8];
+    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], s[k], t[k]));
     if (has_res) {
       // residual is added to the *rounded* activation, as in the reference where y = conv2(...) is materialised first
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res.p + pix * res.pitch + c8), r);
+      unpack8(*reinterpret_cast<const uint4*>(res.p + static_cast<size_t>(pix) * res.pitch + c8), r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k]) + r[k];
     }
     const uint4 o = pack8(f);
-    *reinterpret_cast<uint4*>(a.p + pix * a.pitch + c8) = o;
+    *reinterpret_cast<uint4*>(a.p + static_cast<size_t>(pix) * a.pitch + c8) = o;
     if (has_up) {
-      const int x = static_cast<int>(pix % z.w);
-      const int y = static_cast<int>((pix / z.w) % z.h);
-      const long long b = pix / (1LL * z.w * z.h);
-      __nv_bfloat16* u = up.p + ((b * up.h + 2 * y) * up.w + 2 * x) * up.pitch + c8;
+      const PixXY q = decode_pix(pix, z.w, z.h);
+      __nv_bfloat16* u = up.p + ((static_cast<size_t>(q.b) * up.h + 2 * q.y) * up.w + 2 * q.x) * up.pitch + c8;
       *reinterpret_cast<uint4*>(u) = o;
       *reinterpret_cast<uint4*>(u + up.pitch) = o;
-      *reinterpret_cast<uint4*>(u + (long long)up.w * up.pitch) = o;
-      *reinterpret_cast<uint4*>(u + (long long)(up.w + 1) * up.pitch) = o;
+      *reinterpret_cast<uint4*>(u + static_cast<size_t>(up.w) * up.pitch) = o;
+      *reinterpret_cast<uint4*>(u + static_cast<size_t>(up.w + 1) * up.pitch) = o;
     }
   }
 }
@@ -181,106 +198,100 @@ struct DaSrc {
   int has_b, has_up;
 };
 
-__device__ __forceinline__ void load_da(const DaSrc& s, long long pix, int x, int y, long long bimg, int c8, float* d) {
-  unpack8(*reinterpret_cast<const uint4*>(s.a.p + pix * s.a.pitch + c8), d);
+__device__ __forceinline__ void load_da(const DaSrc& s, unsigned pix, int w, int h, int c8, float* d) {
+  unpack8(*reinterpret_cast<const uint4*>(s.a.p + static_cast<size_t>(pix) * s.a.pitch + c8), d);
   if (s.has_b) {
     float e[8];
-    unpack8(*reinterpret_cast<const uint4*>(s.b.p + pix * s.b.pitch + c8), e);
+    unpack8(*reinterpret_cast<const uint4*>(s.b.p + static_cast<size_t>(pix) * s.b.pitch + c8), e);
 #pragma unroll
     for (int k = 0; k < 8; ++k) d[k] += e[k];
   }
   if (s.has_up) {
-    const __nv_bfloat16* u = s.up.p + ((bimg * s.up.h + 2 * y) * s.up.w + 2 * x) * s.up.pitch + c8;
+    const PixXY q = decode_pix(pix, w, h);
+    const __nv_bfloat16* u = s.up.p + ((static_cast<size_t>(q.b) * s.up.h + 2 * q.y) * s.up.w + 2 * q.x) * s.up.pitch + c8;
     float e[8];
-    const long long offs[4] = {0, s.up.pitch, (long long)s.up.w * s.up.pitch, (long long)(s.up.w + 1) * s.up.pitch};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      unpack8(*reinterpret_cast<const uint4*>(u + offs[q]), e);
+    for (int j = 0; j < 4; ++j) {
+      const size_t off = static_cast<size_t>((j >> 1) * s.up.w + (j & 1)) * s.up.pitch;
+      unpack8(*reinterpret_cast<const uint4*>(u + off), e);
 #pragma unroll
       for (int k = 0; k < 8; ++k) d[k] += e[k];
     }
   }
 }
 
-constexpr int kBnBwdThreads = 256;
+constexpr int kBnRedIters = 32;  // pixels per thread in the reduction pass
 
-// grid.x covers pixel chunks, each block reduces its chunk for all channels into fp64 atomics
-__global__ void __launch_bounds__(kBnBwdThreads)
+__global__ void __launch_bounds__(kEwThreads)
 bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-                          const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, int pix_per_block) {
+                          const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, unsigned npix) {
   extern __shared__ float sm[];  // [2][c]
-  const int cv = z.c / 8;
-  for (int i = threadIdx.x; i < 2 * z.c; i += blockDim.x) sm[i] = 0.f;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < 2 * z.c; i += blockDim.x * blockDim.y) sm[i] = 0.f;
   __syncthreads();
-  const long long npix = 1LL * z.n * z.h * z.w;
-  const long long p0 = 1LL * blockIdx.x * pix_per_block;
-  const long long p1 = min(npix, p0 + pix_per_block);
-  // thread t owns channel vector (t % cv) and walks pixels with stride blockDim/cv -> per-thread partial sums in registers
-  const int lanes_per_pix = cv;
-  const int my_cv = threadIdx.x % lanes_per_pix;
-  const int pix_stride = blockDim.x / lanes_per_pix;
-  const int c8 = my_cv * 8;
+  const int c8 = threadIdx.x * 8;
+  float s[8], t[8], mu[8], is[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; mu[k] = mean[c8 + k]; is[k] = invstd[c8 + k]; }
   float gs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (threadIdx.x < pix_stride * lanes_per_pix) {
-    float s[8], t[8], mu[8], is[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; mu[k] = mean[c8 + k]; is[k] = invstd[c8 + k]; }
-    for (long long pix = p0 + threadIdx.x / lanes_per_pix; pix < p1; pix += pix_stride) {
-      const int x = static_cast<int>(pix % z.w);
-      const int y = static_cast<int>((pix / z.w) % z.h);
-      const long long b = pix / (1LL * z.w * z.h);
-      float zf[8], d[8];
-      unpack8_f16(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
-      load_da(da, pix, x, y, b, c8, d);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float u = fmaf(zf[k], s[k], t[k]);
-        const float sg = 1.f / (1.f + __expf(-u));
-        const float du = d[k] * sg * (1.f + u * (1.f - sg));
-        bs[k] += du;
-        gs[k] += du * (zf[k] - mu[k]) * is[k];
-      }
-    }
+  const unsigned p0 = blockIdx.x * (blockDim.y * kBnRedIters) + threadIdx.y;
+#pragma unroll 4
+  for (int it = 0; it < kBnRedIters; ++it) {
+    const unsigned pix = p0 + it * blockDim.y;
+    if (pix >= npix) break;
+    float zf[8], d[8];
+    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), zf);
+    load_da(da, pix, z.w, z.h, c8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&sm[c8 + k], gs[k]);
-      atomicAdd(&sm[z.c + c8 + k], bs[k]);
+      const float u = fmaf(zf[k], s[k], t[k]);
+      const float sg = 1.f / (1.f + __expf(-u));
+      const float du = d[k] * sg * (1.f + u * (1.f - sg));
+      bs[k] += du;
+      gs[k] += du * (zf[k] - mu[k]) * is[k];
     }
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(&sm[c8 + k], gs[k]);
+    atomicAdd(&sm[z.c + c8 + k], bs[k]);
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < z.c; i += blockDim.x) {
+  for (int i = tid; i < z.c; i += blockDim.x * blockDim.y) {
     atomicAdd(dgamma_acc + i, static_cast<double>(sm[i]));
     atomicAdd(dbeta_acc + i, static_cast<double>(sm[z.c + i]));
   }
 }
 
-__global__ void bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
-                                         const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
-                                         const double* __restrict__ dbeta_acc, double inv_count) {
-  const int cv = z.c / 8;
-  const long long total = 1LL * z.n * z.h * z.w * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = static_cast<int>(i % cv) * 8;
-    const long long pix = i / cv;
-    const int x = static_cast<int>(pix % z.w);
-    const int y = static_cast<int>((pix / z.w) % z.h);
-    const long long b = pix / (1LL * z.w * z.h);
+__global__ void __launch_bounds__(kEwThreads)
+bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
+                         const double* __restrict__ dbeta_acc, double inv_count, unsigned npix) {
+  const int c8 = threadIdx.x * 8;
+  float s[8], t[8], mu[8], is[8], mg[8], mb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; mu[k] = mean[c8 + k]; is[k] = invstd[c8 + k];
+    mg[k] = static_cast<float>(dgamma_acc[c8 + k] * inv_count);
+    mb[k] = static_cast<float>(dbeta_acc[c8 + k] * inv_count);
+  }
+  const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
+#pragma unroll 4
+  for (int it = 0; it < kEwIters; ++it) {
+    const unsigned pix = p0 + it * blockDim.y;
+    if (pix >= npix) break;
     float zf[8], d[8], o[8];
-    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + pix * z.pitch + c8), zf);
-    load_da(da, pix, x, y, b, c8, d);
+    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), zf);
+    load_da(da, pix, z.w, z.h, c8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = c8 + k;
-      const float s = scale[c], is = invstd[c];
-      const float u = fmaf(zf[k], s, shift[c]);
+      const float u = fmaf(zf[k], s[k], t[k]);
       const float sg = 1.f / (1.f + __expf(-u));
       const float du = d[k] * sg * (1.f + u * (1.f - sg));
-      const float zh = (zf[k] - mean[c]) * is;
-      const float mg = static_cast<float>(dgamma_acc[c] * inv_count);
-      const float mb = static_cast<float>(dbeta_acc[c] * inv_count);
-      o[k] = s * (du - mb - zh * mg);  // s = gamma*invstd
+      const float zh = (zf[k] - mu[k]) * is[k];
+      o[k] = s[k] * (du - mb[k] - zh * mg[k]);  // s = gamma*invstd
     }
-    *reinterpret_cast<uint4*>(dz.p + pix * dz.pitch + c8) = pack8(o);
+    *reinterpret_cast<uint4*>(dz.p + static_cast<size_t>(pix) * dz.pitch + c8) = pack8(o);
   }
 }
 
@@ -445,8 +456,13 @@ extern "C" int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const
   YB_REQUIRE(!out_up2x || (out_up2x->n == z->n && out_up2x->h == 2 * z->h && out_up2x->w == 2 * z->w && out_up2x->c == z->c), YB200_ERR_INVALID,
              "bn_apply_silu: upsampled view must be [n,2h,2w,c]");
   View vz = mk(z), vo = mk(out), vr = residual ? mk(residual) : vz, vu = out_up2x ? mk(out_up2x) : vz;
-  const long long total = 1LL * z->n * z->h * z->w * (z->c / 8);
-  bn_apply_silu_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(vz, vo, vr, vu, scale, shift, residual != nullptr, out_up2x != nullptr);
+  const long long npix = 1LL * z->n * z->h * z->w;
+  const int cv = z->c / 8;
+  YB_REQUIRE(cv <= kEwThreads && npix < (1LL << 31), YB200_ERR_UNSUPPORTED, "bn_apply_silu: %d channels / %lld pixels", z->c, npix);
+  dim3 block(cv, kEwThreads / cv);
+  const unsigned grid = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
+  bn_apply_silu_kernel<<<grid, block, 0, as_stream(stream)>>>(vz, vo, vr, vu, scale, shift, residual != nullptr, out_up2x != nullptr,
+                                                             static_cast<unsigned>(npix));
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -462,7 +478,9 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
   YB_REQUIRE(same_shape(z, da) && same_shape(z, dz) && (!da2 || same_shape(z, da2)), YB200_ERR_INVALID, "bn_silu_bwd: shape mismatch");
   YB_REQUIRE(!da_up2x || (da_up2x->n == z->n && da_up2x->h == 2 * z->h && da_up2x->w == 2 * z->w && da_up2x->c == z->c), YB200_ERR_INVALID,
              "bn_silu_bwd: upsampled gradient view must be [n,2h,2w,c]");
-  YB_REQUIRE(z->c / 8 <= kBnBwdThreads, YB200_ERR_UNSUPPORTED, "bn_silu_bwd: %d channels", z->c);
+  const long long npix = 1LL * z->n * z->h * z->w;
+  const int cv = z->c / 8;
+  YB_REQUIRE(cv <= kEwThreads && npix < (1LL << 31), YB200_ERR_UNSUPPORTED, "bn_silu_bwd: %d channels / %lld pixels", z->c, npix);
   cudaStream_t st = as_stream(stream);
   DaSrc src;
   src.a = mk(da);
@@ -471,18 +489,14 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
   src.has_b = da2 != nullptr;
   src.has_up = da_up2x != nullptr;
   View vz = mk(z), vdz = mk(dz);
-  const long long npix = 1LL * z->n * z->h * z->w;
-  const int pix_stride = kBnBwdThreads / (z->c / 8);
-  // enough blocks to fill the machine, each walking >= 8 pixel rows per thread
-  int blocks = static_cast<int>(std::min<long long>(8LL * sm_count(), std::max<long long>(1, npix / (8LL * pix_stride))));
-  const int ppb = static_cast<int>((npix + blocks - 1) / blocks);
-  blocks = static_cast<int>((npix + ppb - 1) / ppb);
-  bn_silu_bwd_reduce_kernel<<<blocks, kBnBwdThreads, 2 * z->c * sizeof(float), st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma,
-                                                                                      acc_dbeta, ppb);
+  dim3 block(cv, kEwThreads / cv);
+  const unsigned grid_r = static_cast<unsigned>((npix + block.y * kBnRedIters - 1) / (block.y * kBnRedIters));
+  bn_silu_bwd_reduce_kernel<<<grid_r, block, 2 * z->c * sizeof(float), st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                                              static_cast<unsigned>(npix));
   YB_CHECK_CUDA(cudaGetLastError());
-  const long long total = npix * (z->c / 8);
-  bn_silu_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                                  1.0 / static_cast<double>(npix));
+  const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
+  bn_silu_bwd_apply_kernel<<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                      1.0 / static_cast<double>(npix), static_cast<unsigned>(npix));
   YB_CHECK_CUDA(cudaGetLastError());
   bn_param_grad_kernel<<<ceil_div(z->c, 128), 128, 0, st>>>(acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());

@@ -180,17 +180,25 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
 // Sum the split-K partials and scatter into the reference's OIHW fp32 gradient layout
 // (torch.nn.Conv2d.weight.grad: [Cout][Cin][kh][kw]); padded input channels (ci >= cin_real) are dropped.
 // accumulate != 0 adds to the existing gradient (gradient accumulation across micro-batches).
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad_oihw, int splits, int cout,
-                                    int num_taps, int cin_pad, int cin_real, int accumulate) {
-  const long long total = (long long)cout * num_taps * cin_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ci = static_cast<int>(i % cin_pad);
-    const int tap = static_cast<int>((i / cin_pad) % num_taps);
-    const int co = static_cast<int>(i / ((long long)cin_pad * num_taps));
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad_oihw, int splits, int cout, int num_taps, int cin_pad,
+                                    int cin_real, int accumulate) {
+  const unsigned total = static_cast<unsigned>(cout) * num_taps * cin_pad;
+  const unsigned tc = static_cast<unsigned>(num_taps) * cin_pad;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned co = i / tc;
+    const unsigned r = i - co * tc;
+    const unsigned tap = r / cin_pad;
+    const unsigned ci = r - tap * cin_pad;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[s * total + i];
-    if (ci < cin_real) {
-      float* g = grad_oihw + ((long long)co * cin_real + ci) * num_taps + tap;
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {  // four independent loads in flight
+      const float a0 = ws[static_cast<size_t>(s) * total + i], a1 = ws[static_cast<size_t>(s + 1) * total + i];
+      const float a2 = ws[static_cast<size_t>(s + 2) * total + i], a3 = ws[static_cast<size_t>(s + 3) * total + i];
+      acc += (a0 + a1) + (a2 + a3);
+    }
+    for (; s < splits; ++s) acc += ws[static_cast<size_t>(s) * total + i];
+    if (ci < static_cast<unsigned>(cin_real)) {
+      float* g = grad_oihw + (static_cast<size_t>(co) * cin_real + ci) * num_taps + tap;
       *g = accumulate ? (*g + acc) : acc;
     }
   }
