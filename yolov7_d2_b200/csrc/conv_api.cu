@@ -37,6 +37,14 @@ static int launch_conv(int bn, int bk, const CUtensorMap& tmA, const CUtensorMap
   return fail(YB200_ERR_UNSUPPORTED, "no conv_gemm instantiation for BLOCK_N=%d BLOCK_K=%d", bn, bk);
 }
 
+// pipeline depth: at most kMaxStages, never more than the K loop, and shallow enough that two CTAs fit in one SM's shared
+// memory (one CTA computes one tile: a second resident CTA hides its prologue / epilogue behind the other's MMAs)
+static int pick_stages(int bn, int bk, int num_kb) {
+  const int stage_bytes = (128 + bn) * bk * 2;
+  int st = num_kb < kMaxStages ? num_kb : kMaxStages;
+  while (st > 2 && 2 * (st * stage_bytes + 2048) > 227 * 1024) --st;
+  return st;
+}
 static int pick_block_k(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
 static int pick_block_n(int c) { return c > 64 ? 128 : (c > 32 ? 64 : (c > 16 ? 32 : 16)); }
 
@@ -146,9 +154,8 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   rc = make_mat_map(&tmB, w_fwd, cout, 1LL * p.num_taps * x->c, bn, bk);
   if (rc) return rc;
   const int num_kb = p.num_taps * p.cin_blocks;
-  const int stages = num_kb < kMaxStages ? num_kb : kMaxStages;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cout, bn));
-  return launch_conv(bn, bk, tmA, tmB, p, grid, stages, st);
+  return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, num_kb), st);
 }
 
 extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride,
@@ -241,8 +248,7 @@ extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, cons
         for (int kw = 0; kw < 3; ++kw) p.taps[nt++] = ConvTap{dz->c_off, 1 - kw, 0, 1 - kh, (kh * 3 + kw) * dz->c};
     }
     p.num_taps = nt;
-    const int num_kb = nt * p.cin_blocks;
-    return launch_conv(bn, bk, tmA, tmB, p, grid, num_kb < kMaxStages ? num_kb : kMaxStages, st);
+    return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, nt * p.cin_blocks), st);
   }
   // stride 2: input pixel (2i+ph, 2j+pw) receives  kh with (ph + 1 - kh) even:  ph=0 -> kh=1 (row i);  ph=1 -> kh=0 (row i+1), kh=2 (row i)
   for (int ph = 0; ph < 2; ++ph)
@@ -259,8 +265,7 @@ extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, cons
       }
       p.num_taps = nt;
       p.out_mh = 2; p.out_ph = ph; p.out_mw = 2; p.out_pw = pw;
-      const int num_kb = nt * p.cin_blocks;
-      if ((rc = launch_conv(bn, bk, tmA, tmB, p, grid, num_kb < kMaxStages ? num_kb : kMaxStages, st))) return rc;
+      if ((rc = launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, nt * p.cin_blocks), st))) return rc;
     }
   return 0;
 }

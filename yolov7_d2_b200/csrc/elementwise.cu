@@ -51,7 +51,7 @@ __device__ __forceinline__ void unpack8_f16(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
-__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+__device__ __forceinline__ float silu_f(float u) { return __fdividef(u, 1.f + __expf(-u)); }
 
 int grid_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
@@ -222,20 +222,27 @@ __device__ __forceinline__ void load_da(const DaSrc& s, unsigned pix, int w, int
 
 constexpr int kBnRedIters = 32;  // pixels per thread in the reduction pass
 
-__global__ void __launch_bounds__(kEwThreads)
+__device__ __forceinline__ float silu_grad(float u, float d) {  // d * d/du [u * sigmoid(u)]
+  const float sg = __fdividef(1.f, 1.f + __expf(-u));
+  return d * sg * (1.f + u * (1.f - sg));
+}
+
+// pass 1: per channel  S1 = sum du,  S2 = sum du * z   (dgamma = invstd * (S2 - mean * S1), dbeta = S1)
+// Block reduction in a fixed order (warp shuffles, then one shared-memory row per warp summed sequentially): two runs on
+// the same data produce the same fp32 block partials; only the final fp64 atomics are unordered.
+__global__ void __launch_bounds__(kEwThreads, 3)
 bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, unsigned npix) {
-  extern __shared__ float sm[];  // [2][c]
+  extern __shared__ float sm[];  // [rows][2][c], rows = warps (c < 256) or blockDim.y (c >= 256)
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < 2 * z.c; i += blockDim.x * blockDim.y) sm[i] = 0.f;
-  __syncthreads();
+  const int nthreads = blockDim.x * blockDim.y;
   const int c8 = threadIdx.x * 8;
-  float s[8], t[8], mu[8], is[8];
+  float s[8], t[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; mu[k] = mean[c8 + k]; is[k] = invstd[c8 + k]; }
-  float gs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned p0 = blockIdx.x * (blockDim.y * kBnRedIters) + threadIdx.y;
-#pragma unroll 4
+#pragma unroll 2
   for (int it = 0; it < kBnRedIters; ++it) {
     const unsigned pix = p0 + it * blockDim.y;
     if (pix >= npix) break;
@@ -244,39 +251,60 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
     load_da(da, pix, z.w, z.h, c8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float u = fmaf(zf[k], s[k], t[k]);
-      const float sg = 1.f / (1.f + __expf(-u));
-      const float du = d[k] * sg * (1.f + u * (1.f - sg));
-      bs[k] += du;
-      gs[k] += du * (zf[k] - mu[k]) * is[k];
+      const float du = silu_grad(fmaf(zf[k], s[k], t[k]), d[k]);
+      s1[k] += du;
+      s2[k] = fmaf(du, zf[k], s2[k]);
     }
   }
+  // lanes sharing a channel vector (same threadIdx.x) sit blockDim.x apart inside the warp (blockDim.x is a power of two)
+  const int cvx = blockDim.x;
+  for (int off = 16; off >= cvx; off >>= 1) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&sm[c8 + k], gs[k]);
-    atomicAdd(&sm[z.c + c8 + k], bs[k]);
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+    }
+  }
+  const int rows = cvx < 32 ? nthreads / 32 : blockDim.y;
+  const int row = cvx < 32 ? tid / 32 : threadIdx.y;
+  if (cvx >= 32 || (tid & 31) < cvx) {
+    float* dst = sm + static_cast<size_t>(row) * 2 * z.c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dst[c8 + k] = s2[k];
+      dst[z.c + c8 + k] = s1[k];
+    }
   }
   __syncthreads();
-  for (int i = tid; i < z.c; i += blockDim.x * blockDim.y) {
-    atomicAdd(dgamma_acc + i, static_cast<double>(sm[i]));
-    atomicAdd(dbeta_acc + i, static_cast<double>(sm[z.c + i]));
+  for (int i = tid; i < z.c; i += nthreads) {
+    float S1 = 0.f, S2 = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      S2 += sm[static_cast<size_t>(r) * 2 * z.c + i];
+      S1 += sm[static_cast<size_t>(r) * 2 * z.c + z.c + i];
+    }
+    atomicAdd(dgamma_acc + i, static_cast<double>(invstd[i]) * (static_cast<double>(S2) - static_cast<double>(mean[i]) * S1));
+    atomicAdd(dbeta_acc + i, static_cast<double>(S1));
   }
 }
 
-__global__ void __launch_bounds__(kEwThreads)
+// pass 2: dz = gamma*invstd * (du - dbeta/M - zhat*dgamma/M) = s*du + A*z + B  with per-channel A, B
+__global__ void __launch_bounds__(kEwThreads, 3)
 bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
                          const double* __restrict__ dbeta_acc, double inv_count, unsigned npix) {
   const int c8 = threadIdx.x * 8;
-  float s[8], t[8], mu[8], is[8], mg[8], mb[8];
+  float s[8], t[8], A[8], B[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; mu[k] = mean[c8 + k]; is[k] = invstd[c8 + k];
-    mg[k] = static_cast<float>(dgamma_acc[c8 + k] * inv_count);
-    mb[k] = static_cast<float>(dbeta_acc[c8 + k] * inv_count);
+    s[k] = scale[c8 + k]; t[k] = shift[c8 + k];
+    const float is = invstd[c8 + k], mu = mean[c8 + k];
+    const float mg = static_cast<float>(dgamma_acc[c8 + k] * inv_count);
+    const float mb = static_cast<float>(dbeta_acc[c8 + k] * inv_count);
+    A[k] = -s[k] * is * mg;
+    B[k] = -s[k] * mb - A[k] * mu;
   }
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
-#pragma unroll 4
+#pragma unroll 2
   for (int it = 0; it < kEwIters; ++it) {
     const unsigned pix = p0 + it * blockDim.y;
     if (pix >= npix) break;
@@ -284,13 +312,7 @@ bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ sc
     unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), zf);
     load_da(da, pix, z.w, z.h, c8, d);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float u = fmaf(zf[k], s[k], t[k]);
-      const float sg = 1.f / (1.f + __expf(-u));
-      const float du = d[k] * sg * (1.f + u * (1.f - sg));
-      const float zh = (zf[k] - mu[k]) * is[k];
-      o[k] = s[k] * (du - mb[k] - zh * mg[k]);  // s = gamma*invstd
-    }
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(s[k], silu_grad(fmaf(zf[k], s[k], t[k]), d[k]), fmaf(A[k], zf[k], B[k]));
     *reinterpret_cast<uint4*>(dz.p + static_cast<size_t>(pix) * dz.pitch + c8) = pack8(o);
   }
 }
@@ -480,7 +502,8 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
              "bn_silu_bwd: upsampled gradient view must be [n,2h,2w,c]");
   const long long npix = 1LL * z->n * z->h * z->w;
   const int cv = z->c / 8;
-  YB_REQUIRE(cv <= kEwThreads && npix < (1LL << 31), YB200_ERR_UNSUPPORTED, "bn_silu_bwd: %d channels / %lld pixels", z->c, npix);
+  YB_REQUIRE(cv <= kEwThreads && (cv & (cv - 1)) == 0 && npix < (1LL << 31), YB200_ERR_UNSUPPORTED,
+             "bn_silu_bwd: %d channels (need 8 * 2^k <= 2048) / %lld pixels", z->c, npix);
   cudaStream_t st = as_stream(stream);
   DaSrc src;
   src.a = mk(da);
@@ -491,8 +514,15 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
   View vz = mk(z), vdz = mk(dz);
   dim3 block(cv, kEwThreads / cv);
   const unsigned grid_r = static_cast<unsigned>((npix + block.y * kBnRedIters - 1) / (block.y * kBnRedIters));
-  bn_silu_bwd_reduce_kernel<<<grid_r, block, 2 * z->c * sizeof(float), st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                                              static_cast<unsigned>(npix));
+  const int red_rows = cv < 32 ? kEwThreads / 32 : static_cast<int>(block.y);
+  const size_t red_smem = static_cast<size_t>(red_rows) * 2 * z->c * sizeof(float);
+  static size_t red_smem_set = 48 * 1024;
+  if (red_smem > red_smem_set) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(bn_silu_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(red_smem)));
+    red_smem_set = red_smem;
+  }
+  bn_silu_bwd_reduce_kernel<<<grid_r, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                              static_cast<unsigned>(npix));
   YB_CHECK_CUDA(cudaGetLastError());
   const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
   bn_silu_bwd_apply_kernel<<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
