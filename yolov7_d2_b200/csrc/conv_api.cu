@@ -4,23 +4,53 @@
 #include "wgrad_gemm.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace yb {
 
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ------------------------------------------------------------------------------------------------
+static bool use_v1_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB200_CONV_KERNEL");
+    v = (e && strcmp(e, "v1") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int BN, int BK>
 static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid, int stages,
                             cudaStream_t st) {
   using Cfg = ConvGemmCfg<BN, BK>;
-  static int max_set = 0;
-  const int smem = stages * Cfg::kStageBytes + 1024;
-  if (smem > max_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    max_set = smem;
+  if (use_v1_kernel()) {  // one tile per CTA (kept for A/B comparison)
+    static int max_set = 0;
+    const int smem = stages * Cfg::kStageBytes + 1024;
+    if (smem > max_set) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      max_set = smem;
+    }
+    conv_gemm_kernel<BN, BK><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p, stages);
+    YB_CHECK_CUDA(cudaGetLastError());
+    return 0;
   }
-  conv_gemm_kernel<BN, BK><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p, stages);
+  // persistent kernel: two CTAs per SM (2 x 2 x BN TMEM columns <= 512), ring as deep as half an SM's shared memory allows
+  const int m_tiles = grid.x, n_tiles = grid.y;
+  int pst = (110 * 1024 - 1024) / Cfg::kStageBytes;
+  if (pst > kMaxStagesP) pst = kMaxStagesP;
+  if (pst < 2) pst = 2;
+  const int smem = pst * Cfg::kStageBytes + 1024;
+  static int max_set_p = 0;
+  if (smem > max_set_p) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    max_set_p = smem;
+  }
+  int groups = (2 * sm_count()) / n_tiles;
+  if (groups < 1) groups = 1;
+  if (groups > m_tiles) groups = m_tiles;
+  conv_gemm_persistent_kernel<BN, BK><<<groups * n_tiles, kConvThreads, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -307,7 +337,7 @@ int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, W
   p.nb = p.bn / p.kc_b;
   p.cin_tiles = x->c / p.bn;
   p.num_taps = fill_fwd_taps(p.taps, *x, ksize, stride, 0);
-  p.tpc = p.num_taps == 1 ? 1 : kWgMaxTpc;
+  p.tpc = p.num_taps == 1 ? 1 : (p.bn <= 32 ? 9 : 3);  // 9 x 32 = 288 <= 512 TMEM columns: dz is then loaded once, not three times
   p.tap_groups = ceil_div(p.num_taps, p.tpc);
   p.dz_c0 = dz->c_off;
   choose_tile(dz->n, dz->h, dz->w, kWgPix, &p.log_tw, &p.log_th);

@@ -278,4 +278,224 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ================================================================================================
+// Persistent variant: each CTA walks a strided list of 128-pixel tiles for ONE column tile.  The TMA ring runs ahead across
+// tile boundaries, accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1, per-channel statistics are accumulated in shared memory over all tiles of the CTA (one fp64 atomic per
+// channel and CTA instead of per tile), and TMEM allocation / barrier setup / descriptor prefetch are paid once.
+// grid.x = n_tiles * groups;  CTA b: column tile b % n_tiles, pixel tiles (b / n_tiles) + i * groups.
+// ================================================================================================
+constexpr int kMaxStagesP = 8;
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(kConvThreads)
+conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const __grid_constant__ ConvGemmParams p, int num_stages, int n_tiles, int m_tiles) {
+  using Cfg = ConvGemmCfg<BLOCK_N, BLOCK_K>;
+  constexpr int kAccCols = Cfg::kTmemCols;          // columns of one accumulator
+  constexpr int kTmemAlloc = 2 * kAccCols;          // double buffered (power of two >= 64)
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2 * kMaxStagesP + 4];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_part[4][2][BLOCK_N];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&s_bar[0]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kMaxStagesP]);
+  const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kMaxStagesP]);       // [2]
+  const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kMaxStagesP + 2]);  // [2]
+
+  const int n_tile = blockIdx.x % n_tiles;
+  const int group = blockIdx.x / n_tiles;
+  const int groups = gridDim.x / n_tiles;
+  const int col0 = n_tile * BLOCK_N;
+  const int log_tw = p.log_tw, log_th = p.log_th;
+  const int num_kb = p.num_taps * p.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 4 * 2 * BLOCK_N; i += blockDim.x) (&s_part[0][0][0])[i] = 0.f;
+  if (warp == 1) tmem_alloc<kTmemAlloc>(smem_u32(&s_tmem));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m = group; m < m_tiles; m += groups) {
+        int t = m;
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tn = t / p.tiles_h;
+        const int w0 = tw << log_tw, h0 = th << log_th, n0 = tn << (7 - log_tw - log_th);
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, Cfg::kStageBytes);
+          const ConvTap& tp = p.taps[tap];
+          tma_load_5d(sa, &tmA, full, tp.c0 + cb * BLOCK_K, w0 + tp.dw, tp.p, h0 + tp.dh, n0);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, full, tp.kb + cb * BLOCK_K, col0);
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t lcode = umma_layout_code(Cfg::kSwizzle);
+      constexpr uint32_t sbo = 8 * Cfg::kSwizzle;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int m = group; m < m_tiles; m += groups, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_acc_empty + 8 * acc, ((it >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * kAccCols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
+            const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
+            umma_f16(tacc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_acc_full + 8 * acc);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int mrow = q * 32 + lane;
+    const int xl = mrow & ((1 << log_tw) - 1);
+    const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
+    const int nl = mrow >> (log_tw + log_th);
+    constexpr int CH = Cfg::kChunk;
+    int it = 0;
+    for (int m = group; m < m_tiles; m += groups, ++it) {
+      int t = m;
+      const int tw = t % p.tiles_w;
+      t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int tn = t / p.tiles_h;
+      const int x = (tw << log_tw) + xl, y = (th << log_th) + yl, n = (tn << (7 - log_tw - log_th)) + nl;
+      const bool valid = (x < p.w_valid) && (y < p.h_valid) && (n < p.n_valid);
+      const long long pix_off = (long long)n * p.out_sn + (long long)(y * p.out_mh + p.out_ph) * p.out_sh +
+                                (long long)(x * p.out_mw + p.out_pw) * p.out_sw;
+      const long long add_off = (long long)n * p.add_sn + (long long)(y * p.out_mh + p.out_ph) * p.add_sh +
+                                (long long)(x * p.out_mw + p.out_pw) * p.add_sw;
+      const int acc = it & 1;
+      mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += CH) {
+        uint32_t r[CH];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c;
+        if constexpr (CH == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
+        tmem_ld_wait();
+        if (c + CH >= BLOCK_N) {  // last chunk is in registers: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+        }
+        float v[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+        const int cbase = col0 + c;
+        if (p.epi_mode == EPI_F32_BIAS) {
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out) + pix_off;
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (cbase + i < p.cout) o[(long long)(cbase + i) * p.out_sc] = v[i] + p.bias[cbase + i];
+          }
+        } else {
+          if (p.addend != nullptr && valid) {
+            const __nv_bfloat16* a = p.addend + add_off + cbase;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) {
+              if (cbase + i < p.cout) {
+                const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+                v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
+                v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
+                v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
+                v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
+              }
+            }
+          }
+          const bool f16 = p.epi_mode != EPI_BF16;
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
+          if (valid) {
+            if (f16) {
+              __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
+#pragma unroll
+              for (int i = 0; i < CH; i += 8)
+                if (cbase + i < p.cout) store_f16x8(o + i, v + i);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
+#pragma unroll
+              for (int i = 0; i < CH; i += 8)
+                if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+            }
+          }
+          if (p.epi_mode == EPI_F16_STATS) {
+            float sq[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
+            float cs, cq;
+            if constexpr (CH == 32) { cs = warp_colsum32(v, lane); cq = warp_colsum32(sq, lane); }
+            else { cs = warp_colsum16(v, lane); cq = warp_colsum16(sq, lane); }
+            if (lane < CH) {  // slot (warp, column) is owned by this lane for the whole kernel
+              s_part[q][0][c + lane] += cs;
+              s_part[q][1][c + lane] += cq;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemAlloc>(tmem_base);
+  if (p.epi_mode == EPI_F16_STATS) {
+    const int e = threadIdx.x;
+    if (e < BLOCK_N && col0 + e < p.cout) {
+      const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
+      const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
+      atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
+      atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+    }
+  }
+}
+
 }  // namespace yb

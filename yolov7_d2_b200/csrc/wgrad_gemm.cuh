@@ -15,7 +15,7 @@
 namespace yb {
 
 constexpr int kWgPix = 64;      // pixels per K block (4 UMMA K-steps)
-constexpr int kWgMaxTpc = 3;    // taps per CTA
+constexpr int kWgMaxTpc = 9;    // taps per CTA (9 when the cin tile is narrow enough for 9 accumulators in TMEM, else 3)
 constexpr int kWgStages = 3;
 
 struct WgradParams {
