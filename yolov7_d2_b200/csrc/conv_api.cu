@@ -409,7 +409,7 @@ extern "C" int yb200_conv2d_wgrad(const yb200_act* x, const yb200_act* dz, int k
   }
   if (rc) return rc;
   const long long total = 1LL * pl.p.cout * pl.p.num_taps * pl.p.cin;
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8 * sm_count()));
+  const int blocks = static_cast<int>(std::min<long long>((total + 31) / 32, 16 * sm_count()));
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(pl.p.ws, grad_oihw, pl.splits, pl.p.cout, pl.p.num_taps, pl.p.cin, cin_real, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;

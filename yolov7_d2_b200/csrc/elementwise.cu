@@ -232,7 +232,8 @@ __device__ __forceinline__ float silu_grad(float u, float d) {  // d * d/du [u *
 // the same data produce the same fp32 block partials; only the final fp64 atomics are unordered.
 __global__ void __launch_bounds__(kEwThreads, 3)
 bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-                          const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, unsigned npix) {
+                          const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, unsigned npix,
+                          int iters) {
   extern __shared__ float sm[];  // [rows][2][c], rows = warps (c < 256) or blockDim.y (c >= 256)
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthreads = blockDim.x * blockDim.y;
@@ -241,9 +242,9 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const unsigned p0 = blockIdx.x * (blockDim.y * kBnRedIters) + threadIdx.y;
+  const unsigned p0 = blockIdx.x * (blockDim.y * iters) + threadIdx.y;
 #pragma unroll 2
-  for (int it = 0; it < kBnRedIters; ++it) {
+  for (int it = 0; it < iters; ++it) {
     const unsigned pix = p0 + it * blockDim.y;
     if (pix >= npix) break;
     float zf[8], d[8];
@@ -513,7 +514,10 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
   src.has_up = da_up2x != nullptr;
   View vz = mk(z), vdz = mk(dz);
   dim3 block(cv, kEwThreads / cv);
-  const unsigned grid_r = static_cast<unsigned>((npix + block.y * kBnRedIters - 1) / (block.y * kBnRedIters));
+  // pixels per thread in the reduction pass: up to 32, fewer for small tensors so that >= ~6 blocks per SM exist
+  int red_iters = static_cast<int>(npix / (static_cast<long long>(block.y) * 6 * sm_count()));
+  red_iters = red_iters < 4 ? 4 : (red_iters > kBnRedIters ? kBnRedIters : red_iters);
+  const unsigned grid_r = static_cast<unsigned>((npix + block.y * red_iters - 1) / (block.y * red_iters));
   const int red_rows = cv < 32 ? kEwThreads / 32 : static_cast<int>(block.y);
   const size_t red_smem = static_cast<size_t>(red_rows) * 2 * z->c * sizeof(float);
   static size_t red_smem_set = 48 * 1024;
@@ -522,7 +526,7 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
     red_smem_set = red_smem;
   }
   bn_silu_bwd_reduce_kernel<<<grid_r, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                              static_cast<unsigned>(npix));
+                                                              static_cast<unsigned>(npix), red_iters);
   YB_CHECK_CUDA(cudaGetLastError());
   const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
   bn_silu_bwd_apply_kernel<<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,

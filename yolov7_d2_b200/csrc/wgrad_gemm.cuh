@@ -180,27 +180,33 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
 // Sum the split-K partials and scatter into the reference's OIHW fp32 gradient layout
 // (torch.nn.Conv2d.weight.grad: [Cout][Cin][kh][kw]); padded input channels (ci >= cin_real) are dropped.
 // accumulate != 0 adds to the existing gradient (gradient accumulation across micro-batches).
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad_oihw, int splits, int cout, int num_taps, int cin_pad,
-                                    int cin_real, int accumulate) {
+// block = (32 outputs, 8 split lanes): the serial chain over splits is 8x shorter; partials are combined in a fixed order
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad_oihw, int splits, int cout, int num_taps, int cin_pad,
+                    int cin_real, int accumulate) {
+  __shared__ float part[8][33];
   const unsigned total = static_cast<unsigned>(cout) * num_taps * cin_pad;
   const unsigned tc = static_cast<unsigned>(num_taps) * cin_pad;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned co = i / tc;
-    const unsigned r = i - co * tc;
-    const unsigned tap = r / cin_pad;
-    const unsigned ci = r - tap * cin_pad;
+  const int ox = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (unsigned base = blockIdx.x * 32u; base < total; base += gridDim.x * 32u) {
+    const unsigned i = base + ox;
     float acc = 0.f;
-    int s = 0;
-    for (; s + 4 <= splits; s += 4) {  // four independent loads in flight
-      const float a0 = ws[static_cast<size_t>(s) * total + i], a1 = ws[static_cast<size_t>(s + 1) * total + i];
-      const float a2 = ws[static_cast<size_t>(s + 2) * total + i], a3 = ws[static_cast<size_t>(s + 3) * total + i];
-      acc += (a0 + a1) + (a2 + a3);
+    if (i < total)
+      for (int s = sl; s < splits; s += 8) acc += ws[static_cast<size_t>(s) * total + i];
+    part[sl][ox] = acc;
+    __syncthreads();
+    if (sl == 0 && i < total) {
+      const float v = ((part[0][ox] + part[1][ox]) + (part[2][ox] + part[3][ox])) + ((part[4][ox] + part[5][ox]) + (part[6][ox] + part[7][ox]));
+      const unsigned co = i / tc;
+      const unsigned r = i - co * tc;
+      const unsigned tap = r / cin_pad;
+      const unsigned ci = r - tap * cin_pad;
+      if (ci < static_cast<unsigned>(cin_real)) {
+        float* g = grad_oihw + (static_cast<size_t>(co) * cin_real + ci) * num_taps + tap;
+        *g = accumulate ? (*g + v) : v;
+      }
     }
-    for (; s < splits; ++s) acc += ws[static_cast<size_t>(s) * total + i];
-    if (ci < static_cast<unsigned>(cin_real)) {
-      float* g = grad_oihw + (static_cast<size_t>(co) * cin_real + ci) * num_taps + tap;
-      *g = accumulate ? (*g + acc) : acc;
-    }
+    __syncthreads();
   }
 }
 

@@ -293,13 +293,29 @@ class YOLOX(nn.Module):
         wmax = max(i.shape[-1] for i in imgs)
         hp, wp = (hmax + 31) // 32 * 32, (wmax + 31) // 32 * 32
         eng = self._plan(len(imgs), hp, wp)
-        same = all(i.shape[-2:] == (hp, wp) for i in imgs)
-        if same and all(i.dtype == torch.uint8 for i in imgs):
-            host = torch.stack([i for i in imgs]) if not imgs[0].is_cuda else None
-            if host is not None:
-                eng.images_u8.copy_(host.pin_memory() if not host.is_pinned() else host, non_blocking=True)
+        same = all(i.shape[-2:] == (hp, wp) and i.dtype == torch.uint8 for i in imgs)
+        if same and all(i.is_cuda for i in imgs):
+            eng.images_u8.copy_(torch.stack(imgs))
+        elif same:
+            # host images: one H2D copy of the whole batch.  If the images already are consecutive slices of one pinned
+            # tensor (a collated batch) it is used as is; otherwise they are gathered into a persistent pinned staging buffer.
+            nbytes = imgs[0].numel()
+            base = imgs[0]
+            contiguous_run = base.is_pinned() and all(i.is_contiguous() and i.data_ptr() == base.data_ptr() + k * nbytes for k, i in enumerate(imgs))
+            if contiguous_run:
+                src = torch.as_strided(base, (len(imgs), 3, hp, wp), (nbytes, hp * wp, wp, 1))
             else:
-                eng.images_u8.copy_(torch.stack(imgs))
+                if getattr(eng, "_stage", None) is None:
+                    eng._stage = torch.empty(eng.images_u8.shape, dtype=torch.uint8).pin_memory()
+                    eng._stage_evt = torch.cuda.Event()
+                else:
+                    eng._stage_evt.synchronize()  # the previous step's DMA out of the staging buffer has finished
+                for k, im in enumerate(imgs):
+                    eng._stage[k].copy_(im)
+                src = eng._stage
+            eng.images_u8.copy_(src, non_blocking=True)
+            if not contiguous_run:
+                eng._stage_evt.record()
         else:
             for k, im in enumerate(imgs):
                 eng.images_u8[k, :, :im.shape[-2], :im.shape[-1]].copy_(im.to(torch.uint8), non_blocking=True)
