@@ -9,9 +9,6 @@
 
 namespace yb {
 
-// ------------------------------------------------------------------------------------------------
-// kernel dispatch
-// ------------------------------------------------------------------------------------------------
 static bool use_v1_kernel() {
   static int v = -1;
   if (v < 0) {
@@ -21,6 +18,9 @@ static bool use_v1_kernel() {
   return v == 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
 template <int BN, int BK>
 static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid, int stages,
                             cudaStream_t st) {
@@ -36,9 +36,11 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     YB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  // persistent kernel: two CTAs per SM (2 x 2 x BN TMEM columns <= 512), ring as deep as half an SM's shared memory allows
+  // persistent kernel: two CTAs per SM (2 x 2 x BN TMEM columns <= 512; one CTA for BN = 256), ring as deep as the CTA's share
+  // of shared memory allows
   const int m_tiles = grid.x, n_tiles = grid.y;
-  int pst = (110 * 1024 - 1024) / Cfg::kStageBytes;
+  const int occ = BN == 256 ? 1 : 2;
+  int pst = ((occ == 1 ? 216 : 110) * 1024 - 1024) / Cfg::kStageBytes;
   if (pst > kMaxStagesP) pst = kMaxStagesP;
   if (pst < 2) pst = 2;
   const int smem = pst * Cfg::kStageBytes + 1024;
@@ -47,7 +49,7 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     max_set_p = smem;
   }
-  int groups = (2 * sm_count()) / n_tiles;
+  int groups = (occ * sm_count()) / n_tiles;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
   conv_gemm_persistent_kernel<BN, BK><<<groups * n_tiles, kConvThreads, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
@@ -63,6 +65,7 @@ static int launch_conv(int bn, int bk, const CUtensorMap& tmA, const CUtensorMap
   YB_CASE(32, 16) YB_CASE(32, 32) YB_CASE(32, 64)
   YB_CASE(64, 16) YB_CASE(64, 32) YB_CASE(64, 64)
   YB_CASE(128, 16) YB_CASE(128, 32) YB_CASE(128, 64)
+  YB_CASE(256, 16) YB_CASE(256, 32) YB_CASE(256, 64)
 #undef YB_CASE
   return fail(YB200_ERR_UNSUPPORTED, "no conv_gemm instantiation for BLOCK_N=%d BLOCK_K=%d", bn, bk);
 }
@@ -76,7 +79,16 @@ static int pick_stages(int bn, int bk, int num_kb) {
   return st;
 }
 static int pick_block_k(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
-static int pick_block_n(int c) { return c > 64 ? 128 : (c > 32 ? 64 : (c > 16 ? 32 : 16)); }
+// 256-wide column tiles halve the activation (A operand) traffic per MMA: the 3x3 layers are L2-bandwidth bound at 128
+static int pick_block_n(int c) {
+  static int allow256 = -1;
+  if (allow256 < 0) {
+    const char* e = getenv("YB200_CONV_BN256");
+    allow256 = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (c >= 256 && allow256 && !use_v1_kernel()) return 256;
+  return c > 64 ? 128 : (c > 32 ? 64 : (c > 16 ? 32 : 16));
+}
 
 static int check_act(const yb200_act* a, const char* name) {
   YB_REQUIRE(a != nullptr && a->ptr != nullptr, YB200_ERR_INVALID, "%s: null view", name);
@@ -337,7 +349,7 @@ int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, W
   p.nb = p.bn / p.kc_b;
   p.cin_tiles = x->c / p.bn;
   p.num_taps = fill_fwd_taps(p.taps, *x, ksize, stride, 0);
-  p.tpc = p.num_taps == 1 ? 1 : (p.bn <= 32 ? 9 : 3);  // 9 x 32 = 288 <= 512 TMEM columns: dz is then loaded once, not three times
+  p.tpc = p.num_taps == 1 ? 1 : 3;  // (9 taps per CTA for narrow layers was measured slower: many 2 KB TMA boxes per stage)
   p.tap_groups = ceil_div(p.num_taps, p.tpc);
   p.dz_c0 = dz->c_off;
   choose_tile(dz->n, dz->h, dz->w, kWgPix, &p.log_tw, &p.log_th);

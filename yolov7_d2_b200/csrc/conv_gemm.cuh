@@ -68,7 +68,7 @@ struct ConvGemmCfg {
   static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
   static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;  // epilogue column chunk
   static_assert(BLOCK_K == 16 || BLOCK_K == 32 || BLOCK_K == 64, "BLOCK_K");
-  static_assert(BLOCK_N == 16 || BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128, "BLOCK_N");
+  static_assert(BLOCK_N == 16 || BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(kABytes % (8 * kSwizzle) == 0 && kStageBytes % (8 * kSwizzle) == 0, "tiles must start on a swizzle-pattern boundary");
 };
 

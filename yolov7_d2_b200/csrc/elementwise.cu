@@ -159,8 +159,9 @@ bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict_
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
 #pragma unroll 4
   for (int it = 0; it < kEwIters; ++it) {
-    const unsigned pix = p0 + it * blockDim.y;
-    if (pix >= npix) break;
+    const unsigned pix_raw = p0 + it * blockDim.y;
+    const bool ok = pix_raw < npix;
+    const unsigned pix = ok ? pix_raw : npix - 1;  // clamped: loads stay unconditional so the unrolled iterations overlap
     float f[8];
     unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), f);
 #pragma unroll
@@ -173,6 +174,7 @@ bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict_
       for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k]) + r[k];
     }
     const uint4 o = pack8(f);
+    if (!ok) continue;
     *reinterpret_cast<uint4*>(a.p + static_cast<size_t>(pix) * a.pitch + c8) = o;
     if (has_up) {
       const PixXY q = decode_pix(pix, z.w, z.h);
@@ -243,16 +245,17 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned p0 = blockIdx.x * (blockDim.y * iters) + threadIdx.y;
-#pragma unroll 2
+#pragma unroll 4
   for (int it = 0; it < iters; ++it) {
-    const unsigned pix = p0 + it * blockDim.y;
-    if (pix >= npix) break;
+    const unsigned pix_raw = p0 + it * blockDim.y;
+    const bool ok = pix_raw < npix;
+    const unsigned pix = ok ? pix_raw : npix - 1;
     float zf[8], d[8];
     unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), zf);
     load_da(da, pix, z.w, z.h, c8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float du = silu_grad(fmaf(zf[k], s[k], t[k]), d[k]);
+      const float du = ok ? silu_grad(fmaf(zf[k], s[k], t[k]), d[k]) : 0.f;
       s1[k] += du;
       s2[k] = fmaf(du, zf[k], s2[k]);
     }
@@ -305,16 +308,17 @@ bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ sc
     B[k] = -s[k] * mb - A[k] * mu;
   }
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
-#pragma unroll 2
+#pragma unroll 4
   for (int it = 0; it < kEwIters; ++it) {
-    const unsigned pix = p0 + it * blockDim.y;
-    if (pix >= npix) break;
+    const unsigned pix_raw = p0 + it * blockDim.y;
+    const bool ok = pix_raw < npix;
+    const unsigned pix = ok ? pix_raw : npix - 1;
     float zf[8], d[8], o[8];
     unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), zf);
     load_da(da, pix, z.w, z.h, c8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = fmaf(s[k], silu_grad(fmaf(zf[k], s[k], t[k]), d[k]), fmaf(A[k], zf[k], B[k]));
-    *reinterpret_cast<uint4*>(dz.p + static_cast<size_t>(pix) * dz.pitch + c8) = pack8(o);
+    if (ok) *reinterpret_cast<uint4*>(dz.p + static_cast<size_t>(pix) * dz.pitch + c8) = pack8(o);
   }
 }
 
