@@ -22,8 +22,12 @@ eng.images_u8.copy_(images.to(dev)); eng.labels.copy_(labels.to(dev))
 for _ in range(a.warmup):
     eng.eval_forward() if a.eval else eng.train_step()
 torch.cuda.synchronize()
+eng.trace = []
 torch.cuda.profiler.start()
 eng.eval_forward() if a.eval else eng.train_step()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+import json
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(eng.trace, open("gpurun_out/trace.json", "w"))
 print("profiled one step; loss", float(eng.losses[0]))

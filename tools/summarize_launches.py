@@ -26,3 +26,19 @@ if len(sys.argv) > 2:
     print("\nTop launches:")
     for n, ns, g, b in sorted(rows, key=lambda r: -r[1])[: int(sys.argv[2])]:
         print("  %8.1f us  %s grid=%s block=%s" % (ns / 1e3, n, g, b))
+
+# optional per-layer attribution: python tools/summarize_launches.py launches.csv N trace.json
+if len(sys.argv) > 3:
+    import json
+    trace = json.load(open(sys.argv[3]))
+    i = 0
+    per = []
+    for label, k in trace:
+        if label.startswith("?") or k == 0:
+            continue
+        seg = rows[i:i + k]
+        i += k
+        per.append((sum(r[1] for r in seg), label, "+".join(re.sub(r".*::", "", r[0]).replace("void ", "")[:28] for r in seg)))
+    print("\nPer call (aligned with the engine's launch trace; %d of %d launches consumed):" % (i, len(rows)))
+    for ns, label, names in sorted(per, key=lambda t: -t[0])[: int(sys.argv[2]) * 2]:
+        print("  %8.1f us  %-70s %s" % (ns / 1e3, label, names))

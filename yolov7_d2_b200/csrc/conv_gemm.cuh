@@ -268,8 +268,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   if (p.epi_mode == EPI_F16_STATS) {
     // one fp64 atomic per channel and CTA (after the block-wide barrier above: no named barrier, no shared atomics)
-    const int e = threadIdx.x;
-    if (e < BLOCK_N && col0 + e < p.cout) {
+    for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {  // BLOCK_N may exceed the 192 threads
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
       atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
@@ -488,8 +487,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   __syncthreads();
   if (warp == 1) tmem_dealloc<kTmemAlloc>(tmem_base);
   if (p.epi_mode == EPI_F16_STATS) {
-    const int e = threadIdx.x;
-    if (e < BLOCK_N && col0 + e < p.cout) {
+    for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {  // BLOCK_N may exceed the 192 threads
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
       atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));

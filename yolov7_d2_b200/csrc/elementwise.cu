@@ -388,6 +388,63 @@ __global__ void spp_pool_kernel(View x, View o5, View o9, View o13, uint8_t* __r
   }
 }
 
+// Shared-memory version for maps that fit in one SM (the usual case: 20x20 at 640 px): one block per (32 channels, image),
+// separable max with argmax -- row pass keeps (max, first column) per pixel, column pass picks the first row with the
+// largest row-max, which is exactly the first maximum of the 2-D window in row-major order.
+// The low 16 bits of the packed word carry the column code so one 4-byte shared-memory read serves value and index.
+__global__ void __launch_bounds__(256)
+spp_pool_tiled_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ arg) {
+  extern __shared__ uint32_t sp[];  // [hw][32] input (bf16 bits << 16), then [hw][32] row results (bf16 bits << 16 | column code)
+  const int hw = x.h * x.w;
+  uint32_t* sin = sp;
+  uint32_t* srow = sp + hw * 32;
+  const int cg = blockIdx.x * 32;
+  const int b = blockIdx.y;
+  const __nv_bfloat16* src = x.p + static_cast<size_t>(b) * hw * x.pitch + cg;
+  for (int e = threadIdx.x; e < hw * 32; e += blockDim.x) {
+    const int ch = e & 31, p = e >> 5;
+    sin[e] = static_cast<uint32_t>(__bfloat16_as_ushort(src[static_cast<size_t>(p) * x.pitch + ch])) << 16;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int j = 0; j < 3; ++j) {
+    const int r = 2 + 2 * j;  // k = 5, 9, 13
+    for (int e = threadIdx.x; e < hw * 32; e += blockDim.x) {
+      const int ch = e & 31, p = e >> 5;
+      const int px = p % x.w, rowbase = p - px;
+      float best = -INFINITY;
+      uint32_t bw = 0;
+      const int x0 = max(px - r, 0), x1 = min(px + r, x.w - 1);
+      for (int xx = x0; xx <= x1; ++xx) {
+        const uint32_t wv = sin[(rowbase + xx) * 32 + ch];
+        const float v = __uint_as_float(wv);
+        if (v > best) { best = v; bw = wv | static_cast<uint32_t>(xx - px + 6); }
+      }
+      srow[e] = bw;
+    }
+    __syncthreads();
+    const View& o = j == 0 ? o5 : (j == 1 ? o9 : o13);
+    __nv_bfloat16* dst = o.p + static_cast<size_t>(b) * hw * o.pitch + cg;
+    uint8_t* adst = arg ? arg + (static_cast<size_t>(j) * x.n + b) * hw * x.c + cg : nullptr;
+    for (int e = threadIdx.x; e < hw * 32; e += blockDim.x) {
+      const int ch = e & 31, p = e >> 5;
+      const int py = p / x.w, px = p - py * x.w;
+      float best = -INFINITY;
+      uint32_t bw = 0;
+      int bdy = 0;
+      const int y0 = max(py - r, 0), y1 = min(py + r, x.h - 1);
+      for (int yy = y0; yy <= y1; ++yy) {
+        const uint32_t wv = srow[(yy * x.w + px) * 32 + ch];
+        const float v = __uint_as_float(wv & 0xFFFF0000u);
+        if (v > best) { best = v; bw = wv; bdy = yy - py; }
+      }
+      dst[static_cast<size_t>(p) * o.pitch + ch] = __ushort_as_bfloat16(static_cast<unsigned short>(bw >> 16));
+      if (adst) adst[static_cast<size_t>(p) * x.c + ch] = static_cast<uint8_t>((bdy + 6) * 13 + (bw & 0xFFFFu));
+    }
+    __syncthreads();
+  }
+}
+
 // backward: scatter the three pooled gradients to their argmax positions (fp32 atomics into a zeroed scratch), ...
 __global__ void spp_pool_bwd_scatter_kernel(View d5, View d9, View d13, const uint8_t* __restrict__ arg, float* __restrict__ scratch, int n,
                                             int h, int w, int c) {
@@ -547,6 +604,17 @@ extern "C" int yb200_spp_pool(const yb200_act* x, const yb200_act* o5, const yb2
       (rc = check_view(o13, "spp_pool o13")))
     return rc;
   YB_REQUIRE(same_shape(x, o5) && same_shape(x, o9) && same_shape(x, o13), YB200_ERR_INVALID, "spp_pool: shape mismatch");
+  const size_t tiled_smem = static_cast<size_t>(x->h) * x->w * 32 * 2 * sizeof(uint32_t);
+  if (x->c % 32 == 0 && tiled_smem <= 200 * 1024) {
+    static size_t smem_set = 48 * 1024;
+    if (tiled_smem > smem_set) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tiled_smem)));
+      smem_set = tiled_smem;
+    }
+    spp_pool_tiled_kernel<<<dim3(x->c / 32, x->n), 256, tiled_smem, as_stream(stream)>>>(mk(x), mk(o5), mk(o9), mk(o13), argmax);
+    YB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const long long total = 1LL * x->n * x->h * x->w * (x->c / 8);
   spp_pool_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(mk(x), mk(o5), mk(o9), mk(o13), argmax);
   YB_CHECK_CUDA(cudaGetLastError());

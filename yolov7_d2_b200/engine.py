@@ -350,9 +350,18 @@ class YoloxEngine:
         self.spp_scratch = None
         self._dz = {}
         self.kernel_launches = 0
+        self.trace = None  # set to [] to record (label, launches) per call for tools/summarize_launches.py
 
-    def _count(self, k=1):
+    def _count(self, k=1, label=None):
+        """k = number of kernels the preceding C-ABI call(s) launched (memsets excluded); label feeds the per-layer profile"""
         self.kernel_launches += k
+        if self.trace is not None:
+            self.trace.append((label or "?", k))
+
+    @staticmethod
+    def _desc(op):
+        n, h, w, _ = op.x.shape
+        return "%dx%dx%dx%d->%d k%d s%d" % (n, h, w, op.cin_pad, op.cout, op.ksize, op.stride)
 
     def _ensure_ws(self, nbytes):
         if nbytes > self.ws_bytes:
@@ -366,19 +375,19 @@ class YoloxEngine:
             if isinstance(op, ConvOp):
                 capi.check(L.yb200_pack_conv_weight(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad, capi.ptr(op.w_fwd),
                                                     capi.ptr(op.w_dgrad), sp), "pack")
-                self._count()
+                self._count(1, "pack " + op.prefixes[0])
             elif isinstance(op, PredOp):
                 capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wc_src), self.nc, self.hc, 1, self.nc, self.hc, capi.ptr(op.wc_fwd),
                                                     capi.ptr(op.wc_dgrad), sp), "pack cls")
                 capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, capi.ptr(op.wr_fwd), capi.ptr(op.wr_dgrad),
                                                     sp), "pack reg+obj")
-                self._count(2)
+                self._count(2, "pack preds")
 
     def preprocess(self):
         """images_u8 [N,3,H,W] (device) -> focus buffer"""
         capi.check(self.L.yb200_preprocess_focus(capi.ptr(self.images_u8), self.n, self.h, self.w, capi.ptr(self.hw_valid), ctypes.c_float(114.0),
                                                  self.focus.view().act(), capi.stream_ptr()), "preprocess_focus")
-        self._count()
+        self._count(1, "preprocess")
 
     def forward_features(self, training=True):
         L, sp = self.L, capi.stream_ptr()
@@ -401,17 +410,17 @@ class YoloxEngine:
                 else:
                     capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm), pf(self.flat_rv),
                                                       ctypes.c_float(BN_EPS), pf(self.flat_scale), pf(self.flat_shift), sp), "bn_eval_affine")
-                self._count(2)
+                self._count(2, "conv_fwd+bn_finalize %s %s" % (op.prefixes[0], self._desc(op)))
                 for hd in op.heads:
                     zv = op.z.buf.view(hd.c0, hd.c)
                     capi.check(L.yb200_bn_apply_silu(zv.act(), pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
                                                      hd.residual.act() if hd.residual else None, hd.out.act(), hd.up.act() if hd.up else None, sp),
                                "bn_apply_silu " + hd.prefix)
-                    self._count()
+                    self._count(1, "bn_apply %s c=%d px=%d" % (hd.prefix, hd.c, op.z.buf.n * op.z.buf.h * op.z.buf.w))
             elif isinstance(op, SppOp):
                 v = op.views
                 capi.check(L.yb200_spp_pool(v[0].act(), v[1].act(), v[2].act(), v[3].act(), capi.ptr(op.arg) if training else None, sp), "spp_pool")
-                self._count()
+                self._count(1, "spp_pool")
             else:
                 h, w, s, a_off = self.levels[op.level]
                 ch = 5 + self.nc
@@ -419,12 +428,13 @@ class YoloxEngine:
                                                     self.num_anchors, a_off, ch, 5, sp), "cls_pred")
                 capi.check(L.yb200_conv1x1_bias_f32(op.reg_feat.act(), capi.ptr(op.wr_fwd), capi.ptr(op.br), 5, capi.ptr(self.outputs),
                                                     self.num_anchors, a_off, ch, 0, sp), "reg_obj_pred")
-                self._count(2)
+                self._count(2, "pred convs level %d" % op.level)
         if training:
             self.flat_nbt += 1
+            self._count(1, "num_batches_tracked += 1 (torch)")
         capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
                                         0 if training else 1, sp), "decode")
-        self._count()
+        self._count(1, "decode")
 
     def assign_and_loss(self, with_grad=True):
         L, sp = self.L, capi.stream_ptr()
@@ -433,13 +443,13 @@ class YoloxEngine:
                                          capi.ptr(self.simota_ws), capi.ptr(self.num_gt), capi.ptr(self.fg_mask), capi.ptr(self.matched_gt),
                                          capi.ptr(self.matched_iou), capi.ptr(self.matched_cls), capi.ptr(self.num_fg_img), capi.ptr(self.totals), sp),
                    "simota_assign")
-        self._count(5)
+        self._count(4, "simota (count_gt, prep, match, resolve)")
         capi.check(L.yb200_yolox_loss(capi.ptr(self.outputs), capi.ptr(self.labels), n, a, ch, self.max_gt, self.lv, len(self.levels),
                                       capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls),
                                       capi.ptr(self.totals), capi.ptr(self.loss_weights) if with_grad else None, capi.ptr(self.loss_acc),
                                       capi.ptr(self.losses), self.p_dcls if with_grad else None, self.p_dro if with_grad else None, None,
                                       capi.ptr(self.bias_acc) if with_grad else None, sp), "yolox_loss")
-        self._count(2)
+        self._count(2, "yolox_loss + finish")
 
     def loss_grad_only(self):
         """recompute d loss / d head outputs with the current loss_weights (autograd path: upstream gradients arrive late)"""
@@ -449,7 +459,7 @@ class YoloxEngine:
                                       capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls),
                                       capi.ptr(self.totals), capi.ptr(self.loss_weights), capi.ptr(self.loss_acc), None, self.p_dcls, self.p_dro, None,
                                       capi.ptr(self.bias_acc), sp), "yolox_loss grad")
-        self._count()
+        self._count(1, "yolox_loss grad")
 
     # ------------------------------------------------------------------ backward
     def _dz_buf(self, op):
@@ -497,7 +507,7 @@ class YoloxEngine:
                                                     ctypes.c_int64(self.ws_bytes), sp), "pred wgrad")
                     add = self._grad_target(feat)
                     capi.check(L.yb200_conv2d_dgrad(ctypes.byref(dz), capi.ptr(wd), feat.gact(), add.gact() if add else None, 1, 1, sp), "pred dgrad")
-                self._count(7)
+                self._count(7, "pred level %d: bias_grad, 2x(wgrad, reduce, dgrad)" % k)
             elif isinstance(op, SppOp):
                 v = op.views
                 if self.spp_scratch is None:
@@ -505,7 +515,7 @@ class YoloxEngine:
                 # in place: the identity slice of the concat gradient receives the pooled gradients
                 capi.check(L.yb200_spp_pool_bwd(v[0].gact(), v[1].gact(), v[2].gact(), v[3].gact(), capi.ptr(op.arg), capi.ptr(self.spp_scratch),
                                                 v[0].gact(), sp), "spp_pool_bwd")
-                self._count(3)
+                self._count(2, "spp_pool_bwd (scatter, finish)")
             else:
                 dzb = self._dz_buf(op)
                 pf = lambda t, off: ctypes.c_void_p(t.data_ptr() + 4 * off)
@@ -518,7 +528,7 @@ class YoloxEngine:
                                                    ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)), ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)),
                                                    dzv.act(), capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
                                                    acc, sp), "bn_silu_bwd " + hd.prefix)
-                    self._count(3)
+                    self._count(3, "bn_bwd (reduce, apply, param) %s c=%d px=%d" % (hd.prefix, hd.c, op.z.buf.n * op.z.buf.h * op.z.buf.w))
                     if hd.residual is not None:
                         pending_res[(id(hd.residual.buf), hd.residual.off)] = hd.out
                 dz = dzb.view()
@@ -527,7 +537,7 @@ class YoloxEngine:
                 self._ensure_ws(need)
                 capi.check(L.yb200_conv2d_wgrad(op.x.act(), dz.act(), op.ksize, op.stride, op.cin_real, capi.ptr(op.g_dst), acc, capi.ptr(self.ws),
                                                 ctypes.c_int64(self.ws_bytes), sp), "wgrad " + op.prefixes[0])
-                self._count(2)
+                self._count(2, "wgrad+reduce %s %s" % (op.prefixes[0], self._desc(op)))
                 if not op.first:
                     res = pending_res.pop((id(op.x.buf), op.x.off), None)
                     add = self._grad_target(op.x)
@@ -535,7 +545,7 @@ class YoloxEngine:
                     addend = res.gact() if res is not None else (add.gact() if add is not None else None)
                     capi.check(L.yb200_conv2d_dgrad(dz.act(), capi.ptr(op.w_dgrad), op.x.gact(), addend, op.ksize, op.stride, sp),
                                "dgrad " + op.prefixes[0])
-                    self._count(4 if op.stride == 2 else 1)
+                    self._count(4 if op.stride == 2 else 1, "dgrad %s %s" % (op.prefixes[0], self._desc(op)))
 
     # ------------------------------------------------------------------ whole steps
     def train_step(self, accumulate=False):
