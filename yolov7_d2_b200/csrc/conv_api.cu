@@ -40,10 +40,18 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   // of shared memory allows
   const int m_tiles = grid.x, n_tiles = grid.y;
   const int occ = BN == 256 ? 1 : 2;
-  int pst = ((occ == 1 ? 216 : 110) * 1024 - 1024) / Cfg::kStageBytes;
+  const int budget = (occ == 1 ? 216 : 110) * 1024 - 1024;
+  int slots_kb = budget / Cfg::kStageBytes;  // k-blocks that fit in the ring
+  // narrow layers (BLOCK_K 16 / 32) would spend their time on mbarrier round trips: put several k-blocks (up to 144
+  // channels-taps) behind one barrier, keeping at least two ring slots
+  const int num_kb = p.num_taps * p.cin_blocks;
+  int kbs = 1;
+  for (int t = 1; t <= num_kb; ++t)
+    if (num_kb % t == 0 && t * BK <= 144 && 2 * t <= slots_kb) kbs = t;
+  int pst = slots_kb / kbs;
   if (pst > kMaxStagesP) pst = kMaxStagesP;
   if (pst < 2) pst = 2;
-  const int smem = pst * Cfg::kStageBytes + 1024;
+  const int smem = pst * kbs * Cfg::kStageBytes + 1024;
   static int max_set_p = 0;
   if (smem > max_set_p) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -52,7 +60,7 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   int groups = (occ * sm_count()) / n_tiles;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
-  conv_gemm_persistent_kernel<BN, BK><<<groups * n_tiles, kConvThreads, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
+  conv_gemm_persistent_kernel<BN, BK><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

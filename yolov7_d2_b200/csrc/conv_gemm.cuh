@@ -284,15 +284,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // channel and CTA instead of per tile), and TMEM allocation / barrier setup / descriptor prefetch are paid once.
 // grid.x = n_tiles * groups;  CTA b: column tile b % n_tiles, pixel tiles (b / n_tiles) + i * groups.
 // ================================================================================================
-constexpr int kMaxStagesP = 8;
+constexpr int kMaxStagesP = 8;     // ring slots; one slot holds kb_per_slot consecutive k-blocks under a single mbarrier
+constexpr int kConvThreadsP = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue: two warps per TMEM lane quadrant, each
+                                    // draining half of the accumulator columns (memory-bound layers are epilogue-bound)
 
 template <int BLOCK_N, int BLOCK_K>
-__global__ void __launch_bounds__(kConvThreads)
+__global__ void __launch_bounds__(kConvThreadsP, 2)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                            const __grid_constant__ ConvGemmParams p, int num_stages, int n_tiles, int m_tiles) {
+                            const __grid_constant__ ConvGemmParams p, int num_stages, int kb_per_slot, int n_tiles, int m_tiles) {
   using Cfg = ConvGemmCfg<BLOCK_N, BLOCK_K>;
   constexpr int kAccCols = Cfg::kTmemCols;          // columns of one accumulator
   constexpr int kTmemAlloc = 2 * kAccCols;          // double buffered (power of two >= 64)
+  constexpr int kEpiHalves = BLOCK_N >= 32 ? 2 : 1; // column halves, one epilogue warp group (4 warps) each
+  constexpr int kHalfCols = BLOCK_N / kEpiHalves;
+  constexpr int CH = kHalfCols < 32 ? 16 : 32;      // columns per tcgen05.ld
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[2 * kMaxStagesP + 4];
   __shared__ uint32_t s_tmem;
@@ -320,7 +325,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, 4);  // one arrival per epilogue warp
+      mbar_init(bar_acc_empty + 8 * a, 4 * kEpiHalves);  // one arrival per active epilogue warp
     }
     mbar_fence_init();
   }
@@ -346,15 +351,17 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         const int tn = t / p.tiles_h;
         const int w0 = tw << log_tw, h0 = th << log_th, n0 = tn << (7 - log_tw - log_th);
         int tap = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += kb_per_slot) {  // num_kb is a multiple of kb_per_slot
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t full = bar_full + 8 * stage;
-          mbar_expect_tx(full, Cfg::kStageBytes);
-          const ConvTap& tp = p.taps[tap];
-          tma_load_5d(sa, &tmA, full, tp.c0 + cb * BLOCK_K, w0 + tp.dw, tp.p, h0 + tp.dh, n0);
-          tma_load_2d(sa + Cfg::kABytes, &tmB, full, tp.kb + cb * BLOCK_K, col0);
-          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          mbar_expect_tx(full, Cfg::kStageBytes * kb_per_slot);
+          for (int j = 0; j < kb_per_slot; ++j) {
+            const uint32_t sa = smem_base + (stage * kb_per_slot + j) * Cfg::kStageBytes;
+            const ConvTap& tp = p.taps[tap];
+            tma_load_5d(sa, &tmA, full, tp.c0 + cb * BLOCK_K, w0 + tp.dw, tp.p, h0 + tp.dh, n0);
+            tma_load_2d(sa + Cfg::kABytes, &tmB, full, tp.kb + cb * BLOCK_K, col0);
+            if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          }
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -373,16 +380,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         mbar_wait(bar_acc_empty + 8 * acc, ((it >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * kAccCols;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += kb_per_slot) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
+          for (int j = 0; j < kb_per_slot; ++j) {
+            const uint32_t sa = smem_base + (stage * kb_per_slot + j) * Cfg::kStageBytes;
+            const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
-            const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
-            umma_f16(tacc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
+              const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
+              umma_f16(tacc, da, db, idesc, (kb | j | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(bar_empty + 8 * stage);
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }
@@ -390,14 +399,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         umma_commit(bar_acc_full + 8 * acc);
       }
     }
-  } else {
+  } else if ((warp - 2) / 4 < kEpiHalves) {
     // ===================== epilogue =====================
-    const int q = warp & 3;
+    const int q = warp & 3;              // TMEM lane quadrant (must be warp_id % 4)
+    const int half = (warp - 2) >> 2;    // which half of the columns this warp drains
+    const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
     const int nl = mrow >> (log_tw + log_th);
-    constexpr int CH = Cfg::kChunk;
     int it = 0;
     for (int m = group; m < m_tiles; m += groups, ++it) {
       int t = m;
@@ -415,12 +425,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += CH) {
+      for (int c = cbeg; c < cend; c += CH) {
         uint32_t r[CH];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c;
         if constexpr (CH == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
         tmem_ld_wait();
-        if (c + CH >= BLOCK_N) {  // last chunk is in registers: hand the accumulator back to the MMA warp
+        if (c + CH >= cend) {  // this warp's last chunk is in registers: hand its share of the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
