@@ -1,0 +1,88 @@
+"""The drop-in surface: registry entries, state_dict layout, YOLOX.forward contract in training and eval mode."""
+import pytest
+import torch
+
+from oracle import yolox_oracle as orc
+
+
+def test_registry_entries_exist_without_gpu():
+    from yolov7_d2_b200 import modeling
+
+    assert modeling.META_ARCH_REGISTRY.get("YOLOX") is modeling.YOLOX
+    assert modeling.BACKBONE_REGISTRY.get("build_cspdarknetx_backbone") is modeling.build_cspdarknetx_backbone
+    with pytest.raises(KeyError):
+        modeling.META_ARCH_REGISTRY.get("NoSuchArch")
+
+
+def test_postprocess_rejects_cpu_tensors():
+    from yolov7_d2_b200 import capi, modeling
+
+    with pytest.raises(capi.Yb200Error):
+        modeling.postprocess(torch.zeros(1, 10, 85), 80)
+
+
+@pytest.fixture(scope="module")
+def model(cuda):
+    import bench
+    from yolov7_d2_b200.modeling import YOLOX
+
+    m = YOLOX(bench.yolox_s_cfg("cuda"))
+    sd = orc.yolox_state_dict(4)
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+@pytest.mark.gpu
+def test_state_dict_layout_matches_reference(model):
+    m, sd = model
+    got = m.state_dict()
+    assert set(got.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert tuple(got[k].shape) == tuple(v.shape), k
+        assert torch.equal(got[k].cpu(), v), k
+    n_params = sum(p.numel() for p in m.parameters())
+    assert abs(n_params - 8.97e6) < 2e4
+    assert m.size_divisibility == 32 and m.backbone.size_divisibility == 32
+    assert m.backbone.output_shape()["dark5"].channels == 512
+
+
+@pytest.mark.gpu
+def test_forward_training_contract_and_autograd(model, cuda):
+    import bench
+
+    m, _ = model
+    m.train()
+    images, labels = orc.synthetic_batch(2, 128, 11, max_gt=4)
+    bi = bench.batched_inputs_from(images, labels)
+    out = m(bi)
+    assert set(out.keys()) == {"total_loss", "iou_loss", "conf_loss", "cls_loss"}
+    total = float(out["total_loss"])
+    assert abs(total - float(out["iou_loss"] + out["conf_loss"] + out["cls_loss"])) < 1e-4 * abs(total)
+    m.zero_grad(set_to_none=True)
+    sum(out.values()).backward()   # detectron2's SimpleTrainer objective: every entry of the dict (= 2 x total)
+    g2 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    m.zero_grad(set_to_none=True)
+    out = m(bi)
+    out["total_loss"].backward()
+    for k, p in m.named_parameters():
+        assert torch.allclose(g2[k], 2 * p.grad, rtol=2e-2, atol=1e-3 * float(g2[k].abs().max()) + 1e-8), k
+
+
+@pytest.mark.gpu
+def test_forward_eval_contract(model):
+    import bench
+
+    m, _ = model
+    m.eval()
+    images, labels = orc.synthetic_batch(2, 160, 12, max_gt=4)
+    bi = bench.batched_inputs_from(images, labels)
+    for b in bi:
+        b["height"], b["width"] = 320, 320     # detector_postprocess rescales to the original image size
+    res = m(bi)
+    assert len(res) == 2 and all("instances" in r for r in res)
+    inst = res[0]["instances"]
+    n = inst.pred_boxes.tensor.shape[0]
+    assert inst.scores.shape == (n,) and inst.pred_classes.shape == (n,)
+    assert (inst.pred_boxes.tensor[:, 2] <= 320 + 1e-3).all()
+    m.train()

@@ -365,21 +365,24 @@ int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, W
   p.tiles_w = ceil_div(dz->w, pl->tw); p.tiles_h = ceil_div(dz->h, pl->th); p.tiles_n = ceil_div(dz->n, pl->tn);
   p.num_blocks = p.tiles_w * p.tiles_h * p.tiles_n;
   const int base = p.cout_tiles * p.cin_tiles * p.tap_groups;
-  // split the pixel range until ~4 CTAs per SM exist, keeping >= 8 pixel blocks per CTA and <= 128 MB of partials
-  int splits = ceil_div(4 * sm_count(), base);
-  if (splits > p.num_blocks / 8) splits = p.num_blocks / 8;
-  const long long wbytes = 4LL * p.cout * p.num_taps * p.cin;
-  const long long max_splits = (128LL << 20) / wbytes;
-  if (splits > max_splits) splits = static_cast<int>(max_splits);
-  if (splits < 1) splits = 1;
-  p.blocks_per_split = ceil_div(p.num_blocks, splits);
-  pl->splits = ceil_div(p.num_blocks, p.blocks_per_split);
   int cols = p.tpc * p.bn;
   int tc = 32;
   while (tc < cols) tc <<= 1;
   pl->tmem_cols = tc;
   const int stage = kWgPix * 2 * (p.kc_a * p.ma + p.kc_b * p.nb * p.tpc);
   pl->smem = stage * kWgStages + 1024;
+  // Split the pixel range so that ONE wave of CTAs covers the machine (every CTA pays TMEM allocation, pipeline fill and
+  // a full accumulator write-back, so extra waves are pure overhead); occupancy is bounded by TMEM columns and shared memory.
+  int occ = std::min(std::min(512 / tc, (220 * 1024) / pl->smem), 8);
+  if (occ < 1) occ = 1;
+  int splits = (occ * sm_count()) / base;  // floor: a partial second wave would double the tail
+  if (splits > p.num_blocks / 8) splits = p.num_blocks / 8;  // at least 8 pixel blocks per CTA
+  const long long wbytes = 4LL * p.cout * p.num_taps * p.cin;
+  const long long max_splits = (128LL << 20) / wbytes;
+  if (splits > max_splits) splits = static_cast<int>(max_splits);
+  if (splits < 1) splits = 1;
+  p.blocks_per_split = ceil_div(p.num_blocks, splits);
+  pl->splits = ceil_div(p.num_blocks, p.blocks_per_split);
   return 0;
 }
 }  // namespace

@@ -289,7 +289,7 @@ constexpr int kConvThreadsP = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogu
                                     // draining half of the accumulator columns (memory-bound layers are epilogue-bound)
 
 template <int BLOCK_N, int BLOCK_K>
-__global__ void __launch_bounds__(kConvThreadsP, 2)
+__global__ void __launch_bounds__(kConvThreadsP, BLOCK_N == 256 ? 1 : 2)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ ConvGemmParams p, int num_stages, int kb_per_slot, int n_tiles, int m_tiles) {
   using Cfg = ConvGemmCfg<BLOCK_N, BLOCK_K>;

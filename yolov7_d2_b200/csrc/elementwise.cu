@@ -34,19 +34,25 @@ int check_view(const yb200_act* a, const char* name) {
 
 bool same_shape(const yb200_act* a, const yb200_act* b) { return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c; }
 
+// streaming 16-byte load (read once: do not allocate in L1)
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 h2f(uint32_t u) {
+  __half2 h;
+  *reinterpret_cast<uint32_t*>(&h) = u;
+  return __half22float2(h);
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
 // the pre-BatchNorm tensor z is stored in fp16 (see conv_gemm.cuh); the view type only carries the 2-byte element size
 __device__ __forceinline__ void unpack8_f16(const uint4& u, float* f) {
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 t = __half22float2(h[k]);
-    f[2 * k] = t.x;
-    f[2 * k + 1] = t.y;
-  }
+  const float2 a = h2f(u.x), b = h2f(u.y), c = h2f(u.z), d = h2f(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -157,32 +163,45 @@ bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict_
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
-#pragma unroll 4
-  for (int it = 0; it < kEwIters; ++it) {
-    const unsigned pix_raw = p0 + it * blockDim.y;
-    const bool ok = pix_raw < npix;
-    const unsigned pix = ok ? pix_raw : npix - 1;  // clamped: loads stay unconditional so the unrolled iterations overlap
-    float f[8];
-    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), f);
+  constexpr int U = 4;  // loads of U pixels are issued before any of them is consumed
+#pragma unroll 1
+  for (int it0 = 0; it0 < kEwIters; it0 += U) {
+    uint4 zq[U], rq[U];
+    unsigned pixs[U];
+    bool oks[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], s[k], t[k]));
-    if (has_res) {
-      // residual is added to the *rounded* activation, as in the reference where y = conv2(...) is materialised first
-      float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res.p + static_cast<size_t>(pix) * res.pitch + c8), r);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k]) + r[k];
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix_raw = p0 + (it0 + u) * blockDim.y;
+      oks[u] = pix_raw < npix;
+      pixs[u] = oks[u] ? pix_raw : npix - 1;  // clamped: loads stay unconditional
+      zq[u] = ldg_stream(z.p + static_cast<size_t>(pixs[u]) * z.pitch + c8);
+      if (has_res) rq[u] = ldg_stream(res.p + static_cast<size_t>(pixs[u]) * res.pitch + c8);
     }
-    const uint4 o = pack8(f);
-    if (!ok) continue;
-    *reinterpret_cast<uint4*>(a.p + static_cast<size_t>(pix) * a.pitch + c8) = o;
-    if (has_up) {
-      const PixXY q = decode_pix(pix, z.w, z.h);
-      __nv_bfloat16* u = up.p + ((static_cast<size_t>(q.b) * up.h + 2 * q.y) * up.w + 2 * q.x) * up.pitch + c8;
-      *reinterpret_cast<uint4*>(u) = o;
-      *reinterpret_cast<uint4*>(u + up.pitch) = o;
-      *reinterpret_cast<uint4*>(u + static_cast<size_t>(up.w) * up.pitch) = o;
-      *reinterpret_cast<uint4*>(u + static_cast<size_t>(up.w + 1) * up.pitch) = o;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix = pixs[u];
+      float f[8];
+      unpack8_f16(zq[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], s[k], t[k]));
+      if (has_res) {
+        // residual is added to the *rounded* activation, as in the reference where y = conv2(...) is materialised first
+        float r[8];
+        unpack8(rq[u], r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k]) + r[k];
+      }
+      const uint4 o = pack8(f);
+      if (!oks[u]) continue;
+      *reinterpret_cast<uint4*>(a.p + static_cast<size_t>(pix) * a.pitch + c8) = o;
+      if (has_up) {
+        const PixXY q = decode_pix(pix, z.w, z.h);
+        __nv_bfloat16* up_p = up.p + ((static_cast<size_t>(q.b) * up.h + 2 * q.y) * up.w + 2 * q.x) * up.pitch + c8;
+        *reinterpret_cast<uint4*>(up_p) = o;
+        *reinterpret_cast<uint4*>(up_p + up.pitch) = o;
+        *reinterpret_cast<uint4*>(up_p + static_cast<size_t>(up.w) * up.pitch) = o;
+        *reinterpret_cast<uint4*>(up_p + static_cast<size_t>(up.w + 1) * up.pitch) = o;
+      }
     }
   }
 }
@@ -201,7 +220,7 @@ struct DaSrc {
 };
 
 __device__ __forceinline__ void load_da(const DaSrc& s, unsigned pix, int w, int h, int c8, float* d) {
-  unpack8(*reinterpret_cast<const uint4*>(s.a.p + static_cast<size_t>(pix) * s.a.pitch + c8), d);
+  unpack8(ldg_stream(s.a.p + static_cast<size_t>(pix) * s.a.pitch + c8), d);
   if (s.has_b) {
     float e[8];
     unpack8(*reinterpret_cast<const uint4*>(s.b.p + static_cast<size_t>(pix) * s.b.pitch + c8), e);
@@ -245,19 +264,32 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned p0 = blockIdx.x * (blockDim.y * iters) + threadIdx.y;
-#pragma unroll 4
-  for (int it = 0; it < iters; ++it) {
-    const unsigned pix_raw = p0 + it * blockDim.y;
-    const bool ok = pix_raw < npix;
-    const unsigned pix = ok ? pix_raw : npix - 1;
-    float zf[8], d[8];
-    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), zf);
-    load_da(da, pix, z.w, z.h, c8, d);
+  const bool simple = !da.has_b && !da.has_up;
+  constexpr int U = 2;
+#pragma unroll 1
+  for (int it0 = 0; it0 < iters; it0 += U) {
+    uint4 zq[U], dq[U];
+    unsigned pixs[U];
+    bool oks[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float du = ok ? silu_grad(fmaf(zf[k], s[k], t[k]), d[k]) : 0.f;
-      s1[k] += du;
-      s2[k] = fmaf(du, zf[k], s2[k]);
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix_raw = p0 + (it0 + u) * blockDim.y;
+      oks[u] = (it0 + u < iters) && pix_raw < npix;
+      pixs[u] = oks[u] ? pix_raw : npix - 1;
+      zq[u] = ldg_stream(z.p + static_cast<size_t>(pixs[u]) * z.pitch + c8);
+      if (simple) dq[u] = ldg_stream(da.a.p + static_cast<size_t>(pixs[u]) * da.a.pitch + c8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float zf[8], d[8];
+      unpack8_f16(zq[u], zf);
+      if (simple) unpack8(dq[u], d); else load_da(da, pixs[u], z.w, z.h, c8, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float du = oks[u] ? silu_grad(fmaf(zf[k], s[k], t[k]), d[k]) : 0.f;
+        s1[k] += du;
+        s2[k] = fmaf(du, zf[k], s2[k]);
+      }
     }
   }
   // lanes sharing a channel vector (same threadIdx.x) sit blockDim.x apart inside the warp (blockDim.x is a power of two)
@@ -308,17 +340,30 @@ bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ sc
     B[k] = -s[k] * mb - A[k] * mu;
   }
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
-#pragma unroll 4
-  for (int it = 0; it < kEwIters; ++it) {
-    const unsigned pix_raw = p0 + it * blockDim.y;
-    const bool ok = pix_raw < npix;
-    const unsigned pix = ok ? pix_raw : npix - 1;
-    float zf[8], d[8], o[8];
-    unpack8_f16(*reinterpret_cast<const uint4*>(z.p + static_cast<size_t>(pix) * z.pitch + c8), zf);
-    load_da(da, pix, z.w, z.h, c8, d);
+  const bool simple = !da.has_b && !da.has_up;
+  constexpr int U = 2;
+#pragma unroll 1
+  for (int it0 = 0; it0 < kEwIters; it0 += U) {
+    uint4 zq[U], dq[U];
+    unsigned pixs[U];
+    bool oks[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaf(s[k], silu_grad(fmaf(zf[k], s[k], t[k]), d[k]), fmaf(A[k], zf[k], B[k]));
-    if (ok) *reinterpret_cast<uint4*>(dz.p + static_cast<size_t>(pix) * dz.pitch + c8) = pack8(o);
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix_raw = p0 + (it0 + u) * blockDim.y;
+      oks[u] = pix_raw < npix;
+      pixs[u] = oks[u] ? pix_raw : npix - 1;
+      zq[u] = ldg_stream(z.p + static_cast<size_t>(pixs[u]) * z.pitch + c8);
+      if (simple) dq[u] = ldg_stream(da.a.p + static_cast<size_t>(pixs[u]) * da.a.pitch + c8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float zf[8], d[8], o[8];
+      unpack8_f16(zq[u], zf);
+      if (simple) unpack8(dq[u], d); else load_da(da, pixs[u], z.w, z.h, c8, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(s[k], silu_grad(fmaf(zf[k], s[k], t[k]), d[k]), fmaf(A[k], zf[k], B[k]));
+      if (oks[u]) *reinterpret_cast<uint4*>(dz.p + static_cast<size_t>(pixs[u]) * dz.pitch + c8) = pack8(o);
+    }
   }
 }
 
