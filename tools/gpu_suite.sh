@@ -3,7 +3,7 @@
 # usage: tools/gpu_suite.sh [group ...]   logs -> gpurun_out/suite_<group>.log
 mkdir -p gpurun_out
 groups=("$@")
-[ ${#groups[@]} -eq 0 ] && groups=(conv_fwd conv_misc conv_dgrad conv_wgrad elementwise simota engine)
+[ ${#groups[@]} -eq 0 ] && groups=(conv_fwd fwd_b fwd_c fwd_d fwd_e conv_misc conv_dgrad conv_wgrad elementwise simota nms engine modeling)
 for g in "${groups[@]}"; do
   case $g in
     conv_fwd)    sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and not 1x320 and not 16x64 and not 8x80x80'" ;;
@@ -19,6 +19,7 @@ for g in "${groups[@]}"; do
     simota)      sel="tests/test_simota_gpu.py" ;;
     engine)      sel="tests/test_engine_gpu.py" ;;
     nms)         sel="tests/test_nms_gpu.py" ;;
+    modeling)    sel="tests/test_modeling_gpu.py" ;;
     *)           sel="$g" ;;
   esac
   echo "=== $g"

@@ -46,8 +46,9 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   // channels-taps) behind one barrier, keeping at least two ring slots
   const int num_kb = p.num_taps * p.cin_blocks;
   int kbs = 1;
-  for (int t = 1; t <= num_kb; ++t)
-    if (num_kb % t == 0 && t * BK <= 144 && 2 * t <= slots_kb) kbs = t;
+  if (BK <= 32)
+    for (int t = 1; t <= num_kb; ++t)
+      if (num_kb % t == 0 && t * BK <= 144 && 2 * t <= slots_kb) kbs = t;
   int pst = slots_kb / kbs;
   if (pst > kMaxStagesP) pst = kMaxStagesP;
   if (pst < 2) pst = 2;
