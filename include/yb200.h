@@ -156,6 +156,13 @@ int64_t yb200_nms_workspace(int batch, int num_anchors);
 int yb200_postprocess_nms(float* prediction, int batch, int num_anchors, int num_classes, float conf_thre, float nms_thre,
                           int mutate_prediction, void* workspace, float* detections, int32_t* det_count, void* stream);
 
+/* ---- box regression losses ----------------------------------------------------------------------- */
+/* loss[i] and d loss[i] / d pred[i] for n matched (prediction, target) pairs of (cx, cy, w, h) boxes (device fp32 [n][4]).
+ * mode 0: IOUloss "iou" = 1 - iou^2 (boxes.py:125-151, the YOLOX-s loss, yolox_head.py:134); 1: IOUloss "giou" (boxes.py:152-161);
+ * 2 / 3 / 4: IOUlossV6 giou / diou / ciou with eps 1e-7 (boxes.py:666-752, YOLOv6 head).  dloss_dpred may be NULL.            */
+int yb200_iou_loss(const float* pred_cxcywh, const float* target_cxcywh, int n, int mode, float* loss, float* dloss_dpred,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ for g in "${groups[@]}"; do
     engine)      sel="tests/test_engine_gpu.py" ;;
     nms)         sel="tests/test_nms_gpu.py" ;;
     modeling)    sel="tests/test_modeling_gpu.py" ;;
+    iou)         sel="tests/test_iou_loss_gpu.py" ;;
     *)           sel="$g" ;;
   esac
   echo "=== $g"

@@ -140,7 +140,7 @@ __global__ void bn_eval_affine_kernel(int c, const float* __restrict__ gamma, co
 // (per-channel constants live in registers) and no integer division is needed to decode an element index; consecutive
 // linear thread ids touch consecutive 16-byte chunks, i.e. warps read and write whole 128-byte lines.
 constexpr int kEwThreads = 256;
-constexpr int kEwIters = 8;  // pixels per thread
+constexpr int kEwIters = 2;  // pixels per thread (measured with tools/bw_probe.cu: occupancy beats amortising the per-channel constants)
 
 struct PixXY {
   int x, y, b;
@@ -155,7 +155,7 @@ __device__ __forceinline__ PixXY decode_pix(unsigned pix, int w, int h) {
 }
 
 // a = SiLU(z*scale + shift) [+ residual];  optionally also written 2x nearest-upsampled into a second view
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 5)
 bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift, int has_res,
                      int has_up, unsigned npix) {
   const int c8 = threadIdx.x * 8;
@@ -163,7 +163,7 @@ bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict_
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
-  constexpr int U = 4;  // loads of U pixels are issued before any of them is consumed
+  constexpr int U = 2;  // loads of U pixels are issued before any of them is consumed
 #pragma unroll 1
   for (int it0 = 0; it0 < kEwIters; it0 += U) {
     uint4 zq[U], rq[U];
@@ -324,7 +324,8 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
 }
 
 // pass 2: dz = gamma*invstd * (du - dbeta/M - zhat*dgamma/M) = s*du + A*z + B  with per-channel A, B
-__global__ void __launch_bounds__(kEwThreads, 3)
+template <bool SIMPLE>
+__global__ void __launch_bounds__(kEwThreads, SIMPLE ? 4 : 3)
 bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
                          const double* __restrict__ dbeta_acc, double inv_count, unsigned npix) {
@@ -340,7 +341,7 @@ bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ sc
     B[k] = -s[k] * mb - A[k] * mu;
   }
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
-  const bool simple = !da.has_b && !da.has_up;
+  constexpr bool simple = SIMPLE;
   constexpr int U = 2;
 #pragma unroll 1
   for (int it0 = 0; it0 < kEwIters; it0 += U) {
@@ -635,8 +636,12 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
                                                               static_cast<unsigned>(npix), red_iters);
   YB_CHECK_CUDA(cudaGetLastError());
   const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
-  bn_silu_bwd_apply_kernel<<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                      1.0 / static_cast<double>(npix), static_cast<unsigned>(npix));
+  if (!src.has_b && !src.has_up)
+    bn_silu_bwd_apply_kernel<true><<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                              1.0 / static_cast<double>(npix), static_cast<unsigned>(npix));
+  else
+    bn_silu_bwd_apply_kernel<false><<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                               1.0 / static_cast<double>(npix), static_cast<unsigned>(npix));
   YB_CHECK_CUDA(cudaGetLastError());
   bn_param_grad_kernel<<<ceil_div(z->c, 128), 128, 0, st>>>(acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
