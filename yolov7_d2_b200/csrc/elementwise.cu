@@ -140,7 +140,7 @@ __global__ void bn_eval_affine_kernel(int c, const float* __restrict__ gamma, co
 // (per-channel constants live in registers) and no integer division is needed to decode an element index; consecutive
 // linear thread ids touch consecutive 16-byte chunks, i.e. warps read and write whole 128-byte lines.
 constexpr int kEwThreads = 256;
-constexpr int kEwIters = 2;  // pixels per thread (measured with tools/bw_probe.cu: occupancy beats amortising the per-channel constants)
+constexpr int kEwIters = 8;  // pixels per thread (2 was measured slower in the real step: the per-channel constants are re-loaded per thread)
 
 struct PixXY {
   int x, y, b;
@@ -155,7 +155,7 @@ __device__ __forceinline__ PixXY decode_pix(unsigned pix, int w, int h) {
 }
 
 // a = SiLU(z*scale + shift) [+ residual];  optionally also written 2x nearest-upsampled into a second view
-__global__ void __launch_bounds__(kEwThreads, 5)
+__global__ void __launch_bounds__(kEwThreads)
 bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift, int has_res,
                      int has_up, unsigned npix) {
   const int c8 = threadIdx.x * 8;
@@ -163,7 +163,7 @@ bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict_
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
   const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
-  constexpr int U = 2;  // loads of U pixels are issued before any of them is consumed
+  constexpr int U = 4;  // loads of U pixels are issued before any of them is consumed
 #pragma unroll 1
   for (int it0 = 0; it0 < kEwIters; it0 += U) {
     uint4 zq[U], rq[U];
@@ -325,7 +325,7 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
 
 // pass 2: dz = gamma*invstd * (du - dbeta/M - zhat*dgamma/M) = s*du + A*z + B  with per-channel A, B
 template <bool SIMPLE>
-__global__ void __launch_bounds__(kEwThreads, SIMPLE ? 4 : 3)
+__global__ void __launch_bounds__(kEwThreads, 3)
 bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
                          const double* __restrict__ dbeta_acc, double inv_count, unsigned npix) {

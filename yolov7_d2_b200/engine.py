@@ -350,6 +350,9 @@ class YoloxEngine:
         self.spp_scratch = None
         self._dz = {}
         self.kernel_launches = 0
+        self.overlap_wgrad = True
+        self._side = torch.cuda.Stream(device=dev)
+        self._fork_evt = torch.cuda.Event()
         self.trace = None  # set to [] to record (label, launches) per call for tools/summarize_launches.py
 
     def _count(self, k=1, label=None):
@@ -365,7 +368,9 @@ class YoloxEngine:
 
     def _ensure_ws(self, nbytes):
         if nbytes > self.ws_bytes:
+            self._side.synchronize()  # the side stream may still be reading the old workspace (first step only)
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            self.ws.record_stream(self._side)
             self.ws_bytes = nbytes
 
     # ------------------------------------------------------------------ forward
@@ -482,6 +487,25 @@ class YoloxEngine:
         buf.written.append((lo, hi))
         return None
 
+    def _wgrad(self, x_act, dz_act, ksize, stride, cin_real, gdst, acc, label):
+        """Weight gradients are off the backward critical path (nothing downstream reads them): they run on a side stream,
+        overlapping the next layers' data-gradient / BatchNorm-backward chain.  All of them are serialised on that one
+        stream, so a single split-K workspace suffices."""
+        L = self.L
+        need = L.yb200_conv2d_wgrad_workspace(x_act, dz_act, ksize, stride)
+        assert need > 0, L.yb200_last_error()
+        self._ensure_ws(need)
+        if self.overlap_wgrad:
+            main = torch.cuda.current_stream()
+            self._fork_evt.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._fork_evt)
+                capi.check(L.yb200_conv2d_wgrad(x_act, dz_act, ksize, stride, cin_real, capi.ptr(gdst), acc, capi.ptr(self.ws),
+                                                ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad " + label)
+        else:
+            capi.check(L.yb200_conv2d_wgrad(x_act, dz_act, ksize, stride, cin_real, capi.ptr(gdst), acc, capi.ptr(self.ws),
+                                            ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad " + label)
+
     def backward(self, accumulate=False):
         L, sp = self.L, capi.stream_ptr()
         nb = self.nbn
@@ -500,11 +524,7 @@ class YoloxEngine:
                                                   capi.ptr(self.grads[f"head.obj_preds.{k}.bias"]), capi.ptr(self.grads[f"head.cls_preds.{k}.bias"]),
                                                   acc, sp), "head_bias_grad")
                 for feat, dz, gdst, wd, cr in ((op.cls_feat, dcls, op.gc_dst, op.wc_dgrad, self.nc), (op.reg_feat, dro, op.gr_dst, op.wr_dgrad, 16)):
-                    need = L.yb200_conv2d_wgrad_workspace(feat.act(), ctypes.byref(dz), 1, 1)
-                    assert need > 0, L.yb200_last_error()
-                    self._ensure_ws(need)
-                    capi.check(L.yb200_conv2d_wgrad(feat.act(), ctypes.byref(dz), 1, 1, self.hc, capi.ptr(gdst), acc, capi.ptr(self.ws),
-                                                    ctypes.c_int64(self.ws_bytes), sp), "pred wgrad")
+                    self._wgrad(feat.act(), ctypes.byref(dz), 1, 1, self.hc, gdst, acc, "pred")
                     add = self._grad_target(feat)
                     capi.check(L.yb200_conv2d_dgrad(ctypes.byref(dz), capi.ptr(wd), feat.gact(), add.gact() if add else None, 1, 1, sp), "pred dgrad")
                 self._count(7, "pred level %d: bias_grad, 2x(wgrad, reduce, dgrad)" % k)
@@ -532,11 +552,7 @@ class YoloxEngine:
                     if hd.residual is not None:
                         pending_res[(id(hd.residual.buf), hd.residual.off)] = hd.out
                 dz = dzb.view()
-                need = L.yb200_conv2d_wgrad_workspace(op.x.act(), dz.act(), op.ksize, op.stride)
-                assert need > 0, L.yb200_last_error()
-                self._ensure_ws(need)
-                capi.check(L.yb200_conv2d_wgrad(op.x.act(), dz.act(), op.ksize, op.stride, op.cin_real, capi.ptr(op.g_dst), acc, capi.ptr(self.ws),
-                                                ctypes.c_int64(self.ws_bytes), sp), "wgrad " + op.prefixes[0])
+                self._wgrad(op.x.act(), dz.act(), op.ksize, op.stride, op.cin_real, op.g_dst, acc, op.prefixes[0])
                 self._count(2, "wgrad+reduce %s %s" % (op.prefixes[0], self._desc(op)))
                 if not op.first:
                     res = pending_res.pop((id(op.x.buf), op.x.off), None)
@@ -546,6 +562,8 @@ class YoloxEngine:
                     capi.check(L.yb200_conv2d_dgrad(dz.act(), capi.ptr(op.w_dgrad), op.x.gact(), addend, op.ksize, op.stride, sp),
                                "dgrad " + op.prefixes[0])
                     self._count(4 if op.stride == 2 else 1, "dgrad %s %s" % (op.prefixes[0], self._desc(op)))
+        if self.overlap_wgrad:
+            torch.cuda.current_stream().wait_stream(self._side)  # join: gradients are complete when backward() returns
 
     # ------------------------------------------------------------------ whole steps
     def train_step(self, accumulate=False):
