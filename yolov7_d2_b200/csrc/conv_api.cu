@@ -9,6 +9,15 @@
 
 namespace yb {
 
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB200_CONV_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool use_v1_kernel() {
   static int v = -1;
   if (v < 0) {
@@ -35,6 +44,28 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     conv_gemm_kernel<BN, BK><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p, stages);
     YB_CHECK_CUDA(cudaGetLastError());
     return 0;
+  }
+  if constexpr (BN == 256) {
+    if (use_pair_kernel() && p.epi_mode != EPI_F32_BIAS) {
+      // CTA pairs: 2 x 128 pixels x 256 channels per UMMA, one CTA per SM, 32 KB per stage and CTA at BLOCK_K 64
+      const int m_tiles = grid.x, n_tiles = grid.y;
+      constexpr int stage_bytes = 2 * 128 * BK * 2;
+      int pst = (212 * 1024) / stage_bytes;
+      if (pst > kMaxStagesP) pst = kMaxStagesP;
+      const int smem = pst * stage_bytes + 1024;
+      static int max_set_pair = 0;
+      if (smem > max_set_pair) {
+        YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        max_set_pair = smem;
+      }
+      const int pair_tiles = (m_tiles + 1) / 2;
+      int groups = (sm_count() / 2) / n_tiles;
+      if (groups < 1) groups = 1;
+      if (groups > pair_tiles) groups = pair_tiles;
+      conv_gemm_pair_kernel<BK><<<2 * groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
+      YB_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
   }
   // persistent kernel: two CTAs per SM (2 x 2 x BN TMEM columns <= 512; one CTA for BN = 256), ring as deep as the CTA's share
   // of shared memory allows
@@ -202,7 +233,8 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   CUtensorMap tmA, tmB;
   int rc = make_act_map(&tmA, *x, stride == 2, bk, tw, th, tn);
   if (rc) return rc;
-  rc = make_mat_map(&tmB, w_fwd, cout, 1LL * p.num_taps * x->c, bn, bk);
+  // the CTA-pair kernel (column tile 256) loads the weight tile as two 128-row halves, one per CTA
+  rc = make_mat_map(&tmB, w_fwd, cout, 1LL * p.num_taps * x->c, (bn == 256 && use_pair_kernel()) ? 128 : bn, bk);
   if (rc) return rc;
   const int num_kb = p.num_taps * p.cin_blocks;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cout, bn));
@@ -286,7 +318,7 @@ extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, cons
   const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
   CUtensorMap tmA, tmB;
   if ((rc = make_act_map(&tmA, *dz, false, bk, tw, th, tn))) return rc;
-  if ((rc = make_mat_map(&tmB, w_dgrad, cin, 1LL * taps_total * dz->c, bn, bk))) return rc;
+  if ((rc = make_mat_map(&tmB, w_dgrad, cin, 1LL * taps_total * dz->c, (bn == 256 && use_pair_kernel()) ? 128 : bn, bk))) return rc;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cin, bn));
 
   if (stride == 1) {

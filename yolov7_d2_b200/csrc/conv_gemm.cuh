@@ -506,4 +506,220 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   }
 }
 
+// ================================================================================================
+// CTA-pair variant (cta_group::2) for wide layers (column tile 256): the two CTAs of a cluster compute two consecutive
+// 128-pixel tiles as ONE 256 x 256 UMMA.  Each CTA loads its own activation tile and only HALF of the weight tile (the MMA
+// reads B from both CTAs' shared memory), which cuts the L2->SM operand traffic per MMA by a third -- the limiter of the
+// single-CTA kernel on the 3x3 layers (ncu: tensor pipe ~55 % active at 47 % L2 throughput).
+//   leader CTA (cluster rank 0): issues the MMAs; its full / acc_empty barriers collect both CTAs' arrivals
+//   both CTAs: TMA producer (signals the leader's full barrier), epilogue on their own TMEM half (= their own pixel tile)
+// grid.x = 2 * n_tiles * groups;  pair q = blockIdx.x / 2: column tile q % n_tiles, pixel-tile pairs (q / n_tiles) + i * groups.
+// ================================================================================================
+template <int BLOCK_K>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreadsP, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ ConvGemmParams p, int num_stages, int n_tiles, int m_tiles) {
+  constexpr int BLOCK_N = 256;
+  constexpr int kSwizzle = BLOCK_K * 2;
+  constexpr int kABytes = 128 * BLOCK_K * 2;
+  constexpr int kBBytes = 128 * BLOCK_K * 2;          // this CTA's half of the 256-row weight tile
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kAccCols = 256, kTmemAlloc = 512;
+  constexpr int kHalfCols = 128, CH = 32;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2 * kMaxStagesP + 4];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_part[4][2][BLOCK_N];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&s_bar[0]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kMaxStagesP]);
+  const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kMaxStagesP]);
+  const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kMaxStagesP + 2]);
+
+  const int pair = blockIdx.x >> 1;
+  const int n_tile = pair % n_tiles;
+  const int group = pair / n_tiles;
+  const int groups = (gridDim.x >> 1) / n_tiles;
+  const int col0 = n_tile * BLOCK_N;
+  const int pair_tiles = (m_tiles + 1) >> 1;
+  const int log_tw = p.log_tw, log_th = p.log_th;
+  const int num_kb = p.num_taps * p.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);    // leader: its producer's arrive.expect_tx (bytes of BOTH CTAs)
+      mbar_init(bar_empty + 8 * s, 1);   // each CTA: multicast tcgen05.commit of the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 16);  // leader: 8 epilogue warps of each CTA
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 4 * 2 * BLOCK_N; i += blockDim.x) (&s_part[0][0][0])[i] = 0.f;
+  if (warp == 1) tmem_alloc_pair<kTmemAlloc>(smem_u32(&s_tmem));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // barriers of the peer are initialised before any remote arrive / TMA completion can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = group; pt < pair_tiles; pt += groups) {
+        int t = 2 * pt + static_cast<int>(rank);  // a tile index >= m_tiles lands entirely out of bounds: zero fill, masked epilogue
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tn = t / p.tiles_h;
+        const int w0 = tw << log_tw, h0 = th << log_th, n0 = tn << (7 - log_tw - log_th);
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t full = bar_full + 8 * stage;
+          if (leader) mbar_expect_tx(full, 2 * kStageBytes);
+          const ConvTap& tp = p.taps[tap];
+          tma_load_5d_pair(sa, &tmA, full, tp.c0 + cb * BLOCK_K, w0 + tp.dw, tp.p, h0 + tp.dh, n0);
+          tma_load_2d_pair(sa + kABytes, &tmB, full, tp.kb + cb * BLOCK_K, col0 + static_cast<int>(rank) * 128);
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N, 0, 0);
+      constexpr uint32_t lcode = umma_layout_code(kSwizzle);
+      constexpr uint32_t sbo = 8 * kSwizzle;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = group; pt < pair_tiles; pt += groups, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_acc_empty + 8 * acc, ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * kAccCols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
+            const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
+            umma_f16_pair(tacc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(bar_empty + 8 * stage);  // frees the slot in both CTAs
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(bar_acc_full + 8 * acc);   // both epilogues may drain
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own TMEM = own pixel tile) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
+    const int mrow = q * 32 + lane;
+    const int xl = mrow & ((1 << log_tw) - 1);
+    const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
+    const int nl = mrow >> (log_tw + log_th);
+    int it = 0;
+    for (int pt = group; pt < pair_tiles; pt += groups, ++it) {
+      int t = 2 * pt + static_cast<int>(rank);
+      const int tw = t % p.tiles_w;
+      t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int tn = t / p.tiles_h;
+      const int x = (tw << log_tw) + xl, y = (th << log_th) + yl, n = (tn << (7 - log_tw - log_th)) + nl;
+      const bool valid = (x < p.w_valid) && (y < p.h_valid) && (n < p.n_valid);
+      const long long pix_off = (long long)n * p.out_sn + (long long)(y * p.out_mh + p.out_ph) * p.out_sh +
+                                (long long)(x * p.out_mw + p.out_pw) * p.out_sw;
+      const long long add_off = (long long)n * p.add_sn + (long long)(y * p.out_mh + p.out_ph) * p.add_sh +
+                                (long long)(x * p.out_mw + p.out_pw) * p.add_sw;
+      const int acc = it & 1;
+      mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = cbeg; c < cend; c += CH) {
+        uint32_t r[CH];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c, r);
+        tmem_ld_wait();
+        if (c + CH >= cend) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * acc);
+        }
+        float v[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+        const int cbase = col0 + c;
+        if (p.addend != nullptr && valid) {
+          const __nv_bfloat16* a = p.addend + add_off + cbase;
+#pragma unroll
+          for (int i = 0; i < CH; i += 8) {
+            if (cbase + i < p.cout) {
+              const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+              v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
+              v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
+              v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
+              v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
+            }
+          }
+        }
+        const bool f16 = p.epi_mode != EPI_BF16;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
+        if (valid) {
+          if (f16) {
+            __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8)
+              if (cbase + i < p.cout) store_f16x8(o + i, v + i);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8)
+              if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+          }
+        }
+        if (p.epi_mode == EPI_F16_STATS) {
+          float sq[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
+          const float cs = warp_colsum32(v, lane), cq = warp_colsum32(sq, lane);
+          s_part[q][0][c + lane] += cs;
+          s_part[q][1][c + lane] += cq;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // neither CTA may free TMEM / exit while the peer's MMAs or remote arrives can still target it
+  if (warp == 1) tmem_dealloc_pair<kTmemAlloc>(tmem_base);
+  if (p.epi_mode == EPI_F16_STATS) {
+    for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {
+      const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
+      const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
+      atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
+      atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+    }
+  }
+}
+
 }  // namespace yb
