@@ -55,6 +55,12 @@ int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, in
 int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride,
                      double* stat_sum, double* stat_sqsum, void* stream);
 
+/* Eval-mode BaseConv in one kernel: out = SiLU(conv2d(x, w)*scale + shift) [+ residual], bf16 -- nn.Conv2d + nn.BatchNorm2d
+ * (running statistics) + nn.SiLU of wrappers.py:60-83 with the BatchNorm folded as in utils/checkpoint.py:11-43
+ * (scale / shift from yb200_bn_eval_affine); the Bottleneck shortcut (wrappers.py:119-123) is added after the activation. */
+int yb200_conv2d_bn_silu_fwd(const yb200_act* x, const void* w_fwd, const float* scale, const float* shift,
+                             const yb200_act* residual, const yb200_act* out, int ksize, int stride, void* stream);
+
 /* out[n, a_off + y*w + x, c_off + c] = conv1x1(x, w)[n,y,x,c] + bias[c] in fp32 -- the prediction convs
  * yolox_head.py:103-129 fused with the cat/flatten/permute of yolox_head.py:175,238-244.
  * out is [n][a_total][c_total] fp32.                                                                    */

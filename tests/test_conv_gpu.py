@@ -172,3 +172,30 @@ def test_conv_wgrad(cuda, shape):
                                              ctypes.c_int64(ws_bytes), capi.stream_ptr()), "wgrad acc")
     err2 = (grad - 2 * ref).abs().max().item()
     assert err2 <= 4e-4 * ref.abs().max().item() + 2e-5, f"wgrad accumulate max err {err2}"
+
+
+@pytest.mark.parametrize("shape", [(4, 20, 20, 64, 64, 3, 1), (4, 20, 20, 128, 256, 3, 2), (3, 24, 36, 64, 64, 1, 1), (8, 20, 20, 256, 512, 1, 1)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv_bn_silu_eval_fused(cuda, shape, with_res):
+    """eval-mode BaseConv in one kernel: conv + folded BatchNorm + SiLU (+ Bottleneck shortcut) -- wrappers.py:60-83, 119-123"""
+    from yolov7_d2_b200 import capi
+
+    n, h, w, cin, cout, k, s = shape
+    x, wt = _mk(shape, cuda, 21)
+    wf, _ = _pack(capi, wt, cout, cin, dgrad=False)
+    g = torch.Generator().manual_seed(22)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(cuda)
+    shift = (torch.randn(cout, generator=g) * 0.3).to(cuda)
+    res = torch.randn(n, h // s, w // s, cout, generator=g).to(cuda).to(torch.bfloat16) if with_res else None
+    out = torch.full((n, h // s, w // s, cout), float("nan"), dtype=torch.bfloat16, device=cuda)
+    xa, oa = capi.act(x), capi.act(out)
+    ra = capi.act(res) if with_res else None
+    capi.check(capi.lib().yb200_conv2d_bn_silu_fwd(ctypes.byref(xa), capi.ptr(wf), capi.ptr(scale), capi.ptr(shift),
+                                                   ctypes.byref(ra) if with_res else None, ctypes.byref(oa), k, s, capi.stream_ptr()), "fused")
+    z = F.conv2d(x.float().permute(0, 3, 1, 2), wt, stride=s, padding=(k - 1) // 2)
+    u = z * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = (u * torch.sigmoid(u)).permute(0, 2, 3, 1)
+    if with_res:
+        ref = ref.to(torch.bfloat16).float() + res.float()
+    _close(out, ref, 2.0 ** -7, "fused out")

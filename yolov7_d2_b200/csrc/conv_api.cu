@@ -259,6 +259,33 @@ extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb2
   return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream));
 }
 
+extern "C" int yb200_conv2d_bn_silu_fwd(const yb200_act* x, const void* w_fwd, const float* scale, const float* shift,
+                                        const yb200_act* residual, const yb200_act* out, int ksize, int stride, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv2d_bn_silu_fwd x"))) return rc;
+  if ((rc = check_act(out, "conv2d_bn_silu_fwd out"))) return rc;
+  if (residual && (rc = check_act(residual, "conv2d_bn_silu_fwd residual"))) return rc;
+  YB_REQUIRE(scale && shift, YB200_ERR_INVALID, "conv2d_bn_silu_fwd: null scale / shift");
+  YB_REQUIRE(stride == 1 || stride == 2, YB200_ERR_UNSUPPORTED, "conv2d_bn_silu_fwd: stride %d", stride);
+  YB_REQUIRE(out->n == x->n && out->h * stride == x->h && out->w * stride == x->w, YB200_ERR_INVALID,
+             "conv2d_bn_silu_fwd: output %dx%dx%d does not match input %dx%dx%d / stride %d", out->n, out->h, out->w, x->n, x->h, x->w, stride);
+  YB_REQUIRE(!residual || (residual->n == out->n && residual->h == out->h && residual->w == out->w && residual->c == out->c), YB200_ERR_INVALID,
+             "conv2d_bn_silu_fwd: residual shape mismatch");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_out_view(p, *out);
+  p.epi_mode = EPI_BF16_BN_SILU;
+  p.scale = scale;
+  p.shift = shift;
+  if (residual) {
+    p.addend = static_cast<const __nv_bfloat16*>(residual->ptr) + residual->c_off;
+    p.add_sw = residual->c_pitch;
+    p.add_sh = 1LL * residual->c_pitch * residual->w;
+    p.add_sn = 1LL * residual->c_pitch * residual->w * residual->h;
+  }
+  return conv_fwd_common(x, w_fwd, out->c, ksize, stride, p, as_stream(stream));
+}
+
 extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, const float* bias, int cout, float* out,
                                       int a_total, int a_off, int c_total, int c_off, void* stream) {
   int rc;

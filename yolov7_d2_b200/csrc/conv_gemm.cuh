@@ -26,6 +26,8 @@ enum EpiMode : int {
   EPI_F16 = 1,        // out = fp16(acc)                                     (pre-BatchNorm conv output, eval mode)
   EPI_F16_STATS = 2,  // out = fp16(acc) + per-channel sum / sum-of-squares of the stored values (fp64 atomics)
   EPI_F32_BIAS = 3,   // out = acc + bias[c]   (fp32, arbitrary element strides)
+  EPI_BF16_BN_SILU = 4,  // out = bf16(SiLU(acc*scale[c] + shift[c]) [+ addend]): eval-mode BatchNorm folded into the conv
+                         // (the fold of utils/checkpoint.py:11-43 applied as an epilogue), residual added after the activation
 };
 // The pre-BatchNorm tensor is stored in fp16, not bf16: BatchNorm subtracts the channel mean, which turns the
 // *relative* rounding error of the stored value into an error relative to the (often much smaller) channel
@@ -54,6 +56,8 @@ struct ConvGemmParams {
   const __nv_bfloat16* addend;  // optional, bf16, same (n,y,x) -> offset mapping with its own strides, channel stride 1
   long long add_sn, add_sh, add_sw;
   const float* bias;
+  const float* scale;  // EPI_BF16_BN_SILU: per-channel scale / shift (gamma/sqrt(var+eps), beta - mean*scale)
+  const float* shift;
   double* stat_sum;
   double* stat_sq;
   ConvTap taps[kMaxTaps];
@@ -91,6 +95,74 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
   u.z = pack_bf16x2(v[4], v[5]);
   u.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(dst) = u;
+}
+
+// One chunk (CH columns of one accumulator row per lane) of the epilogue, shared by all three kernels.
+//   part_sum / part_sq: this warp's shared-memory slots for the chunk's columns (EPI_F16_STATS); `accumulate` adds to them
+//   (persistent kernels: statistics over all tiles of the CTA) instead of overwriting.
+template <int CH>
+__device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, float (&v)[CH], bool valid, long long pix_off, long long add_off,
+                                                    int cbase, int lane, float* part_sum, float* part_sq, bool accumulate) {
+  if (p.epi_mode == EPI_F32_BIAS) {
+    if (valid) {
+      float* o = reinterpret_cast<float*>(p.out) + pix_off;
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (cbase + i < p.cout) o[(long long)(cbase + i) * p.out_sc] = v[i] + p.bias[cbase + i];
+    }
+    return;
+  }
+  if (p.epi_mode == EPI_BF16_BN_SILU) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (cbase + i < p.cout) {
+        const float u = fmaf(v[i], __ldg(p.scale + cbase + i), __ldg(p.shift + cbase + i));
+        v[i] = bf16_round(__fdividef(u, 1.f + __expf(-u)));  // rounded before the residual add, as a materialised activation
+      }
+    }
+  }
+  if (p.addend != nullptr && valid) {
+    const __nv_bfloat16* a = p.addend + add_off + cbase;
+#pragma unroll
+    for (int i = 0; i < CH; i += 8) {
+      if (cbase + i < p.cout) {
+        const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+        v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
+        v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
+        v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
+        v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
+      }
+    }
+  }
+  // round once; statistics describe exactly the values that are stored
+  const bool f16 = p.epi_mode == EPI_F16 || p.epi_mode == EPI_F16_STATS;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
+  if (valid) {
+    if (f16) {
+      __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
+#pragma unroll
+      for (int i = 0; i < CH; i += 8)
+        if (cbase + i < p.cout) store_f16x8(o + i, v + i);
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
+#pragma unroll
+      for (int i = 0; i < CH; i += 8)
+        if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+    }
+  }
+  if (p.epi_mode == EPI_F16_STATS) {
+    float sq[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
+    float cs, cq;
+    if constexpr (CH == 32) { cs = warp_colsum32(v, lane); cq = warp_colsum32(sq, lane); }
+    else { cs = warp_colsum16(v, lane); cq = warp_colsum16(sq, lane); }
+    if (lane < CH) {  // each (warp, column) slot has exactly one writer
+      part_sum[lane] = accumulate ? part_sum[lane] + cs : cs;
+      part_sq[lane] = accumulate ? part_sq[lane] + cq : cq;
+    }
+  }
 }
 
 template <int BLOCK_N, int BLOCK_K>
@@ -208,58 +280,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
       const int cbase = col0 + c;
-
-      if (p.epi_mode == EPI_F32_BIAS) {
-        if (valid) {
-          float* o = reinterpret_cast<float*>(p.out) + pix_off;
-#pragma unroll
-          for (int i = 0; i < CH; ++i)
-            if (cbase + i < p.cout) o[(long long)(cbase + i) * p.out_sc] = v[i] + p.bias[cbase + i];
-        }
-      } else {
-        if (p.addend != nullptr && valid) {
-          const __nv_bfloat16* a = p.addend + add_off + cbase;
-#pragma unroll
-          for (int i = 0; i < CH; i += 8) {
-            if (cbase + i < p.cout) {
-              const uint4 u = *reinterpret_cast<const uint4*>(a + i);
-              v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
-              v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
-              v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
-              v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
-            }
-          }
-        }
-        // round once; statistics describe exactly the values that are stored
-        const bool f16 = p.epi_mode != EPI_BF16;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
-        if (valid) {
-          if (f16) {
-            __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
-#pragma unroll
-            for (int i = 0; i < CH; i += 8)
-              if (cbase + i < p.cout) store_f16x8(o + i, v + i);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
-#pragma unroll
-            for (int i = 0; i < CH; i += 8)
-              if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
-          }
-        }
-        if (p.epi_mode == EPI_F16_STATS) {
-          float sq[CH];
-#pragma unroll
-          for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
-          float cs, cq;
-          if constexpr (CH == 32) { cs = warp_colsum32(v, lane); cq = warp_colsum32(sq, lane); }
-          else { cs = warp_colsum16(v, lane); cq = warp_colsum16(sq, lane); }
-          if (lane < CH) {  // plain stores: each (warp, column) slot has exactly one writer
-            s_part[q][0][c + lane] = cs;
-            s_part[q][1][c + lane] = cq;
-          }
-        }
-      }
+      conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], false);
     }
   }
 
@@ -439,56 +460,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
-        if (p.epi_mode == EPI_F32_BIAS) {
-          if (valid) {
-            float* o = reinterpret_cast<float*>(p.out) + pix_off;
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-              if (cbase + i < p.cout) o[(long long)(cbase + i) * p.out_sc] = v[i] + p.bias[cbase + i];
-          }
-        } else {
-          if (p.addend != nullptr && valid) {
-            const __nv_bfloat16* a = p.addend + add_off + cbase;
-#pragma unroll
-            for (int i = 0; i < CH; i += 8) {
-              if (cbase + i < p.cout) {
-                const uint4 u = *reinterpret_cast<const uint4*>(a + i);
-                v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
-                v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
-                v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
-                v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
-              }
-            }
-          }
-          const bool f16 = p.epi_mode != EPI_BF16;
-#pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
-          if (valid) {
-            if (f16) {
-              __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
-#pragma unroll
-              for (int i = 0; i < CH; i += 8)
-                if (cbase + i < p.cout) store_f16x8(o + i, v + i);
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
-#pragma unroll
-              for (int i = 0; i < CH; i += 8)
-                if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
-            }
-          }
-          if (p.epi_mode == EPI_F16_STATS) {
-            float sq[CH];
-#pragma unroll
-            for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
-            float cs, cq;
-            if constexpr (CH == 32) { cs = warp_colsum32(v, lane); cq = warp_colsum32(sq, lane); }
-            else { cs = warp_colsum16(v, lane); cq = warp_colsum16(sq, lane); }
-            if (lane < CH) {  // slot (warp, column) is owned by this lane for the whole kernel
-              s_part[q][0][c + lane] += cs;
-              s_part[q][1][c + lane] += cq;
-            }
-          }
-        }
+        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true);
       }
     }
   }
@@ -667,43 +639,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
-        if (p.addend != nullptr && valid) {
-          const __nv_bfloat16* a = p.addend + add_off + cbase;
-#pragma unroll
-          for (int i = 0; i < CH; i += 8) {
-            if (cbase + i < p.cout) {
-              const uint4 u = *reinterpret_cast<const uint4*>(a + i);
-              v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
-              v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
-              v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
-              v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
-            }
-          }
-        }
-        const bool f16 = p.epi_mode != EPI_BF16;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
-        if (valid) {
-          if (f16) {
-            __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
-#pragma unroll
-            for (int i = 0; i < CH; i += 8)
-              if (cbase + i < p.cout) store_f16x8(o + i, v + i);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
-#pragma unroll
-            for (int i = 0; i < CH; i += 8)
-              if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
-          }
-        }
-        if (p.epi_mode == EPI_F16_STATS) {
-          float sq[CH];
-#pragma unroll
-          for (int i = 0; i < CH; ++i) sq[i] = v[i] * v[i];
-          const float cs = warp_colsum32(v, lane), cq = warp_colsum32(sq, lane);
-          s_part[q][0][c + lane] += cs;
-          s_part[q][1][c + lane] += cq;
-        }
+        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true);
       }
     }
   }

@@ -401,12 +401,25 @@ class YoloxEngine:
         for op in self.ops:
             if isinstance(op, ConvOp):
                 o = op.bn_off
-                ssum = ctypes.c_void_p(f8.data_ptr() + 8 * o) if training else None
-                ssq = ctypes.c_void_p(f8.data_ptr() + 8 * (nb + o)) if training else None
-                capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, ssum, ssq, sp), op.prefixes[0])
                 gamma = self.params[op.prefixes[0] + ".bn.weight"]
                 beta = self.params[op.heads[0].prefix + ".bn.bias"]
                 pf = lambda t, off=o: ctypes.c_void_p(t.data_ptr() + 4 * off)
+                if not training and all(hd.up is None for hd in op.heads):
+                    # eval: BatchNorm (running statistics) + SiLU + shortcut folded into the convolution's epilogue
+                    capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm), pf(self.flat_rv),
+                                                      ctypes.c_float(BN_EPS), pf(self.flat_scale), pf(self.flat_shift), sp), "bn_eval_affine")
+                    self._count(1, "bn_eval_affine " + op.prefixes[0])
+                    kk = op.ksize * op.ksize
+                    for hd in op.heads:
+                        w_head = ctypes.c_void_p(op.w_fwd.data_ptr() + 2 * hd.c0 * kk * op.cin_pad)
+                        capi.check(L.yb200_conv2d_bn_silu_fwd(op.x.act(), w_head, pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
+                                                             hd.residual.act() if hd.residual else None, hd.out.act(), op.ksize, op.stride, sp),
+                                   "conv_bn_silu " + hd.prefix)
+                        self._count(1, "conv+bn+silu (eval) %s %s" % (hd.prefix, self._desc(op)))
+                    continue
+                ssum = ctypes.c_void_p(f8.data_ptr() + 8 * o) if training else None
+                ssq = ctypes.c_void_p(f8.data_ptr() + 8 * (nb + o)) if training else None
+                capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, ssum, ssq, sp), op.prefixes[0])
                 if training:
                     cnt = op.z.buf.n * op.z.buf.h * op.z.buf.w
                     capi.check(L.yb200_bn_finalize(ssum, ssq, op.cout, ctypes.c_int64(cnt), capi.ptr(gamma), capi.ptr(beta), ctypes.c_float(BN_EPS),
