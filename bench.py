@@ -288,7 +288,7 @@ def main():
         if os.path.exists(tp):
             with open(tp) as fh:
                 traffic = json.load(fh).get("conv_gemm_head3x3_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": "conv_gemm_persistent_kernel<256,64> (head 3x3 128->256 @80x80: implicit GEMM M=%d N=%d K=%d)" % (n * oh * ow, cout, op.cin_pad * 9),
+        roof = {"bound": "tensor", "kernel": "conv_gemm_pair_kernel<64> (cta_group::2, 256x256 tile; head 3x3 128->256 @80x80: implicit GEMM M=%d N=%d K=%d)" % (n * oh * ow, cout, op.cin_pad * 9),
                 "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
                 "peak_source": pk["source"] + " bf16_tflops (burst: kernel timed alone between events)", "us_per_launch": 1e3 * t_ms,
                 "step_frac_of_sustained_peak": value / world * FLOP_PER_IMAGE / 1e12 / pk["tf_sust"]}

@@ -169,6 +169,25 @@ int yb200_postprocess_nms(float* prediction, int batch, int num_anchors, int num
 int yb200_iou_loss(const float* pred_cxcywh, const float* target_cxcywh, int n, int mode, float* loss, float* dloss_dpred,
                    void* stream);
 
+/* ---- parameter update on the flat fp32 buffers -------------------------------------------------------
+ * Per-parameter hyper-parameters come from a segment table in device memory: seg_begin[nseg] ascending element offsets
+ * (seg_begin[0] == 0), seg_wd[nseg] weight decay, seg_lr_mult[nseg] learning-rate multiplier (NULL = 1): the param groups that
+ * yolov7/optimizer/build.py:77-170 builds (norm / bias / embedding decay, bias_lr_factor, lr_multipliers_overwrite).
+ * grad_scale multiplies every gradient first (1/world_size of the DDP mean); total_norm (device scalar from yb200_grad_norm, may be
+ * NULL) with max_norm > 0 applies clip_grad_norm_ over the whole model (FullModelGradientClippingOptimizer, build.py:206-223).       */
+int64_t yb200_grad_norm_workspace(void);
+/* out_norm[0] = || grad * grad_scale ||_2, deterministic two-stage reduction (fp64 accumulation) */
+int yb200_grad_norm(const float* grad, int64_t n, float grad_scale, void* workspace, float* out_norm, void* stream);
+/* torch.optim.SGD.step (build.py:234-245): d = g + wd*p; buf = first_step ? d : momentum*buf + (1-dampening)*d;
+ * d = nesterov ? d + momentum*buf : buf; p -= lr*d.  momentum_buf may be NULL when momentum == 0.                                   */
+int yb200_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, const int64_t* seg_begin, const float* seg_wd,
+                   const float* seg_lr_mult, int nseg, float lr, float momentum, float dampening, int nesterov, int first_step,
+                   float grad_scale, const float* total_norm, float max_norm, void* stream);
+/* torch.optim.AdamW.step (build.py:248-256): p *= 1 - lr*wd; m, v moments; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps); step t >= 1 */
+int yb200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_begin,
+                     const float* seg_wd, const float* seg_lr_mult, int nseg, float lr, float beta1, float beta2, float eps, int step,
+                     float grad_scale, const float* total_norm, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ def lib():
         _lib.yb200_conv2d_wgrad_workspace.restype = c_i64
         _lib.yb200_simota_workspace.restype = c_i64
         _lib.yb200_nms_workspace.restype = c_i64
+        _lib.yb200_grad_norm_workspace.restype = c_i64
         for name in declared_symbols():
             if not hasattr(_lib, name):
                 raise Yb200Error(f"libyb200.so does not export {name} declared in include/yb200.h")

@@ -242,6 +242,7 @@ class YoloxEngine:
             self.params[name] = self.flat_param[offs[name]:offs[name] + n].view(shape)
             self.grads[name] = self.flat_grad[offs[name]:offs[name] + n].view(shape)
         self.param_names = [n for n, _ in specs]
+        self.param_layout = [(n, offs[n], math.prod(shape)) for n, shape in specs]  # (name, element offset, numel); gaps are padding
         # BatchNorm buffers
         nbn = sum(hd.c for op in self.ops if isinstance(op, ConvOp) for hd in op.heads)
         self.flat_rm = share.flat_rm if share is not None else torch.zeros(nbn, device=dev)

@@ -211,7 +211,8 @@ class _TrainStep(torch.autograd.Function):
     parameters so that autograd / DDP / optimizers see ordinary per-parameter gradients."""
 
     @staticmethod
-    def forward(ctx, engine, *params):
+    def forward(ctx, engine, flat_grads, *params):
+        ctx.flat_grads = flat_grads
         engine.pack_weights()
         engine.preprocess()
         engine.forward_features(True)
@@ -226,8 +227,12 @@ class _TrainStep(torch.autograd.Function):
         # outputs: total = 5*iou + obj + cls, iou_loss = 5*iou, conf_loss = obj, cls_loss = cls   (yolox.py:201-206)
         eng.loss_weights.copy_(torch.stack([5.0 * (g_total + g_iou), g_total + g_obj, g_total + g_cls]).float())
         eng.loss_grad_only()
+        if ctx.flat_grads:
+            # every parameter's .grad already is its slice of the flat gradient buffer (YOLOX.attach_flat_grads): accumulate in place
+            eng.backward(accumulate=True)
+            return (None, None) + (None,) * len(eng.param_names)
         eng.backward()
-        return (None,) + tuple(eng.grads[n].clone() for n in eng.param_names)
+        return (None, None) + tuple(eng.grads[n].clone() for n in eng.param_names)
 
 
 @META_ARCH_REGISTRY.register()
@@ -267,6 +272,19 @@ class YOLOX(nn.Module):
         self.head._adopt(self._root, "head.")
         self.head.initialize_biases(1e-2)
         self._param_list = None
+        self._flat_grads = False
+
+    @property
+    def engine(self):
+        """the plan that owns the flat parameter / gradient buffers (yolov7_d2_b200.optim builds its optimizers on them)"""
+        return self._root
+
+    def attach_flat_grads(self):
+        """Make every parameter's .grad a view into the flat gradient buffer, so that backward writes gradients where the flat
+        optimizer and the single all-reduce read them (no per-parameter copies).  Needs zero_grad(set_to_none=False)."""
+        for name, p in zip(self._root.param_names, self._params_in_engine_order()):
+            p.grad = self._root.grads[name]
+        self._flat_grads = True
 
     def update_iter(self, i):
         self.iter = i
@@ -342,7 +360,7 @@ class YOLOX(nn.Module):
     def forward(self, batched_inputs):
         eng, image_sizes = self.preprocess_image(batched_inputs, self.training)
         if self.training:
-            total, iou, conf, cls = _TrainStep.apply(eng, *self._params_in_engine_order())
+            total, iou, conf, cls = _TrainStep.apply(eng, self._flat_grads, *self._params_in_engine_order())
             return {"total_loss": total, "iou_loss": iou, "conf_loss": conf, "cls_loss": cls}
         with torch.no_grad():
             outputs = eng.eval_forward()

@@ -1,0 +1,175 @@
+"""Host mirror of the reference's optimizer builders (yolov7/optimizer/build.py) on top of the flat fp32 buffers.
+
+`sgd(cfg, model)` / `adamw(cfg, model)` / `build_optimizer_mapper(cfg, model)` keep the reference's names and the meaning of
+the `cfg.SOLVER.*` keys they read (build.py:24-60, 234-256, 294-300).  The returned object is a `torch.optim.Optimizer`
+(LR schedulers and detectron2's trainer only touch `param_groups[i]["lr"]`, `step()` and `zero_grad()`), but `step()` is ONE
+kernel launch over the whole model (csrc/optim.cu) instead of a Python loop over ~250 tensors: per-parameter weight decay
+and learning-rate multipliers are a segment table in device memory.  There is no CPU implementation.
+"""
+import ctypes
+
+import torch
+
+from . import capi
+
+_NORM_SUFFIXES = (".bn.weight", ".bn.bias", ".norm.weight", ".norm.bias")
+
+
+def _solver(cfg, key, default):
+    solver = getattr(cfg, "SOLVER", None)
+    if solver is None:
+        return default
+    if isinstance(solver, dict):
+        return solver.get(key, default)
+    return getattr(solver, key, default)
+
+
+def param_segments(param_layout, total, weight_decay, weight_decay_norm=None, weight_decay_bias=None, bias_lr_factor=1.0,
+                   lr_multipliers_overwrite=None):
+    """[(begin, weight_decay, lr_multiplier)] covering [0, total) for parameters placed at `param_layout` = [(name, offset, numel)]
+    (ascending offsets; gaps are alignment padding and get lr multiplier 0, i.e. they are never modified).
+
+    Follows get_optimizer_param_groups_lr / _weight_decay (build.py:77-170): normalisation-layer parameters take
+    weight_decay_norm, parameters *named* "bias" take weight_decay_bias and lr * bias_lr_factor, and a multiplier applies
+    to every parameter whose module name contains one of the override keys.  Adjacent equal segments are merged
+    (the reference's reduce_param_groups)."""
+    wd_norm = weight_decay if weight_decay_norm is None else weight_decay_norm
+    wd_bias = weight_decay if weight_decay_bias is None else weight_decay_bias
+    segs = []
+
+    def push(off, wd, mult):
+        if not segs or (segs[-1][1], segs[-1][2]) != (wd, mult):
+            segs.append((off, float(wd), float(mult)))
+
+    end = 0
+    for name, off, n in param_layout:
+        assert off >= end, "param_layout must be sorted and non-overlapping"
+        if off > end:
+            push(end, 0.0, 0.0)
+        module_name, _, pname = name.rpartition(".")
+        wd, mult = weight_decay, 1.0
+        if name.endswith(_NORM_SUFFIXES):
+            wd = wd_norm
+        elif pname == "bias":
+            wd = wd_bias
+        if pname == "bias":
+            mult *= bias_lr_factor
+        for key, m in (lr_multipliers_overwrite or {}).items():
+            if key in module_name:
+                mult *= m
+        push(off, wd, mult)
+        end = off + n
+    if end < total:
+        push(end, 0.0, 0.0)
+    if not segs:
+        segs.append((0, 0.0, 0.0))
+    return segs
+
+
+class FlatOptimizer(torch.optim.Optimizer):
+    """one param group holding the flat parameter tensor; `param_groups[0]["lr"]` is what schedulers drive"""
+
+    def __init__(self, flat_param, flat_grad, segments, lr, kind, momentum=0.0, dampening=0.0, nesterov=False, betas=(0.9, 0.999), eps=1e-8,
+                 clip_norm=0.0, grad_scale=1.0):
+        if not flat_param.is_cuda:
+            raise capi.Yb200Error("FlatOptimizer needs the engine's CUDA buffers; the hot path has no CPU implementation")
+        assert flat_param.dtype == torch.float32 and flat_param.is_contiguous() and flat_grad.shape == flat_param.shape
+        self.flat_param, self.flat_grad = flat_param, flat_grad
+        self.kind = kind
+        dev = flat_param.device
+        self.seg_begin = torch.tensor([s[0] for s in segments], dtype=torch.int64, device=dev)
+        self.seg_wd = torch.tensor([s[1] for s in segments], dtype=torch.float32, device=dev)
+        self.seg_lr = torch.tensor([s[2] for s in segments], dtype=torch.float32, device=dev)
+        self.nseg = len(segments)
+        self.clip_norm = float(clip_norm)
+        self.grad_scale = float(grad_scale)
+        self.steps = 0
+        self.state_a = torch.zeros_like(flat_param) if (kind == "adamw" or momentum != 0.0) else None  # momentum buffer / exp_avg
+        self.state_b = torch.zeros_like(flat_param) if kind == "adamw" else None                         # exp_avg_sq
+        L = capi.lib()
+        self.norm_ws = torch.empty(int(L.yb200_grad_norm_workspace()), dtype=torch.uint8, device=dev)
+        self.total_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, nesterov=nesterov, betas=betas, eps=eps)
+        super().__init__([flat_param], defaults)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        L, sp = capi.lib(), capi.stream_ptr()
+        g = self.param_groups[0]
+        n = self.flat_param.numel()
+        f = ctypes.c_float
+        norm = None
+        if self.clip_norm > 0:
+            capi.check(L.yb200_grad_norm(capi.ptr(self.flat_grad), ctypes.c_int64(n), f(self.grad_scale), capi.ptr(self.norm_ws), capi.ptr(self.total_norm),
+                                         sp), "grad_norm")
+            norm = self.total_norm
+        self.steps += 1
+        if self.kind == "sgd":
+            capi.check(L.yb200_sgd_step(capi.ptr(self.flat_param), capi.ptr(self.flat_grad), capi.ptr(self.state_a), ctypes.c_int64(n),
+                                        capi.ptr(self.seg_begin), capi.ptr(self.seg_wd), capi.ptr(self.seg_lr), self.nseg, f(g["lr"]),
+                                        f(g["momentum"]), f(g["dampening"]), int(bool(g["nesterov"])), int(self.steps == 1), f(self.grad_scale),
+                                        capi.ptr(norm), f(self.clip_norm), sp), "sgd_step")
+        else:
+            capi.check(L.yb200_adamw_step(capi.ptr(self.flat_param), capi.ptr(self.flat_grad), capi.ptr(self.state_a), capi.ptr(self.state_b),
+                                          ctypes.c_int64(n), capi.ptr(self.seg_begin), capi.ptr(self.seg_wd), capi.ptr(self.seg_lr), self.nseg,
+                                          f(g["lr"]), f(g["betas"][0]), f(g["betas"][1]), f(g["eps"]), self.steps, f(self.grad_scale), capi.ptr(norm),
+                                          f(self.clip_norm), sp), "adamw_step")
+        return loss
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+
+
+def _flat_buffers(model):
+    eng = getattr(model, "engine", None) or getattr(getattr(model, "module", None), "engine", None) or model
+    if not hasattr(eng, "flat_param"):
+        raise capi.Yb200Error("optimizer needs a model that exposes the engine's flat_param / flat_grad / param_layout")
+    inner = getattr(model, "module", model)
+    if hasattr(inner, "attach_flat_grads"):
+        inner.attach_flat_grads()
+    return eng
+
+
+def _clip_norm(cfg):
+    clip = _solver(cfg, "CLIP_GRADIENTS", None)
+    if clip is None:
+        return 0.0
+    get = clip.get if isinstance(clip, dict) else lambda k, d=None: getattr(clip, k, d)
+    if get("ENABLED", False) and get("CLIP_TYPE", "value") == "full_model" and get("CLIP_VALUE", 0.0) > 0.0:
+        return float(get("CLIP_VALUE"))
+    return 0.0
+
+
+def _build(cfg, model, kind, **kw):
+    eng = _flat_buffers(model)
+    overrides = {}
+    for d in _solver(cfg, "LR_MULTIPLIER_OVERWRITE", None) or []:
+        overrides.update(d)  # build.py:226-231 _merge_dict
+    segs = param_segments(eng.param_layout, eng.flat_param.numel(), _solver(cfg, "WEIGHT_DECAY", 1e-4), _solver(cfg, "WEIGHT_DECAY_NORM", None),
+                          _solver(cfg, "WEIGHT_DECAY_BIAS", None), bias_lr_factor=_solver(cfg, "BIAS_LR_FACTOR", 1.0),
+                          lr_multipliers_overwrite=overrides)
+    return FlatOptimizer(eng.flat_param, eng.flat_grad, segs, _solver(cfg, "BASE_LR", 0.001), kind, clip_norm=_clip_norm(cfg), **kw)
+
+
+def sgd(cfg, model):
+    """build.py:234-245"""
+    return _build(cfg, model, "sgd", momentum=_solver(cfg, "MOMENTUM", 0.9), nesterov=_solver(cfg, "NESTEROV", False))
+
+
+def adamw(cfg, model):
+    """build.py:248-256"""
+    return _build(cfg, model, "adamw")
+
+
+sgd_mt, adamw_mt = sgd, adamw  # build.py:259-288: the multi-tensor variants are what this file always is
+
+_MAPPER = {"sgd": sgd, "adamw": adamw, "sgd_mt": sgd_mt, "adamw_mt": adamw_mt}
+
+
+def build_optimizer_mapper(cfg, model):
+    """build.py:291-300"""
+    name = str(_solver(cfg, "OPTIMIZER", "sgd")).lower()
+    if name not in _MAPPER:
+        raise KeyError(f"No object named '{name}' found in 'D2GO_OPTIM_MAPPER' registry!")
+    return _MAPPER[name](cfg, model)
