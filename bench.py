@@ -71,6 +71,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# the optimizer step is part of the timed step; a tiny learning rate keeps 1000s of steps on one synthetic batch from diverging
+BENCH_LR = 1e-5
+
+
 def ns(**kw):
     return types.SimpleNamespace(**kw)
 
@@ -81,7 +85,8 @@ def yolox_s_cfg(device="cuda"):
                        BACKBONE=ns(NAME="build_cspdarknetx_backbone"), DARKNET=ns(DEPTH_WISE=False, OUT_FEATURES=["dark3", "dark4", "dark5"]),
                        YOLO=ns(CLASSES=80, CONF_THRESHOLD=0.001, NMS_THRESHOLD=0.65, WIDTH_MUL=0.50, DEPTH_MUL=0.33, LOSS_TYPE="v7",
                                MAX_BOXES_NUM=100, IN_FEATURES=["dark3", "dark4", "dark5"])),
-              SOLVER=ns(MAX_ITER=230000), INPUT=ns(MOSAIC_AND_MIXUP=ns(DISABLE_AT_ITER=120000)))
+              SOLVER=ns(MAX_ITER=230000, OPTIMIZER="SGD", BASE_LR=BENCH_LR, MOMENTUM=0.9, NESTEROV=False, WEIGHT_DECAY=5e-4, WEIGHT_DECAY_NORM=0.0),
+              INPUT=ns(MOSAIC_AND_MIXUP=ns(DISABLE_AT_ITER=120000)))
 
 
 class _GtBoxes:
@@ -133,12 +138,16 @@ def run_reference(args, rank, world):
     images, labels = orc.synthetic_batch(bs, 640, 0)
     x = images.float()
 
+    ropt = None if args.no_optimizer else torch.optim.SGD([v for v in sd.values() if v.requires_grad], lr=BENCH_LR, momentum=0.9, weight_decay=5e-4)
+
     def step():
         for v in sd.values():
             if v.requires_grad and v.grad is not None:
                 v.grad = None
         out = orc.yolox_forward_train(x, labels, sd)
         out[0].backward()
+        if ropt is not None:
+            ropt.step()
         return float(out[0])
 
     threads, avail = pick_cpu_threads(step, torch)  # doubles as the warm-up
@@ -167,6 +176,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward(+all-reduce) only, without the fused SGD step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,7 +200,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
 
-    model = YOLOX(yolox_s_cfg("cuda"))
+    cfg = yolox_s_cfg("cuda")
+    model = YOLOX(cfg)
     sd = orc.yolox_state_dict(0)
     model.load_state_dict({k: v for k, v in sd.items()}, strict=True)
     model.train()
@@ -199,11 +210,23 @@ def main():
     eng.images_u8.copy_(images.to(dev))
     eng.labels.copy_(labels.to(dev))
     flat_grad = eng.flat_grad
+    opt = None
+    if not args.no_optimizer:
+        from yolov7_d2_b200 import optim as yopt
+        opt = yopt.build_optimizer_mapper(cfg, model)  # one fused SGD launch over the flat buffers (optimizer/build.py:234-245)
+        opt.grad_scale = 1.0 / world                    # the mean of DDP, folded into the update
+
+    def train_step():
+        eng.train_step()
+        if opt is not None and world == 1:
+            opt.step()
 
     def step_eager():
         eng.train_step()
         if world > 1:
-            dist.all_reduce(flat_grad)  # the single gradient all-reduce (sum; /world folded into the optimizer's lr in DDP terms)
+            dist.all_reduce(flat_grad)  # the single gradient all-reduce of the path (sum; the 1/world is folded into the update)
+        if opt is not None:
+            opt.step()
 
     # probe: CUDA events around the dominant kernel (head 3x3 128->128 @80x80, merged cls|reg: 128->256) on the launch stream
     probe = {"ev": [], "op": None}
@@ -223,11 +246,11 @@ def main():
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                eng.train_step()
+                train_step()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
-                eng.train_step()
+                train_step()
             graph = g
             for _ in range(2):
                 graph.replay()
@@ -299,20 +322,23 @@ def main():
         host_imgs = images.pin_memory()
         bi = batched_inputs_from(host_imgs, labels)
         h2d = host_imgs.numel() + labels.numel() * 4 + B * 8
-        for _ in range(2):
+        def api_step():
+            if opt is not None:
+                opt.zero_grad()
             losses = model(bi)
             sum(losses.values()).backward()
             if world > 1:
                 dist.all_reduce(flat_grad)
-            _ = float(losses["total_loss"])
+            if opt is not None:
+                opt.step()
+            return float(losses["total_loss"])  # device -> host read of the step's result
+
+        for _ in range(2):
+            api_step()
         barrier()
         e0.record()
         for _ in range(args.steps):
-            losses = model(bi)
-            sum(losses.values()).backward()
-            if world > 1:
-                dist.all_reduce(flat_grad)
-            _ = float(losses["total_loss"])  # device -> host read of the step's result
+            api_step()
         e1.record()
         barrier()
         ms2 = e0.elapsed_time(e1)
@@ -321,7 +347,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t)
         e2e = {"value": world * B * args.steps / (ms2 / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-               "api": "YOLOX.forward(batched_inputs) + sum(loss_dict.values()).backward() + loss.item()"}
+               "api": ("optimizer.zero_grad() + " if opt is not None else "") + "YOLOX.forward(batched_inputs) + sum(loss_dict.values()).backward()"
+                      + (" + optimizer.step()" if opt is not None else "") + " + loss.item()"}
 
     # ---- NMS boxes/s (second half of the BASELINE metric) ----
     nms = None
@@ -351,11 +378,15 @@ def main():
         ci, cl = orc.synthetic_batch(2, 640, 0)
         cx = ci.float()
 
+        copt = None if opt is None else torch.optim.SGD([v for v in csd.values() if v.requires_grad], lr=BENCH_LR, momentum=0.9, weight_decay=5e-4)
+
         def cstep():
             for v in csd.values():
                 if v.requires_grad:
                     v.grad = None
             orc.yolox_forward_train(cx, cl, csd)[0].backward()
+            if copt is not None:
+                copt.step()
 
         threads, avail = pick_cpu_threads(cstep, torch)
         t0 = time.perf_counter()
@@ -372,8 +403,9 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": graph is not None,
+                           "optimizer": None if opt is None else "fused SGD step inside the timed step (momentum 0.9, wd 5e-4, lr %g)" % BENCH_LR,
                            "l2": "per-step working set (~%.0f GB of activations and gradients) exceeds the 126 MB L2; no explicit flush" % (0.245 * B)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu, "nms": nms,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "cpu_baseline": cpu, "nms": nms,
                 "loss": float(eng.losses[0])}
         print(json.dumps(line), flush=True)
     if world > 1:
