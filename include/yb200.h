@@ -188,6 +188,53 @@ int yb200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp
                      const float* seg_wd, const float* seg_lr_mult, int nseg, float lr, float beta1, float beta2, float eps, int step,
                      float grad_scale, const float* total_norm, float max_norm, void* stream);
 
+/* ---- ConvNeXt block (yolov7/modeling/backbone/convnext.py) ------------------------------------------------
+ * The two Linear layers of the block and the 2x2 / 4x4 strided convolutions run on the implicit-GEMM kernels above with these
+ * epilogues; everything else is in csrc/convnext.cu.  Linear weights [out][in] are packed with yb200_pack_conv_weight(ksize 1).      */
+/* as yb200_pack_conv_weight with every output row scaled by cout_scale[co] first (layer scale gamma folded into pwconv2, convnext.py:54-56);
+ * scaled_bias[co] = cout_scale[co] * bias[co] (both NULL or both given): the shift of the matching yb200_conv2d_affine_fwd call              */
+int yb200_pack_conv_weight_scaled(const float* w_oihw, const float* cout_scale, const float* bias, int cout, int cin, int ksize, int cout_pad,
+                                  int cin_pad, void* w_fwd, void* w_dgrad, float* scaled_bias, void* stream);
+/* out = bf16(conv(x) * scale[c] + shift[c] [+ residual]); scale / shift may be NULL (1 / 0).  ksize/stride: 1/1, 3/1, 3/2 or 2/2 (no padding:
+ * the downsample convolutions, convnext.py:86-91).  nn.Conv2d / nn.Linear with bias: shift = bias.                                      */
+int yb200_conv2d_affine_fwd(const yb200_act* x, const void* w_fwd, const float* scale, const float* shift, const yb200_act* residual,
+                            const yb200_act* out, int ksize, int stride, void* stream);
+/* pwconv1 + GELU (convnext.py:52-53): u = bf16(x W^T + bias) -> u_out (may be NULL), h = bf16(GELU(u)) -> h_out (exact erf form)       */
+int yb200_linear_gelu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* u_out, const yb200_act* h_out, void* stream);
+/* du = bf16((dz W) * GELU'(u)) and, when bias_grad_sum != NULL, bias_grad_sum[c] += sum over pixels of du[.., c] (fp64, caller zeroes it):
+ * the data gradient of pwconv2 fused with the GELU backward and the bias gradient of pwconv1.                                            */
+int yb200_linear_dgrad_gelu(const yb200_act* dz, const void* w_dgrad, const yb200_act* u, const yb200_act* du, double* bias_grad_sum,
+                            void* stream);
+/* depthwise 7x7, stride 1, zero padding 3 (convnext.py:41,49): out = dwconv(x; w) [+ bias] [+ addend].  w_c49: fp32 [C][7][7] (the
+ * nn.Conv2d(groups=C) weight [C][1][7][7]).  flip != 0 correlates with the flipped kernel = the data gradient (addend: the residual branch). */
+int yb200_dwconv7(const yb200_act* x, const float* w_c49, const float* bias, const yb200_act* addend, const yb200_act* out, int flip,
+                  void* stream);
+int64_t yb200_dwconv7_wgrad_workspace(const yb200_act* x);
+/* grad_w_c49[c][ky][kx] = sum dy[p][c] x[p + (ky-3, kx-3)][c]; grad_bias[c] = sum dy[p][c] (may be NULL); fixed summation order          */
+int yb200_dwconv7_wgrad(const yb200_act* x, const yb200_act* dy, float* grad_w_c49, float* grad_bias, int accumulate, void* workspace,
+                        void* stream);
+/* LayerNorm over the channel dimension of every pixel (convnext.py:196-206, both data formats; biased variance, eps inside the sqrt).
+ * stats_mean_rstd: fp32 [pixels][2], may be NULL in forward-only use.                                                                    */
+int yb200_layernorm_fwd(const yb200_act* x, const float* gamma, const float* beta, float eps, const yb200_act* y, float* stats_mean_rstd,
+                        void* stream);
+int64_t yb200_layernorm_bwd_workspace(const yb200_act* x);
+/* dx = LayerNorm-backward(dy) [+ addend]; grad_gamma / grad_beta fp32 [C], fixed summation order                                         */
+int yb200_layernorm_bwd(const yb200_act* dy, const yb200_act* x, const float* stats_mean_rstd, const float* gamma, const yb200_act* addend,
+                        const yb200_act* dx, float* grad_gamma, float* grad_beta, int accumulate, void* workspace, void* stream);
+int64_t yb200_colsum_workspace(const yb200_act* x);
+/* out[c] = scale * sum over pixels of x[.., c] (bias gradients), fixed summation order                                                    */
+int yb200_colsum(const yb200_act* x, float scale, float* out, int accumulate, void* workspace, void* stream);
+/* Layer scale gamma (convnext.py:44-45,55-56) folded into pwconv2: given raw_wgrad = dOut^T h (weight gradient w.r.t. the UNscaled output
+ * gradient, [C][hidden]) and gout_colsum[c] = sum of dOut:  grad_w2 = gamma[c] * raw, grad_gamma[c] = <w2[c], raw[c]> + b2[c] * colsum[c],
+ * grad_b2[c] = gamma[c] * colsum[c].  raw_wgrad may alias grad_w2.                                                                         */
+int yb200_layer_scale_grad(const float* raw_wgrad, const float* w2, const float* b2, const float* gamma, const float* gout_colsum, int channels,
+                           int hidden, float* grad_w2, float* grad_gamma, float* grad_b2, int accumulate, void* stream);
+/* stem input (convnext.py:81-84): uint8 (is_f32 = 0) or fp32 NCHW image -> [N][H/4][W/4][48] bf16 patches, channel = c*16 + kh*4 + kw (the OIHW flattening of
+ * the 4x4 stride-4 stem weight), so the stem is a K = 48 GEMM (yb200_conv2d_affine_fwd, ksize 1).                                          */
+int yb200_patchify4(const void* images_nchw, int is_f32, int n, int h, int w, const yb200_act* out, void* stream);
+/* dst[i] = (accumulate ? dst[i] : 0) + (float)src[i]; src[i] = 0 when zero_src (fp64 accumulators of the GEMM epilogues -> fp32 gradients) */
+int yb200_f64_to_f32(double* src, int n, float* dst, int accumulate, int zero_src, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,8 @@ def lib():
         _lib.yb200_simota_workspace.restype = c_i64
         _lib.yb200_nms_workspace.restype = c_i64
         _lib.yb200_grad_norm_workspace.restype = c_i64
+        for _n in ("yb200_dwconv7_wgrad_workspace", "yb200_layernorm_bwd_workspace", "yb200_colsum_workspace"):
+            getattr(_lib, _n).restype = c_i64
         for name in declared_symbols():
             if not hasattr(_lib, name):
                 raise Yb200Error(f"libyb200.so does not export {name} declared in include/yb200.h")

@@ -143,6 +143,9 @@ static int fill_fwd_taps(ConvTap* taps, const yb200_act& x, int ksize, int strid
   int nt = 0;
   if (ksize == 1) {
     taps[nt++] = ConvTap{x.c_off, 0, 0, 0, 0};
+  } else if (ksize == 2) {  // 2x2 stride 2, no padding: input pixel (2*o + kh, 2*o + kw) = (row parity kh, column parity kw) of cell o
+    for (int kh = 0; kh < 2; ++kh)
+      for (int kw = 0; kw < 2; ++kw) taps[nt++] = ConvTap{kw * x.c_pitch + x.c_off, 0, kh, 0, (kh * 2 + kw) * k_per_tap};
   } else {
     for (int kh = 0; kh < 3; ++kh)
       for (int kw = 0; kw < 3; ++kw) {
@@ -185,32 +188,51 @@ using namespace yb;
 // ------------------------------------------------------------------------------------------------
 // weights
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad, int cin_pad,
-                                        __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ cout_scale, int cout, int cin, int taps, int cout_pad,
+                                        int cin_pad, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
   const long long total = 1LL * cout_pad * taps * cin_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = static_cast<int>(i % cin_pad);
     const int t = static_cast<int>((i / cin_pad) % taps);
     const int co = static_cast<int>(i / (1LL * cin_pad * taps));
-    const float v = (co < cout && ci < cin) ? w[(1LL * co * cin + ci) * taps + t] : 0.f;
+    float v = (co < cout && ci < cin) ? w[(1LL * co * cin + ci) * taps + t] : 0.f;
+    if (cout_scale != nullptr && co < cout) v *= cout_scale[co];
     const __nv_bfloat16 b = __float2bfloat16_rn(v);
     if (wf) wf[i] = b;
     if (wd) wd[(1LL * ci * taps + t) * cout_pad + co] = b;
   }
 }
 
-extern "C" int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, void* w_fwd,
-                                      void* w_dgrad, void* stream) {
+static int pack_weight_impl(const float* w_oihw, const float* cout_scale, int cout, int cin, int ksize, int cout_pad, int cin_pad, void* w_fwd,
+                            void* w_dgrad, void* stream) {
   YB_REQUIRE(w_oihw && (w_fwd || w_dgrad), YB200_ERR_INVALID, "pack_conv_weight: null pointer");
-  YB_REQUIRE(cout > 0 && cin > 0 && (ksize == 1 || ksize == 3) && cout_pad >= cout && cin_pad >= cin, YB200_ERR_INVALID,
+  YB_REQUIRE(cout > 0 && cin > 0 && (ksize >= 1 && ksize <= 3) && cout_pad >= cout && cin_pad >= cin, YB200_ERR_INVALID,
              "pack_conv_weight: bad sizes cout=%d cin=%d k=%d pads=%d,%d", cout, cin, ksize, cout_pad, cin_pad);
   const long long total = 1LL * cout_pad * ksize * ksize * cin_pad;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
-  pack_conv_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, cout_pad, cin_pad,
+  pack_conv_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout_scale, cout, cin, ksize * ksize, cout_pad, cin_pad,
                                                                  static_cast<__nv_bfloat16*>(w_fwd),
                                                                  static_cast<__nv_bfloat16*>(w_dgrad));
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, void* w_fwd,
+                                      void* w_dgrad, void* stream) {
+  return pack_weight_impl(w_oihw, nullptr, cout, cin, ksize, cout_pad, cin_pad, w_fwd, w_dgrad, stream);
+}
+
+__global__ void scale_bias_kernel(const float* __restrict__ scale, const float* __restrict__ bias, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = scale[i] * bias[i];
+}
+
+extern "C" int yb200_pack_conv_weight_scaled(const float* w_oihw, const float* cout_scale, const float* bias, int cout, int cin, int ksize,
+                                             int cout_pad, int cin_pad, void* w_fwd, void* w_dgrad, float* scaled_bias, void* stream) {
+  YB_REQUIRE(cout_scale != nullptr, YB200_ERR_INVALID, "pack_conv_weight_scaled: null scale");
+  YB_REQUIRE((bias == nullptr) == (scaled_bias == nullptr), YB200_ERR_INVALID, "pack_conv_weight_scaled: pass both bias and scaled_bias or neither");
+  if (bias) scale_bias_kernel<<<ceil_div(cout, 256), 256, 0, as_stream(stream)>>>(cout_scale, bias, cout, scaled_bias);
+  return pack_weight_impl(w_oihw, cout_scale, cout, cin, ksize, cout_pad, cin_pad, w_fwd, w_dgrad, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -219,7 +241,7 @@ extern "C" int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, in
 static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int ksize, int stride, ConvGemmParams& p,
                            cudaStream_t st) {
   YB_REQUIRE(w_fwd != nullptr, YB200_ERR_INVALID, "conv fwd: null weights");
-  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
+  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 2 && stride == 2) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
              "conv fwd: ksize=%d stride=%d not implemented", ksize, stride);
   const int bk = pick_block_k(x->c);
   YB_REQUIRE(bk != 0, YB200_ERR_UNSUPPORTED, "conv fwd: input channels %d must be a multiple of 16", x->c);
@@ -286,6 +308,54 @@ extern "C" int yb200_conv2d_bn_silu_fwd(const yb200_act* x, const void* w_fwd, c
   return conv_fwd_common(x, w_fwd, out->c, ksize, stride, p, as_stream(stream));
 }
 
+static void set_addend(ConvGemmParams& p, const yb200_act* a) {
+  p.addend = static_cast<const __nv_bfloat16*>(a->ptr) + a->c_off;
+  p.add_sw = a->c_pitch;
+  p.add_sh = 1LL * a->c_pitch * a->w;
+  p.add_sn = 1LL * a->c_pitch * a->w * a->h;
+}
+static bool same_geometry(const yb200_act* a, const yb200_act* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c && a->c_pitch == b->c_pitch;
+}
+
+extern "C" int yb200_conv2d_affine_fwd(const yb200_act* x, const void* w_fwd, const float* scale, const float* shift,
+                                       const yb200_act* residual, const yb200_act* out, int ksize, int stride, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv2d_affine_fwd x"))) return rc;
+  if ((rc = check_act(out, "conv2d_affine_fwd out"))) return rc;
+  if (residual && (rc = check_act(residual, "conv2d_affine_fwd residual"))) return rc;
+  YB_REQUIRE(stride == 1 || stride == 2, YB200_ERR_UNSUPPORTED, "conv2d_affine_fwd: stride %d", stride);
+  YB_REQUIRE(out->n == x->n && out->h * stride == x->h && out->w * stride == x->w, YB200_ERR_INVALID,
+             "conv2d_affine_fwd: output %dx%dx%d does not match input %dx%dx%d / stride %d", out->n, out->h, out->w, x->n, x->h, x->w, stride);
+  YB_REQUIRE(!residual || (residual->n == out->n && residual->h == out->h && residual->w == out->w && residual->c == out->c), YB200_ERR_INVALID,
+             "conv2d_affine_fwd: residual shape mismatch");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_out_view(p, *out);
+  p.epi_mode = EPI_BF16_AFFINE;
+  p.scale = scale;
+  p.shift = shift;
+  if (residual) set_addend(p, residual);
+  return conv_fwd_common(x, w_fwd, out->c, ksize, stride, p, as_stream(stream));
+}
+
+extern "C" int yb200_linear_gelu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* u_out, const yb200_act* h_out,
+                                     void* stream) {
+  int rc;
+  if ((rc = check_act(x, "linear_gelu_fwd x"))) return rc;
+  if ((rc = check_act(h_out, "linear_gelu_fwd h"))) return rc;
+  if (u_out && (rc = check_act(u_out, "linear_gelu_fwd u"))) return rc;
+  YB_REQUIRE(h_out->n == x->n && h_out->h == x->h && h_out->w == x->w, YB200_ERR_INVALID, "linear_gelu_fwd: pixel grids differ");
+  YB_REQUIRE(!u_out || same_geometry(u_out, h_out), YB200_ERR_INVALID, "linear_gelu_fwd: u and h must have the same shape and channel pitch");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_out_view(p, *h_out);
+  p.epi_mode = EPI_BF16_BIAS_GELU;
+  p.shift = bias;
+  if (u_out) p.aux_out = static_cast<__nv_bfloat16*>(u_out->ptr) + u_out->c_off;
+  return conv_fwd_common(x, w_fwd, h_out->c, 1, 1, p, as_stream(stream));
+}
+
 extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, const float* bias, int cout, float* out,
                                       int a_total, int a_off, int c_total, int c_off, void* stream) {
   int rc;
@@ -309,14 +379,14 @@ extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, con
 // ------------------------------------------------------------------------------------------------
 // data gradient
 // ------------------------------------------------------------------------------------------------
-extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend,
-                                  int ksize, int stride, void* stream) {
+static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend, int ksize, int stride,
+                      const yb200_act* gelu_u, double* colsum, void* stream) {
   int rc;
   if ((rc = check_act(dz, "conv2d_dgrad dz"))) return rc;
   if ((rc = check_act(dx, "conv2d_dgrad dx"))) return rc;
   if (addend && (rc = check_act(addend, "conv2d_dgrad addend"))) return rc;
   YB_REQUIRE(w_dgrad != nullptr, YB200_ERR_INVALID, "conv2d_dgrad: null weights");
-  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
+  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 2 && stride == 2) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
              "conv2d_dgrad: ksize=%d stride=%d not implemented", ksize, stride);
   YB_REQUIRE(dz->n == dx->n && dz->h * stride == dx->h && dz->w * stride == dx->w, YB200_ERR_INVALID,
              "conv2d_dgrad: dz %dx%dx%d vs dx %dx%dx%d stride %d", dz->n, dz->h, dz->w, dx->n, dx->h, dx->w, stride);
@@ -333,6 +403,11 @@ extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, cons
   memset(&p, 0, sizeof(p));
   set_out_view(p, *dx);
   p.epi_mode = EPI_BF16;
+  if (gelu_u) {
+    p.epi_mode = EPI_BF16_GELU_BWD;
+    p.aux_in = static_cast<const __nv_bfloat16*>(gelu_u->ptr) + gelu_u->c_off;
+    p.stat_sum = colsum;
+  }
   p.cout = cin;
   p.cin_blocks = dz->c / bk;
   if (addend) {
@@ -364,7 +439,8 @@ extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, cons
   for (int ph = 0; ph < 2; ++ph)
     for (int pw = 0; pw < 2; ++pw) {
       int nt = 0;
-      for (int kh = 0; kh < 3; ++kh) {
+      if (ksize == 2) p.taps[nt++] = ConvTap{dz->c_off, 0, 0, 0, (ph * 2 + pw) * dz->c};  // 2x2 s2: input pixel (2i+ph, 2j+pw) sees only tap (ph, pw)
+      for (int kh = 0; kh < 3 && ksize == 3; ++kh) {
         if (((ph + 1 - kh) & 1) != 0) continue;
         const int dh = (ph + 1 - kh) / 2;
         for (int kw = 0; kw < 3; ++kw) {
@@ -378,6 +454,20 @@ extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, cons
       if ((rc = launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, nt * p.cin_blocks), st))) return rc;
     }
   return 0;
+}
+
+extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend,
+                                  int ksize, int stride, void* stream) {
+  return dgrad_impl(dz, w_dgrad, dx, addend, ksize, stride, nullptr, nullptr, stream);
+}
+
+extern "C" int yb200_linear_dgrad_gelu(const yb200_act* dh_src, const void* w_dgrad, const yb200_act* u, const yb200_act* du, double* bias_grad_sum,
+                                       void* stream) {
+  int rc;
+  if ((rc = check_act(u, "linear_dgrad_gelu u"))) return rc;
+  if ((rc = check_act(du, "linear_dgrad_gelu du"))) return rc;
+  YB_REQUIRE(same_geometry(u, du), YB200_ERR_INVALID, "linear_dgrad_gelu: u and du must have the same shape and channel pitch");
+  return dgrad_impl(dh_src, w_dgrad, du, nullptr, 1, 1, u, bias_grad_sum, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,7 +486,7 @@ int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, W
   int rc;
   if ((rc = check_act(x, "conv2d_wgrad x"))) return rc;
   if ((rc = check_act(dz, "conv2d_wgrad dz"))) return rc;
-  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
+  YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 2 && stride == 2) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
              "conv2d_wgrad: ksize=%d stride=%d not implemented", ksize, stride);
   YB_REQUIRE(dz->n == x->n && dz->h * stride == x->h && dz->w * stride == x->w, YB200_ERR_INVALID,
              "conv2d_wgrad: dz %dx%dx%d vs x %dx%dx%d stride %d", dz->n, dz->h, dz->w, x->n, x->h, x->w, stride);

@@ -28,7 +28,20 @@ enum EpiMode : int {
   EPI_F32_BIAS = 3,   // out = acc + bias[c]   (fp32, arbitrary element strides)
   EPI_BF16_BN_SILU = 4,  // out = bf16(SiLU(acc*scale[c] + shift[c]) [+ addend]): eval-mode BatchNorm folded into the conv
                          // (the fold of utils/checkpoint.py:11-43 applied as an epilogue), residual added after the activation
+  EPI_BF16_AFFINE = 5,   // out = bf16(acc*scale[c] + shift[c] [+ addend]); scale / shift may be null (1 / 0): Linear / Conv bias,
+                         // ConvNeXt layer scale + residual (convnext.py:54-59)
+  EPI_BF16_BIAS_GELU = 6,  // u = bf16(acc + shift[c]) -> aux_out (optional), out = bf16(GELU(u)), exact erf form (convnext.py:52-53)
+  EPI_BF16_GELU_BWD = 7,   // out = bf16(acc * GELU'(u)), u read from aux_in; optional per-channel sums of the stored values -> stat_sum
+                           // (gradient of the Linear bias that produced u)
 };
+
+__device__ __forceinline__ bool epi_has_stats(int mode, const double* stat_sum) {
+  return mode == EPI_F16_STATS || (mode == EPI_BF16_GELU_BWD && stat_sum != nullptr);
+}
+__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float u) {
+  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+}
 // The pre-BatchNorm tensor is stored in fp16, not bf16: BatchNorm subtracts the channel mean, which turns the
 // *relative* rounding error of the stored value into an error relative to the (often much smaller) channel
 // standard deviation.  fp16 has 3 more mantissa bits; its range (65504) is ample for a convolution of normalised
@@ -60,6 +73,8 @@ struct ConvGemmParams {
   const float* shift;
   double* stat_sum;
   double* stat_sq;
+  const __nv_bfloat16* aux_in;  // EPI_BF16_GELU_BWD: pre-activation u, same geometry as `out`
+  __nv_bfloat16* aux_out;       // EPI_BF16_BIAS_GELU: where u is stored (may be null), same geometry as `out`
   ConvTap taps[kMaxTaps];
 };
 
@@ -121,6 +136,41 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       }
     }
   }
+  if (p.epi_mode == EPI_BF16_AFFINE) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (cbase + i < p.cout) {
+        const float sc = p.scale ? __ldg(p.scale + cbase + i) : 1.f;
+        const float sh = p.shift ? __ldg(p.shift + cbase + i) : 0.f;
+        v[i] = fmaf(v[i], sc, sh);
+      }
+    }
+  }
+  if (p.epi_mode == EPI_BF16_BIAS_GELU) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = (cbase + i < p.cout) ? bf16_round(v[i] + (p.shift ? __ldg(p.shift + cbase + i) : 0.f)) : 0.f;
+    if (p.aux_out != nullptr && valid) {
+      __nv_bfloat16* o = p.aux_out + pix_off + cbase;
+#pragma unroll
+      for (int i = 0; i < CH; i += 8)
+        if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.epi_mode == EPI_BF16_GELU_BWD && valid) {
+    const __nv_bfloat16* a = p.aux_in + pix_off + cbase;
+#pragma unroll
+    for (int i = 0; i < CH; i += 8) {
+      if (cbase + i < p.cout) {
+        const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+        v[i + 0] *= gelu_erf_grad(bf16_lo(u.x)); v[i + 1] *= gelu_erf_grad(bf16_hi(u.x));
+        v[i + 2] *= gelu_erf_grad(bf16_lo(u.y)); v[i + 3] *= gelu_erf_grad(bf16_hi(u.y));
+        v[i + 4] *= gelu_erf_grad(bf16_lo(u.z)); v[i + 5] *= gelu_erf_grad(bf16_hi(u.z));
+        v[i + 6] *= gelu_erf_grad(bf16_lo(u.w)); v[i + 7] *= gelu_erf_grad(bf16_hi(u.w));
+      }
+    }
+  }
   if (p.addend != nullptr && valid) {
     const __nv_bfloat16* a = p.addend + add_off + cbase;
 #pragma unroll
@@ -162,6 +212,11 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       part_sum[lane] = accumulate ? part_sum[lane] + cs : cs;
       part_sq[lane] = accumulate ? part_sq[lane] + cq : cq;
     }
+  } else if (p.epi_mode == EPI_BF16_GELU_BWD && p.stat_sum != nullptr) {
+    float cs;
+    if constexpr (CH == 32) cs = warp_colsum32(v, lane);
+    else cs = warp_colsum16(v, lane);
+    if (lane < CH) part_sum[lane] = accumulate ? part_sum[lane] + cs : cs;
   }
 }
 
@@ -287,13 +342,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  if (p.epi_mode == EPI_F16_STATS) {
+  if (epi_has_stats(p.epi_mode, p.stat_sum)) {
     // one fp64 atomic per channel and CTA (after the block-wide barrier above: no named barrier, no shared atomics)
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {  // BLOCK_N may exceed the 192 threads
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
       atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
-      atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
     }
   }
 }
@@ -468,12 +523,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kTmemAlloc>(tmem_base);
-  if (p.epi_mode == EPI_F16_STATS) {
+  if (epi_has_stats(p.epi_mode, p.stat_sum)) {
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {  // BLOCK_N may exceed the 192 threads
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
       atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
-      atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
     }
   }
 }
@@ -648,12 +703,12 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   cluster_sync();  // neither CTA may free TMEM / exit while the peer's MMAs or remote arrives can still target it
   if (warp == 1) tmem_dealloc_pair<kTmemAlloc>(tmem_base);
-  if (p.epi_mode == EPI_F16_STATS) {
+  if (epi_has_stats(p.epi_mode, p.stat_sum)) {
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
       atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
-      atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
     }
   }
 }
