@@ -18,6 +18,8 @@ def cuda():
 
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # reference computations run in torch on the host: more threads than the container is granted make them slower, not faster
+    torch.set_num_threads(min(16, torch.get_num_threads()))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device("cuda:0")

@@ -28,6 +28,6 @@ for g in "${groups[@]}"; do
     *)           sel="$g" ;;
   esac
   echo "=== $g"
-  eval timeout 300 python -m pytest $sel -m gpu -q -x --timeout=120 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -60 | cut -c1-400 > gpurun_out/suite_$g.log
+  eval timeout ${SUITE_TIMEOUT:-300} python -u -m pytest $sel -m gpu -q -x --durations=5 --timeout=120 --timeout-method=thread -p no:cacheprovider ${SUITE_ARGS:-} 2>&1 | tail -80 | cut -c1-400 > gpurun_out/suite_$g.log
   tail -4 gpurun_out/suite_$g.log
 done

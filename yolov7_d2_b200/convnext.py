@@ -156,15 +156,18 @@ class ConvNeXtEngine:
             # gradient temporaries shared by the blocks of the stage
             st.g = [_T(n, h, w, c, dev), _T(n, h, w, c, dev)]   # ping-pong: gradient w.r.t. a block's output / input
             st.gout = _T(n, h, w, c, dev)                        # gradient of the returned feature (filled by the caller)
-            st.dy, st.dd = _T(n, h, w, c, dev), _T(n, h, w, c, dev)
-            st.du = _T(n, h, w, 4 * c, dev)
+            st.dy = _T(n, h, w, c, dev)
+            # double buffered: the weight-gradient kernels of block j (side stream) read them while block j-1 is being processed
+            st.dd = [_T(n, h, w, c, dev), _T(n, h, w, c, dev)]
+            st.du = [_T(n, h, w, 4 * c, dev), _T(n, h, w, 4 * c, dev)]
             st.bias_acc = torch.zeros(4 * c, dtype=torch.float64, device=dev)
             st.colsum = torch.zeros(c, device=dev)
+            st.gamma_scratch = torch.zeros(c, device=dev)
             st.raw = torch.zeros(c, 4 * c, device=dev)
             if i > 0:
                 st.g_ds = _T(n, 2 * h, 2 * w, self.dims[i - 1], dev)  # gradient w.r.t. the downsample LayerNorm output
             ws_need += [L.yb200_conv2d_wgrad_workspace(st.blocks[0].hh.a, st.g[0].a, 1, 1) if st.blocks else 16,
-                        L.yb200_conv2d_wgrad_workspace(st.blocks[0].y.a, st.du.a, 1, 1) if st.blocks else 16,
+                        L.yb200_conv2d_wgrad_workspace(st.blocks[0].y.a, st.du[0].a, 1, 1) if st.blocks else 16,
                         L.yb200_dwconv7_wgrad_workspace(st.x0.a), L.yb200_layernorm_bwd_workspace(st.x0.a), L.yb200_colsum_workspace(st.x0.a)]
             if i == 0:
                 ws_need.append(L.yb200_conv2d_wgrad_workspace(self.patches.a, st.ds_conv.a, 1, 1))
@@ -173,7 +176,12 @@ class ConvNeXtEngine:
             self.stage.append(st)
             h, w = h // 2, w // 2
         assert min(ws_need) > 0, self.L.yb200_last_error()
-        self.ws = torch.empty(max(ws_need), dtype=torch.uint8, device=dev)
+        self.ws = torch.empty(max(ws_need), dtype=torch.uint8, device=dev)        # main stream
+        self.ws_side = torch.empty(max(ws_need), dtype=torch.uint8, device=dev)   # weight-gradient stream
+        self.overlap_wgrad = True
+        self._side = torch.cuda.Stream(device=dev)
+        self._fork = [[torch.cuda.Event() for _ in st.blocks] for st in self.stage]
+        self._done = [[torch.cuda.Event() for _ in st.blocks] for st in self.stage]
         # packed bf16 weights
         d = self.dims
         bf = dict(dtype=torch.bfloat16, device=dev)
@@ -257,10 +265,30 @@ class ConvNeXtEngine:
         return tuple(self.stage[i].out.t for i in self.out_indices)
 
     # ------------------------------------------------------------------ backward
-    def _wgrad(self, x_a, dz_a, k, s, cin_real, dst, acc, label):
-        capi.check(self.L.yb200_conv2d_wgrad(x_a, dz_a, k, s, cin_real, capi.ptr(dst), acc, capi.ptr(self.ws), ctypes.c_int64(self.ws.numel()), capi.stream_ptr()),
+    def _wgrad(self, x_a, dz_a, k, s, cin_real, dst, acc, label, ws=None):
+        ws = self.ws if ws is None else ws
+        capi.check(self.L.yb200_conv2d_wgrad(x_a, dz_a, k, s, cin_real, capi.ptr(dst), acc, capi.ptr(ws), ctypes.c_int64(ws.numel()), capi.stream_ptr()),
                    "wgrad " + label)
         self._count(2, "wgrad " + label)
+
+    def _block_param_grads(self, i, j, st, b, gout, du, dd, xin, acc):
+        """every parameter gradient of one block that needs a reduction over pixels; nothing downstream reads them, so they run on the side
+        stream (own workspace) while the main stream continues with the data-gradient chain of the next block"""
+        L, sp, P, G = self.L, capi.stream_ptr(), self.params, self.grads
+        p, c = f"stages.{i}.{j}.", st.c
+        ws = self.ws_side
+        capi.check(L.yb200_colsum(gout.a, ctypes.c_float(1.0), capi.ptr(st.colsum), 0, capi.ptr(ws), sp), "colsum")
+        self._count(2, f"colsum s{i}")
+        self._wgrad(b.hh.a, gout.a, 1, 1, 4 * c, st.raw, 0, f"pwconv2 s{i}", ws)
+        has_gamma = (p + "gamma") in G
+        gg = G[p + "gamma"] if has_gamma else st.gamma_scratch
+        capi.check(L.yb200_layer_scale_grad(capi.ptr(st.raw), capi.ptr(P[p + "pwconv2.weight"]), capi.ptr(P[p + "pwconv2.bias"]), capi.ptr(self._gamma(i, j)),
+                                            capi.ptr(st.colsum), c, 4 * c, capi.ptr(G[p + "pwconv2.weight"]), capi.ptr(gg), capi.ptr(G[p + "pwconv2.bias"]),
+                                            acc if has_gamma else 0, sp), "layer scale grad")
+        self._count(1, "layer_scale_grad")
+        self._wgrad(b.y.a, du.a, 1, 1, c, G[p + "pwconv1.weight"], acc, f"pwconv1 s{i}", ws)
+        capi.check(L.yb200_dwconv7_wgrad(xin.a, dd.a, capi.ptr(G[p + "dwconv.weight"]), capi.ptr(G[p + "dwconv.bias"]), acc, capi.ptr(ws), sp), "dwconv7 wgrad")
+        self._count(2, f"dwconv7 wgrad s{i}")
 
     def backward(self, accumulate=False):
         """gradients of sum_i <out_i, gout_i> w.r.t. every parameter; the caller has filled stage[i].gout.t for i in out_indices"""
@@ -290,44 +318,51 @@ class ConvNeXtEngine:
                 G[f"norm{i}.bias"].zero_()
             assert have, "no gradient reaches stage %d" % i
             c = st.c
+            main = torch.cuda.current_stream()
+            t, last_done = 0, None
             for j in reversed(range(len(st.blocks))):
                 b = st.blocks[j]
                 p = f"stages.{i}.{j}."
                 xin = st.blocks[j - 1].out if j > 0 else st.x0
                 _, w1d, _, w2d, _ = self.packed[f"b{i}.{j}"]
                 gout, gin = st.g[cur], st.g[1 - cur]
-                capi.check(L.yb200_colsum(gout.a, ctypes.c_float(1.0), capi.ptr(st.colsum), 0, ws, sp), "colsum")
-                self._count(2, f"colsum s{i}")
-                capi.check(L.yb200_linear_dgrad_gelu(gout.a, capi.ptr(w2d), b.u.a, st.du.a, capi.ptr(st.bias_acc), sp), "dgrad pwconv2 + gelu bwd")
+                du, dd = st.du[t & 1], st.dd[t & 1]
+                capi.check(L.yb200_linear_dgrad_gelu(gout.a, capi.ptr(w2d), b.u.a, du.a, capi.ptr(st.bias_acc), sp), "dgrad pwconv2 + gelu bwd")
                 self._count(1, f"dgrad2+gelu' s{i}")
                 capi.check(L.yb200_f64_to_f32(capi.ptr(st.bias_acc), 4 * c, capi.ptr(G[p + "pwconv1.bias"]), acc, 1, sp), "db1")
                 self._count(1, "db1")
-                self._wgrad(b.hh.a, gout.a, 1, 1, 4 * c, st.raw, 0, f"pwconv2 s{i}")
-                has_gamma = (p + "gamma") in G
-                gg = G[p + "gamma"] if has_gamma else st.colsum.new_empty(c)
-                capi.check(L.yb200_layer_scale_grad(capi.ptr(st.raw), capi.ptr(P[p + "pwconv2.weight"]), capi.ptr(P[p + "pwconv2.bias"]), capi.ptr(self._gamma(i, j)),
-                                                    capi.ptr(st.colsum), c, 4 * c, capi.ptr(G[p + "pwconv2.weight"]), capi.ptr(gg), capi.ptr(G[p + "pwconv2.bias"]),
-                                                    acc if has_gamma else 0, sp), "layer scale grad")
-                self._count(1, "layer_scale_grad")
-                capi.check(L.yb200_conv2d_dgrad(st.du.a, capi.ptr(w1d), st.dy.a, None, 1, 1, sp), "dgrad pwconv1")
+                capi.check(L.yb200_conv2d_dgrad(du.a, capi.ptr(w1d), st.dy.a, None, 1, 1, sp), "dgrad pwconv1")
                 self._count(1, f"dgrad1 s{i}")
-                self._wgrad(b.y.a, st.du.a, 1, 1, c, G[p + "pwconv1.weight"], acc, f"pwconv1 s{i}")
-                capi.check(L.yb200_layernorm_bwd(st.dy.a, b.d.a, capi.ptr(b.stats), capi.ptr(P[p + "norm.weight"]), None, st.dd.a, capi.ptr(G[p + "norm.weight"]),
+                capi.check(L.yb200_layernorm_bwd(st.dy.a, b.d.a, capi.ptr(b.stats), capi.ptr(P[p + "norm.weight"]), None, dd.a, capi.ptr(G[p + "norm.weight"]),
                                                  capi.ptr(G[p + "norm.bias"]), acc, ws, sp), "block norm bwd")
                 self._count(2, f"layernorm bwd s{i}")
-                capi.check(L.yb200_dwconv7(st.dd.a, capi.ptr(P[p + "dwconv.weight"]), None, gout.a, gin.a, 1, sp), "dwconv7 dgrad")
+                if self.overlap_wgrad:
+                    self._fork[i][j].record(main)
+                    with torch.cuda.stream(self._side):
+                        self._side.wait_event(self._fork[i][j])
+                        self._block_param_grads(i, j, st, b, gout, du, dd, xin, acc)
+                        self._done[i][j].record(self._side)
+                    # the next kernel overwrites gin = the output-gradient buffer of the previous iteration, which that iteration's
+                    # weight-gradient kernels read (this also protects du / dd of two iterations ago)
+                    if last_done is not None:
+                        main.wait_event(last_done)
+                    last_done = self._done[i][j]
+                else:
+                    self._block_param_grads(i, j, st, b, gout, du, dd, xin, acc)
+                capi.check(L.yb200_dwconv7(dd.a, capi.ptr(P[p + "dwconv.weight"]), None, gout.a, gin.a, 1, sp), "dwconv7 dgrad")
                 self._count(1, f"dwconv7 dgrad s{i}")
-                capi.check(L.yb200_dwconv7_wgrad(xin.a, st.dd.a, capi.ptr(G[p + "dwconv.weight"]), capi.ptr(G[p + "dwconv.bias"]), acc, ws, sp), "dwconv7 wgrad")
-                self._count(2, f"dwconv7 wgrad s{i}")
                 cur = 1 - cur
+                t += 1
+            if last_done is not None:
+                main.wait_event(last_done)  # join before the downsample layer reuses the stage's buffers and the workspace
             g = st.g[cur]  # gradient w.r.t. the stage input x0
             if i == 0:
                 pre = "downsample_layers.0."
-                capi.check(L.yb200_layernorm_bwd(g.a, st.ds_conv.a, capi.ptr(st.ds_stats), capi.ptr(P[pre + "1.weight"]), None, st.dd.a, capi.ptr(G[pre + "1.weight"]),
+                capi.check(L.yb200_layernorm_bwd(g.a, st.ds_conv.a, capi.ptr(st.ds_stats), capi.ptr(P[pre + "1.weight"]), None, st.dd[0].a, capi.ptr(G[pre + "1.weight"]),
                                                  capi.ptr(G[pre + "1.bias"]), acc, ws, sp), "stem norm bwd")
-                capi.check(L.yb200_colsum(st.dd.a, ctypes.c_float(1.0), capi.ptr(G[pre + "0.bias"]), acc, ws, sp), "stem bias grad")
+                capi.check(L.yb200_colsum(st.dd[0].a, ctypes.c_float(1.0), capi.ptr(G[pre + "0.bias"]), acc, ws, sp), "stem bias grad")
                 self._count(4, "stem norm bwd + bias")
-                self._wgrad(self.patches.a, st.dd.a, 1, 1, 48, G[pre + "0.weight"], acc, "stem")
+                self._wgrad(self.patches.a, st.dd[0].a, 1, 1, 48, G[pre + "0.weight"], acc, "stem")
             else:
                 pre = f"downsample_layers.{i}."
                 prev = self.stage[i - 1]

@@ -126,6 +126,7 @@ static int pick_block_n(int c) {
     const char* e = getenv("YB200_CONV_BN256");
     allow256 = (e && e[0] == '0') ? 0 : 1;
   }
+  if (c > 256 && c % 256 == 128) return 128;  // e.g. 384 = 3 x 128: no half-empty 256-wide tile
   if (c >= 256 && allow256 && !use_v1_kernel()) return 256;
   return c > 64 ? 128 : (c > 32 ? 64 : (c > 16 ? 32 : 16));
 }

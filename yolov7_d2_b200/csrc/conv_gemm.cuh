@@ -38,14 +38,26 @@ enum EpiMode : int {
 __device__ __forceinline__ bool epi_has_stats(int mode, const double* stat_sum) {
   return mode == EPI_F16_STATS || (mode == EPI_BF16_GELU_BWD && stat_sum != nullptr);
 }
-__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float u) {
-  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+// Phi(u) = 0.5 (1 + erf(u / sqrt 2)) through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 resolution of the stored
+// result): one MUFU.RCP, one MUFU.EX2 and 7 FMAs instead of erff's branchy polynomial -- the GEMMs that carry these epilogues have
+// K = C and N = 4C, so they are bound by epilogue instruction issue, not by the tensor pipe.  e = exp(-u^2 / 2) is shared with GELU'.
+__device__ __forceinline__ float gelu_phi(float u, float& e) {
+  const float z = fabsf(u) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  e = __expf(-z * z);
+  const float q = 0.5f * poly * e;
+  return u >= 0.f ? 1.f - q : q;
 }
-// The pre-BatchNorm tensor is stored in fp16, not bf16: BatchNorm subtracts the channel mean, which turns the
-// *relative* rounding error of the stored value into an error relative to the (often much smaller) channel
-// standard deviation.  fp16 has 3 more mantissa bits; its range (65504) is ample for a convolution of normalised
-// activations (same exposure as the reference's AMP fp16 path).
+__device__ __forceinline__ float gelu_erf(float u) {
+  float e;
+  return u * gelu_phi(u, e);
+}
+__device__ __forceinline__ float gelu_erf_grad(float u) {
+  float e;
+  const float phi = gelu_phi(u, e);
+  return fmaf(u * 0.3989422804014327f, e, phi);
+}
 
 struct ConvTap {
   int c0;  // coordinate offset in the innermost (channel) dimension of the A map
@@ -480,6 +492,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int q = warp & 3;              // TMEM lane quadrant (must be warp_id % 4)
     const int half = (warp - 2) >> 2;    // which half of the columns this warp drains
     const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
+    // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
+    const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
@@ -500,13 +514,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int acc = it & 1;
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
+      if (cend_live <= cbeg) {  // every column of this warp's share lies beyond cout: nothing to read
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+        continue;
+      }
 #pragma unroll 1
-      for (int c = cbeg; c < cend; c += CH) {
+      for (int c = cbeg; c < cend_live; c += CH) {
         uint32_t r[CH];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c;
         if constexpr (CH == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
         tmem_ld_wait();
-        if (c + CH >= cend) {  // this warp's last chunk is in registers: hand its share of the accumulator back
+        if (c + CH >= cend_live) {  // this warp's last chunk is in registers: hand its share of the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
@@ -660,6 +679,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
+    // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
+    const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
@@ -680,12 +701,17 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int acc = it & 1;
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
+      if (cend_live <= cbeg) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * acc);
+        continue;
+      }
 #pragma unroll 1
-      for (int c = cbeg; c < cend; c += CH) {
+      for (int c = cbeg; c < cend_live; c += CH) {
         uint32_t r[CH];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c, r);
         tmem_ld_wait();
-        if (c + CH >= cend) {
+        if (c + CH >= cend_live) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * acc);
