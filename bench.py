@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-convnext", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward(+all-reduce) only, without the fused SGD step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -368,6 +369,35 @@ def main():
         nms = {"value": cand * len(clones) / (e0.elapsed_time(e1) / 1e3), "unit": "boxes/s", "candidates_per_call": cand,
                "workload": "postprocess on [%d,8400,85] clustered stress set, conf 0.001, IoU 0.65" % B}
 
+    # ---- secondary workload (BASELINE.json configs[2], per-GPU share): ConvNeXt-T backbone fwd+bwd, 32 x 640x640 ----
+    cnx_line = None
+    if rank == 0 and world == 1 and not args.no_convnext:
+        try:
+            from oracle import convnext_oracle as cnxo  # synthetic parameters / images only
+            from yolov7_d2_b200.convnext import ConvNeXtEngine
+            ce = ConvNeXtEngine(32, 640, 640, device=dev)
+            ce.load_state_dict(cnxo.convnext_state_dict(0, trained_like=True))
+            ce.images_u8.copy_(cnxo.synthetic_images(32, 640, 1).to(dev))
+            gen = torch.Generator(device=dev).manual_seed(2)
+            for st in ce.stage:
+                st.gout.t.copy_(torch.randn(st.gout.t.shape, generator=gen, device=dev) * 1e-2)
+            for _ in range(3):
+                ce.train_step()
+            torch.cuda.synchronize()
+            cl = ce.kernel_launches // 3
+            e0.record()
+            for _ in range(5):
+                ce.train_step()
+            e1.record()
+            torch.cuda.synchronize()
+            cms = e0.elapsed_time(e1) / 5
+            cnx_line = {"workload": "ConvNeXt-T backbone fwd+bwd, 32 x 640x640 (BASELINE.json configs[2] per-GPU share), eager launches", "images_per_s": 32 / cms * 1e3,
+                        "ms_per_step": cms, "tflops": 3 * 72.7 * 32 / cms, "launches_per_step": cl}
+            del ce
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            cnx_line = {"error": str(e)[:200]}
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -405,7 +435,7 @@ def main():
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                            "optimizer": None if opt is None else "fused SGD step inside the timed step (momentum 0.9, wd 5e-4, lr %g)" % BENCH_LR,
                            "l2": "per-step working set (~%.0f GB of activations and gradients) exceeds the 126 MB L2; no explicit flush" % (0.245 * B)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "cpu_baseline": cpu, "nms": nms,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "cpu_baseline": cpu, "nms": nms, "convnext": cnx_line,
                 "loss": float(eng.losses[0])}
         print(json.dumps(line), flush=True)
     if world > 1:

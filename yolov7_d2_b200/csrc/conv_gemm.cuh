@@ -127,40 +127,79 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 // One chunk (CH columns of one accumulator row per lane) of the epilogue, shared by all three kernels.
 //   part_sum / part_sq: this warp's shared-memory slots for the chunk's columns (EPI_F16_STATS); `accumulate` adds to them
 //   (persistent kernels: statistics over all tiles of the CTA) instead of overwriting.
+// Per-column parameters (scale | shift / bias) of the CTA's column tile are staged in shared memory once per CTA; the epilogue reads
+// them with 16-byte broadcast loads (per-element __ldg plus a null test per element made the parameterised epilogues 2-3x slower
+// than the plain one).  Columns beyond cout hold (1, 0).
+template <int BLOCK_N>
+__device__ __forceinline__ void stage_col_params(const ConvGemmParams& p, int col0, float (*s_col)[BLOCK_N]) {
+  const float* sh = p.shift ? p.shift : p.bias;
+  for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) {
+    const bool ok = col0 + i < p.cout;
+    s_col[0][i] = (ok && p.scale) ? p.scale[col0 + i] : 1.f;
+    s_col[1][i] = (ok && sh) ? sh[col0 + i] : 0.f;
+  }
+}
+
+// The epilogue's per-element side input (GELU_BWD: the pre-activation u; otherwise the addend / residual) is a dependent global load in
+// a warp that has nothing else to do: the persistent kernels fetch it one chunk ahead (before the accumulator barrier for the first
+// chunk of a tile) so that its latency overlaps the TMEM load and the arithmetic of the previous chunk.
+template <int CH>
+__device__ __forceinline__ void load_side_chunk(const __nv_bfloat16* side_row, bool valid, int cbase, int cout, uint4 (&dst)[CH / 8]) {
+#pragma unroll
+  for (int k = 0; k < CH / 8; ++k) {
+    dst[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid && cbase + 8 * k < cout) dst[k] = *reinterpret_cast<const uint4*>(side_row + cbase + 8 * k);
+  }
+}
+
 template <int CH>
 __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, float (&v)[CH], bool valid, long long pix_off, long long add_off,
-                                                    int cbase, int lane, float* part_sum, float* part_sq, bool accumulate) {
+                                                    int cbase, int lane, float* part_sum, float* part_sq, bool accumulate,
+                                                    const float* col_scale, const float* col_shift, const uint4* side = nullptr) {
   if (p.epi_mode == EPI_F32_BIAS) {
     if (valid) {
       float* o = reinterpret_cast<float*>(p.out) + pix_off;
 #pragma unroll
       for (int i = 0; i < CH; ++i)
-        if (cbase + i < p.cout) o[(long long)(cbase + i) * p.out_sc] = v[i] + p.bias[cbase + i];
+        if (cbase + i < p.cout) o[(long long)(cbase + i) * p.out_sc] = v[i] + col_shift[i];
     }
     return;
   }
   if (p.epi_mode == EPI_BF16_BN_SILU) {
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      if (cbase + i < p.cout) {
-        const float u = fmaf(v[i], __ldg(p.scale + cbase + i), __ldg(p.shift + cbase + i));
-        v[i] = bf16_round(__fdividef(u, 1.f + __expf(-u)));  // rounded before the residual add, as a materialised activation
-      }
+    for (int i = 0; i < CH; i += 4) {
+      const float4 sc = *reinterpret_cast<const float4*>(col_scale + i), sh = *reinterpret_cast<const float4*>(col_shift + i);
+      const float u0 = fmaf(v[i], sc.x, sh.x), u1 = fmaf(v[i + 1], sc.y, sh.y), u2 = fmaf(v[i + 2], sc.z, sh.z), u3 = fmaf(v[i + 3], sc.w, sh.w);
+      // rounded before the residual add, as a materialised activation
+      v[i] = bf16_round(__fdividef(u0, 1.f + __expf(-u0)));
+      v[i + 1] = bf16_round(__fdividef(u1, 1.f + __expf(-u1)));
+      v[i + 2] = bf16_round(__fdividef(u2, 1.f + __expf(-u2)));
+      v[i + 3] = bf16_round(__fdividef(u3, 1.f + __expf(-u3)));
     }
   }
   if (p.epi_mode == EPI_BF16_AFFINE) {
+    if (p.scale != nullptr) {
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      if (cbase + i < p.cout) {
-        const float sc = p.scale ? __ldg(p.scale + cbase + i) : 1.f;
-        const float sh = p.shift ? __ldg(p.shift + cbase + i) : 0.f;
-        v[i] = fmaf(v[i], sc, sh);
+      for (int i = 0; i < CH; i += 4) {
+        const float4 sc = *reinterpret_cast<const float4*>(col_scale + i);
+        v[i] *= sc.x; v[i + 1] *= sc.y; v[i + 2] *= sc.z; v[i + 3] *= sc.w;
+      }
+    }
+    if (p.shift != nullptr) {
+#pragma unroll
+      for (int i = 0; i < CH; i += 4) {
+        const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
+        v[i] += sh.x; v[i + 1] += sh.y; v[i + 2] += sh.z; v[i + 3] += sh.w;
       }
     }
   }
   if (p.epi_mode == EPI_BF16_BIAS_GELU) {
 #pragma unroll
-    for (int i = 0; i < CH; ++i) v[i] = (cbase + i < p.cout) ? bf16_round(v[i] + (p.shift ? __ldg(p.shift + cbase + i) : 0.f)) : 0.f;
+    for (int i = 0; i < CH; i += 4) {
+      const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
+      v[i] = bf16_round(v[i] + sh.x); v[i + 1] = bf16_round(v[i + 1] + sh.y);
+      v[i + 2] = bf16_round(v[i + 2] + sh.z); v[i + 3] = bf16_round(v[i + 3] + sh.w);
+    }
     if (p.aux_out != nullptr && valid) {
       __nv_bfloat16* o = p.aux_out + pix_off + cbase;
 #pragma unroll
@@ -175,7 +214,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
 #pragma unroll
     for (int i = 0; i < CH; i += 8) {
       if (cbase + i < p.cout) {
-        const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+        const uint4 u = side ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
         v[i + 0] *= gelu_erf_grad(bf16_lo(u.x)); v[i + 1] *= gelu_erf_grad(bf16_hi(u.x));
         v[i + 2] *= gelu_erf_grad(bf16_lo(u.y)); v[i + 3] *= gelu_erf_grad(bf16_hi(u.y));
         v[i + 4] *= gelu_erf_grad(bf16_lo(u.z)); v[i + 5] *= gelu_erf_grad(bf16_hi(u.z));
@@ -188,7 +227,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
 #pragma unroll
     for (int i = 0; i < CH; i += 8) {
       if (cbase + i < p.cout) {
-        const uint4 u = *reinterpret_cast<const uint4*>(a + i);
+        const uint4 u = (side && p.epi_mode != EPI_BF16_GELU_BWD) ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
         v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
         v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
         v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
@@ -241,6 +280,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t s_bar[2 * kMaxStages + 1];
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[4][2][BLOCK_N];  // per epilogue warp: column sums / sums of squares of its 32 rows
+  __shared__ __align__(16) float s_col[2][BLOCK_N];  // per-column scale | shift of this column tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -268,6 +308,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(bar_acc, 1);
     mbar_fence_init();
   }
+  stage_col_params<BLOCK_N>(p, col0, s_col);
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(&s_tmem));
   tc_fence_before();
   __syncthreads();
@@ -347,7 +388,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
       const int cbase = col0 + c;
-      conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], false);
+      conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], false, &s_col[0][c], &s_col[1][c]);
     }
   }
 
@@ -390,6 +431,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   __shared__ __align__(8) uint64_t s_bar[2 * kMaxStagesP + 4];
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[4][2][BLOCK_N];
+  __shared__ __align__(16) float s_col[2][BLOCK_N];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -418,6 +460,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 4 * 2 * BLOCK_N; i += blockDim.x) (&s_part[0][0][0])[i] = 0.f;
+  stage_col_params<BLOCK_N>(p, col0, s_col);
   if (warp == 1) tmem_alloc<kTmemAlloc>(smem_u32(&s_tmem));
   tc_fence_before();
   __syncthreads();
@@ -494,6 +537,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
     // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
     const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
+    const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD;
+    const __nv_bfloat16* side_base = (BLOCK_N == 256) ? (side_is_aux ? p.aux_in : p.addend) : nullptr;  // narrower tiles run 2 CTAs / SM at 96 registers: no room
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
@@ -512,6 +557,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const long long add_off = (long long)n * p.add_sn + (long long)(y * p.out_mh + p.out_ph) * p.add_sh +
                                 (long long)(x * p.out_mw + p.out_pw) * p.add_sw;
       const int acc = it & 1;
+      const __nv_bfloat16* side_row = side_base ? side_base + (side_is_aux ? pix_off : add_off) : nullptr;
+      uint4 side[CH / 8];
+      if constexpr (BLOCK_N == 256) {
+        if (side_base != nullptr && cend_live > cbeg) load_side_chunk<CH>(side_row, valid, col0 + cbeg, p.cout, side);  // in flight during the barrier wait
+      }
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       if (cend_live <= cbeg) {  // every column of this warp's share lies beyond cout: nothing to read
@@ -524,6 +574,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         uint32_t r[CH];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c;
         if constexpr (CH == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
+        uint4 side_next[CH / 8];
+        const bool more = side_base != nullptr && c + CH < cend_live;
+        if constexpr (BLOCK_N == 256) {  // registers to spare (one CTA per SM): fetch the next chunk's side input before using this one
+          if (more) load_side_chunk<CH>(side_row, valid, col0 + c + CH, p.cout, side_next);
+        }
         tmem_ld_wait();
         if (c + CH >= cend_live) {  // this warp's last chunk is in registers: hand its share of the accumulator back
           tc_fence_before();
@@ -534,7 +589,14 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
-        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true);
+        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
+                                (BLOCK_N == 256 && side_base) ? side : nullptr);
+        if constexpr (BLOCK_N == 256) {
+          if (more) {
+#pragma unroll
+            for (int k = 0; k < CH / 8; ++k) side[k] = side_next[k];
+          }
+        }
       }
     }
   }
@@ -576,6 +638,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ __align__(8) uint64_t s_bar[2 * kMaxStagesP + 4];
   __shared__ uint32_t s_tmem;
   __shared__ float s_part[4][2][BLOCK_N];
+  __shared__ __align__(16) float s_col[2][BLOCK_N];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -608,6 +671,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 4 * 2 * BLOCK_N; i += blockDim.x) (&s_part[0][0][0])[i] = 0.f;
+  stage_col_params<BLOCK_N>(p, col0, s_col);
   if (warp == 1) tmem_alloc_pair<kTmemAlloc>(smem_u32(&s_tmem));
   tc_fence_before();
   __syncthreads();
@@ -681,6 +745,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
     // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
     const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
+    const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD;
+    const __nv_bfloat16* side_base = side_is_aux ? p.aux_in : p.addend;
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
@@ -699,6 +765,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const long long add_off = (long long)n * p.add_sn + (long long)(y * p.out_mh + p.out_ph) * p.add_sh +
                                 (long long)(x * p.out_mw + p.out_pw) * p.add_sw;
       const int acc = it & 1;
+      const __nv_bfloat16* side_row = side_base ? side_base + (side_is_aux ? pix_off : add_off) : nullptr;
+      uint4 side[CH / 8];
+      if (side_base != nullptr && cend_live > cbeg) load_side_chunk<CH>(side_row, valid, col0 + cbeg, p.cout, side);  // in flight during the barrier wait
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       if (cend_live <= cbeg) {
@@ -710,6 +779,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int c = cbeg; c < cend_live; c += CH) {
         uint32_t r[CH];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c, r);
+        uint4 side_next[CH / 8];
+        const bool more = side_base != nullptr && c + CH < cend_live;
+        if (more) load_side_chunk<CH>(side_row, valid, col0 + c + CH, p.cout, side_next);
         tmem_ld_wait();
         if (c + CH >= cend_live) {
           tc_fence_before();
@@ -720,7 +792,12 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
-        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true);
+        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
+                                side_base ? side : nullptr);
+        if (more) {
+#pragma unroll
+          for (int k = 0; k < CH / 8; ++k) side[k] = side_next[k];
+        }
       }
     }
   }
