@@ -86,3 +86,48 @@ def test_forward_eval_contract(model):
     assert inst.scores.shape == (n,) and inst.pred_classes.shape == (n,)
     assert (inst.pred_boxes.tensor[:, 2] <= 320 + 1e-3).all()
     m.train()
+
+
+@pytest.mark.gpu
+def test_prefetch_gives_identical_steps_and_flat_optimizer_trains(model, cuda):
+    """model.prefetch(next) + forward(next) equals forward(next) alone (same buffers content, same kernels); the flat optimizer built by
+    the reference-named mapper updates the very tensors the module exposes"""
+    import bench
+    from yolov7_d2_b200 import optim
+
+    m, _ = model
+    m.train()
+    ba = bench.batched_inputs_from(*orc.synthetic_batch(2, 160, 31, max_gt=4))
+    bb = bench.batched_inputs_from(*orc.synthetic_batch(2, 160, 32, max_gt=4))
+    with torch.no_grad():
+        ref_a = float(m(ba)["total_loss"])
+        ref_b = float(m(bb)["total_loss"])
+        la = m(ba)["total_loss"]
+        m.prefetch(bb)                  # copies run behind forward(ba)
+        lb = m(bb)["total_loss"]        # swaps buffers
+        m.prefetch(ba)
+        la2 = m(ba)["total_loss"]
+    assert float(la) == ref_a and float(lb) == ref_b and float(la2) == ref_a
+    # a stale prefetch (different list object) is ignored
+    m.prefetch(bb)
+    with torch.no_grad():
+        assert float(m(bench.batched_inputs_from(*orc.synthetic_batch(2, 160, 31, max_gt=4)))["total_loss"]) == ref_a
+
+    class S:
+        OPTIMIZER, BASE_LR, MOMENTUM, NESTEROV, WEIGHT_DECAY, WEIGHT_DECAY_NORM = "SGD", 1e-3, 0.9, False, 5e-4, 0.0
+
+    class C:
+        SOLVER = S()
+
+    opt = optim.build_optimizer_mapper(C(), m)
+    w = dict(m.named_parameters())["head.cls_preds.0.bias"]
+    before = w.detach().clone()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        out = m(ba)
+        out["total_loss"].backward()
+        assert w.grad.data_ptr() == m.engine.grads["head.cls_preds.0.bias"].data_ptr()  # gradients land in the flat buffer
+        opt.step()
+        losses.append(float(out["total_loss"].detach()))
+    assert not torch.equal(before, w.detach()) and losses[-1] < losses[0]

@@ -273,6 +273,8 @@ class YOLOX(nn.Module):
         self.head.initialize_biases(1e-2)
         self._param_list = None
         self._flat_grads = False
+        self._copy_stream = None
+        self._prefetched = None
 
     @property
     def engine(self):
@@ -285,6 +287,14 @@ class YOLOX(nn.Module):
         for name, p in zip(self._root.param_names, self._params_in_engine_order()):
             p.grad = self._root.grads[name]
         self._flat_grads = True
+
+    def _ensure_flat_grads(self):
+        """zero_grad(set_to_none=True) (torch's default) drops the views: re-attach them, zeroed, which is what "none" means to autograd"""
+        for name, p in zip(self._root.param_names, self._params_in_engine_order()):
+            view = self._root.grads[name]
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                view.zero_()
+                p.grad = view
 
     def update_iter(self, i):
         self.iter = i
@@ -303,17 +313,19 @@ class YOLOX(nn.Module):
             self._param_list = [by_name[n] for n in self._root.param_names]
         return self._param_list
 
-    def preprocess_image(self, batched_inputs, training):
-        """yolox.py:95-162: stack uint8 CHW images (padded bottom/right to a multiple of 32; pad pixels = PADDED_VALUE on the
-        device), build [B, max_boxes, 5] = (cls, cx, cy, w, h) labels from XYXY gt boxes."""
+    def _plan_for(self, batched_inputs):
         imgs = [x["image"] for x in batched_inputs]
         hmax = max(i.shape[-2] for i in imgs)
         wmax = max(i.shape[-1] for i in imgs)
         hp, wp = (hmax + 31) // 32 * 32, (wmax + 31) // 32 * 32
-        eng = self._plan(len(imgs), hp, wp)
+        return self._plan(len(imgs), hp, wp), imgs, hp, wp
+
+    def _stage_batch(self, batched_inputs, training, eng, imgs, hp, wp, images_dst, labels_dst, hw_dst):
+        """copies of one batch into device buffers on the CURRENT stream (yolox.py:95-162: uint8 CHW images padded bottom/right to a
+        multiple of 32 -- pad pixels become PADDED_VALUE on the device --, labels [B, max_boxes, 5] = (cls, cx, cy, w, h) from XYXY boxes)"""
         same = all(i.shape[-2:] == (hp, wp) and i.dtype == torch.uint8 for i in imgs)
         if same and all(i.is_cuda for i in imgs):
-            eng.images_u8.copy_(torch.stack(imgs))
+            images_dst.copy_(torch.stack(imgs))
         elif same:
             # host images: one H2D copy of the whole batch.  If the images already are consecutive slices of one pinned
             # tensor (a collated batch) it is used as is; otherwise they are gathered into a persistent pinned staging buffer.
@@ -324,21 +336,20 @@ class YOLOX(nn.Module):
                 src = torch.as_strided(base, (len(imgs), 3, hp, wp), (nbytes, hp * wp, wp, 1))
             else:
                 if getattr(eng, "_stage", None) is None:
-                    eng._stage = torch.empty(eng.images_u8.shape, dtype=torch.uint8).pin_memory()
+                    eng._stage = torch.empty(images_dst.shape, dtype=torch.uint8).pin_memory()
                     eng._stage_evt = torch.cuda.Event()
                 else:
-                    eng._stage_evt.synchronize()  # the previous step's DMA out of the staging buffer has finished
+                    eng._stage_evt.synchronize()  # the previous DMA out of the staging buffer has finished
                 for k, im in enumerate(imgs):
                     eng._stage[k].copy_(im)
                 src = eng._stage
-            eng.images_u8.copy_(src, non_blocking=True)
+            images_dst.copy_(src, non_blocking=True)
             if not contiguous_run:
                 eng._stage_evt.record()
         else:
             for k, im in enumerate(imgs):
-                eng.images_u8[k, :, :im.shape[-2], :im.shape[-1]].copy_(im.to(torch.uint8), non_blocking=True)
-        eng.hw_valid.copy_(torch.tensor([[i.shape[-2], i.shape[-1]] for i in imgs], dtype=torch.int32), non_blocking=True)
-        image_sizes = [(i.shape[-2], i.shape[-1]) for i in imgs]
+                images_dst[k, :, :im.shape[-2], :im.shape[-1]].copy_(im.to(torch.uint8), non_blocking=True)
+        hw_dst.copy_(torch.tensor([[i.shape[-2], i.shape[-1]] for i in imgs], dtype=torch.int32), non_blocking=True)
         if training:
             labels = torch.zeros(len(imgs), self.max_boxes_num, 5)
             for k, x in enumerate(batched_inputs):
@@ -353,13 +364,46 @@ class YOLOX(nn.Module):
                 labels[k, :n, 2] = (boxes[:, 1] + boxes[:, 3]) / 2
                 labels[k, :n, 3] = boxes[:, 2] - boxes[:, 0]
                 labels[k, :n, 4] = boxes[:, 3] - boxes[:, 1]
-            eng.labels.copy_(labels, non_blocking=True)
+            labels_dst.copy_(labels, non_blocking=True)
+
+    def prefetch(self, batched_inputs):
+        """Input-side pipelining: start the host->device copies of the NEXT batch on a copy stream while the
+        current step is still running; the following `forward(batched_inputs)` with this same list only swaps buffers.  The copies go
+        into the plan's alternate buffers, after everything already enqueued on the compute stream (so the step that last used them has
+        finished).  Optional: forward() alone behaves exactly like the reference (copy, then compute)."""
+        eng, imgs, hp, wp = self._plan_for(batched_inputs)
+        if getattr(eng, "_alt", None) is None:
+            eng._alt = (torch.empty_like(eng.images_u8), torch.empty_like(eng.labels), torch.empty_like(eng.hw_valid))
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copy_fence, self._copy_done = torch.cuda.Event(), torch.cuda.Event()
+        self._copy_fence.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._copy_fence)
+            self._stage_batch(batched_inputs, self.training, eng, imgs, hp, wp, *eng._alt)
+            self._copy_done.record(self._copy_stream)
+        self._prefetched = (batched_inputs, eng)
+
+    def preprocess_image(self, batched_inputs, training):
+        eng, imgs, hp, wp = self._plan_for(batched_inputs)
+        image_sizes = [(i.shape[-2], i.shape[-1]) for i in imgs]
+        pre = self._prefetched
+        if pre is not None and pre[0] is batched_inputs and pre[1] is eng:
+            torch.cuda.current_stream().wait_event(self._copy_done)
+            alt = eng._alt
+            eng._alt = (eng.images_u8, eng.labels, eng.hw_valid)
+            eng.images_u8, eng.labels, eng.hw_valid = alt
+            self._prefetched = None
+            return eng, image_sizes
+        self._stage_batch(batched_inputs, training, eng, imgs, hp, wp, eng.images_u8, eng.labels, eng.hw_valid)
         return eng, image_sizes
 
     # -- forward ---------------------------------------------------------------------------------
     def forward(self, batched_inputs):
         eng, image_sizes = self.preprocess_image(batched_inputs, self.training)
         if self.training:
+            if self._flat_grads:
+                self._ensure_flat_grads()
             total, iou, conf, cls = _TrainStep.apply(eng, self._flat_grads, *self._params_in_engine_order())
             return {"total_loss": total, "iou_loss": iou, "conf_loss": conf, "cls_loss": cls}
         with torch.no_grad():
