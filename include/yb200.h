@@ -235,6 +235,16 @@ int yb200_patchify4(const void* images_nchw, int is_f32, int n, int h, int w, co
 /* dst[i] = (accumulate ? dst[i] : 0) + (float)src[i]; src[i] = 0 when zero_src (fp64 accumulators of the GEMM epilogues -> fp32 gradients) */
 int yb200_f64_to_f32(double* src, int n, float* dst, int accumulate, int zero_src, void* stream);
 
+/* ---- DETR transformer attention (yolov7/modeling/backbone/detr_backbone.py:140,157-161,200-236) -------------
+ * The core of nn.MultiheadAttention between in_proj and out_proj, head dimension 32:
+ *   out[b, i, h, :] = softmax_j(scale * <q[b,i,h,:], k[b,j,h,:]> + (key_padding_mask[b,j] ? -inf : 0)) . v[b,j,h,:]
+ * q / out: views [B][1][Lq][heads*32], k / v: [B][1][Lk][heads*32] (token-major, head h = channels [32h, 32h+32) of the view; q, k, v may be
+ * slices of one packed in_proj output).  key_padding_mask: uint8 [B][Lk], 1 = ignore, or NULL.  scale: head_dim^-0.5 in the reference.
+ * lse (fp32 [B][heads][Lq], may be NULL) receives log sum_j exp(scaled masked score), the statistic a backward pass needs.
+ * A query whose keys are all masked yields zeros (torch yields NaN).  in_proj / out_proj / FFN are yb200_conv2d_affine_fwd calls.          */
+int yb200_attention_fwd(const yb200_act* q, const yb200_act* k, const yb200_act* v, const uint8_t* key_padding_mask, float scale,
+                        const yb200_act* out, float* lse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
