@@ -244,6 +244,12 @@ int yb200_f64_to_f32(double* src, int n, float* dst, int accumulate, int zero_sr
  * A query whose keys are all masked yields zeros (torch yields NaN).  in_proj / out_proj / FFN are yb200_conv2d_affine_fwd calls.          */
 int yb200_attention_fwd(const yb200_act* q, const yb200_act* k, const yb200_act* v, const uint8_t* key_padding_mask, float scale,
                         const yb200_act* out, float* lse, void* stream);
+/* Linear + ReLU of the transformer FFN (detr_backbone.py:167, 239): h = bf16(max(x W^T + bias, 0))                                        */
+int yb200_linear_relu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* h_out, void* stream);
+/* du = bf16(h > 0 ? dz W : 0) and optionally bias_grad_sum[c] += column sums of du (fp64): data gradient of linear2 fused with ReLU backward */
+int yb200_linear_dgrad_relu(const yb200_act* dz, const void* w_dgrad, const yb200_act* h, const yb200_act* du, double* bias_grad_sum, void* stream);
+/* out = a + b (bf16 views of equal shape): tensor + positional embedding (detr_backbone.py:154-155, 218-219)                                */
+int yb200_add(const yb200_act* a, const yb200_act* b, const yb200_act* out, void* stream);
 
 #ifdef __cplusplus
 }

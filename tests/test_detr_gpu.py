@@ -1,0 +1,96 @@
+"""DETR transformer layers (yolov7_d2_b200.detr) against the outputs of the unmodified reference layers (tests/golden/detr.npz).
+The CUDA path stores every intermediate in bf16 (the reference is fp32): tolerance 4e-2 of the output's max and correlation > 0.999
+(LayerNorm outputs are O(1); each of the ~8 stored intermediates contributes rel 2^-8 rounding)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import detr_oracle as dto
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "detr.npz")
+
+
+def _check(got, ref, what):
+    got, ref = got.float().cpu(), torch.as_tensor(np.asarray(ref)).float()
+    assert torch.isfinite(got).all(), what
+    err = (got - ref).abs().max().item()
+    cos = torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm())
+    assert err <= 4e-2 * ref.abs().max().item() and cos > 0.999, f"{what}: max err {err:.4f} (max |ref| {ref.abs().max().item():.3f}), cos {cos:.5f}"
+
+
+def test_encoder_layer_matches_reference(cuda):
+    from yolov7_d2_b200.detr import TransformerEncoderLayer
+
+    gold = np.load(GOLD, allow_pickle=False)
+    d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
+    layer = TransformerEncoderLayer(d, nhead, dim_feedforward=ffn, dropout=0.0)
+    layer.load_state_dict({k: v.to(cuda) for k, v in dto.layer_state_dict("encoder", d, ffn, seed=2).items()}, strict=True)
+    layer.eval()
+    out = layer(torch.tensor(gold["enc_src"]).to(cuda), src_key_padding_mask=torch.tensor(gold["enc_mask"]).to(cuda), pos=torch.tensor(gold["enc_pos"]).to(cuda))
+    assert out.shape == (L, b, d) and out.dtype == torch.float32
+    _check(out, gold["enc_out"], "encoder layer output")
+    # without mask / positional embedding: against the oracle (pinned to the reference by tests/test_detr_oracle_golden.py)
+    sd = {"l." + k: v for k, v in dto.layer_state_dict("encoder", d, ffn, seed=2).items()}
+    src = torch.tensor(gold["enc_src"])
+    _check(layer(src.to(cuda)), dto.encoder_layer_post(src, sd, "l.", nhead), "encoder layer, no mask / pos")
+
+
+def test_decoder_layer_matches_reference(cuda):
+    from yolov7_d2_b200.detr import TransformerDecoderLayer
+
+    gold = np.load(GOLD, allow_pickle=False)
+    d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
+    layer = TransformerDecoderLayer(d, nhead, dim_feedforward=ffn, dropout=0.0)
+    layer.load_state_dict({k: v.to(cuda) for k, v in dto.layer_state_dict("decoder", d, ffn, seed=3).items()}, strict=True)
+    layer.eval()
+    t = lambda k: torch.tensor(gold[k]).to(cuda)
+    out = layer(t("dec_tgt"), t("dec_mem"), memory_key_padding_mask=t("enc_mask"), pos=t("enc_pos"), query_pos=t("dec_qpos"))
+    _check(out, gold["dec_out"], "decoder layer output")
+
+
+def test_layers_refuse_what_is_not_built(cuda):
+    from yolov7_d2_b200 import capi
+    from yolov7_d2_b200.detr import TransformerEncoderLayer
+
+    with pytest.raises(capi.Yb200Error):
+        TransformerEncoderLayer(96, 2)  # head dimension 48
+    layer = TransformerEncoderLayer(64, 2, dim_feedforward=128)
+    with pytest.raises(capi.Yb200Error):
+        layer(torch.randn(10, 1, 64))  # CPU tensor
+    with pytest.raises(capi.Yb200Error):
+        layer(torch.randn(10, 1, 64, device=cuda), src_mask=torch.zeros(10, 10, device=cuda))
+
+
+def test_relu_epilogues(cuda):
+    """Linear + ReLU forward and the ReLU-masked data gradient with bias-gradient sums (FFN of detr_backbone.py:167)"""
+    import ctypes
+    import torch.nn.functional as F
+    from yolov7_d2_b200 import capi
+
+    L_ = capi.lib()
+    b, l, e, ff = 2, 150, 64, 256
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(b, 1, l, e, generator=g).to(cuda).to(torch.bfloat16)
+    w1 = (torch.randn(ff, e, generator=g) / e ** 0.5).to(cuda).to(torch.bfloat16).float()
+    b1 = (torch.randn(ff, generator=g) * 0.3).to(cuda)
+    wf = torch.empty(ff, 1, e, dtype=torch.bfloat16, device=cuda)
+    capi.check(L_.yb200_pack_conv_weight(capi.ptr(w1), ff, e, 1, ff, e, capi.ptr(wf), None, capi.stream_ptr()), "pack")
+    h = torch.full((b, 1, l, ff), float("nan"), dtype=torch.bfloat16, device=cuda)
+    xa, ha = capi.act(x), capi.act(h)
+    capi.check(L_.yb200_linear_relu_fwd(ctypes.byref(xa), capi.ptr(wf), capi.ptr(b1), ctypes.byref(ha), capi.stream_ptr()), "linear_relu")
+    ref = F.relu(F.linear(x.float(), w1, b1))
+    assert (h.float() - ref).abs().max() <= 2.0 ** -7 * ref.abs().max()
+    dz = torch.randn(b, 1, l, e, generator=g).to(cuda).to(torch.bfloat16)
+    w2 = (torch.randn(e, ff, generator=g) / ff ** 0.5).to(cuda).to(torch.bfloat16).float()
+    wd = torch.empty(ff, 1, e, dtype=torch.bfloat16, device=cuda)
+    capi.check(L_.yb200_pack_conv_weight(capi.ptr(w2), e, ff, 1, e, ff, None, capi.ptr(wd), capi.stream_ptr()), "pack")
+    du = torch.full_like(h, float("nan"))
+    acc = torch.zeros(ff, dtype=torch.float64, device=cuda)
+    dza, dua = capi.act(dz), capi.act(du)
+    capi.check(L_.yb200_linear_dgrad_relu(ctypes.byref(dza), capi.ptr(wd), ctypes.byref(ha), ctypes.byref(dua), capi.ptr(acc), capi.stream_ptr()), "dgrad_relu")
+    refd = F.linear(dz.float(), w2.t()) * (h.float() > 0)
+    assert (du.float() - refd).abs().max() <= 2.0 ** -7 * refd.abs().max()
+    assert (acc.float() - du.float().sum((0, 1, 2))).abs().max() <= 1e-4 * du.float().sum((0, 1, 2)).abs().max() + 1e-4

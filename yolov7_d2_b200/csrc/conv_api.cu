@@ -340,6 +340,19 @@ extern "C" int yb200_conv2d_affine_fwd(const yb200_act* x, const void* w_fwd, co
   return conv_fwd_common(x, w_fwd, out->c, ksize, stride, p, as_stream(stream));
 }
 
+extern "C" int yb200_linear_relu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* h_out, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "linear_relu_fwd x"))) return rc;
+  if ((rc = check_act(h_out, "linear_relu_fwd h"))) return rc;
+  YB_REQUIRE(h_out->n == x->n && h_out->h == x->h && h_out->w == x->w, YB200_ERR_INVALID, "linear_relu_fwd: pixel grids differ");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_out_view(p, *h_out);
+  p.epi_mode = EPI_BF16_BIAS_RELU;
+  p.shift = bias;
+  return conv_fwd_common(x, w_fwd, h_out->c, 1, 1, p, as_stream(stream));
+}
+
 extern "C" int yb200_linear_gelu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* u_out, const yb200_act* h_out,
                                      void* stream) {
   int rc;
@@ -381,7 +394,7 @@ extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, con
 // data gradient
 // ------------------------------------------------------------------------------------------------
 static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend, int ksize, int stride,
-                      const yb200_act* gelu_u, double* colsum, void* stream) {
+                      const yb200_act* gelu_u, double* colsum, void* stream, int act_mode = EPI_BF16_GELU_BWD) {
   int rc;
   if ((rc = check_act(dz, "conv2d_dgrad dz"))) return rc;
   if ((rc = check_act(dx, "conv2d_dgrad dx"))) return rc;
@@ -405,7 +418,7 @@ static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act*
   set_out_view(p, *dx);
   p.epi_mode = EPI_BF16;
   if (gelu_u) {
-    p.epi_mode = EPI_BF16_GELU_BWD;
+    p.epi_mode = act_mode;
     p.aux_in = static_cast<const __nv_bfloat16*>(gelu_u->ptr) + gelu_u->c_off;
     p.stat_sum = colsum;
   }
@@ -469,6 +482,15 @@ extern "C" int yb200_linear_dgrad_gelu(const yb200_act* dh_src, const void* w_dg
   if ((rc = check_act(du, "linear_dgrad_gelu du"))) return rc;
   YB_REQUIRE(same_geometry(u, du), YB200_ERR_INVALID, "linear_dgrad_gelu: u and du must have the same shape and channel pitch");
   return dgrad_impl(dh_src, w_dgrad, du, nullptr, 1, 1, u, bias_grad_sum, stream);
+}
+
+extern "C" int yb200_linear_dgrad_relu(const yb200_act* dz, const void* w_dgrad, const yb200_act* h, const yb200_act* du, double* bias_grad_sum,
+                                       void* stream) {
+  int rc;
+  if ((rc = check_act(h, "linear_dgrad_relu h"))) return rc;
+  if ((rc = check_act(du, "linear_dgrad_relu du"))) return rc;
+  YB_REQUIRE(same_geometry(h, du), YB200_ERR_INVALID, "linear_dgrad_relu: h and du must have the same shape and channel pitch");
+  return dgrad_impl(dz, w_dgrad, du, nullptr, 1, 1, h, bias_grad_sum, stream, EPI_BF16_RELU_BWD);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,10 +33,12 @@ enum EpiMode : int {
   EPI_BF16_BIAS_GELU = 6,  // u = bf16(acc + shift[c]) -> aux_out (optional), out = bf16(GELU(u)), exact erf form (convnext.py:52-53)
   EPI_BF16_GELU_BWD = 7,   // out = bf16(acc * GELU'(u)), u read from aux_in; optional per-channel sums of the stored values -> stat_sum
                            // (gradient of the Linear bias that produced u)
+  EPI_BF16_BIAS_RELU = 8,  // out = bf16(max(acc + shift[c], 0)): Linear + ReLU of the transformer FFN (detr_backbone.py:167)
+  EPI_BF16_RELU_BWD = 9,   // out = bf16(aux_in > 0 ? acc : 0) (aux_in = the ReLU output); optional column sums -> stat_sum
 };
 
 __device__ __forceinline__ bool epi_has_stats(int mode, const double* stat_sum) {
-  return mode == EPI_F16_STATS || (mode == EPI_BF16_GELU_BWD && stat_sum != nullptr);
+  return mode == EPI_F16_STATS || ((mode == EPI_BF16_GELU_BWD || mode == EPI_BF16_RELU_BWD) && stat_sum != nullptr);
 }
 // Phi(u) = 0.5 (1 + erf(u / sqrt 2)) through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 resolution of the stored
 // result): one MUFU.RCP, one MUFU.EX2 and 7 FMAs instead of erff's branchy polynomial -- the GEMMs that carry these epilogues have
@@ -193,6 +195,28 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       }
     }
   }
+  if (p.epi_mode == EPI_BF16_BIAS_RELU) {
+#pragma unroll
+    for (int i = 0; i < CH; i += 4) {
+      const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
+      v[i] = fmaxf(v[i] + sh.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + sh.y, 0.f);
+      v[i + 2] = fmaxf(v[i + 2] + sh.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + sh.w, 0.f);
+    }
+  }
+  if (p.epi_mode == EPI_BF16_RELU_BWD && valid) {
+    const __nv_bfloat16* a = p.aux_in + pix_off + cbase;
+#pragma unroll
+    for (int i = 0; i < CH; i += 8) {
+      if (cbase + i < p.cout) {
+        const uint4 u = side ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
+        // bf16 sign / zero test on the raw bits: positive and non-zero
+        v[i + 0] = (u.x & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 0] : 0.f; v[i + 1] = (u.x >> 16) - 1u < 0x7FFFu ? v[i + 1] : 0.f;
+        v[i + 2] = (u.y & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 2] : 0.f; v[i + 3] = (u.y >> 16) - 1u < 0x7FFFu ? v[i + 3] : 0.f;
+        v[i + 4] = (u.z & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 4] : 0.f; v[i + 5] = (u.z >> 16) - 1u < 0x7FFFu ? v[i + 5] : 0.f;
+        v[i + 6] = (u.w & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 6] : 0.f; v[i + 7] = (u.w >> 16) - 1u < 0x7FFFu ? v[i + 7] : 0.f;
+      }
+    }
+  }
   if (p.epi_mode == EPI_BF16_BIAS_GELU) {
 #pragma unroll
     for (int i = 0; i < CH; i += 4) {
@@ -227,7 +251,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
 #pragma unroll
     for (int i = 0; i < CH; i += 8) {
       if (cbase + i < p.cout) {
-        const uint4 u = (side && p.epi_mode != EPI_BF16_GELU_BWD) ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
+        const uint4 u = (side && p.epi_mode != EPI_BF16_GELU_BWD && p.epi_mode != EPI_BF16_RELU_BWD) ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
         v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
         v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
         v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
@@ -263,7 +287,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       part_sum[lane] = accumulate ? part_sum[lane] + cs : cs;
       part_sq[lane] = accumulate ? part_sq[lane] + cq : cq;
     }
-  } else if (p.epi_mode == EPI_BF16_GELU_BWD && p.stat_sum != nullptr) {
+  } else if ((p.epi_mode == EPI_BF16_GELU_BWD || p.epi_mode == EPI_BF16_RELU_BWD) && p.stat_sum != nullptr) {
     float cs;
     if constexpr (CH == 32) cs = warp_colsum32(v, lane);
     else cs = warp_colsum16(v, lane);
@@ -537,7 +561,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
     // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
     const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
-    const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD;
+    const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD || p.epi_mode == EPI_BF16_RELU_BWD;
     const __nv_bfloat16* side_base = (BLOCK_N == 256) ? (side_is_aux ? p.aux_in : p.addend) : nullptr;  // narrower tiles run 2 CTAs / SM at 96 registers: no room
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
@@ -745,7 +769,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int cbeg = half * kHalfCols, cend = cbeg + kHalfCols;
     // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
     const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
-    const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD;
+    const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD || p.epi_mode == EPI_BF16_RELU_BWD;
     const __nv_bfloat16* side_base = side_is_aux ? p.aux_in : p.addend;
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);

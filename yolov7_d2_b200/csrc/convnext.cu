@@ -491,6 +491,23 @@ __global__ void f64_to_f32_kernel(double* __restrict__ src, int n, float* __rest
   if (zero_src) src[i] = 0.0;
 }
 
+// out = a + b on bf16 views of equal shape (tensor + positional embedding, detr_backbone.py:154-155)
+__global__ void __launch_bounds__(256) add_bf16_kernel(ActV a, ActV b, __nv_bfloat16* __restrict__ out, int out_pitch, long long npix) {
+  const int groups = a.c >> 3;
+  const long long total = npix * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / groups;
+    const int c8 = static_cast<int>(i - pix * groups) * 8;
+    const uint4 x = *reinterpret_cast<const uint4*>(a.p + pix * a.pitch + c8), y = *reinterpret_cast<const uint4*>(b.p + pix * b.pitch + c8);
+    uint4 o;
+    o.x = pack_bf16x2(bf16_lo(x.x) + bf16_lo(y.x), bf16_hi(x.x) + bf16_hi(y.x));
+    o.y = pack_bf16x2(bf16_lo(x.y) + bf16_lo(y.y), bf16_hi(x.y) + bf16_hi(y.y));
+    o.z = pack_bf16x2(bf16_lo(x.z) + bf16_lo(y.z), bf16_hi(x.z) + bf16_hi(y.z));
+    o.w = pack_bf16x2(bf16_lo(x.w) + bf16_lo(y.w), bf16_hi(x.w) + bf16_hi(y.w));
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + c8) = o;
+  }
+}
+
 template <typename F>
 int dispatch_steps(int c, F&& f) {
   const int steps = (c / 4 + 31) / 32;
@@ -683,6 +700,20 @@ extern "C" int yb200_f64_to_f32(double* src, int n, float* dst, int accumulate, 
   YB_REQUIRE(src && dst && n >= 0, YB200_ERR_INVALID, "f64_to_f32: null pointer");
   if (n == 0) return 0;
   f64_to_f32_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(src, n, dst, accumulate, zero_src);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_add(const yb200_act* a, const yb200_act* b, const yb200_act* out, void* stream) {
+  int rc;
+  if ((rc = check_view(a, "add a", 8))) return rc;
+  if ((rc = check_view(b, "add b", 8))) return rc;
+  if ((rc = check_view(out, "add out", 8))) return rc;
+  YB_REQUIRE(same_shape(a, b) && same_shape(a, out), YB200_ERR_INVALID, "add: shapes differ");
+  const long long npix = 1LL * a->n * a->h * a->w;
+  const long long total = npix * (a->c / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
+  add_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewc(a), viewc(b), static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, npix);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
