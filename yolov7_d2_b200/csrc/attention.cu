@@ -50,7 +50,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[8];  // q_full, kv_full[2], kv_empty[2], s_full, p_ready, o_full
   __shared__ uint32_t s_tmem;
-  __shared__ float s_bias[2][kAttTile];
+  __shared__ __align__(16) float s_bias[2][kAttTile];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAttTile, h = blockIdx.y, b = blockIdx.z;
@@ -145,7 +145,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_32x32(tmem_s + lane_base + c, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(r[i]), p.scale_log2, bias[c + i]));
+        for (int i = 0; i < 32; i += 4) {  // 16-byte broadcast loads of the mask bias: per-element LDS made the LSU the busiest pipe
+          const float4 bb = *reinterpret_cast<const float4*>(bias + c + i);
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[i]), p.scale_log2, bb.x));
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[i + 1]), p.scale_log2, bb.y));
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[i + 2]), p.scale_log2, bb.z));
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[i + 3]), p.scale_log2, bb.w));
+        }
       }
       const float m_safe = mx == -INFINITY ? 0.f : mx;  // every key so far is masked: keep everything at zero without NaNs
       const float alpha = ex2(m - m_safe);               // m = -inf -> 0
@@ -169,11 +175,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, bias[c + i]) - m_safe);
-          const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, bias[c + i + 1]) - m_safe);
-          rowsum += p0 + p1;
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + c + i);
+          const float p0 = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, bb.x - m_safe));
+          const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, bb.y - m_safe));
+          const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), p.scale_log2, bb.z - m_safe));
+          const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), p.scale_log2, bb.w - m_safe));
+          rowsum += (p0 + p1) + (p2 + p3);
           pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
         }
         const uint32_t blk = sP + (c >> 6) * (kAttTile * 128) + row * 128;
 #pragma unroll
