@@ -251,6 +251,18 @@ int yb200_linear_dgrad_relu(const yb200_act* dz, const void* w_dgrad, const yb20
 /* out = a + b (bf16 views of equal shape): tensor + positional embedding (detr_backbone.py:154-155, 218-219)                                */
 int yb200_add(const yb200_act* a, const yb200_act* b, const yb200_act* out, void* stream);
 
+/* ---- SparseInst IAM decoder forward (yolov7/modeling/transcoders/decoder_sparseinst.py:27-169) ------------------
+ * 3x3 convolution + bias + ReLU (`_make_stack_3x3_convs` :18-24); ksize / stride as yb200_conv2d_affine_fwd                                 */
+int yb200_conv2d_relu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* out, int ksize, int stride, void* stream);
+/* 1x1 convolution with fp32 NCHW output [N][cout][H][W] (+ bias, may be NULL): with per-image weights = pred_kernel[b] this is
+ * `torch.bmm(pred_kernel, mask_features.view(B, C, HW))` (:143-146); cout <= 128                                                            */
+int yb200_conv1x1_nchw_f32(const yb200_act* x, const void* w_fwd, const float* bias, int cout, float* out_nchw, void* stream);
+/* out = sigmoid(x): instance activation maps (:67)                                                                                           */
+int yb200_sigmoid(const yb200_act* x, const yb200_act* out, void* stream);
+/* inst[r][c] = raw[r][c] / max(normalizer[r], 1e-6) -> bf16 [1][1][rows][cols] view (:75-76).  raw = iam_prob^T features of one image is
+ * yb200_conv2d_wgrad(x = features, dz = iam_prob, ksize 1) (the pixel contraction of :74), normalizer = yb200_colsum(iam_prob).              */
+int yb200_iam_normalize(const float* raw, const float* normalizer, int rows, int cols, const yb200_act* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

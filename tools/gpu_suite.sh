@@ -3,7 +3,7 @@
 # usage: tools/gpu_suite.sh [group ...]   logs -> gpurun_out/suite_<group>.log
 mkdir -p gpurun_out
 groups=("$@")
-[ ${#groups[@]} -eq 0 ] && groups=(conv_fwd fwd_b fwd_c fwd_d fwd_e conv_misc conv_dgrad conv_wgrad elementwise simota nms engine modeling iou fused optim cnx_ops cnx_engine attention detr)
+[ ${#groups[@]} -eq 0 ] && groups=(conv_fwd fwd_b fwd_c fwd_d fwd_e conv_misc conv_dgrad conv_wgrad elementwise simota nms engine modeling iou fused optim cnx_ops cnx_engine attention detr sparseinst)
 for g in "${groups[@]}"; do
   case $g in
     conv_fwd)    sel="tests/test_conv_gpu.py -k 'test_conv_fwd_stats and not 1x320 and not 16x64 and not 8x80x80'" ;;
@@ -25,6 +25,7 @@ for g in "${groups[@]}"; do
     optim)       sel="tests/test_optim_gpu.py" ;;
     attention)   sel="tests/test_attention_gpu.py" ;;
     detr)        sel="tests/test_detr_gpu.py" ;;
+    sparseinst)  sel="tests/test_sparseinst_gpu.py" ;;
     cnx_ops)     sel="tests/test_convnext_gpu.py -k 'not engine and not block_against'" ;;
     cnx_engine)  sel="tests/test_convnext_gpu.py -k 'engine or block_against'" ;;
     *)           sel="$g" ;;

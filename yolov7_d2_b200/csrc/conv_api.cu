@@ -340,17 +340,43 @@ extern "C" int yb200_conv2d_affine_fwd(const yb200_act* x, const void* w_fwd, co
   return conv_fwd_common(x, w_fwd, out->c, ksize, stride, p, as_stream(stream));
 }
 
-extern "C" int yb200_linear_relu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* h_out, void* stream) {
+extern "C" int yb200_conv2d_relu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* out, int ksize, int stride,
+                                     void* stream) {
   int rc;
-  if ((rc = check_act(x, "linear_relu_fwd x"))) return rc;
-  if ((rc = check_act(h_out, "linear_relu_fwd h"))) return rc;
-  YB_REQUIRE(h_out->n == x->n && h_out->h == x->h && h_out->w == x->w, YB200_ERR_INVALID, "linear_relu_fwd: pixel grids differ");
+  if ((rc = check_act(x, "conv2d_relu_fwd x"))) return rc;
+  if ((rc = check_act(out, "conv2d_relu_fwd out"))) return rc;
+  YB_REQUIRE(stride == 1 || stride == 2, YB200_ERR_UNSUPPORTED, "conv2d_relu_fwd: stride %d", stride);
+  YB_REQUIRE(out->n == x->n && out->h * stride == x->h && out->w * stride == x->w, YB200_ERR_INVALID,
+             "conv2d_relu_fwd: output %dx%dx%d does not match input %dx%dx%d / stride %d", out->n, out->h, out->w, x->n, x->h, x->w, stride);
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  set_out_view(p, *h_out);
+  set_out_view(p, *out);
   p.epi_mode = EPI_BF16_BIAS_RELU;
   p.shift = bias;
-  return conv_fwd_common(x, w_fwd, h_out->c, 1, 1, p, as_stream(stream));
+  return conv_fwd_common(x, w_fwd, out->c, ksize, stride, p, as_stream(stream));
+}
+
+extern "C" int yb200_linear_relu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* h_out, void* stream) {
+  return yb200_conv2d_relu_fwd(x, w_fwd, bias, h_out, 1, 1, stream);
+}
+
+extern "C" int yb200_conv1x1_nchw_f32(const yb200_act* x, const void* w_fwd, const float* bias, int cout, float* out_nchw, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv1x1_nchw_f32 x"))) return rc;
+  YB_REQUIRE(out_nchw && cout > 0 && cout <= 128, YB200_ERR_INVALID, "conv1x1_nchw_f32: bad arguments (cout=%d)", cout);
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const long long hw = 1LL * x->h * x->w;
+  p.out = out_nchw;                 // element (n, y, x, c) at n*cout*hw + c*hw + y*w + x: lanes (pixels) write consecutive floats per channel
+  p.out_sn = 1LL * cout * hw;
+  p.out_sh = x->w;
+  p.out_sw = 1;
+  YB_REQUIRE(hw < (1LL << 31), YB200_ERR_UNSUPPORTED, "conv1x1_nchw_f32: plane too large");
+  p.out_sc = static_cast<int>(hw);
+  p.out_mh = 1; p.out_mw = 1;
+  p.bias = bias;                    // may be null (staged as zeros)
+  p.epi_mode = EPI_F32_BIAS;
+  return conv_fwd_common(x, w_fwd, cout, 1, 1, p, as_stream(stream));
 }
 
 extern "C" int yb200_linear_gelu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* u_out, const yb200_act* h_out,

@@ -508,6 +508,31 @@ __global__ void __launch_bounds__(256) add_bf16_kernel(ActV a, ActV b, __nv_bflo
   }
 }
 
+// out = sigmoid(x) on bf16 views (instance activation maps, decoder_sparseinst.py:67)
+__global__ void __launch_bounds__(256) sigmoid_bf16_kernel(ActV a, __nv_bfloat16* __restrict__ out, int out_pitch, long long npix) {
+  const int groups = a.c >> 3;
+  const long long total = npix * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / groups;
+    const int c8 = static_cast<int>(i - pix * groups) * 8;
+    const uint4 x = *reinterpret_cast<const uint4*>(a.p + pix * a.pitch + c8);
+    auto sg = [](float v) { return __fdividef(1.f, 1.f + __expf(-v)); };
+    uint4 o;
+    o.x = pack_bf16x2(sg(bf16_lo(x.x)), sg(bf16_hi(x.x)));
+    o.y = pack_bf16x2(sg(bf16_lo(x.y)), sg(bf16_hi(x.y)));
+    o.z = pack_bf16x2(sg(bf16_lo(x.z)), sg(bf16_hi(x.z)));
+    o.w = pack_bf16x2(sg(bf16_lo(x.w)), sg(bf16_hi(x.w)));
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + c8) = o;
+  }
+}
+// inst[r][c] = raw[r][c] / max(norm[r], 1e-6) -> bf16 (decoder_sparseinst.py:75-76)
+__global__ void iam_normalize_kernel(const float* __restrict__ raw, const float* __restrict__ norm, int rows, int cols, __nv_bfloat16* __restrict__ out, int out_pitch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  out[static_cast<size_t>(r) * out_pitch + c] = __float2bfloat16_rn(raw[i] / fmaxf(norm[r], 1e-6f));
+}
+
 template <typename F>
 int dispatch_steps(int c, F&& f) {
   const int steps = (c / 4 + 31) / 32;
@@ -714,6 +739,30 @@ extern "C" int yb200_add(const yb200_act* a, const yb200_act* b, const yb200_act
   const long long total = npix * (a->c / 8);
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
   add_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewc(a), viewc(b), static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, npix);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_sigmoid(const yb200_act* x, const yb200_act* out, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "sigmoid x", 8))) return rc;
+  if ((rc = check_view(out, "sigmoid out", 8))) return rc;
+  YB_REQUIRE(same_shape(x, out), YB200_ERR_INVALID, "sigmoid: shapes differ");
+  const long long npix = 1LL * x->n * x->h * x->w;
+  const long long total = npix * (x->c / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
+  sigmoid_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewc(x), static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, npix);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_iam_normalize(const float* raw, const float* normalizer, int rows, int cols, const yb200_act* out, void* stream) {
+  int rc;
+  if ((rc = check_view(out, "iam_normalize out", 8))) return rc;
+  YB_REQUIRE(raw && normalizer && rows > 0 && cols > 0, YB200_ERR_INVALID, "iam_normalize: bad arguments");
+  YB_REQUIRE(out->n == 1 && out->h == 1 && out->w == rows && out->c == cols, YB200_ERR_INVALID, "iam_normalize: output must be a [1][1][%d][%d] view", rows, cols);
+  iam_normalize_kernel<<<ceil_div(rows * cols, 256), 256, 0, as_stream(stream)>>>(raw, normalizer, rows, cols, static_cast<__nv_bfloat16*>(out->ptr) + out->c_off,
+                                                                                  out->c_pitch);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
