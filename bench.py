@@ -242,7 +242,9 @@ def main():
     launches_per_step = eng.kernel_launches // max(args.warmup, 3)
 
     graph = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
+        # N = 1: the whole step (forward, backward, optimizer) is one graph.  N > 1: forward + backward are replayed as a graph, the NCCL
+        # all-reduce and the optimizer step follow on the same stream (capture is thread-local: NCCL's watchdog thread polls CUDA events)
         try:
             g = torch.cuda.CUDAGraph()
             s = torch.cuda.Stream()
@@ -251,7 +253,7 @@ def main():
                 train_step()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 train_step()
             graph = g
             for _ in range(2):
@@ -265,6 +267,10 @@ def main():
     def step():
         if graph is not None:
             graph.replay()
+            if world > 1:
+                dist.all_reduce(flat_grad)
+                if opt is not None:
+                    opt.step()
         else:
             step_eager()
 

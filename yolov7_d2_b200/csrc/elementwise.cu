@@ -35,6 +35,16 @@ int check_view(const yb200_act* a, const char* name) {
 bool same_shape(const yb200_act* a, const yb200_act* b) { return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c; }
 
 // streaming 16-byte load (read once: do not allocate in L1)
+// YB200_L2_ORDER=1: element-wise passes walk their tensors in the direction that meets the producer's most recent (L2-resident) output first
+static int l2_order() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB200_L2_ORDER");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -157,12 +167,13 @@ __device__ __forceinline__ PixXY decode_pix(unsigned pix, int w, int h) {
 // a = SiLU(z*scale + shift) [+ residual];  optionally also written 2x nearest-upsampled into a second view
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift, int has_res,
-                     int has_up, unsigned npix) {
+                     int has_up, unsigned npix, int rev) {
   const int c8 = threadIdx.x * 8;
   float s[8], t[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
-  const unsigned p0 = blockIdx.x * (blockDim.y * kEwIters) + threadIdx.y;
+  // rev: walk the tensor from its end -- the convolution that produced z wrote its tail last, so the tail is what the L2 still holds
+  const unsigned p0 = (rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.y * kEwIters) + threadIdx.y;
   constexpr int U = 4;  // loads of U pixels are issued before any of them is consumed
 #pragma unroll 1
   for (int it0 = 0; it0 < kEwIters; it0 += U) {
@@ -254,7 +265,7 @@ __device__ __forceinline__ float silu_grad(float u, float d) {  // d * d/du [u *
 __global__ void __launch_bounds__(kEwThreads, 3)
 bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, unsigned npix,
-                          int iters) {
+                          int iters, int rev) {
   extern __shared__ float sm[];  // [rows][2][c], rows = warps (c < 256) or blockDim.y (c >= 256)
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthreads = blockDim.x * blockDim.y;
@@ -263,7 +274,8 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const unsigned p0 = blockIdx.x * (blockDim.y * iters) + threadIdx.y;
+  // rev: start at the tail (written last by the data-gradient kernel, still in L2) and finish at the head, which the apply pass reads first
+  const unsigned p0 = (rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.y * iters) + threadIdx.y;
   const bool simple = !da.has_b && !da.has_up;
   constexpr int U = 2;
 #pragma unroll 1
@@ -592,7 +604,7 @@ extern "C" int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const
   dim3 block(cv, kEwThreads / cv);
   const unsigned grid = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
   bn_apply_silu_kernel<<<grid, block, 0, as_stream(stream)>>>(vz, vo, vr, vu, scale, shift, residual != nullptr, out_up2x != nullptr,
-                                                             static_cast<unsigned>(npix));
+                                                             static_cast<unsigned>(npix), l2_order());
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -633,7 +645,7 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
     red_smem_set = red_smem;
   }
   bn_silu_bwd_reduce_kernel<<<grid_r, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                              static_cast<unsigned>(npix), red_iters);
+                                                              static_cast<unsigned>(npix), red_iters, l2_order());
   YB_CHECK_CUDA(cudaGetLastError());
   const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
   if (!src.has_b && !src.has_up)
