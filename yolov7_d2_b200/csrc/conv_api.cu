@@ -34,6 +34,7 @@ template <int BN, int BK>
 static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid, int stages,
                             cudaStream_t st) {
   using Cfg = ConvGemmCfg<BN, BK>;
+  const bool ext = p.epi_mode >= EPI_BF16_AFFINE;  // ConvNeXt / transformer epilogues live in their own instantiations
   if (use_v1_kernel()) {  // one tile per CTA (kept for A/B comparison)
     static int max_set = 0;
     const int smem = stages * Cfg::kStageBytes + 1024;
@@ -55,14 +56,18 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
       const int smem = pst * stage_bytes + 1024;
       static int max_set_pair = 0;
       if (smem > max_set_pair) {
-        YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         max_set_pair = smem;
       }
       const int pair_tiles = (m_tiles + 1) / 2;
       int groups = (sm_count() / 2) / n_tiles;
       if (groups < 1) groups = 1;
       if (groups > pair_tiles) groups = pair_tiles;
-      conv_gemm_pair_kernel<BK><<<2 * groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
+      if (ext)
+        conv_gemm_pair_kernel<BK, true><<<2 * groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
+      else
+        conv_gemm_pair_kernel<BK, false><<<2 * groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
       YB_CHECK_CUDA(cudaGetLastError());
       return 0;
     }
@@ -86,13 +91,17 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   const int smem = pst * kbs * Cfg::kStageBytes + 1024;
   static int max_set_p = 0;
   if (smem > max_set_p) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     max_set_p = smem;
   }
   int groups = (occ * sm_count()) / n_tiles;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
-  conv_gemm_persistent_kernel<BN, BK><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+  if (ext)
+    conv_gemm_persistent_kernel<BN, BK, true><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+  else
+    conv_gemm_persistent_kernel<BN, BK, false><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -154,7 +154,10 @@ __device__ __forceinline__ void load_side_chunk(const __nv_bfloat16* side_row, b
   }
 }
 
-template <int CH>
+// EXT = false: the YOLOX training / inference modes only (EPI_BF16 .. EPI_BF16_BN_SILU); EXT = true adds the ConvNeXt / transformer
+// modes and the prefetched side input.  Two instantiations per kernel keep the hot YOLOX kernels as small as they were before the
+// extra modes existed (the combined epilogue cost the 3x3 kernels 2-13 % through registers and code size).
+template <int CH, bool EXT = true>
 __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, float (&v)[CH], bool valid, long long pix_off, long long add_off,
                                                     int cbase, int lane, float* part_sum, float* part_sq, bool accumulate,
                                                     const float* col_scale, const float* col_shift, const uint4* side = nullptr) {
@@ -179,70 +182,72 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       v[i + 3] = bf16_round(__fdividef(u3, 1.f + __expf(-u3)));
     }
   }
-  if (p.epi_mode == EPI_BF16_AFFINE) {
-    if (p.scale != nullptr) {
-#pragma unroll
-      for (int i = 0; i < CH; i += 4) {
-        const float4 sc = *reinterpret_cast<const float4*>(col_scale + i);
-        v[i] *= sc.x; v[i + 1] *= sc.y; v[i + 2] *= sc.z; v[i + 3] *= sc.w;
+  if constexpr (EXT) {
+    if (p.epi_mode == EPI_BF16_AFFINE) {
+      if (p.scale != nullptr) {
+  #pragma unroll
+        for (int i = 0; i < CH; i += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(col_scale + i);
+          v[i] *= sc.x; v[i + 1] *= sc.y; v[i + 2] *= sc.z; v[i + 3] *= sc.w;
+        }
+      }
+      if (p.shift != nullptr) {
+  #pragma unroll
+        for (int i = 0; i < CH; i += 4) {
+          const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
+          v[i] += sh.x; v[i + 1] += sh.y; v[i + 2] += sh.z; v[i + 3] += sh.w;
+        }
       }
     }
-    if (p.shift != nullptr) {
-#pragma unroll
+    if (p.epi_mode == EPI_BF16_BIAS_RELU) {
+  #pragma unroll
       for (int i = 0; i < CH; i += 4) {
         const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
-        v[i] += sh.x; v[i + 1] += sh.y; v[i + 2] += sh.z; v[i + 3] += sh.w;
+        v[i] = fmaxf(v[i] + sh.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + sh.y, 0.f);
+        v[i + 2] = fmaxf(v[i + 2] + sh.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + sh.w, 0.f);
       }
     }
-  }
-  if (p.epi_mode == EPI_BF16_BIAS_RELU) {
-#pragma unroll
-    for (int i = 0; i < CH; i += 4) {
-      const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
-      v[i] = fmaxf(v[i] + sh.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + sh.y, 0.f);
-      v[i + 2] = fmaxf(v[i + 2] + sh.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + sh.w, 0.f);
-    }
-  }
-  if (p.epi_mode == EPI_BF16_RELU_BWD && valid) {
-    const __nv_bfloat16* a = p.aux_in + pix_off + cbase;
-#pragma unroll
-    for (int i = 0; i < CH; i += 8) {
-      if (cbase + i < p.cout) {
-        const uint4 u = side ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
-        // bf16 sign / zero test on the raw bits: positive and non-zero
-        v[i + 0] = (u.x & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 0] : 0.f; v[i + 1] = (u.x >> 16) - 1u < 0x7FFFu ? v[i + 1] : 0.f;
-        v[i + 2] = (u.y & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 2] : 0.f; v[i + 3] = (u.y >> 16) - 1u < 0x7FFFu ? v[i + 3] : 0.f;
-        v[i + 4] = (u.z & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 4] : 0.f; v[i + 5] = (u.z >> 16) - 1u < 0x7FFFu ? v[i + 5] : 0.f;
-        v[i + 6] = (u.w & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 6] : 0.f; v[i + 7] = (u.w >> 16) - 1u < 0x7FFFu ? v[i + 7] : 0.f;
+    if (p.epi_mode == EPI_BF16_RELU_BWD && valid) {
+      const __nv_bfloat16* a = p.aux_in + pix_off + cbase;
+  #pragma unroll
+      for (int i = 0; i < CH; i += 8) {
+        if (cbase + i < p.cout) {
+          const uint4 u = side ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
+          // bf16 sign / zero test on the raw bits: positive and non-zero
+          v[i + 0] = (u.x & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 0] : 0.f; v[i + 1] = (u.x >> 16) - 1u < 0x7FFFu ? v[i + 1] : 0.f;
+          v[i + 2] = (u.y & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 2] : 0.f; v[i + 3] = (u.y >> 16) - 1u < 0x7FFFu ? v[i + 3] : 0.f;
+          v[i + 4] = (u.z & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 4] : 0.f; v[i + 5] = (u.z >> 16) - 1u < 0x7FFFu ? v[i + 5] : 0.f;
+          v[i + 6] = (u.w & 0xFFFFu) - 1u < 0x7FFFu ? v[i + 6] : 0.f; v[i + 7] = (u.w >> 16) - 1u < 0x7FFFu ? v[i + 7] : 0.f;
+        }
       }
     }
-  }
-  if (p.epi_mode == EPI_BF16_BIAS_GELU) {
-#pragma unroll
-    for (int i = 0; i < CH; i += 4) {
-      const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
-      v[i] = bf16_round(v[i] + sh.x); v[i + 1] = bf16_round(v[i + 1] + sh.y);
-      v[i + 2] = bf16_round(v[i + 2] + sh.z); v[i + 3] = bf16_round(v[i + 3] + sh.w);
+    if (p.epi_mode == EPI_BF16_BIAS_GELU) {
+  #pragma unroll
+      for (int i = 0; i < CH; i += 4) {
+        const float4 sh = *reinterpret_cast<const float4*>(col_shift + i);
+        v[i] = bf16_round(v[i] + sh.x); v[i + 1] = bf16_round(v[i + 1] + sh.y);
+        v[i + 2] = bf16_round(v[i + 2] + sh.z); v[i + 3] = bf16_round(v[i + 3] + sh.w);
+      }
+      if (p.aux_out != nullptr && valid) {
+        __nv_bfloat16* o = p.aux_out + pix_off + cbase;
+  #pragma unroll
+        for (int i = 0; i < CH; i += 8)
+          if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+      }
+  #pragma unroll
+      for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
     }
-    if (p.aux_out != nullptr && valid) {
-      __nv_bfloat16* o = p.aux_out + pix_off + cbase;
-#pragma unroll
-      for (int i = 0; i < CH; i += 8)
-        if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
-    }
-#pragma unroll
-    for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
-  }
-  if (p.epi_mode == EPI_BF16_GELU_BWD && valid) {
-    const __nv_bfloat16* a = p.aux_in + pix_off + cbase;
-#pragma unroll
-    for (int i = 0; i < CH; i += 8) {
-      if (cbase + i < p.cout) {
-        const uint4 u = side ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
-        v[i + 0] *= gelu_erf_grad(bf16_lo(u.x)); v[i + 1] *= gelu_erf_grad(bf16_hi(u.x));
-        v[i + 2] *= gelu_erf_grad(bf16_lo(u.y)); v[i + 3] *= gelu_erf_grad(bf16_hi(u.y));
-        v[i + 4] *= gelu_erf_grad(bf16_lo(u.z)); v[i + 5] *= gelu_erf_grad(bf16_hi(u.z));
-        v[i + 6] *= gelu_erf_grad(bf16_lo(u.w)); v[i + 7] *= gelu_erf_grad(bf16_hi(u.w));
+    if (p.epi_mode == EPI_BF16_GELU_BWD && valid) {
+      const __nv_bfloat16* a = p.aux_in + pix_off + cbase;
+  #pragma unroll
+      for (int i = 0; i < CH; i += 8) {
+        if (cbase + i < p.cout) {
+          const uint4 u = side ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
+          v[i + 0] *= gelu_erf_grad(bf16_lo(u.x)); v[i + 1] *= gelu_erf_grad(bf16_hi(u.x));
+          v[i + 2] *= gelu_erf_grad(bf16_lo(u.y)); v[i + 3] *= gelu_erf_grad(bf16_hi(u.y));
+          v[i + 4] *= gelu_erf_grad(bf16_lo(u.z)); v[i + 5] *= gelu_erf_grad(bf16_hi(u.z));
+          v[i + 6] *= gelu_erf_grad(bf16_lo(u.w)); v[i + 7] *= gelu_erf_grad(bf16_hi(u.w));
+        }
       }
     }
   }
@@ -251,7 +256,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
 #pragma unroll
     for (int i = 0; i < CH; i += 8) {
       if (cbase + i < p.cout) {
-        const uint4 u = (side && p.epi_mode != EPI_BF16_GELU_BWD && p.epi_mode != EPI_BF16_RELU_BWD) ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
+        const uint4 u = (EXT && side && p.epi_mode != EPI_BF16_GELU_BWD && p.epi_mode != EPI_BF16_RELU_BWD) ? side[i >> 3] : *reinterpret_cast<const uint4*>(a + i);
         v[i + 0] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x);
         v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
         v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z);
@@ -287,7 +292,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       part_sum[lane] = accumulate ? part_sum[lane] + cs : cs;
       part_sq[lane] = accumulate ? part_sq[lane] + cq : cq;
     }
-  } else if ((p.epi_mode == EPI_BF16_GELU_BWD || p.epi_mode == EPI_BF16_RELU_BWD) && p.stat_sum != nullptr) {
+  } else if (EXT && (p.epi_mode == EPI_BF16_GELU_BWD || p.epi_mode == EPI_BF16_RELU_BWD) && p.stat_sum != nullptr) {
     float cs;
     if constexpr (CH == 32) cs = warp_colsum32(v, lane);
     else cs = warp_colsum16(v, lane);
@@ -441,7 +446,7 @@ constexpr int kMaxStagesP = 8;     // ring slots; one slot holds kb_per_slot con
 constexpr int kConvThreadsP = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue: two warps per TMEM lane quadrant, each
                                     // draining half of the accumulator columns (memory-bound layers are epilogue-bound)
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool EXT>
 __global__ void __launch_bounds__(kConvThreadsP, BLOCK_N == 256 ? 1 : 2)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ ConvGemmParams p, int num_stages, int kb_per_slot, int n_tiles, int m_tiles) {
@@ -562,7 +567,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
     const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
     const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD || p.epi_mode == EPI_BF16_RELU_BWD;
-    const __nv_bfloat16* side_base = (BLOCK_N == 256) ? (side_is_aux ? p.aux_in : p.addend) : nullptr;  // narrower tiles run 2 CTAs / SM at 96 registers: no room
+    const __nv_bfloat16* side_base = (EXT && BLOCK_N == 256) ? (side_is_aux ? p.aux_in : p.addend) : nullptr;  // narrower tiles run 2 CTAs / SM at 96 registers: no room
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
@@ -583,7 +588,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int acc = it & 1;
       const __nv_bfloat16* side_row = side_base ? side_base + (side_is_aux ? pix_off : add_off) : nullptr;
       uint4 side[CH / 8];
-      if constexpr (BLOCK_N == 256) {
+      if constexpr (EXT && BLOCK_N == 256) {
         if (side_base != nullptr && cend_live > cbeg) load_side_chunk<CH>(side_row, valid, col0 + cbeg, p.cout, side);  // in flight during the barrier wait
       }
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
@@ -600,7 +605,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         if constexpr (CH == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
         uint4 side_next[CH / 8];
         const bool more = side_base != nullptr && c + CH < cend_live;
-        if constexpr (BLOCK_N == 256) {  // registers to spare (one CTA per SM): fetch the next chunk's side input before using this one
+        if constexpr (EXT && BLOCK_N == 256) {  // registers to spare (one CTA per SM): fetch the next chunk's side input before using this one
           if (more) load_side_chunk<CH>(side_row, valid, col0 + c + CH, p.cout, side_next);
         }
         tmem_ld_wait();
@@ -613,9 +618,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
-        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
-                                (BLOCK_N == 256 && side_base) ? side : nullptr);
-        if constexpr (BLOCK_N == 256) {
+        conv_epilogue_chunk<CH, EXT>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
+                                (EXT && BLOCK_N == 256 && side_base) ? side : nullptr);
+        if constexpr (EXT && BLOCK_N == 256) {
           if (more) {
 #pragma unroll
             for (int k = 0; k < CH / 8; ++k) side[k] = side_next[k];
@@ -628,7 +633,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kTmemAlloc>(tmem_base);
-  if (epi_has_stats(p.epi_mode, p.stat_sum)) {
+  if (EXT ? epi_has_stats(p.epi_mode, p.stat_sum) : p.epi_mode == EPI_F16_STATS) {
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {  // BLOCK_N may exceed the 192 threads
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
@@ -647,7 +652,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 //   both CTAs: TMA producer (signals the leader's full barrier), epilogue on their own TMEM half (= their own pixel tile)
 // grid.x = 2 * n_tiles * groups;  pair q = blockIdx.x / 2: column tile q % n_tiles, pixel-tile pairs (q / n_tiles) + i * groups.
 // ================================================================================================
-template <int BLOCK_K>
+template <int BLOCK_K, bool EXT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreadsP, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ ConvGemmParams p, int num_stages, int n_tiles, int m_tiles) {
@@ -770,7 +775,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // chunks that start at or beyond the last valid output channel are dead (cout not a multiple of the column tile): skip them
     const int cend_live = min(cend, ((p.cout - col0 + CH - 1) / CH) * CH);
     const bool side_is_aux = p.epi_mode == EPI_BF16_GELU_BWD || p.epi_mode == EPI_BF16_RELU_BWD;
-    const __nv_bfloat16* side_base = side_is_aux ? p.aux_in : p.addend;
+    const __nv_bfloat16* side_base = EXT ? (side_is_aux ? p.aux_in : p.addend) : nullptr;
     const int mrow = q * 32 + lane;
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
@@ -816,7 +821,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
-        conv_epilogue_chunk<CH>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
+        conv_epilogue_chunk<CH, EXT>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
                                 side_base ? side : nullptr);
         if (more) {
 #pragma unroll
@@ -830,7 +835,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   cluster_sync();  // neither CTA may free TMEM / exit while the peer's MMAs or remote arrives can still target it
   if (warp == 1) tmem_dealloc_pair<kTmemAlloc>(tmem_base);
-  if (epi_has_stats(p.epi_mode, p.stat_sum)) {
+  if (EXT ? epi_has_stats(p.epi_mode, p.stat_sum) : p.epi_mode == EPI_F16_STATS) {
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
