@@ -43,3 +43,40 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass, "tcgen05 / TMA instructions missing from the sm_100a build"
+
+
+def test_attention_and_pair_kernels_use_tensor_memory():
+    """per kernel: the attention core and the CTA-pair convolution must themselves contain tcgen05 MMA / TMA / TMEM-load instructions
+    (not just some other kernel of the library), and the pair kernel the 2-CTA MMA form"""
+    import re
+    import shutil
+    import subprocess
+
+    from yolov7_d2_b200 import capi
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = {}
+    for part in re.split(r"\n\s*Function : ", sass)[1:]:
+        name, _, body = part.partition("\n")
+        funcs[name.strip()] = body
+    att = [b for n, b in funcs.items() if "attention_fwd_kernel" in n]
+    assert att, "attention_fwd_kernel not found in the library"
+    assert all("UTCHMMA" in b and "UTMALDG" in b and "LDTM" in b and "MUFU.EX2" in b for b in att)
+    pair = [b for n, b in funcs.items() if "conv_gemm_pair_kernel" in n]
+    assert pair and all("UTCHMMA.2CTA" in b for b in pair), "CTA-pair kernels must issue cta_group::2 MMAs"
+    wg = [b for n, b in funcs.items() if "wgrad_gemm_kernel" in n]
+    assert wg and all("UTCHMMA" in b for b in wg)
+
+
+def test_extended_entry_points_validate_arguments_without_gpu():
+    from yolov7_d2_b200 import capi
+
+    L = capi.lib()
+    a = capi.Act(0, 1, 1, 8, 64, 64, 0)
+    assert L.yb200_attention_fwd(ctypes.byref(a), ctypes.byref(a), ctypes.byref(a), None, ctypes.c_float(1.0), ctypes.byref(a), None, None) != 0
+    assert L.yb200_layernorm_fwd(ctypes.byref(a), None, None, ctypes.c_float(1e-6), ctypes.byref(a), None, None) != 0
+    assert L.yb200_sgd_step(None, None, None, ctypes.c_int64(0), None, None, None, 0, ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0), 0, 0,
+                            ctypes.c_float(1), None, ctypes.c_float(0), None) != 0
+    assert b"null" in L.yb200_last_error() or b"sgd_step" in L.yb200_last_error()
