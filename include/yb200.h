@@ -262,6 +262,13 @@ int yb200_sigmoid(const yb200_act* x, const yb200_act* out, void* stream);
 /* inst[r][c] = raw[r][c] / max(normalizer[r], 1e-6) -> bf16 [1][1][rows][cols] view (:75-76).  raw = iam_prob^T features of one image is
  * yb200_conv2d_wgrad(x = features, dz = iam_prob, ksize 1) (the pixel contraction of :74), normalizer = yb200_colsum(iam_prob).              */
 int yb200_iam_normalize(const float* raw, const float* normalizer, int rows, int cols, const yb200_act* out, void* stream);
+/* Backward of yb200_attention_fwd: given out, its gradient dout and the saved lse, dq / dk / dv (bf16 views shaped like q / k / k; they may be
+ * slices of one packed buffer).  P is recomputed from lse; two kernels (per key tile: dK, dV; per query tile: dQ), accumulation in TMEM,
+ * no atomics.  workspace: yb200_attention_bwd_workspace(q) bytes (D = <dout, out> per query row and head).                                     */
+int64_t yb200_attention_bwd_workspace(const yb200_act* q);
+int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const yb200_act* v, const yb200_act* out, const yb200_act* dout,
+                        const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
+                        const yb200_act* dv, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ for g in "${groups[@]}"; do
     iou)         sel="tests/test_iou_loss_gpu.py" ;;
     fused)       sel="tests/test_conv_gpu.py -k fused" ;;
     optim)       sel="tests/test_optim_gpu.py" ;;
-    attention)   sel="tests/test_attention_gpu.py" ;;
+    attention)   sel="tests/test_attention_gpu.py tests/test_attention_bwd_gpu.py" ;;
     detr)        sel="tests/test_detr_gpu.py" ;;
     sparseinst)  sel="tests/test_sparseinst_gpu.py" ;;
     cnx_ops)     sel="tests/test_convnext_gpu.py -k 'not engine and not block_against'" ;;

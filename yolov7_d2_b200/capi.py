@@ -63,7 +63,7 @@ def lib():
         _lib.yb200_simota_workspace.restype = c_i64
         _lib.yb200_nms_workspace.restype = c_i64
         _lib.yb200_grad_norm_workspace.restype = c_i64
-        for _n in ("yb200_dwconv7_wgrad_workspace", "yb200_layernorm_bwd_workspace", "yb200_colsum_workspace"):
+        for _n in ("yb200_dwconv7_wgrad_workspace", "yb200_layernorm_bwd_workspace", "yb200_colsum_workspace", "yb200_attention_bwd_workspace"):
             getattr(_lib, _n).restype = c_i64
         for name in declared_symbols():
             if not hasattr(_lib, name):

@@ -231,6 +231,320 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 1) tmem_dealloc<256>(s_tmem);
 }
 
+// ================================================================================================================================
+// Backward of the attention core.  With P = softmax(S), S = scale * Q K^T + mask, O = P V and D_i = <dO_i, O_i>:
+//   dV = P^T dO,   dP = dO V^T,   dS = P o (dP - D) * scale,   dQ = dS K,   dK = dS^T Q
+// P is recomputed from the saved log-sum-exp (fp32 per query row).  Two kernels, no atomics (bit-reproducible):
+//   attention_bwd_kv_kernel  one CTA per (128-key tile, head, image), streams over query tiles, dK / dV accumulate in TMEM
+//   attention_bwd_q_kernel   one CTA per (128-query tile, head, image), streams over key tiles, dQ accumulates in TMEM
+// Operand forms (all already used by the forward kernel or the weight-gradient GEMM): S and dP are K-major x K-major UMMAs on the TMA tiles;
+// P / dS are written by the softmax threads as bf16 [query][key] tiles (128-byte rows, swizzle 128) and consumed either K-major (dQ = dS K)
+// or MN-major (dV = P^T dO, dK = dS^T Q: the contraction index is the tile row); dO / Q / K enter those products as MN-major B operands
+// straight from their token-major tiles.
+// ================================================================================================================================
+struct AttnBwdParams {
+  int lq, lk, heads;
+  int q_coff, k_coff, v_coff, do_coff;
+  float scale, scale_log2;
+  const uint8_t* mask;
+  const float* lse;    // [B][heads][lq], natural log
+  const float* dsum;   // [B][heads][lq], D = <dO, O>
+  __nv_bfloat16 *dq, *dk, *dv;
+  int dq_pitch, dq_coff, dk_pitch, dk_coff, dv_pitch, dv_coff;
+};
+
+constexpr int kBwdSmemKV = 2 * kKVBytes + 4 * kQBytes + 2 * kPBytes + 1024;  // K, V | Q x2, dO x2 | P, dS
+constexpr int kBwdSmemQ = 2 * kQBytes + 4 * kKVBytes + kPBytes + 1024;       // Q, dO | K x2, V x2 | dS
+
+// D[b][h][q] = sum_d dO[b][q][h][d] * O[b][q][h][d]
+__global__ void attention_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int o_pitch, int o_coff, const __nv_bfloat16* __restrict__ d_o, int do_pitch,
+                                          int do_coff, int batch, int lq, int heads, float* __restrict__ dsum) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(batch) * lq * heads) return;
+  const int h = static_cast<int>(i % heads);
+  const long long t = i / heads;  // b * lq + q
+  const int q = static_cast<int>(t % lq), b = static_cast<int>(t / lq);
+  const __nv_bfloat16* po = o + t * o_pitch + o_coff + h * kAttD;
+  const __nv_bfloat16* pd = d_o + t * do_pitch + do_coff + h * kAttD;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < kAttD; c += 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(po + c), g = *reinterpret_cast<const uint4*>(pd + c);
+    acc += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y) +
+           bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) + bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+  }
+  dsum[(static_cast<size_t>(b) * heads + h) * lq + q] = acc;
+}
+
+// one 32-column chunk of P and dS for the thread's query row: reads S and dP from TMEM, writes both bf16 tiles ([query][key], swizzle 128)
+__device__ __forceinline__ void bwd_chunk(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_base, int c, int row, const float* bias, float lse_log2, float dsum,
+                                          float scale, float scale_log2, uint32_t sP, uint32_t sDS, bool write_p) {
+  uint32_t r[32], g[32];
+  tmem_ld_32x32(tmem_s + lane_base + c, r);
+  tmem_ld_32x32(tmem_dp + lane_base + c, g);
+  tmem_ld_wait();
+  uint32_t pk[16], dk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + c + i);
+    const float p0 = ex2(fmaf(__uint_as_float(r[i]), scale_log2, bb.x - lse_log2));
+    const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), scale_log2, bb.y - lse_log2));
+    const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), scale_log2, bb.z - lse_log2));
+    const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), scale_log2, bb.w - lse_log2));
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+    dk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(g[i]) - dsum) * scale, p1 * (__uint_as_float(g[i + 1]) - dsum) * scale);
+    dk[(i >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(g[i + 2]) - dsum) * scale, p3 * (__uint_as_float(g[i + 3]) - dsum) * scale);
+  }
+  const uint32_t off = (c >> 6) * (kAttTile * 128) + row * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = ((c & 32) >> 3) + q;
+    const uint32_t sw = off + (((chunk ^ (row & 7))) << 4);
+    if (write_p)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + sw), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + sw), "r"(dk[4 * q]), "r"(dk[4 * q + 1]), "r"(dk[4 * q + 2]), "r"(dk[4 * q + 3]) : "memory");
+  }
+}
+
+__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (&o)[32]) {
+#pragma unroll
+  for (int i = 0; i < kAttD; i += 8) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1]));
+    u.y = pack_bf16x2(__uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+    u.z = pack_bf16x2(__uint_as_float(o[i + 4]), __uint_as_float(o[i + 5]));
+    u.w = pack_bf16x2(__uint_as_float(o[i + 6]), __uint_as_float(o[i + 7]));
+    *reinterpret_cast<uint4*>(dst + i) = u;
+  }
+}
+
+__global__ void __launch_bounds__(kAttThreads)
+attention_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[8];  // kv_full, qdo_full[2], qdo_empty[2], sdp_full, pds_ready, mma_done
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[kAttTile];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kAttTile, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = sK + kKVBytes, sQ = sV + kKVBytes, sDO = sQ + 2 * kQBytes, sP = sDO + 2 * kQBytes, sDS = sP + kPBytes;
+  const uint32_t bar_kv = smem_u32(&s_bar[0]), bar_full = smem_u32(&s_bar[1]), bar_empty = smem_u32(&s_bar[3]);
+  const uint32_t bar_sdp = smem_u32(&s_bar[5]), bar_pds = smem_u32(&s_bar[6]), bar_done = smem_u32(&s_bar[7]);
+  const int ntiles = (p.lq + kAttTile - 1) / kAttTile;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_pds, kAttTile);
+    mbar_init(bar_done, 1);
+    mbar_fence_init();
+  }
+  if (threadIdx.x >= 64) {  // additive mask of this CTA's key tile
+    const int tid = threadIdx.x - 64, key = k0 + tid;
+    const bool dead = key >= p.lk || (p.mask != nullptr && p.mask[static_cast<size_t>(b) * p.lk + key] != 0);
+    s_bias[tid] = dead ? -INFINITY : 0.f;
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&s_tmem));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = s_tmem, tmem_dp = s_tmem + 128, tmem_dv = s_tmem + 256, tmem_dk = s_tmem + 288;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_kv, 2 * kKVBytes);
+      tma_load_5d(sK, &tmK, bar_kv, p.k_coff + h * kAttD, k0, 0, 0, b);
+      tma_load_5d(sV, &tmV, bar_kv, p.v_coff + h * kAttD, k0, 0, 0, b);
+      for (int i = 0; i < ntiles; ++i) {
+        const int st = i & 1;
+        mbar_wait(bar_empty + 8 * st, ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar_full + 8 * st, 2 * kQBytes);
+        tma_load_5d(sQ + st * kQBytes, &tmQ, bar_full + 8 * st, p.q_coff + h * kAttD, i * kAttTile, 0, 0, b);
+        tma_load_5d(sDO + st * kQBytes, &tmDO, bar_full + 8 * st, p.do_coff + h * kAttD, i * kAttTile, 0, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_t = umma_idesc_bf16(128, kAttD, 1, 1);  // A = P^T / dS^T (MN-major), B = dO / Q tile (MN-major)
+      const uint32_t l64 = umma_layout_code(64), l128 = umma_layout_code(128);
+      mbar_wait(bar_kv, 0);
+      for (int i = 0; i < ntiles; ++i) {
+        const int st = i & 1;
+        mbar_wait(bar_full + 8 * st, (i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kAttD / 16; ++k) {
+          umma_f16(tmem_s, umma_smem_desc(sQ + st * kQBytes + k * 32, 16, 512, l64), umma_smem_desc(sK + k * 32, 16, 512, l64), idesc_s, k != 0 ? 1u : 0u);
+          umma_f16(tmem_dp, umma_smem_desc(sDO + st * kQBytes + k * 32, 16, 512, l64), umma_smem_desc(sV + k * 32, 16, 512, l64), idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_sdp);
+        mbar_wait(bar_pds, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kAttTile / 16; ++kk) {  // contraction over the 128 query rows of the tile, 16 at a time
+          const uint64_t a_p = umma_smem_desc(sP + kk * 16 * 128, kAttTile * 128, 8 * 128, l128);
+          const uint64_t a_ds = umma_smem_desc(sDS + kk * 16 * 128, kAttTile * 128, 8 * 128, l128);
+          const uint64_t b_do = umma_smem_desc(sDO + st * kQBytes + kk * 16 * (kAttD * 2), kQBytes, 8 * (kAttD * 2), l64);
+          const uint64_t b_q = umma_smem_desc(sQ + st * kQBytes + kk * 16 * (kAttD * 2), kQBytes, 8 * (kAttD * 2), l64);
+          umma_f16(tmem_dv, a_p, b_do, idesc_t, (i | kk) != 0 ? 1u : 0u);
+          umma_f16(tmem_dk, a_ds, b_q, idesc_t, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_done);
+        umma_commit(bar_empty + 8 * st);
+      }
+    }
+  } else {
+    const int quad = warp & 3, row = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    for (int i = 0; i < ntiles; ++i) {
+      const int qi = i * kAttTile + row;
+      const size_t stat = (static_cast<size_t>(b) * p.heads + h) * p.lq + qi;
+      float lse_log2 = qi < p.lq ? p.lse[stat] * 1.4426950408889634f : INFINITY;  // rows beyond lq: p = 0
+      if (lse_log2 == -INFINITY) lse_log2 = INFINITY;                                 // fully masked query: zero gradients instead of NaN
+      const float dsum = qi < p.lq ? p.dsum[stat] : 0.f;
+      mbar_wait(bar_sdp, i & 1);
+      tc_fence_after();
+      if (i > 0) mbar_wait(bar_done, (i - 1) & 1);  // the previous tile's P / dS have been consumed
+#pragma unroll 1
+      for (int c = 0; c < kAttTile; c += 32) bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias, lse_log2, dsum, p.scale, p.scale_log2, sP, sDS, true);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+    }
+    mbar_wait(bar_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    const int key = k0 + row;  // accumulator row = key index
+    uint32_t o[32];
+    tmem_ld_32x32(tmem_dv + lane_base, o);
+    tmem_ld_wait();
+    if (key < p.lk) store_row32(p.dv + (static_cast<size_t>(b) * p.lk + key) * p.dv_pitch + p.dv_coff + h * kAttD, o);
+    tmem_ld_32x32(tmem_dk + lane_base, o);
+    tmem_ld_wait();
+    if (key < p.lk) store_row32(p.dk + (static_cast<size_t>(b) * p.lk + key) * p.dk_pitch + p.dk_coff + h * kAttD, o);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(s_tmem);
+}
+
+__global__ void __launch_bounds__(kAttThreads)
+attention_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                       const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[8];  // qdo_full, kv_full[2], kv_empty[2], sdp_full, ds_ready, mma_done
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[2][kAttTile];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kAttTile, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sDO = sQ + kQBytes, sK = sDO + kQBytes, sV = sK + 2 * kKVBytes, sDS = sV + 2 * kKVBytes;
+  const uint32_t bar_q = smem_u32(&s_bar[0]), bar_full = smem_u32(&s_bar[1]), bar_empty = smem_u32(&s_bar[3]);
+  const uint32_t bar_sdp = smem_u32(&s_bar[5]), bar_ds = smem_u32(&s_bar[6]), bar_done = smem_u32(&s_bar[7]);
+  const int ntiles = (p.lk + kAttTile - 1) / kAttTile;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_ds, kAttTile);
+    mbar_init(bar_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&s_tmem));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = s_tmem, tmem_dp = s_tmem + 128, tmem_dq = s_tmem + 256;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, 2 * kQBytes);
+      tma_load_5d(sQ, &tmQ, bar_q, p.q_coff + h * kAttD, q0, 0, 0, b);
+      tma_load_5d(sDO, &tmDO, bar_q, p.do_coff + h * kAttD, q0, 0, 0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar_empty + 8 * st, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar_full + 8 * st, 2 * kKVBytes);
+        tma_load_5d(sK + st * kKVBytes, &tmK, bar_full + 8 * st, p.k_coff + h * kAttD, j * kAttTile, 0, 0, b);
+        tma_load_5d(sV + st * kKVBytes, &tmV, bar_full + 8 * st, p.v_coff + h * kAttD, j * kAttTile, 0, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_q = umma_idesc_bf16(128, kAttD, 0, 1);  // A = dS (K-major), B = K tile (MN-major): as P V in the forward kernel
+      const uint32_t l64 = umma_layout_code(64), l128 = umma_layout_code(128);
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar_full + 8 * st, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kAttD / 16; ++k) {
+          umma_f16(tmem_s, umma_smem_desc(sQ + k * 32, 16, 512, l64), umma_smem_desc(sK + st * kKVBytes + k * 32, 16, 512, l64), idesc_s, k != 0 ? 1u : 0u);
+          umma_f16(tmem_dp, umma_smem_desc(sDO + k * 32, 16, 512, l64), umma_smem_desc(sV + st * kKVBytes + k * 32, 16, 512, l64), idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_sdp);
+        mbar_wait(bar_ds, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kAttTile / 16; ++kk) {
+          const uint64_t da = umma_smem_desc(sDS + (kk >> 2) * (kAttTile * 128) + (kk & 3) * 32, 16, 1024, l128);
+          const uint64_t db = umma_smem_desc(sK + st * kKVBytes + kk * 16 * (kAttD * 2), kKVBytes, 8 * (kAttD * 2), l64);
+          umma_f16(tmem_dq, da, db, idesc_q, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_done);
+        umma_commit(bar_empty + 8 * st);
+      }
+    }
+  } else {
+    const int quad = warp & 3, row = quad * 32 + lane, tid = threadIdx.x - 64;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const int qi = q0 + row;
+    const size_t stat = (static_cast<size_t>(b) * p.heads + h) * p.lq + qi;
+    float lse_log2 = qi < p.lq ? p.lse[stat] * 1.4426950408889634f : INFINITY;
+    if (lse_log2 == -INFINITY) lse_log2 = INFINITY;
+    const float dsum = qi < p.lq ? p.dsum[stat] : 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      {
+        const int key = j * kAttTile + tid;
+        const bool dead = key >= p.lk || (p.mask != nullptr && p.mask[static_cast<size_t>(b) * p.lk + key] != 0);
+        s_bias[j & 1][tid] = dead ? -INFINITY : 0.f;
+      }
+      named_bar_sync(1, kAttTile);
+      mbar_wait(bar_sdp, j & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(bar_done, (j - 1) & 1);
+#pragma unroll 1
+      for (int c = 0; c < kAttTile; c += 32) bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias[j & 1], lse_log2, dsum, p.scale, p.scale_log2, sDS, sDS, false);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_ds);
+    }
+    mbar_wait(bar_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld_32x32(tmem_dq + lane_base, o);
+    tmem_ld_wait();
+    if (qi < p.lq) store_row32(p.dq + (static_cast<size_t>(b) * p.lq + qi) * p.dq_pitch + p.dq_coff + h * kAttD, o);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(s_tmem);
+}
+
 int check_seq(const yb200_act* a, const char* name) {
   YB_REQUIRE(a && a->ptr, YB200_ERR_INVALID, "%s: null view", name);
   YB_REQUIRE(a->n > 0 && a->h == 1 && a->w > 0 && a->c > 0, YB200_ERR_INVALID, "%s: expected a [B][1][L][E] view (got %dx%dx%dx%d)", name, a->n, a->h, a->w, a->c);
@@ -270,6 +584,57 @@ extern "C" int yb200_attention_fwd(const yb200_act* q, const yb200_act* k, const
   }
   dim3 grid(ceil_div(p.lq, kAttTile), p.heads, q->n);
   attention_fwd_kernel<<<grid, kAttThreads, kAttSmem, as_stream(stream)>>>(tmQ, tmK, tmV, p);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t yb200_attention_bwd_workspace(const yb200_act* q) {
+  if (!q || q->n <= 0 || q->w <= 0 || q->c <= 0 || q->c % kAttD != 0) return YB200_ERR_INVALID;
+  return 4LL * q->n * (q->c / kAttD) * q->w;
+}
+
+extern "C" int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const yb200_act* v, const yb200_act* out, const yb200_act* dout,
+                                   const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
+                                   const yb200_act* dv, void* workspace, void* stream) {
+  int rc;
+  const yb200_act* all[8] = {q, k, v, out, dout, dq, dk, dv};
+  const char* names[8] = {"attention_bwd q", "attention_bwd k", "attention_bwd v", "attention_bwd out", "attention_bwd dout", "attention_bwd dq", "attention_bwd dk",
+                          "attention_bwd dv"};
+  for (int i = 0; i < 8; ++i)
+    if ((rc = check_seq(all[i], names[i]))) return rc;
+  YB_REQUIRE(lse && workspace, YB200_ERR_INVALID, "attention_bwd: null lse / workspace");
+  const yb200_act* qlike[3] = {out, dout, dq};
+  for (const yb200_act* t : qlike) YB_REQUIRE(t->n == q->n && t->w == q->w && t->c == q->c, YB200_ERR_INVALID, "attention_bwd: query-side shapes differ");
+  const yb200_act* klike[4] = {k, v, dk, dv};
+  for (const yb200_act* t : klike) YB_REQUIRE(t->n == q->n && t->w == k->w && t->c == q->c, YB200_ERR_INVALID, "attention_bwd: key-side shapes differ");
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  if ((rc = make_act_map(&tmQ, *q, false, kAttD, kAttTile, 1, 1))) return rc;
+  if ((rc = make_act_map(&tmK, *k, false, kAttD, kAttTile, 1, 1))) return rc;
+  if ((rc = make_act_map(&tmV, *v, false, kAttD, kAttTile, 1, 1))) return rc;
+  if ((rc = make_act_map(&tmDO, *dout, false, kAttD, kAttTile, 1, 1))) return rc;
+  AttnBwdParams p;
+  p.lq = q->w; p.lk = k->w; p.heads = q->c / kAttD;
+  p.q_coff = q->c_off; p.k_coff = k->c_off; p.v_coff = v->c_off; p.do_coff = dout->c_off;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.mask = key_padding_mask;
+  p.lse = lse;
+  p.dsum = static_cast<const float*>(workspace);
+  p.dq = static_cast<__nv_bfloat16*>(dq->ptr); p.dq_pitch = dq->c_pitch; p.dq_coff = dq->c_off;
+  p.dk = static_cast<__nv_bfloat16*>(dk->ptr); p.dk_pitch = dk->c_pitch; p.dk_coff = dk->c_off;
+  p.dv = static_cast<__nv_bfloat16*>(dv->ptr); p.dv_pitch = dv->c_pitch; p.dv_coff = dv->c_off;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemKV));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemQ));
+    attr_set = true;
+  }
+  cudaStream_t st = as_stream(stream);
+  const long long rows = 1LL * q->n * q->w * p.heads;
+  attention_bwd_prep_kernel<<<static_cast<int>((rows + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out->ptr), out->c_pitch, out->c_off,
+                                                                                  static_cast<const __nv_bfloat16*>(dout->ptr), dout->c_pitch, dout->c_off, q->n,
+                                                                                  q->w, p.heads, static_cast<float*>(workspace));
+  attention_bwd_kv_kernel<<<dim3(ceil_div(p.lk, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemKV, st>>>(tmQ, tmK, tmV, tmDO, p);
+  attention_bwd_q_kernel<<<dim3(ceil_div(p.lq, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemQ, st>>>(tmQ, tmK, tmV, tmDO, p);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
