@@ -14,6 +14,7 @@ Dropout (p = 0.1 in the reference) is identity here: parity runs use eval mode /
 reference's DETR) and `normalize_before=True` are not supported.  There is no CPU implementation.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -21,6 +22,9 @@ import torch.nn as nn
 from . import capi
 
 LN_EPS = 1e-5
+# The encoder layer's backward wiring (autograd.Function over the attention-backward / dgrad / wgrad / LayerNorm-backward kernels) is
+# opt-in until it has been validated on hardware against tests/golden/detr.npz: YB200_DETR_TRAINING=1
+TRAINING_PATH = os.environ.get("YB200_DETR_TRAINING", "0") == "1"
 
 
 def _bl(t):
@@ -79,6 +83,82 @@ class _Kernels:
         capi.check(self.L.yb200_layernorm_fwd(ctypes.byref(xa), capi.ptr(weight.detach().contiguous()), capi.ptr(bias.detach().contiguous()), ctypes.c_float(LN_EPS),
                                               ctypes.byref(ya), None, capi.stream_ptr()), "layernorm")
         return y
+
+    # ---- helpers of the training path ------------------------------------------------------------------------------------------
+    def pack2(self, w):
+        out_f, in_f = w.shape
+        wf = torch.empty(out_f, 1, in_f, dtype=torch.bfloat16, device=w.device)
+        wd = torch.empty(in_f, 1, out_f, dtype=torch.bfloat16, device=w.device)
+        capi.check(self.L.yb200_pack_conv_weight(capi.ptr(w.detach().contiguous()), out_f, in_f, 1, out_f, in_f, capi.ptr(wf), capi.ptr(wd), capi.stream_ptr()), "pack")
+        return wf, wd
+
+    def _ws(self, nbytes, dev):
+        return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+    def layernorm_train(self, x, weight, bias):
+        b, _, l, _ = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(b * l, 2, device=x.device)
+        xa, ya = self._a(x), self._a(y)
+        capi.check(self.L.yb200_layernorm_fwd(ctypes.byref(xa), capi.ptr(weight.detach().contiguous()), capi.ptr(bias.detach().contiguous()), ctypes.c_float(LN_EPS),
+                                              ctypes.byref(ya), capi.ptr(stats), capi.stream_ptr()), "layernorm")
+        return y, stats
+
+    def layernorm_bwd(self, dy, x, stats, weight):
+        dx = torch.empty_like(x)
+        c = x.shape[-1]
+        gw, gb = torch.empty(c, device=x.device), torch.empty(c, device=x.device)
+        da, xa, dxa = self._a(dy), self._a(x), self._a(dx)
+        ws = self._ws(self.L.yb200_layernorm_bwd_workspace(ctypes.byref(xa)), x.device)
+        capi.check(self.L.yb200_layernorm_bwd(ctypes.byref(da), ctypes.byref(xa), capi.ptr(stats), capi.ptr(weight.detach().contiguous()), None, ctypes.byref(dxa),
+                                              capi.ptr(gw), capi.ptr(gb), 0, capi.ptr(ws), capi.stream_ptr()), "layernorm bwd")
+        return dx, gw, gb
+
+    def dgrad(self, dz, w_dgrad, cin, addend=None):
+        """dx = dz W (+ addend); dz may be a (tensor, off, c) slice"""
+        dt, do, dc = dz if isinstance(dz, tuple) else (dz, 0, None)
+        b, _, l, _ = dt.shape
+        dx = torch.empty(b, 1, l, cin, dtype=torch.bfloat16, device=dt.device)
+        da, xa = self._a(dt, do, dc), self._a(dx)
+        aa = self._a(addend) if addend is not None else None
+        capi.check(self.L.yb200_conv2d_dgrad(ctypes.byref(da), capi.ptr(w_dgrad), ctypes.byref(xa), ctypes.byref(aa) if aa is not None else None, 1, 1, capi.stream_ptr()),
+                   "dgrad")
+        return dx
+
+    def wgrad(self, x, dz, out):
+        """out[cout, cin] (fp32, contiguous) = dz^T x"""
+        xt, xo, xc = x if isinstance(x, tuple) else (x, 0, None)
+        dt, do, dc = dz if isinstance(dz, tuple) else (dz, 0, None)
+        xa, da = self._a(xt, xo, xc), self._a(dt, do, dc)
+        ws = self._ws(self.L.yb200_conv2d_wgrad_workspace(ctypes.byref(xa), ctypes.byref(da), 1, 1), xt.device)
+        assert out.is_contiguous() and out.shape == (da.c, xa.c)
+        capi.check(self.L.yb200_conv2d_wgrad(ctypes.byref(xa), ctypes.byref(da), 1, 1, xa.c, capi.ptr(out), 0, capi.ptr(ws), ctypes.c_int64(ws.numel()), capi.stream_ptr()),
+                   "wgrad")
+
+    def colsum(self, dz, out):
+        dt, do, dc = dz if isinstance(dz, tuple) else (dz, 0, None)
+        da = self._a(dt, do, dc)
+        ws = self._ws(self.L.yb200_colsum_workspace(ctypes.byref(da)), dt.device)
+        capi.check(self.L.yb200_colsum(ctypes.byref(da), ctypes.c_float(1.0), capi.ptr(out), 0, capi.ptr(ws), capi.stream_ptr()), "colsum")
+
+    def attention_train(self, q, k, v, mask, heads):
+        qt, _, e = q
+        b, _, lq, _ = qt.shape
+        out = torch.empty(b, 1, lq, e, dtype=torch.bfloat16, device=qt.device)
+        lse = torch.empty(b, heads, lq, device=qt.device)
+        qa, ka, va, oa = self._a(*q), self._a(*k), self._a(*v), self._a(out)
+        capi.check(self.L.yb200_attention_fwd(ctypes.byref(qa), ctypes.byref(ka), ctypes.byref(va), capi.ptr(mask), ctypes.c_float((e // heads) ** -0.5),
+                                              ctypes.byref(oa), capi.ptr(lse), capi.stream_ptr()), "attention")
+        return out, lse
+
+    def attention_bwd(self, q, k, v, out, dout, mask, heads, lse, dq, dk, dv):
+        e = q[2]
+        qa, ka, va, oa, da = self._a(*q), self._a(*k), self._a(*v), self._a(out), self._a(dout)
+        dqa, dka, dva = self._a(*dq), self._a(*dk), self._a(*dv)
+        ws = self._ws(self.L.yb200_attention_bwd_workspace(ctypes.byref(qa)), out.device)
+        capi.check(self.L.yb200_attention_bwd(ctypes.byref(qa), ctypes.byref(ka), ctypes.byref(va), ctypes.byref(oa), ctypes.byref(da), capi.ptr(mask),
+                                              ctypes.c_float((e // heads) ** -0.5), capi.ptr(lse), ctypes.byref(dqa), ctypes.byref(dka), ctypes.byref(dva), capi.ptr(ws),
+                                              capi.stream_ptr()), "attention bwd")
 
     def attention(self, q, k, v, mask, heads):
         """q, k, v: (tensor, channel offset, E) slices of [B,1,L,*] buffers; mask: uint8 [B, Lk] or None"""
@@ -166,6 +246,90 @@ class _LayerBase(nn.Module):
         return kn.layernorm(y, norm.weight, norm.bias)
 
 
+class _EncoderLayerFn(torch.autograd.Function):
+    """forward_post (detr_backbone.py:157-170) with everything the backward needs kept in bf16; backward = the chain
+    LayerNorm2 <- linear2 (+ReLU mask, fused) <- linear1 <- LayerNorm1 <- out_proj <- attention core <- in_proj on the B200 kernels"""
+
+    NAMES = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias", "linear1.weight", "linear1.bias",
+             "linear2.weight", "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")
+
+    @staticmethod
+    def forward(ctx, layer, src, pos, mask, *params):
+        kn, e, heads = layer.k, layer.d_model, layer.nhead
+        w_in, b_in, w_o, b_o, w1, b1, w2, b2, g1, be1, g2, be2 = params
+        x = _bl(src)
+        qk = x if pos is None else kn.add(x, _bl(pos))
+        b, _, l, _ = x.shape
+        qkv = torch.empty(b, 1, l, 3 * e, dtype=torch.bfloat16, device=x.device)
+        kn.linear(qk, w_in[:2 * e], b_in[:2 * e], out=qkv, out_off=0)
+        kn.linear(x, w_in[2 * e:], b_in[2 * e:], out=qkv, out_off=2 * e)
+        att, lse = kn.attention_train((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), mask, heads)
+        y1 = kn.linear(att, w_o, b_o, residual=x)
+        x1, st1 = kn.layernorm_train(y1, g1, be1)
+        h = kn.linear(x1, w1, b1, relu=True)
+        y2 = kn.linear(h, w2, b2, residual=x1)
+        out, st2 = kn.layernorm_train(y2, g2, be2)
+        ctx.layer, ctx.mask, ctx.has_pos = layer, mask, pos is not None
+        ctx.saved = (x, qk, qkv, att, lse, y1, st1, x1, h, y2, st2)
+        ctx.params = params
+        return _lb(out)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        layer = ctx.layer
+        kn, e, heads = layer.k, layer.d_model, layer.nhead
+        x, qk, qkv, att, lse, y1, st1, x1, h, y2, st2 = ctx.saved
+        w_in, b_in, w_o, b_o, w1, b1, w2, b2, g1, be1, g2, be2 = ctx.params
+        dev = x.device
+        ff = w1.shape[0]
+        L = kn.L
+        g = _bl(g_out)
+        # LayerNorm 2
+        g_y2, gg2, gb2 = kn.layernorm_bwd(g, y2, st2, g2)
+        # linear2 (+ residual to x1) and the ReLU in front of it
+        _, w2d = kn.pack2(w2)
+        du = torch.empty_like(h)
+        acc = torch.zeros(ff, dtype=torch.float64, device=dev)
+        ya, ha, dua = kn._a(g_y2), kn._a(h), kn._a(du)
+        capi.check(L.yb200_linear_dgrad_relu(ctypes.byref(ya), capi.ptr(w2d), ctypes.byref(ha), ctypes.byref(dua), capi.ptr(acc), capi.stream_ptr()), "dgrad linear2 + relu bwd")
+        gb1 = torch.empty(ff, device=dev)
+        capi.check(L.yb200_f64_to_f32(capi.ptr(acc), ff, capi.ptr(gb1), 0, 1, capi.stream_ptr()), "db1")
+        gw2 = torch.empty(e, ff, device=dev)
+        kn.wgrad(h, g_y2, gw2)
+        gb2_lin = torch.empty(e, device=dev)
+        kn.colsum(g_y2, gb2_lin)
+        # linear1; the residual branch of x1 joins through the addend
+        _, w1d = kn.pack2(w1)
+        g_x1 = kn.dgrad(du, w1d, e, addend=g_y2)
+        gw1 = torch.empty(ff, e, device=dev)
+        kn.wgrad(x1, du, gw1)
+        # LayerNorm 1
+        g_y1, gg1, gb1n = kn.layernorm_bwd(g_x1, y1, st1, g1)
+        # out_proj (+ residual to x)
+        _, wod = kn.pack2(w_o)
+        g_att = kn.dgrad(g_y1, wod, e)
+        gwo = torch.empty(e, e, device=dev)
+        kn.wgrad(att, g_y1, gwo)
+        gbo = torch.empty(e, device=dev)
+        kn.colsum(g_y1, gbo)
+        # attention core
+        dqkv = torch.empty_like(qkv)
+        kn.attention_bwd((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), att, g_att, ctx.mask, heads, lse, (dqkv, 0, e), (dqkv, e, e), (dqkv, 2 * e, e))
+        # in_proj: q, k from qk = x + pos; v from x
+        _, wqkd = kn.pack2(w_in[:2 * e])
+        _, wvd = kn.pack2(w_in[2 * e:])
+        g_qk = kn.dgrad((dqkv, 0, 2 * e), wqkd, e)
+        g_x = kn.dgrad((dqkv, 2 * e, e), wvd, e, addend=g_y1)
+        g_src = kn.add(g_x, g_qk)
+        gw_in = torch.empty(3 * e, e, device=dev)
+        kn.wgrad(qk, (dqkv, 0, 2 * e), gw_in[:2 * e])
+        kn.wgrad(x, (dqkv, 2 * e, e), gw_in[2 * e:])
+        gb_in = torch.empty(3 * e, device=dev)
+        kn.colsum(dqkv, gb_in)
+        grads = (gw_in, gb_in, gwo, gbo, gw1, gb1, gw2, gb2_lin, gg1, gb1n, gg2, gb2)
+        return (None, _lb(g_src), _lb(g_qk) if ctx.has_pos else None, None) + grads
+
+
 class TransformerEncoderLayer(_LayerBase):
     """detr_backbone.py:128-187"""
 
@@ -174,10 +338,19 @@ class TransformerEncoderLayer(_LayerBase):
         self.self_attn = _MhaParams(d_model, device)
         self.norm1, self.norm2 = _Norm(d_model, device), _Norm(d_model, device)
 
-    @torch.no_grad()
     def forward(self, src, src_mask=None, src_key_padding_mask=None, pos=None):
         if src_mask is not None:
             raise capi.Yb200Error("attn_mask is not supported (the reference's DETR never passes one)")
+        if not src.is_cuda:
+            raise capi.Yb200Error("DETR layers: inputs must be CUDA tensors (no CPU path)")
+        if TRAINING_PATH and torch.is_grad_enabled():
+            params = [dict(self.named_parameters())[n] for n in _EncoderLayerFn.NAMES]
+            if src.requires_grad or any(p.requires_grad for p in params):
+                return _EncoderLayerFn.apply(self, src, pos, _mask_u8(src_key_padding_mask), *params)
+        with torch.no_grad():
+            return self._forward_inference(src, src_key_padding_mask, pos)
+
+    def _forward_inference(self, src, src_key_padding_mask, pos):
         _check_inputs(src, pos)
         x = _bl(src)
         qk = x if pos is None else self.k.add(x, _bl(pos))
