@@ -9,7 +9,9 @@ constructor arguments, parameter names / shapes (`self_attn.in_proj_weight` [3E,
       -> out_proj GEMM (+bias +residual epilogue) -> LayerNorm -> linear1 GEMM (+bias +ReLU epilogue) -> linear2 GEMM (+bias +residual) -> LayerNorm
 
 Internally tokens are batch-first bf16 `[B, 1, L, E]` views (yb200_act).  Scope of round 1: the forward pass (inference, and the forward half
-of training); the attention backward kernel is not built yet, so these modules run under no_grad and refuse inputs that require grad.
+of training) plus the attention-core backward kernel (yb200_attention_bwd, validated).  The encoder layer's full backward (`_EncoderLayerFn`)
+is opt-in (YB200_DETR_TRAINING=1) until its parameter gradients pass tests/test_detr_gpu.py on hardware; by default the modules run under
+no_grad and refuse inputs that require grad.
 Dropout (p = 0.1 in the reference) is identity here: parity runs use eval mode / p = 0.  `attn_mask` (never passed by the
 reference's DETR) and `normalize_before=True` are not supported.  There is no CPU implementation.
 """
