@@ -127,6 +127,18 @@ class _Kernels:
                    "dgrad")
         return dx
 
+    def dgrad_relu(self, dz, w_dgrad, h):
+        """du = (dz W) masked by h > 0, and its column sums (= bias gradient of the Linear that produced h)"""
+        ff = h.shape[-1]
+        du = torch.empty_like(h)
+        acc = torch.zeros(ff, dtype=torch.float64, device=h.device)
+        gb = torch.empty(ff, device=h.device)
+        za, ha, dua = self._a(dz), self._a(h), self._a(du)
+        capi.check(self.L.yb200_linear_dgrad_relu(ctypes.byref(za), capi.ptr(w_dgrad), ctypes.byref(ha), ctypes.byref(dua), capi.ptr(acc), capi.stream_ptr()),
+                   "dgrad + relu bwd")
+        capi.check(self.L.yb200_f64_to_f32(capi.ptr(acc), ff, capi.ptr(gb), 0, 1, capi.stream_ptr()), "bias grad")
+        return du, gb
+
     def wgrad(self, x, dz, out):
         """out[cout, cin] (fp32, contiguous) = dz^T x"""
         xt, xo, xc = x if isinstance(x, tuple) else (x, 0, None)
@@ -284,18 +296,12 @@ class _EncoderLayerFn(torch.autograd.Function):
         w_in, b_in, w_o, b_o, w1, b1, w2, b2, g1, be1, g2, be2 = ctx.params
         dev = x.device
         ff = w1.shape[0]
-        L = kn.L
         g = _bl(g_out)
         # LayerNorm 2
         g_y2, gg2, gb2 = kn.layernorm_bwd(g, y2, st2, g2)
         # linear2 (+ residual to x1) and the ReLU in front of it
         _, w2d = kn.pack2(w2)
-        du = torch.empty_like(h)
-        acc = torch.zeros(ff, dtype=torch.float64, device=dev)
-        ya, ha, dua = kn._a(g_y2), kn._a(h), kn._a(du)
-        capi.check(L.yb200_linear_dgrad_relu(ctypes.byref(ya), capi.ptr(w2d), ctypes.byref(ha), ctypes.byref(dua), capi.ptr(acc), capi.stream_ptr()), "dgrad linear2 + relu bwd")
-        gb1 = torch.empty(ff, device=dev)
-        capi.check(L.yb200_f64_to_f32(capi.ptr(acc), ff, capi.ptr(gb1), 0, 1, capi.stream_ptr()), "db1")
+        du, gb1 = kn.dgrad_relu(g_y2, w2d, h)
         gw2 = torch.empty(e, ff, device=dev)
         kn.wgrad(h, g_y2, gw2)
         gb2_lin = torch.empty(e, device=dev)
