@@ -11,6 +11,13 @@ import torch
 import torch.nn.functional as F
 
 LN_EPS = 1e-5  # nn.LayerNorm default (detr_backbone.py:146-147)
+# True: round every tensor the CUDA path stores in bf16 (activations and the packed weights) -- the yardstick for judging the 16-bit path
+# against this fp32 restatement (same idea as oracle/yolox_oracle.py).  Rounding has an identity gradient, so autograd still works.
+EMULATE_STORAGE = False
+
+
+def _q(t):
+    return t.to(torch.bfloat16).to(torch.float32) if EMULATE_STORAGE else t
 
 
 def mha(query, key, value, sd, prefix, nhead, key_padding_mask=None, need_probs=False):
@@ -21,9 +28,9 @@ def mha(query, key, value, sd, prefix, nhead, key_padding_mask=None, need_probs=
     lk = key.shape[0]
     dh = e // nhead
     w, bias = sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"]
-    q = F.linear(query, w[:e], bias[:e]) * (dh ** -0.5)
-    k = F.linear(key, w[e:2 * e], bias[e:2 * e])
-    v = F.linear(value, w[2 * e:], bias[2 * e:])
+    q = _q(F.linear(query, _q(w[:e]), bias[:e])) * (dh ** -0.5)
+    k = _q(F.linear(key, _q(w[e:2 * e]), bias[e:2 * e]))
+    v = _q(F.linear(value, _q(w[2 * e:]), bias[2 * e:]))
     q = q.reshape(lq, b * nhead, dh).transpose(0, 1)          # [B*H, Lq, dh]
     k = k.reshape(lk, b * nhead, dh).transpose(0, 1)
     v = v.reshape(lk, b * nhead, dh).transpose(0, 1)
@@ -31,8 +38,8 @@ def mha(query, key, value, sd, prefix, nhead, key_padding_mask=None, need_probs=
     if key_padding_mask is not None:
         s = s.view(b, nhead, lq, lk).masked_fill(key_padding_mask[:, None, None, :], float("-inf")).view(b * nhead, lq, lk)
     p = torch.softmax(s, dim=-1)
-    o = torch.bmm(p, v).transpose(0, 1).reshape(lq, b, e)
-    out = F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
+    o = _q(torch.bmm(_q(p), v)).transpose(0, 1).reshape(lq, b, e)
+    out = F.linear(o, _q(sd[prefix + "out_proj.weight"]), sd[prefix + "out_proj.bias"])
     return (out, p) if need_probs else out
 
 
@@ -46,10 +53,12 @@ def _pos(t, pos):
 
 def encoder_layer_post(src, sd, prefix, nhead, key_padding_mask=None, pos=None):
     """TransformerEncoderLayer.forward_post, detr_backbone.py:157-170 (dropout = identity)"""
-    qk = _pos(src, pos)
-    src = _ln(src + mha(qk, qk, src, sd, prefix + "self_attn.", nhead, key_padding_mask), sd, prefix + "norm1")
-    ff = F.linear(F.relu(F.linear(src, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])), sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
-    return _ln(src + ff, sd, prefix + "norm2")
+    src = _q(src)
+    qk = _q(_pos(src, pos))
+    src = _q(_ln(_q(src + mha(qk, qk, src, sd, prefix + "self_attn.", nhead, key_padding_mask)), sd, prefix + "norm1"))
+    h = _q(F.relu(F.linear(src, _q(sd[prefix + "linear1.weight"]), sd[prefix + "linear1.bias"])))
+    ff = F.linear(h, _q(sd[prefix + "linear2.weight"]), sd[prefix + "linear2.bias"])
+    return _q(_ln(_q(src + ff), sd, prefix + "norm2"))
 
 
 def decoder_layer_post(tgt, memory, sd, prefix, nhead, memory_key_padding_mask=None, pos=None, query_pos=None):

@@ -99,7 +99,8 @@ def test_relu_epilogues(cuda):
 @pytest.mark.skipif(os.environ.get("YB200_DETR_TRAINING", "0") != "1", reason="encoder-layer backward wiring is opt-in until validated on hardware")
 def test_encoder_layer_backward_matches_reference(cuda):
     """training path: gradients w.r.t. the input and every parameter of the encoder layer against the reference layer's autograd
-    (tests/golden/detr.npz).  bf16 storage of every saved tensor: cosine > 0.99 and 8e-2 of each gradient's max."""
+    (tests/golden/detr.npz).  bf16 storage of every saved tensor: cosine > 0.995 and at most 2.5x the error of the oracle's own
+    bf16-storage emulation (+2 % of the gradient's max)."""
     from yolov7_d2_b200.detr import TransformerEncoderLayer
 
     gold = np.load(GOLD, allow_pickle=False)
@@ -111,13 +112,24 @@ def test_encoder_layer_backward_matches_reference(cuda):
     _check(out.detach(), gold["enc_out"], "encoder layer output (training path)")
     out.backward(torch.tensor(gold["enc_gout"]).to(cuda))
 
-    def chk(got, ref, what):
-        got, ref = got.float().cpu(), torch.as_tensor(np.asarray(ref)).float()
-        assert torch.isfinite(got).all(), what
-        err = (got - ref).abs().max().item()
-        cos = torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm())
-        assert cos > 0.99 and err <= 8e-2 * ref.abs().max().item(), f"{what}: cos {cos:.4f}, max err {err:.4f} (max |ref| {ref.abs().max().item():.3f})"
+    # yardstick: the oracle with every stored tensor rounded to bf16.  Rounding the FFN hidden activations flips ReLU masks near zero,
+    # which alone moves linear1's gradients by ~10 % of their max on this layer (fp32 vs bf16 storage, both on the CPU).
+    dto.EMULATE_STORAGE = True
+    try:
+        sde = {"l." + k: v.clone().requires_grad_(True) for k, v in dto.layer_state_dict("encoder", d, ffn, seed=2).items()}
+        se = torch.tensor(gold["enc_src"]).requires_grad_(True)
+        dto.encoder_layer_post(se, sde, "l.", nhead, torch.tensor(gold["enc_mask"]), torch.tensor(gold["enc_pos"])).backward(torch.tensor(gold["enc_gout"]))
+    finally:
+        dto.EMULATE_STORAGE = False
 
-    chk(src.grad, gold["enc_gsrc"], "src gradient")
+    def chk(got, ref, emu, what):
+        got, ref, emu = got.float().cpu(), torch.as_tensor(np.asarray(ref)).float(), emu.float()
+        assert torch.isfinite(got).all(), what
+        scale = ref.abs().max().item()
+        err, yard = (got - ref).abs().max().item() / scale, (emu - ref).abs().max().item() / scale
+        cos = torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm())
+        assert cos > 0.995 and err <= 2.5 * yard + 2e-2, f"{what}: cos {cos:.4f}, rel err {err:.4f} vs emulated-storage yardstick {yard:.4f}"
+
+    chk(src.grad, gold["enc_gsrc"], se.grad, "src gradient")
     for name, p in layer.named_parameters():
-        chk(p.grad, gold["enc_grad/" + name], name)
+        chk(p.grad, gold["enc_grad/" + name], sde["l." + name].grad, name)
