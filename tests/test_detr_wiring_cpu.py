@@ -1,0 +1,127 @@
+"""Host logic of the DETR encoder layer's training path without a GPU: `_EncoderLayerFn` (which tensor goes into which kernel, which slice
+of the packed q|k|v buffer, which residual joins where, which gradient lands in which parameter) is executed with every kernel wrapper
+replaced by its torch fp32 equivalent, and must reproduce the reference layer's autograd (tests/golden/detr.npz) to 1e-5.
+The stand-ins live in this test only -- the product has no CPU path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import detr_oracle as dto
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "detr.npz")
+
+
+def _sl(x):
+    if isinstance(x, tuple):
+        t, o, c = x
+        return t[..., o:o + c]
+    return x
+
+
+class TorchKernels:
+    """same method names / argument conventions as yolov7_d2_b200.detr._Kernels"""
+
+    def add(self, a, b):
+        return a + b
+
+    def linear(self, x, w, bias, out=None, out_off=0, residual=None, relu=False):
+        y = F.linear(_sl(x), w.detach(), bias.detach())
+        if residual is not None:
+            y = y + residual
+        if relu:
+            y = F.relu(y)
+        if out is None:
+            return y
+        out[..., out_off:out_off + y.shape[-1]] = y
+        return out
+
+    def pack2(self, w):
+        return w.detach(), w.detach()
+
+    def layernorm_train(self, x, w, b):
+        stats = torch.stack([x.mean(-1).flatten(), (x.var(-1, unbiased=False) + 1e-5).rsqrt().flatten()], 1)
+        return F.layer_norm(x, (x.shape[-1],), w.detach(), b.detach(), 1e-5), stats
+
+    def layernorm_bwd(self, dy, x, stats, w):
+        with torch.enable_grad():
+            xr, wr = x.clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+            br = torch.zeros_like(wr).requires_grad_(True)
+            F.layer_norm(xr, (x.shape[-1],), wr, br, 1e-5).backward(dy)
+        return xr.grad, wr.grad, br.grad
+
+    def dgrad(self, dz, w, cin, addend=None):
+        y = _sl(dz) @ w
+        return y + addend if addend is not None else y
+
+    def dgrad_relu(self, dz, w, h):
+        du = (dz @ w) * (h > 0)
+        return du, du.sum((0, 1, 2))
+
+    def wgrad(self, x, dz, out):
+        out.copy_(torch.einsum("bhlo,bhli->oi", _sl(dz), _sl(x)))
+
+    def colsum(self, dz, out):
+        out.copy_(_sl(dz).sum((0, 1, 2)))
+
+    @staticmethod
+    def _heads(t, heads):
+        b, _, l, e = t.shape
+        return t.view(b, l, heads, e // heads).permute(0, 2, 1, 3)
+
+    def attention_train(self, q, k, v, mask, heads):
+        qt = _sl(q)
+        b, _, lq, e = qt.shape
+        o = dto.attention_core(self._heads(qt, heads), self._heads(_sl(k), heads), self._heads(_sl(v), heads), mask.bool() if mask is not None else None)
+        return o.permute(0, 2, 1, 3).reshape(b, 1, lq, e), None
+
+    def attention_bwd(self, q, k, v, out, dout, mask, heads, lse, dq, dk, dv):
+        with torch.enable_grad():
+            qt, kt, vt = (_sl(t).clone().requires_grad_(True) for t in (q, k, v))
+            b, _, lq, e = qt.shape
+            o = dto.attention_core(self._heads(qt, heads), self._heads(kt, heads), self._heads(vt, heads), mask.bool() if mask is not None else None)
+            o.permute(0, 2, 1, 3).reshape(b, 1, lq, e).backward(dout)
+        for (t, off, c), g in zip((dq, dk, dv), (qt.grad, kt.grad, vt.grad)):
+            t[..., off:off + c] = g
+
+
+@pytest.fixture()
+def detr_fp32(monkeypatch):
+    """import the module without the CUDA library and keep its internal buffers in fp32"""
+    from yolov7_d2_b200 import detr
+
+    monkeypatch.setattr(detr, "_bl", lambda t: t.detach().permute(1, 0, 2).float().contiguous().unsqueeze(1))
+    monkeypatch.setattr(detr, "_lb", lambda t: t.squeeze(1).permute(1, 0, 2).float().contiguous())
+    monkeypatch.setattr(torch, "bfloat16", torch.float32)  # the Function allocates its packed buffers with torch.bfloat16
+    return detr
+
+
+def test_encoder_layer_training_wiring(detr_fp32):
+    detr = detr_fp32
+    gold = np.load(GOLD, allow_pickle=False)
+    d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
+    layer = type("Layer", (), {})()
+    layer.k, layer.d_model, layer.nhead = TorchKernels(), d, nhead
+    sd = dto.layer_state_dict("encoder", d, ffn, seed=2)
+    params = [sd[n].clone().requires_grad_(True) for n in detr._EncoderLayerFn.NAMES]
+    src = torch.tensor(gold["enc_src"]).requires_grad_(True)
+    pos = torch.tensor(gold["enc_pos"]).requires_grad_(True)
+    out = detr._EncoderLayerFn.apply(layer, src, pos, torch.tensor(gold["enc_mask"]).to(torch.uint8), *params)
+
+    def close(a, ref, what):
+        ref = torch.as_tensor(np.asarray(ref))
+        err = (a - ref).abs().max().item()
+        assert err <= 1e-5 * ref.abs().max().item(), f"{what}: {err:.3e}"
+
+    close(out.detach(), gold["enc_out"], "output")
+    out.backward(torch.tensor(gold["enc_gout"]))
+    close(src.grad, gold["enc_gsrc"], "src gradient")
+    for n, p in zip(detr._EncoderLayerFn.NAMES, params):
+        close(p.grad, gold["enc_grad/" + n], n)
+    # the positional embedding receives the gradient of the query / key path only
+    sdr = {"l." + k: v for k, v in sd.items()}
+    s2, p2 = torch.tensor(gold["enc_src"]), torch.tensor(gold["enc_pos"]).requires_grad_(True)
+    dto.encoder_layer_post(s2, sdr, "l.", nhead, torch.tensor(gold["enc_mask"]), p2).backward(torch.tensor(gold["enc_gout"]))
+    close(pos.grad, p2.grad, "pos gradient")
