@@ -63,11 +63,14 @@ def encoder_layer_post(src, sd, prefix, nhead, key_padding_mask=None, pos=None):
 
 def decoder_layer_post(tgt, memory, sd, prefix, nhead, memory_key_padding_mask=None, pos=None, query_pos=None):
     """TransformerDecoderLayer.forward_post, detr_backbone.py:221-242 (dropout = identity)"""
-    qk = _pos(tgt, query_pos)
-    tgt = _ln(tgt + mha(qk, qk, tgt, sd, prefix + "self_attn.", nhead), sd, prefix + "norm1")
-    tgt = _ln(tgt + mha(_pos(tgt, query_pos), _pos(memory, pos), memory, sd, prefix + "multihead_attn.", nhead, memory_key_padding_mask), sd, prefix + "norm2")
-    ff = F.linear(F.relu(F.linear(tgt, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])), sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
-    return _ln(tgt + ff, sd, prefix + "norm3")
+    tgt, memory = _q(tgt), _q(memory)
+    qk = _q(_pos(tgt, query_pos))
+    tgt = _q(_ln(_q(tgt + mha(qk, qk, tgt, sd, prefix + "self_attn.", nhead)), sd, prefix + "norm1"))
+    tgt = _q(_ln(_q(tgt + mha(_q(_pos(tgt, query_pos)), _q(_pos(memory, pos)), memory, sd, prefix + "multihead_attn.", nhead, memory_key_padding_mask)), sd,
+                 prefix + "norm2"))
+    h = _q(F.relu(F.linear(tgt, _q(sd[prefix + "linear1.weight"]), sd[prefix + "linear1.bias"])))
+    ff = F.linear(h, _q(sd[prefix + "linear2.weight"]), sd[prefix + "linear2.bias"])
+    return _q(_ln(_q(tgt + ff), sd, prefix + "norm3"))
 
 
 def attention_core(q, k, v, key_padding_mask=None, scale=None):

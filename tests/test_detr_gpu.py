@@ -133,3 +133,49 @@ def test_encoder_layer_backward_matches_reference(cuda):
     chk(src.grad, gold["enc_gsrc"], se.grad, "src gradient")
     for name, p in layer.named_parameters():
         chk(p.grad, gold["enc_grad/" + name], sde["l." + name].grad, name)
+
+
+@pytest.mark.skipif(os.environ.get("YB200_DETR_TRAINING", "0") != "1", reason="decoder-layer backward wiring is opt-in until validated on hardware")
+def test_decoder_layer_backward_matches_oracle(cuda):
+    """training path of the decoder layer against the autograd of the oracle (forward pinned to the reference layer), judged with the oracle's
+    bf16-storage emulation as yardstick (see the encoder test)"""
+    import torch.nn.functional as F
+    from yolov7_d2_b200.detr import TransformerDecoderLayer
+
+    gold = np.load(GOLD, allow_pickle=False)
+    d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
+    sd = dto.layer_state_dict("decoder", d, ffn, seed=3)
+    layer = TransformerDecoderLayer(d, nhead, dim_feedforward=ffn, dropout=0.0)
+    layer.load_state_dict({k: v.to(cuda) for k, v in sd.items()}, strict=True)
+    names = ("dec_tgt", "dec_mem", "enc_pos", "dec_qpos")
+    mask = torch.tensor(gold["enc_mask"])
+    gout = torch.randn(gold["dec_out"].shape, generator=torch.Generator().manual_seed(4))
+
+    def oracle_run(emulate):
+        dto.EMULATE_STORAGE = emulate
+        try:
+            ins = [torch.tensor(gold[k]).requires_grad_(True) for k in names]
+            sdr = {"l." + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            dto.decoder_layer_post(ins[0], ins[1], sdr, "l.", nhead, mask, ins[2], ins[3]).backward(gout)
+        finally:
+            dto.EMULATE_STORAGE = False
+        return ins, sdr
+
+    ref_in, ref_sd = oracle_run(False)
+    emu_in, emu_sd = oracle_run(True)
+    ours = [torch.tensor(gold[k]).to(cuda).requires_grad_(True) for k in names]
+    out = layer(ours[0], ours[1], memory_key_padding_mask=mask.to(cuda), pos=ours[2], query_pos=ours[3])
+    _check(out.detach(), gold["dec_out"], "decoder layer output (training path)")
+    out.backward(gout.to(cuda))
+
+    def chk(got, ref, emu, what):
+        got, ref, emu = got.float().cpu(), ref.float(), emu.float()
+        scale = ref.abs().max().item()
+        err, yard = (got - ref).abs().max().item() / scale, (emu - ref).abs().max().item() / scale
+        cos = torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm())
+        assert torch.isfinite(got).all() and cos > 0.995 and err <= 2.5 * yard + 2e-2, f"{what}: cos {cos:.4f}, rel err {err:.4f} vs yardstick {yard:.4f}"
+
+    for k, a, r, m in zip(names, ours, ref_in, emu_in):
+        chk(a.grad, r.grad, m.grad, k + " gradient")
+    for name, p in layer.named_parameters():
+        chk(p.grad, ref_sd["l." + name].grad, emu_sd["l." + name].grad, name)

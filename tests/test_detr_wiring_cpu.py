@@ -125,3 +125,42 @@ def test_encoder_layer_training_wiring(detr_fp32):
     s2, p2 = torch.tensor(gold["enc_src"]), torch.tensor(gold["enc_pos"]).requires_grad_(True)
     dto.encoder_layer_post(s2, sdr, "l.", nhead, torch.tensor(gold["enc_mask"]), p2).backward(torch.tensor(gold["enc_gout"]))
     close(pos.grad, p2.grad, "pos gradient")
+
+
+def test_decoder_layer_training_wiring(detr_fp32):
+    """`_DecoderLayerFn` against the autograd of oracle.detr_oracle.decoder_layer_post (whose forward is pinned to the reference layer)"""
+    detr = detr_fp32
+    gold = np.load(GOLD, allow_pickle=False)
+    d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
+    layer = type("Layer", (), {})()
+    layer.k, layer.d_model, layer.nhead = TorchKernels(), d, nhead
+    sd = dto.layer_state_dict("decoder", d, ffn, seed=3)
+    params = [sd[n].clone().requires_grad_(True) for n in detr._DecoderLayerFn.NAMES]
+    names = ("dec_tgt", "dec_mem", "enc_pos", "dec_qpos")
+    ours = [torch.tensor(gold[k]).requires_grad_(True) for k in names]
+    mem_mask = torch.tensor(gold["enc_mask"])
+    tgt_mask = torch.zeros(b, ours[0].shape[0], dtype=torch.bool)
+    tgt_mask[1, 15:] = True
+    out = detr._DecoderLayerFn.apply(layer, ours[0], ours[1], ours[2], ours[3], tgt_mask.to(torch.uint8), mem_mask.to(torch.uint8), *params)
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+    out.backward(gout)
+    # reference: autograd of the oracle (self-attention key padding is not an argument of decoder_layer_post: restate the block here)
+    refs = [torch.tensor(gold[k]).requires_grad_(True) for k in names]
+    sdr = {"l." + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    tgt, mem, pos, qpos = refs
+    qk = tgt + qpos
+    t1 = dto._ln(tgt + dto.mha(qk, qk, tgt, sdr, "l.self_attn.", nhead, tgt_mask), sdr, "l.norm1")
+    t2 = dto._ln(t1 + dto.mha(t1 + qpos, mem + pos, mem, sdr, "l.multihead_attn.", nhead, mem_mask), sdr, "l.norm2")
+    ff = F.linear(F.relu(F.linear(t2, sdr["l.linear1.weight"], sdr["l.linear1.bias"])), sdr["l.linear2.weight"], sdr["l.linear2.bias"])
+    ref_out = dto._ln(t2 + ff, sdr, "l.norm3")
+    ref_out.backward(gout)
+
+    def close(a, ref, what):
+        err = (a - ref).abs().max().item()
+        assert err <= 2e-5 * ref.abs().max().item(), f"{what}: {err:.3e}"
+
+    close(out.detach(), ref_out.detach(), "output")
+    for k, a, r in zip(names, ours, refs):
+        close(a.grad, r.grad, k + " gradient")
+    for n, p in zip(detr._DecoderLayerFn.NAMES, params):
+        close(p.grad, sdr["l." + n].grad, n)

@@ -338,6 +338,105 @@ class _EncoderLayerFn(torch.autograd.Function):
         return (None, _lb(g_src), _lb(g_qk) if ctx.has_pos else None, None) + grads
 
 
+class _DecoderLayerFn(torch.autograd.Function):
+    """TransformerDecoderLayer.forward_post (detr_backbone.py:221-242) and its backward on the same kernels as `_EncoderLayerFn`:
+    self-attention block, cross-attention block (queries from the decoder stream, keys / values from the encoder memory), FFN block"""
+
+    NAMES = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+             "multihead_attn.in_proj_weight", "multihead_attn.in_proj_bias", "multihead_attn.out_proj.weight", "multihead_attn.out_proj.bias",
+             "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias", "norm3.weight", "norm3.bias")
+
+    @staticmethod
+    def forward(ctx, layer, tgt, memory, pos, query_pos, tgt_mask, mem_mask, *params):
+        kn, e, heads = layer.k, layer.d_model, layer.nhead
+        ws, bs, wso, bso, wc, bc, wco, bco, w1, b1, w2, b2, g1, be1, g2, be2, g3, be3 = params
+        x = _bl(tgt)
+        qp = None if query_pos is None else _bl(query_pos)
+        qk = x if qp is None else kn.add(x, qp)
+        b, _, lq, _ = x.shape
+        qkv = torch.empty(b, 1, lq, 3 * e, dtype=torch.bfloat16, device=x.device)
+        kn.linear(qk, ws[:2 * e], bs[:2 * e], out=qkv, out_off=0)
+        kn.linear(x, ws[2 * e:], bs[2 * e:], out=qkv, out_off=2 * e)
+        att1, lse1 = kn.attention_train((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), tgt_mask, heads)
+        y1 = kn.linear(att1, wso, bso, residual=x)
+        x1, st1 = kn.layernorm_train(y1, g1, be1)
+        mem = _bl(memory)
+        memk = mem if pos is None else kn.add(mem, _bl(pos))
+        q2 = x1 if qp is None else kn.add(x1, qp)
+        qc = kn.linear(q2, wc[:e], bc[:e])
+        lk = mem.shape[2]
+        kv = torch.empty(b, 1, lk, 2 * e, dtype=torch.bfloat16, device=x.device)
+        kn.linear(memk, wc[e:2 * e], bc[e:2 * e], out=kv, out_off=0)
+        kn.linear(mem, wc[2 * e:], bc[2 * e:], out=kv, out_off=e)
+        att2, lse2 = kn.attention_train((qc, 0, e), (kv, 0, e), (kv, e, e), mem_mask, heads)
+        y2 = kn.linear(att2, wco, bco, residual=x1)
+        x2, st2 = kn.layernorm_train(y2, g2, be2)
+        h = kn.linear(x2, w1, b1, relu=True)
+        y3 = kn.linear(h, w2, b2, residual=x2)
+        out, st3 = kn.layernorm_train(y3, g3, be3)
+        ctx.layer, ctx.masks, ctx.has = layer, (tgt_mask, mem_mask), (pos is not None, query_pos is not None)
+        ctx.saved = (x, qk, qkv, att1, lse1, y1, st1, x1, mem, memk, q2, qc, kv, att2, lse2, y2, st2, x2, h, y3, st3)
+        ctx.params = params
+        return _lb(out)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        layer = ctx.layer
+        kn, e, heads = layer.k, layer.d_model, layer.nhead
+        x, qk, qkv, att1, lse1, y1, st1, x1, mem, memk, q2, qc, kv, att2, lse2, y2, st2, x2, h, y3, st3 = ctx.saved
+        ws, bs, wso, bso, wc, bc, wco, bco, w1, b1, w2, b2, g1, be1, g2, be2, g3, be3 = ctx.params
+        tgt_mask, mem_mask = ctx.masks
+        has_pos, has_qpos = ctx.has
+        dev, ff = x.device, w1.shape[0]
+        f32 = lambda *shape: torch.empty(*shape, device=dev)
+        g = _bl(g_out)
+        # FFN block
+        g_y3, gg3, gbn3 = kn.layernorm_bwd(g, y3, st3, g3)
+        du, gb1 = kn.dgrad_relu(g_y3, kn.pack2(w2)[1], h)
+        gw2, gb2 = f32(e, ff), f32(e)
+        kn.wgrad(h, g_y3, gw2)
+        kn.colsum(g_y3, gb2)
+        g_x2 = kn.dgrad(du, kn.pack2(w1)[1], e, addend=g_y3)
+        gw1 = f32(ff, e)
+        kn.wgrad(x2, du, gw1)
+        # cross-attention block
+        g_y2, gg2, gbn2 = kn.layernorm_bwd(g_x2, y2, st2, g2)
+        g_att2 = kn.dgrad(g_y2, kn.pack2(wco)[1], e)
+        gwco, gbco = f32(e, e), f32(e)
+        kn.wgrad(att2, g_y2, gwco)
+        kn.colsum(g_y2, gbco)
+        dqc, dkv = torch.empty_like(qc), torch.empty_like(kv)
+        kn.attention_bwd((qc, 0, e), (kv, 0, e), (kv, e, e), att2, g_att2, mem_mask, heads, lse2, (dqc, 0, e), (dkv, 0, e), (dkv, e, e))
+        g_q2 = kn.dgrad(dqc, kn.pack2(wc[:e])[1], e)
+        g_memk = kn.dgrad((dkv, 0, e), kn.pack2(wc[e:2 * e])[1], e)
+        g_mem = kn.dgrad((dkv, e, e), kn.pack2(wc[2 * e:])[1], e, addend=g_memk)  # memory feeds keys (through + pos) and values
+        gwc, gbc = f32(3 * e, e), f32(3 * e)
+        kn.wgrad(q2, dqc, gwc[:e])
+        kn.wgrad(memk, (dkv, 0, e), gwc[e:2 * e])
+        kn.wgrad(mem, (dkv, e, e), gwc[2 * e:])
+        kn.colsum(dqc, gbc[:e])
+        kn.colsum(dkv, gbc[e:])
+        g_x1 = kn.add(g_y2, g_q2)  # residual branch + query path
+        # self-attention block
+        g_y1, gg1, gbn1 = kn.layernorm_bwd(g_x1, y1, st1, g1)
+        g_att1 = kn.dgrad(g_y1, kn.pack2(wso)[1], e)
+        gwso, gbso = f32(e, e), f32(e)
+        kn.wgrad(att1, g_y1, gwso)
+        kn.colsum(g_y1, gbso)
+        dqkv = torch.empty_like(qkv)
+        kn.attention_bwd((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), att1, g_att1, tgt_mask, heads, lse1, (dqkv, 0, e), (dqkv, e, e), (dqkv, 2 * e, e))
+        g_qk = kn.dgrad((dqkv, 0, 2 * e), kn.pack2(ws[:2 * e])[1], e)
+        g_x = kn.dgrad((dqkv, 2 * e, e), kn.pack2(ws[2 * e:])[1], e, addend=g_y1)
+        g_tgt = kn.add(g_x, g_qk)
+        gws, gbs = f32(3 * e, e), f32(3 * e)
+        kn.wgrad(qk, (dqkv, 0, 2 * e), gws[:2 * e])
+        kn.wgrad(x, (dqkv, 2 * e, e), gws[2 * e:])
+        kn.colsum(dqkv, gbs)
+        g_qpos = _lb(kn.add(g_qk, g_q2)) if has_qpos else None
+        grads = (gws, gbs, gwso, gbso, gwc, gbc, gwco, gbco, gw1, gb1, gw2, gb2, gg1, gbn1, gg2, gbn2, gg3, gbn3)
+        return (None, _lb(g_tgt), _lb(g_mem), _lb(g_memk) if has_pos else None, g_qpos, None, None) + grads
+
+
 class TransformerEncoderLayer(_LayerBase):
     """detr_backbone.py:128-187"""
 
@@ -376,10 +475,17 @@ class TransformerDecoderLayer(_LayerBase):
         self.multihead_attn = _MhaParams(d_model, device)
         self.norm1, self.norm2, self.norm3 = _Norm(d_model, device), _Norm(d_model, device), _Norm(d_model, device)
 
-    @torch.no_grad()
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
         if tgt_mask is not None or memory_mask is not None:
             raise capi.Yb200Error("attn_mask is not supported (the reference's DETR never passes one)")
+        if TRAINING_PATH and torch.is_grad_enabled():
+            params = [dict(self.named_parameters())[n] for n in _DecoderLayerFn.NAMES]
+            if tgt.requires_grad or memory.requires_grad or any(p.requires_grad for p in params):
+                return _DecoderLayerFn.apply(self, tgt, memory, pos, query_pos, _mask_u8(tgt_key_padding_mask), _mask_u8(memory_key_padding_mask), *params)
+        with torch.no_grad():
+            return self._forward_inference(tgt, memory, tgt_key_padding_mask, memory_key_padding_mask, pos, query_pos)
+
+    def _forward_inference(self, tgt, memory, tgt_key_padding_mask, memory_key_padding_mask, pos, query_pos):
         _check_inputs(tgt, memory, pos, query_pos)
         kn, e = self.k, self.d_model
         x = _bl(tgt)
