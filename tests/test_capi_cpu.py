@@ -80,3 +80,19 @@ def test_extended_entry_points_validate_arguments_without_gpu():
     assert L.yb200_sgd_step(None, None, None, ctypes.c_int64(0), None, None, None, 0, ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0), 0, 0,
                             ctypes.c_float(1), None, ctypes.c_float(0), None) != 0
     assert b"null" in L.yb200_last_error() or b"sgd_step" in L.yb200_last_error()
+
+
+def test_public_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/yb200.h must compile as C99 without any C++ or torch type"""
+    import shutil
+    import subprocess
+    import tempfile
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "h.c")
+        with open(src, "w") as fh:
+            fh.write('#include "yb200.h"\nint main(void) { return yb200_version == 0; }\n')
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
