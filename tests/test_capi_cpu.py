@@ -96,3 +96,41 @@ def test_public_header_is_plain_c():
             fh.write('#include "yb200.h"\nint main(void) { return 0; }\n')
         r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_every_python_call_site_matches_the_header_arity():
+    """ctypes does not check argument counts: compare every `.yb200_*( ... )` call in the repo with the prototype in include/yb200.h"""
+    import glob
+    import re
+
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "yb200.h")).read(), flags=re.S)
+    arity = {}
+    for m in re.finditer(r"\b(yb200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        arity[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+
+    def count_args(src, i):
+        depth, j, n, seen = 1, i, 0, False
+        while depth > 0:
+            c = src[j]
+            if c in "([{":
+                depth += 1
+            elif c in ")]}":
+                depth -= 1
+            elif c == "," and depth == 1:
+                n += 1
+            if depth >= 1 and not c.isspace() and c != ")":
+                seen = True
+            j += 1
+        return n + 1 if seen else 0
+
+    bad = []
+    files = [f for pat in ("*.py", "yolov7_d2_b200/*.py", "tests/*.py", "tools/*.py") for f in glob.glob(os.path.join(ROOT, pat))]
+    assert len(files) > 20
+    for f in files:
+        src = open(f).read()
+        for m in re.finditer(r"\.(yb200_[a-z0-9_]+)\(", src):
+            name = m.group(1)
+            if name in arity and count_args(src, m.end()) != arity[name]:
+                bad.append((os.path.relpath(f, ROOT), name, count_args(src, m.end()), arity[name]))
+    assert not bad, bad
