@@ -188,8 +188,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import yolox_oracle as orc  # cpu_baseline leg + synthetic data generator only
-    from yolov7_d2_b200 import capi
+    from yolov7_d2_b200 import capi, synth  # the GPU arm never imports oracle/: inputs come from yolov7_d2_b200.synth
     from yolov7_d2_b200.engine import YoloxEngine
     from yolov7_d2_b200.modeling import YOLOX, postprocess
 
@@ -203,12 +202,10 @@ def main():
     B = args.batch
 
     cfg = yolox_s_cfg("cuda")
-    model = YOLOX(cfg)
-    sd = orc.yolox_state_dict(0)
-    model.load_state_dict({k: v for k, v in sd.items()}, strict=True)
+    model = YOLOX(cfg)  # random initialisation of the reference architecture (seeded; wrappers.py / yolox_head.py defaults)
     model.train()
     eng = model._plan(B, 640, 640)
-    images, labels = orc.synthetic_batch(B, 640, seed=100 + rank)
+    images, labels = synth.synthetic_batch(B, 640, seed=100 + rank)
     eng.images_u8.copy_(images.to(dev))
     eng.labels.copy_(labels.to(dev))
     flat_grad = eng.flat_grad
@@ -369,8 +366,7 @@ def main():
     # ---- NMS boxes/s (second half of the BASELINE metric) ----
     nms = None
     if rank == 0:
-        from oracle.gen_golden import clustered_predictions
-        pred = clustered_predictions(4, 8400, 80, 7).repeat(B // 4, 1, 1).to(dev)
+        pred = synth.clustered_predictions(4, 8400, 80, 7).repeat(B // 4, 1, 1).to(dev)
         cand = int(((pred[..., 4] * pred[..., 5:].max(-1).values) >= 0.001).sum())
         for _ in range(3):
             postprocess(pred.clone(), 80, 0.001, 0.65)
@@ -388,11 +384,13 @@ def main():
     cnx_line = None
     if rank == 0 and world == 1 and not args.no_convnext:
         try:
-            from oracle import convnext_oracle as cnxo  # synthetic parameters / images only
             from yolov7_d2_b200.convnext import ConvNeXtEngine
             ce = ConvNeXtEngine(32, 640, 640, device=dev)
-            ce.load_state_dict(cnxo.convnext_state_dict(0, trained_like=True))
-            ce.images_u8.copy_(cnxo.synthetic_images(32, 640, 1).to(dev))
+            ce.init_weights(0)
+            for pname in ce.param_names:  # a trained-like layer scale instead of the 1e-6 initial value, so the residual branches carry signal
+                if pname.endswith("gamma"):
+                    ce.params[pname].fill_(0.1)
+            ce.images_u8.copy_(synth.synthetic_images(32, 640, 1).to(dev))
             gen = torch.Generator(device=dev).manual_seed(2)
             for st in ce.stage:
                 st.gout.t.copy_(torch.randn(st.gout.t.shape, generator=gen, device=dev) * 1e-2)
@@ -416,6 +414,7 @@ def main():
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import yolox_oracle as orc  # the only place the GPU arm's process touches oracle/: the CPU baseline being timed
         csd = orc.yolox_state_dict(0)
         for k, v in csd.items():
             if v.dtype == torch.float32 and "running" not in k:

@@ -113,6 +113,4 @@ def convnext_state_dict(seed=0, in_chans=3, depths=(3, 3, 9, 3), dims=(96, 192, 
     return sd
 
 
-def synthetic_images(batch, size, seed=0):
-    g = torch.Generator().manual_seed(seed)
-    return torch.randint(0, 256, (batch, 3, size, size), generator=g, dtype=torch.uint8)
+from yolov7_d2_b200.synth import synthetic_images  # noqa: E402,F401

@@ -178,27 +178,7 @@ def gen_simota(mods, size=256, num_classes=80):
     np.savez_compressed(os.path.join(OUT, "simota.npz"), **res)
 
 
-def clustered_predictions(batch, anchors, num_classes, seed):
-    """NMS stress set: per image 30 GT boxes x jittered copies, scores ~ Beta(2,5)"""
-    g = torch.Generator().manual_seed(seed)
-    pred = torch.zeros(batch, anchors, 5 + num_classes)
-    per = anchors // 30
-    beta = torch.distributions.Beta(2.0, 5.0)
-    for b in range(batch):
-        gt = torch.cat([torch.rand(30, 2, generator=g) * 500 + 70, torch.exp(torch.rand(30, 2, generator=g) * 2.5 + 2.5)], 1)
-        cls = torch.randint(0, num_classes, (30,), generator=g)
-        idx = torch.arange(anchors) % 30
-        box = gt[idx] * (1 + torch.randn(anchors, 4, generator=g) * 0.1)
-        box[:, 2:] = box[:, 2:].abs() + 1
-        pred[b, :, :4] = box
-        u = torch.rand(anchors, 2, generator=g)
-        pred[b, :, 4] = u[:, 0] ** 0.6 * 0.9 + 0.05
-        c = cls[idx].clone()
-        flip = torch.rand(anchors, generator=g) < 0.1
-        c[flip] = torch.randint(0, num_classes, (int(flip.sum()),), generator=g)
-        pred[b, :, 5:] = torch.rand(anchors, num_classes, generator=g) * 0.05
-        pred[b, torch.arange(anchors), 5 + c] = u[:, 1] ** 0.5 * 0.9 + 0.08
-    return pred
+from yolov7_d2_b200.synth import clustered_predictions  # noqa: E402,F401
 
 
 def gen_nms(mods, num_classes=80):

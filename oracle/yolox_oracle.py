@@ -482,22 +482,4 @@ def yolox_state_dict(seed=0, width=0.5, depth=0.33, num_classes=80, prior_prob=1
     return sd
 
 
-def synthetic_batch(batch, size=640, seed=0, max_gt=20, max_boxes=100, empty_every=0):
-    """COCO-shaped synthetic batch: uint8 images U{0..255}; labels [B,100,5] with 1..max_gt boxes
-    (cls U{0..79}, centre U(0.1,0.9)*size, w/h log-uniform(16, 0.6*size)), clipped to the image."""
-    g = torch.Generator().manual_seed(seed)
-    images = torch.randint(0, 256, (batch, 3, size, size), generator=g, dtype=torch.uint8)
-    labels = torch.zeros(batch, max_boxes, 5)
-    for b in range(batch):
-        if empty_every and (b % empty_every) == empty_every - 1:
-            continue
-        k = int(torch.randint(1, max_gt + 1, (1,), generator=g))
-        cxy = (torch.rand(k, 2, generator=g) * 0.8 + 0.1) * size
-        lo, hi = math.log(16.0), math.log(0.6 * size)
-        wh = torch.exp(torch.rand(k, 2, generator=g) * (hi - lo) + lo)
-        x1y1 = (cxy - wh / 2).clamp(0, size)
-        x2y2 = (cxy + wh / 2).clamp(0, size)
-        labels[b, :k, 0] = torch.randint(0, 80, (k,), generator=g).float()
-        labels[b, :k, 1:3] = (x1y1 + x2y2) / 2
-        labels[b, :k, 3:5] = (x2y2 - x1y1).clamp(min=2.0)
-    return images, labels
+from yolov7_d2_b200.synth import synthetic_batch  # noqa: E402,F401  (shared generator: same inputs for every arm and every fixture)

@@ -3,7 +3,7 @@
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import convnext_oracle as cnx
+from yolov7_d2_b200 import synth
 from yolov7_d2_b200.convnext import ConvNeXtEngine
 
 ap = argparse.ArgumentParser()
@@ -16,9 +16,12 @@ ap.add_argument("--no-overlap", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 eng = ConvNeXtEngine(a.batch, a.size, a.size, device=dev)
-eng.load_state_dict(cnx.convnext_state_dict(0, trained_like=True))
+eng.init_weights(0)
+for _n in eng.param_names:  # trained-like layer scale instead of the 1e-6 initial value
+    if _n.endswith("gamma"):
+        eng.params[_n].fill_(0.1)
 eng.overlap_wgrad = not a.no_overlap
-eng.images_u8.copy_(cnx.synthetic_images(a.batch, a.size, 1).to(dev))
+eng.images_u8.copy_(synth.synthetic_images(a.batch, a.size, 1).to(dev))
 g = torch.Generator(device=dev).manual_seed(2)
 for st in eng.stage:
     st.gout.t.copy_(torch.randn(st.gout.t.shape, generator=g, device=dev) * 1e-2)

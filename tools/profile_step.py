@@ -5,7 +5,7 @@
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import yolox_oracle as orc
+from yolov7_d2_b200 import synth
 from yolov7_d2_b200.engine import YoloxEngine
 
 ap = argparse.ArgumentParser()
@@ -16,8 +16,8 @@ ap.add_argument("--eval", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 eng = YoloxEngine(a.batch, a.size, a.size, device=dev)
-eng.load_state_dict(orc.yolox_state_dict(0))
-images, labels = orc.synthetic_batch(a.batch, a.size, 100)
+eng.init_weights(0)
+images, labels = synth.synthetic_batch(a.batch, a.size, 100)
 eng.images_u8.copy_(images.to(dev)); eng.labels.copy_(labels.to(dev))
 for _ in range(a.warmup):
     eng.eval_forward() if a.eval else eng.train_step()
