@@ -134,3 +134,17 @@ def test_every_python_call_site_matches_the_header_arity():
             if name in arity and count_args(src, m.end()) != arity[name]:
                 bad.append((os.path.relpath(f, ROOT), name, count_args(src, m.end()), arity[name]))
     assert not bad, bad
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: the package must not import it, and bench.py only inside its two CPU legs"""
+    import glob
+    import re
+
+    for f in glob.glob(os.path.join(ROOT, "yolov7_d2_b200", "*.py")):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", open(f).read(), flags=re.M), f
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    hits = [m.start() for m in re.finditer(r"^\s*from oracle\b", src, flags=re.M)]
+    assert len(hits) == 2
+    assert src.rfind("def run_reference", 0, hits[0]) > src.rfind("\ndef ", 0, src.rfind("def run_reference", 0, hits[0]))  # first one inside run_reference
+    assert "no_cpu_baseline" in src[src.rfind("\n    if ", 0, hits[1]):hits[1]]  # second one inside the cpu_baseline block
