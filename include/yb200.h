@@ -161,6 +161,14 @@ int yb200_head_bias_grad(double* bias_acc, int num_levels, int channels, int lev
 int64_t yb200_nms_workspace(int batch, int num_anchors);
 int yb200_postprocess_nms(float* prediction, int batch, int num_anchors, int num_classes, float conf_thre, float nms_thre,
                           int mutate_prediction, void* workspace, float* detections, int32_t* det_count, void* stream);
+/* Same, plus (both nullable): det_anchor [batch][A] = anchor index of every emitted row, and tie_count[batch] = number of
+ * adjacent emitted rows with bit-identical scores.  Equal scores are emitted lower-anchor-first (the stable order of
+ * torchvision's `nms`, i.e. the reference on CUDA and on CPU with <= 1000 candidates); the CPU `_batched_nms_vanilla`
+ * path ends with an UNSTABLE torch.sort whose permutation of ties a caller can re-apply from det_anchor when
+ * tie_count > 0 (yolov7_d2_b200.modeling.postprocess(tie_order="torch_cpu_sort")).                                      */
+int yb200_postprocess_nms_indexed(float* prediction, int batch, int num_anchors, int num_classes, float conf_thre,
+                                  float nms_thre, int mutate_prediction, void* workspace, float* detections,
+                                  int32_t* det_count, int32_t* det_anchor, int32_t* tie_count, void* stream);
 
 /* ---- box regression losses ----------------------------------------------------------------------- */
 /* loss[i] and d loss[i] / d pred[i] for n matched (prediction, target) pairs of (cx, cy, w, h) boxes (device fp32 [n][4]).

@@ -367,18 +367,26 @@ def nms_greedy(boxes, scores, thr):
     return order[torch.tensor(keep, dtype=torch.int64)]
 
 
-def batched_nms_vanilla(boxes, scores, classes, thr):
+def batched_nms_vanilla(boxes, scores, classes, thr, tie_order="stable"):
     """per-class NMS on un-offset coordinates, survivors ordered by descending score (torchvision
-    `_batched_nms_vanilla`; SURVEY.md par.0.3 explains why this is the canonical semantics)."""
+    `_batched_nms_vanilla`; SURVEY.md par.0.3 explains why this is the canonical semantics).
+    tie_order: how EQUAL scores are ordered in the result --
+      "stable"         lower index first: what torchvision's `nms` returns (stable sort in both its CPU and CUDA kernels), hence what the
+                       reference produces on CUDA (coordinate-trick strategy for < 25 000 boxes) and on the CPU for <= 1000 candidates;
+      "torch_cpu_sort" the literal last line of `_batched_nms_vanilla`, `scores[keep].sort(descending=True)`: torch's UNSTABLE CPU sort, whose
+                       permutation of ties is an artefact of its introsort (pinned by tests/golden/nms_ties.npz, `big` case)."""
     keep = torch.zeros(scores.shape[0], dtype=torch.bool)
     for c in torch.unique(classes):
         idx = torch.where(classes == c)[0]
         keep[idx[nms_greedy(boxes[idx], scores[idx], thr)]] = True
     k = torch.where(keep)[0]
+    if tie_order == "torch_cpu_sort":
+        return k[scores[k].sort(descending=True)[1]]
+    assert tie_order == "stable", tie_order
     return k[torch.sort(scores[k], descending=True, stable=True).indices]
 
 
-def postprocess(prediction, num_classes, conf_thre, nms_thre):
+def postprocess(prediction, num_classes, conf_thre, nms_thre, tie_order="stable"):
     """boxes.py:171-210 (without the in-place mutation): per image [n,7] = (x1,y1,x2,y2,obj,cls_conf,cls) or None."""
     pred = prediction.clone()
     pred[..., 0] = prediction[..., 0] - prediction[..., 2] / 2
@@ -393,7 +401,7 @@ def postprocess(prediction, num_classes, conf_thre, nms_thre):
         if det.shape[0] == 0:
             out.append(None)
             continue
-        out.append(det[batched_nms_vanilla(det[:, :4], det[:, 4] * det[:, 5], det[:, 6], nms_thre)])
+        out.append(det[batched_nms_vanilla(det[:, :4], det[:, 4] * det[:, 5], det[:, 6], nms_thre, tie_order)])
     return out
 
 

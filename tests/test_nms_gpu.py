@@ -72,3 +72,25 @@ def test_nms_single_class_chain(cuda):
     dets, _ = run_nms(capi, pred, 0.001, 0.5, cuda)
     ref = orc.postprocess(pred, 80, 0.001, 0.5)
     assert torch.equal(dets[0], ref[0])
+
+
+def test_nms_tied_scores_vs_reference_golden(cuda):
+    """tests/golden/nms_ties.npz (reference `postprocess` on colliding scores, oracle/gen_golden_nms_ties.py): the device order for equal
+    scores is the stable one (= reference on CUDA / <= 1000 candidates: `small`, bit-exact); postprocess(tie_order="torch_cpu_sort")
+    reproduces the reference's CPU `_batched_nms_vanilla` order (`big`, bit-exact)."""
+    from yolov7_d2_b200 import capi
+    from yolov7_d2_b200.modeling import postprocess
+
+    g = np.load(os.path.join(GOLD, "nms_ties.npz"))
+    dets, _ = run_nms(capi, torch.from_numpy(g["small.pred"]), 0.001, 0.65, cuda)
+    for i, d in enumerate(dets):
+        assert torch.equal(d, torch.from_numpy(g[f"small.det{i}"])), f"small image {i}"
+    big = torch.from_numpy(g["big.pred"]).to(cuda)
+    got = postprocess(big.clone(), 80, 0.001, 0.65, tie_order="torch_cpu_sort")
+    canon = postprocess(big.clone(), 80, 0.001, 0.65)
+    ref_canon = orc.postprocess(torch.from_numpy(g["big.pred"]), 80, 0.001, 0.65)
+    for i, d in enumerate(got):
+        ref = torch.from_numpy(g[f"big.det{i}"])
+        assert torch.equal(d.cpu(), ref), f"big image {i}: tie_order=torch_cpu_sort differs from the reference"
+        assert torch.equal(canon[i].cpu(), ref_canon[i]), f"big image {i}: canonical order differs from the oracle"
+        assert not torch.equal(canon[i].cpu(), ref)

@@ -132,6 +132,42 @@ def test_postprocess_nms(tag, conf, thr):
     assert any(d is None for d in dets) and any(d is not None and d.shape[0] > 100 for d in dets)
 
 
+def _tie_groups_equal(d, ref):
+    """same rows, same score sequence; rows may only be permuted inside runs of bit-identical scores"""
+    if d.shape != ref.shape:
+        return False
+    sd, sr = d[:, 4] * d[:, 5], ref[:, 4] * ref[:, 5]
+    if not torch.equal(sd, sr):
+        return False
+    bounds = [0] + (torch.nonzero(sr[1:] != sr[:-1]).flatten() + 1).tolist() + [len(sr)]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        if sorted(map(tuple, d[lo:hi].tolist())) != sorted(map(tuple, ref[lo:hi].tolist())):
+            return False
+    return True
+
+
+def test_postprocess_nms_tied_scores():
+    """tests/golden/nms_ties.npz: reference `postprocess` on inputs whose scores collide (oracle/gen_golden_nms_ties.py).
+    `small` (<= 1000 candidates: torchvision's coordinate-trick strategy = the order of `nms`, a STABLE sort -- also what the reference
+    does on CUDA): the oracle's canonical order must match bit-exactly.  `big` (> 1000 candidates on the CPU: `_batched_nms_vanilla`,
+    whose last line is an UNSTABLE torch.sort): tie_order="torch_cpu_sort" must match bit-exactly; the canonical order is the same
+    detections with permutations only inside runs of equal scores."""
+    g = load("nms_ties.npz")
+    assert str(g["small.strategy"]) == "coordinate_trick" and str(g["big.strategy"]) == "vanilla"
+    for tag, order in (("small", "stable"), ("big", "torch_cpu_sort")):
+        dets = orc.postprocess(T(g[f"{tag}.pred"]), 80, 0.001, 0.65, tie_order=order)
+        for i, d in enumerate(dets):
+            ref = T(g[f"{tag}.det{i}"])
+            sc = ref[:, 4] * ref[:, 5]
+            assert int((sc[1:] == sc[:-1]).sum()) > 10, "fixture has no ties"
+            assert d.shape == ref.shape and torch.equal(d, ref), f"{tag} image {i}: order differs from the reference under tie_order={order}"
+    canon = orc.postprocess(T(g["big.pred"]), 80, 0.001, 0.65)
+    for i, d in enumerate(canon):
+        ref = T(g[f"big.det{i}"])
+        assert not torch.equal(d, ref), "fixture does not exercise the unstable sort"
+        assert _tie_groups_equal(d, ref), f"big image {i}: canonical order differs by more than a permutation of equal scores"
+
+
 def golden_model_sd(g):
     sd = {}
     for k in g.files:

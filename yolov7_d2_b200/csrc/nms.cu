@@ -80,17 +80,18 @@ __device__ __forceinline__ int lower_bound_smem(const unsigned long long* k, int
 // ---- stage 2: one block per image: sort, per-class greedy suppression, order survivors by score, emit ----
 __global__ void __launch_bounds__(kNmsThreads)
 nms_suppress_kernel(const unsigned long long* __restrict__ keys_in, const float4* __restrict__ boxes, const float4* __restrict__ meta,
-                    int num_anchors, int num_classes, int apad, float nms_thre, float* __restrict__ det, int* __restrict__ det_count) {
+                    int num_anchors, int num_classes, int apad, float nms_thre, float* __restrict__ det, int* __restrict__ det_count,
+                    int* __restrict__ det_anchor, int* __restrict__ tie_count) {
   extern __shared__ unsigned long long sk[];                          // [apad]
   unsigned char* sup = reinterpret_cast<unsigned char*>(sk + apad);   // [apad]
-  __shared__ int s_n, s_keep;
+  __shared__ int s_n, s_keep, s_ties;
   const int b = blockIdx.x;
   const float4* bx = boxes + 1LL * b * num_anchors;
   for (int i = threadIdx.x; i < apad; i += blockDim.x) {
     sk[i] = keys_in[1LL * b * apad + i];
     sup[i] = 0;
   }
-  if (threadIdx.x == 0) s_keep = 0;
+  if (threadIdx.x == 0) { s_keep = 0; s_ties = 0; }
   __syncthreads();
   bitonic_sort_smem(sk, apad);
   if (threadIdx.x == 0) s_n = lower_bound_smem(sk, apad, kEmpty);
@@ -146,6 +147,12 @@ nms_suppress_kernel(const unsigned long long* __restrict__ keys_in, const float4
     const float4 m = mt[a];
     float* o = d + 7LL * r;  // (x1, y1, x2, y2, obj_conf, class_conf, class_pred)   boxes.py:193
     o[0] = bb.x; o[1] = bb.y; o[2] = bb.z; o[3] = bb.w; o[4] = m.x; o[5] = m.y; o[6] = m.z;
+    if (det_anchor) det_anchor[1LL * b * num_anchors + r] = a;
+    if (tie_count && r + 1 < nk && (sk[r] >> kIdxBits) == (sk[r + 1] >> kIdxBits)) atomicAdd(&s_ties, 1);  // bit-identical scores
+  }
+  if (tie_count) {
+    __syncthreads();
+    if (threadIdx.x == 0) tie_count[b] = s_ties;
   }
 }
 
@@ -160,8 +167,9 @@ extern "C" int64_t yb200_nms_workspace(int batch, int num_anchors) {
   return pad256(16 * ba) + pad256(16 * ba) + pad256(8LL * batch * next_pow2(num_anchors)) + 256;
 }
 
-extern "C" int yb200_postprocess_nms(float* prediction, int batch, int num_anchors, int num_classes, float conf_thre, float nms_thre,
-                                     int mutate_prediction, void* workspace, float* detections, int32_t* det_count, void* stream) {
+extern "C" int yb200_postprocess_nms_indexed(float* prediction, int batch, int num_anchors, int num_classes, float conf_thre, float nms_thre,
+                                             int mutate_prediction, void* workspace, float* detections, int32_t* det_count,
+                                             int32_t* det_anchor, int32_t* tie_count, void* stream) {
   YB_REQUIRE(prediction && workspace && detections && det_count, YB200_ERR_INVALID, "postprocess_nms: null pointer");
   YB_REQUIRE(batch > 0 && num_anchors > 0 && num_anchors < (1 << kIdxBits) && num_classes > 0 && num_classes < (1 << 14), YB200_ERR_INVALID,
              "postprocess_nms: batch=%d anchors=%d classes=%d", batch, num_anchors, num_classes);
@@ -177,12 +185,15 @@ extern "C" int yb200_postprocess_nms(float* prediction, int batch, int num_ancho
   nms_prepare_kernel<<<dim3(ceil_div(apad, 256), batch), 256, 0, st>>>(prediction, num_anchors, 5 + num_classes, apad, conf_thre, mutate_prediction,
                                                                       boxes, meta, keys);
   YB_CHECK_CUDA(cudaGetLastError());
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(nms_suppress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
-  }
-  nms_suppress_kernel<<<batch, kNmsThreads, smem, st>>>(keys, boxes, meta, num_anchors, num_classes, apad, nms_thre, detections, det_count);
+  YB_CHECK_CUDA(cudaFuncSetAttribute(nms_suppress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));  // per device, cheap
+  nms_suppress_kernel<<<batch, kNmsThreads, smem, st>>>(keys, boxes, meta, num_anchors, num_classes, apad, nms_thre, detections, det_count,
+                                                        det_anchor, tie_count);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int yb200_postprocess_nms(float* prediction, int batch, int num_anchors, int num_classes, float conf_thre, float nms_thre,
+                                     int mutate_prediction, void* workspace, float* detections, int32_t* det_count, void* stream) {
+  return yb200_postprocess_nms_indexed(prediction, batch, num_anchors, num_classes, conf_thre, nms_thre, mutate_prediction, workspace, detections,
+                                       det_count, nullptr, nullptr, stream);
 }

@@ -85,11 +85,17 @@ except Exception:  # noqa: BLE001
 _nms_ws = {}
 
 
-def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45):
+def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45, tie_order="stable"):
     """boxes.py:171-210: returns a list with one [n_i, 7] tensor (x1,y1,x2,y2,obj,cls_conf,cls) or None per image and, like
-    the reference, rewrites prediction[:, :, :4] to corner format in place."""
+    the reference, rewrites prediction[:, :, :4] to corner format in place.
+    tie_order: order of detections with bit-identical scores.  "stable" (default) = lower anchor first, the order of torchvision's `nms`
+    (the reference on CUDA, and on the CPU for <= 1000 candidates).  "torch_cpu_sort" re-applies, for images that contain ties, the
+    permutation of the UNSTABLE `scores[keep].sort(descending=True)` that ends torchvision's CPU `_batched_nms_vanilla` (the reference on
+    the CPU with > 1000 candidates) -- by issuing that very call on the kept scores; images without ties never leave the device path."""
     if not (prediction.is_cuda and prediction.dtype == torch.float32 and prediction.dim() == 3):
         raise capi.Yb200Error("postprocess: expects a CUDA fp32 [B, A, 5+C] tensor (no CPU fallback)")
+    if tie_order not in ("stable", "torch_cpu_sort"):
+        raise ValueError(f"postprocess: unknown tie_order {tie_order!r}")
     pred = prediction if prediction.is_contiguous() else prediction.contiguous()
     b, a, ch = pred.shape
     if ch != 5 + num_classes:
@@ -98,14 +104,28 @@ def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45):
     key = (pred.device.index, b, a)
     if key not in _nms_ws:
         _nms_ws[key] = (torch.empty(L.yb200_nms_workspace(b, a), dtype=torch.uint8, device=pred.device),
-                        torch.empty(b, a, 7, device=pred.device), torch.empty(b, dtype=torch.int32, device=pred.device))
-    ws, det, cnt = _nms_ws[key]
-    capi.check(L.yb200_postprocess_nms(capi.ptr(pred), b, a, num_classes, ctypes.c_float(conf_thre), ctypes.c_float(nms_thre), 1, capi.ptr(ws),
-                                       capi.ptr(det), capi.ptr(cnt), capi.stream_ptr()), "postprocess_nms")
+                        torch.empty(b, a, 7, device=pred.device), torch.empty(2, b, dtype=torch.int32, device=pred.device),
+                        torch.empty(b, a, dtype=torch.int32, device=pred.device))
+    ws, det, cnt, anchor = _nms_ws[key]
+    want_ties = tie_order == "torch_cpu_sort"
+    capi.check(L.yb200_postprocess_nms_indexed(capi.ptr(pred), b, a, num_classes, ctypes.c_float(conf_thre), ctypes.c_float(nms_thre), 1, capi.ptr(ws),
+                                               capi.ptr(det), capi.ptr(cnt[0]), capi.ptr(anchor) if want_ties else None,
+                                               capi.ptr(cnt[1]) if want_ties else None, capi.stream_ptr()), "postprocess_nms")
     if pred is not prediction:
         prediction.copy_(pred)
-    counts = cnt.tolist()  # the one host synchronisation: the output is a ragged Python list
-    return [det[i, :n].clone() if n > 0 else None for i, n in enumerate(counts)]
+    counts, ties = cnt.tolist()  # the one host synchronisation: the output is a ragged Python list
+    out = []
+    for i, n in enumerate(counts):
+        if n == 0:
+            out.append(None)
+            continue
+        d = det[i, :n].clone()
+        if want_ties and ties[i] > 0:
+            d = d[anchor[i, :n].argsort()]                       # ascending anchor = the order of `torch.where(keep_mask)`
+            perm = (d[:, 4] * d[:, 5]).cpu().sort(descending=True)[1]  # boxes.py:199-203 scores; torchvision/ops/boxes.py `_batched_nms_vanilla` last line
+            d = d[perm.to(d.device)]
+        out.append(d)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
