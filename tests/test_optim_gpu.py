@@ -106,3 +106,62 @@ def test_model_optimizer_step_changes_weights_like_torch(cuda):
     ref.step()
     for n in eng.param_names:
         torch.testing.assert_close(eng.params[n].cpu(), ref_p[n].detach(), rtol=2e-6, atol=1e-7, msg=lambda m: f"{n}: {m}")
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adamw"])
+def test_state_dict_round_trip_resumes_identically(kind, cuda):
+    """checkpoint / resume (detectron2's DetectionCheckpointer saves optimizer.state_dict()): momentum / moments / step count travel, so the
+    step after a resume equals the step of the uninterrupted run"""
+    layout, total, tensors, g = _setup(3)
+    segs = optim.param_segments(layout, total, 5e-4, 0.0)
+    grads = [_flat(layout, total, {n: torch.randn(t.shape, generator=g) for n, t in tensors.items()}, cuda) for _ in range(3)]
+
+    def make():
+        p = _flat(layout, total, tensors, cuda)
+        gbuf = torch.zeros(total, device=cuda)
+        return p, gbuf, optim.FlatOptimizer(p, gbuf, segs, 0.05 if kind == "sgd" else 1e-2, kind, momentum=0.9 if kind == "sgd" else 0.0)
+
+    p1, g1, o1 = make()
+    for k in range(3):
+        g1.copy_(grads[k])
+        o1.step()
+    p2, g2, o2 = make()
+    for k in range(2):
+        g2.copy_(grads[k])
+        o2.step()
+    saved = o2.state_dict()
+    assert saved["state"][0]["step"] == 2 and any(torch.is_tensor(v) and v.abs().sum() > 0 for v in saved["state"][0].values())
+    p3, g3, o3 = make()
+    p3.copy_(p2)
+    o3.load_state_dict(saved)
+    g3.copy_(grads[2])
+    o3.step()
+    assert o3.steps == 3
+    assert torch.equal(p3, p1), "resumed step differs from the uninterrupted run"
+
+
+def test_grad_scaler_drives_the_flat_optimizer(cuda):
+    """torch.amp.GradScaler (detectron2 AMPTrainer, SOLVER.AMP.ENABLED) unscales / inf-checks through flat_param.grad = flat_grad:
+    a scaled gradient gives the same update as the unscaled one, an inf gradient skips the step and halves the scale"""
+    layout, total, tensors, g = _setup(4)
+    segs = optim.param_segments(layout, total, 0.0)
+    p = _flat(layout, total, tensors, cuda)
+    gbuf = torch.zeros(total, device=cuda)
+    opt = optim.FlatOptimizer(p, gbuf, segs, 0.1, "sgd", momentum=0.0)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    grad = torch.randn(total, device=cuda, generator=torch.Generator(device=cuda).manual_seed(5))
+    p0 = p.clone()
+    gbuf.copy_(grad * 1024.0)  # what backward of scaler.scale(loss) leaves in the flat buffer
+    scaler.step(opt)
+    scaler.update()
+    mask = torch.zeros(total, dtype=torch.bool)
+    for _, off, n in layout:
+        mask[off:off + n] = True
+    mask = mask.to(cuda)
+    torch.testing.assert_close(p[mask], (p0 - 0.1 * grad)[mask], rtol=1e-6, atol=1e-7)
+    p1 = p.clone()
+    gbuf.copy_(grad * 1024.0)
+    gbuf[3] = float("inf")
+    scaler.step(opt)
+    scaler.update()
+    assert torch.equal(p, p1) and scaler.get_scale() == 512.0

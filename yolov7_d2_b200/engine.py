@@ -105,6 +105,7 @@ class YoloxEngine:
         self.dev = torch.device(device)
         self.n, self.h, self.w, self.nc, self.max_gt = batch, height, width, num_classes, max_gt
         self.wm, self.dm = width_mul, depth_mul
+        self.pad_value = 114.0  # cfg.MODEL.PADDED_VALUE; YOLOX sets it per plan (modeling.py)
         self.ops = []
         self.bufs = {}
         self.param_specs = []   # (name, shape) in flat order
@@ -391,7 +392,7 @@ class YoloxEngine:
 
     def preprocess(self):
         """images_u8 [N,3,H,W] (device) -> focus buffer"""
-        capi.check(self.L.yb200_preprocess_focus(capi.ptr(self.images_u8), self.n, self.h, self.w, capi.ptr(self.hw_valid), ctypes.c_float(114.0),
+        capi.check(self.L.yb200_preprocess_focus(capi.ptr(self.images_u8), self.n, self.h, self.w, capi.ptr(self.hw_valid), ctypes.c_float(self.pad_value),
                                                  self.focus.view().act(), capi.stream_ptr()), "preprocess_focus")
         self._count(1, "preprocess")
 

@@ -325,6 +325,7 @@ class YOLOX(nn.Module):
         if key not in self._plans:
             self._plans[key] = YoloxEngine(batch, h, w, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device,
                                            share_params_of=self._root)
+            self._plans[key].pad_value = float(self.padded_value)  # cfg.MODEL.PADDED_VALUE (yolox.py:55, ImageList.from_tensors pad_value)
         return self._plans[key]
 
     def _params_in_engine_order(self):
@@ -368,23 +369,42 @@ class YOLOX(nn.Module):
                 eng._stage_evt.record()
         else:
             for k, im in enumerate(imgs):
-                images_dst[k, :, :im.shape[-2], :im.shape[-1]].copy_(im.to(torch.uint8), non_blocking=True)
+                images_dst[k, :, :im.shape[-2], :im.shape[-1]].copy_(im if im.dtype == torch.uint8 else im.round().clamp_(0, 255).to(torch.uint8), non_blocking=True)  # pixel values are integers 0..255 (detectron2 mappers emit uint8); a float image is rounded, never truncated
         hw_dst.copy_(torch.tensor([[i.shape[-2], i.shape[-1]] for i in imgs], dtype=torch.int32), non_blocking=True)
         if training:
-            labels = torch.zeros(len(imgs), self.max_boxes_num, 5)
-            for k, x in enumerate(batched_inputs):
-                inst = x.get("instances", x.get("targets"))
-                if inst is None:
-                    continue
-                boxes = inst.gt_boxes.tensor.detach().float().cpu()[: self.max_boxes_num]
-                cls = inst.gt_classes.detach().float().cpu()[: self.max_boxes_num]
-                n = boxes.shape[0]
-                labels[k, :n, 0] = cls
-                labels[k, :n, 1] = (boxes[:, 0] + boxes[:, 2]) / 2  # BoxModeMy XYXY_ABS -> (cx, cy, w, h)   boxes.py:547-551
-                labels[k, :n, 2] = (boxes[:, 1] + boxes[:, 3]) / 2
-                labels[k, :n, 3] = boxes[:, 2] - boxes[:, 0]
-                labels[k, :n, 4] = boxes[:, 3] - boxes[:, 1]
-            labels_dst.copy_(labels, non_blocking=True)
+            self._stage_labels(batched_inputs, labels_dst)
+
+    def _stage_labels(self, batched_inputs, labels_dst):
+        """[B, max_boxes, 5] = (cls, cx, cy, w, h), zero padded (yolox.py:150-162, BoxModeMy XYXY_ABS -> cxcywh boxes.py:547-551).
+        One concatenation + one scatter on whichever device the ground truth lives on: no per-image device->host round trip (the
+        reference pays one per image, yolox.py:157).  Row counts come from tensor shapes, which are host-side metadata."""
+        boxes, classes, bi, ji = [], [], [], []
+        for k, x in enumerate(batched_inputs):
+            inst = x.get("instances", x.get("targets"))
+            if inst is None:
+                continue
+            b = inst.gt_boxes.tensor[: self.max_boxes_num]
+            n = b.shape[0]
+            if n == 0:
+                continue
+            boxes.append(b.detach())
+            classes.append(inst.gt_classes[:n].detach())
+            bi.append(torch.full((n,), k, dtype=torch.int64))
+            ji.append(torch.arange(n, dtype=torch.int64))
+        labels_dst.zero_()
+        if not boxes:
+            return
+        on_dev = boxes[0].is_cuda
+        bx = torch.cat(boxes).float()
+        cl = torch.cat(classes).float()
+        rows = torch.stack([cl, (bx[:, 0] + bx[:, 2]) / 2, (bx[:, 1] + bx[:, 3]) / 2, bx[:, 2] - bx[:, 0], bx[:, 3] - bx[:, 1]], 1)
+        flat_idx = torch.cat(bi) * self.max_boxes_num + torch.cat(ji)
+        if on_dev:
+            labels_dst.view(-1, 5).index_copy_(0, flat_idx.to(labels_dst.device, non_blocking=True), rows.to(labels_dst.device))
+        else:
+            host = torch.zeros(labels_dst.shape[0] * self.max_boxes_num, 5)
+            host.index_copy_(0, flat_idx, rows)
+            labels_dst.copy_(host.view_as(labels_dst), non_blocking=True)
 
     def prefetch(self, batched_inputs):
         """Input-side pipelining: start the host->device copies of the NEXT batch on a copy stream while the

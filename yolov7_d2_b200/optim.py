@@ -12,7 +12,11 @@ import torch
 
 from . import capi
 
-_NORM_SUFFIXES = (".bn.weight", ".bn.bias", ".norm.weight", ".norm.bias")
+# Parameters of torch normalisation modules (build.py:96-110 tests isinstance against BatchNorm / LayerNorm / GroupNorm ...).  In the
+# YOLOX plan those are exactly the `.bn.` tensors.  ConvNeXt's LayerNorm is a custom nn.Module (convnext.py:182-206), NOT in the
+# reference's norm_module_types: its weight takes WEIGHT_DECAY and its bias WEIGHT_DECAY_BIAS, like any other parameter.  An engine
+# can override the rule by exposing `norm_param_names` (a set of parameter names).
+_NORM_SUFFIXES = (".bn.weight", ".bn.bias")
 
 
 def _solver(cfg, key, default):
@@ -25,7 +29,7 @@ def _solver(cfg, key, default):
 
 
 def param_segments(param_layout, total, weight_decay, weight_decay_norm=None, weight_decay_bias=None, bias_lr_factor=1.0,
-                   lr_multipliers_overwrite=None):
+                   lr_multipliers_overwrite=None, norm_param_names=None):
     """[(begin, weight_decay, lr_multiplier)] covering [0, total) for parameters placed at `param_layout` = [(name, offset, numel)]
     (ascending offsets; gaps are alignment padding and get lr multiplier 0, i.e. they are never modified).
 
@@ -48,7 +52,7 @@ def param_segments(param_layout, total, weight_decay, weight_decay_norm=None, we
             push(end, 0.0, 0.0)
         module_name, _, pname = name.rpartition(".")
         wd, mult = weight_decay, 1.0
-        if name.endswith(_NORM_SUFFIXES):
+        if (name in norm_param_names) if norm_param_names is not None else name.endswith(_NORM_SUFFIXES):
             wd = wd_norm
         elif pname == "bias":
             wd = wd_bias
@@ -83,14 +87,35 @@ class FlatOptimizer(torch.optim.Optimizer):
         self.nseg = len(segments)
         self.clip_norm = float(clip_norm)
         self.grad_scale = float(grad_scale)
-        self.steps = 0
-        self.state_a = torch.zeros_like(flat_param) if (kind == "adamw" or momentum != 0.0) else None  # momentum buffer / exp_avg
-        self.state_b = torch.zeros_like(flat_param) if kind == "adamw" else None                         # exp_avg_sq
         L = capi.lib()
         self.norm_ws = torch.empty(int(L.yb200_grad_norm_workspace()), dtype=torch.uint8, device=dev)
         self.total_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         defaults = dict(lr=lr, momentum=momentum, dampening=dampening, nesterov=nesterov, betas=betas, eps=eps)
         super().__init__([flat_param], defaults)
+        # The optimizer state lives in torch's own `self.state` (names as torch.optim.SGD / AdamW), so state_dict() /
+        # load_state_dict() -- detectron2's checkpointer -- carry momentum / moments / the step count across a resume.
+        st = self.state[flat_param]
+        st["step"] = 0
+        if kind == "adamw":
+            st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(flat_param), torch.zeros_like(flat_param)
+        elif momentum != 0.0:
+            st["momentum_buffer"] = torch.zeros_like(flat_param)
+        # torch.cuda.amp.GradScaler finds, unscales and inf-checks gradients through `param.grad`: the flat parameter's gradient IS
+        # the flat gradient buffer, so scaler.unscale_() / scaler.step() / scaler.update() work unchanged (SOLVER.AMP.ENABLED configs).
+        flat_param.grad = flat_grad
+
+    @property
+    def steps(self):
+        return int(self.state[self.flat_param]["step"])
+
+    @property
+    def state_a(self):
+        st = self.state[self.flat_param]
+        return st.get("exp_avg") if self.kind == "adamw" else st.get("momentum_buffer")
+
+    @property
+    def state_b(self):
+        return self.state[self.flat_param].get("exp_avg_sq")
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -104,7 +129,10 @@ class FlatOptimizer(torch.optim.Optimizer):
             capi.check(L.yb200_grad_norm(capi.ptr(self.flat_grad), ctypes.c_int64(n), f(self.grad_scale), capi.ptr(self.norm_ws), capi.ptr(self.total_norm),
                                          sp), "grad_norm")
             norm = self.total_norm
-        self.steps += 1
+        if self.flat_param.grad is None or self.flat_param.grad.data_ptr() != self.flat_grad.data_ptr():
+            self.flat_param.grad = self.flat_grad  # zero_grad(set_to_none=True) / load_state_dict dropped the alias
+        st = self.state[self.flat_param]
+        st["step"] = int(st["step"]) + 1
         if self.kind == "sgd":
             capi.check(L.yb200_sgd_step(capi.ptr(self.flat_param), capi.ptr(self.flat_grad), capi.ptr(self.state_a), ctypes.c_int64(n),
                                         capi.ptr(self.seg_begin), capi.ptr(self.seg_wd), capi.ptr(self.seg_lr), self.nseg, f(g["lr"]),
@@ -120,11 +148,23 @@ class FlatOptimizer(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        st = self.state[self.flat_param]
+        for k in ("momentum_buffer", "exp_avg", "exp_avg_sq"):
+            if k in st and (st[k].shape != self.flat_param.shape or st[k].dtype != torch.float32 or not st[k].is_contiguous()):
+                raise capi.Yb200Error(f"optimizer state {k} does not match the flat parameter buffer")
+        st["step"] = int(st.get("step", 0))
+
 
 def _flat_buffers(model):
     eng = getattr(model, "engine", None) or getattr(getattr(model, "module", None), "engine", None) or model
     if not hasattr(eng, "flat_param"):
         raise capi.Yb200Error("optimizer needs a model that exposes the engine's flat_param / flat_grad / param_layout")
+    if type(model).__name__ == "DistributedDataParallel":
+        raise capi.Yb200Error("the flat optimizer writes gradients straight into the flat buffer, so torch DDP's per-parameter reducer hooks never "
+                              "fire: do not wrap the model in DistributedDataParallel; all-reduce `model.engine.flat_grad` instead "
+                              "(yolov7_d2_b200.dist.GradientBuckets, INTEGRATION.md par.4)")
     inner = getattr(model, "module", model)
     if hasattr(inner, "attach_flat_grads"):
         inner.attach_flat_grads()
@@ -136,9 +176,13 @@ def _clip_norm(cfg):
     if clip is None:
         return 0.0
     get = clip.get if isinstance(clip, dict) else lambda k, d=None: getattr(clip, k, d)
-    if get("ENABLED", False) and get("CLIP_TYPE", "value") == "full_model" and get("CLIP_VALUE", 0.0) > 0.0:
-        return float(get("CLIP_VALUE"))
-    return 0.0
+    if not get("ENABLED", False):
+        return 0.0
+    if get("CLIP_TYPE", "value") == "full_model":
+        return float(get("CLIP_VALUE")) if get("CLIP_VALUE", 0.0) > 0.0 else 0.0
+    # build.py:206-223 falls back to detectron2's per-parameter clipping for "value" / "norm": not a flat-buffer operation
+    raise capi.Yb200Error("SOLVER.CLIP_GRADIENTS.CLIP_TYPE %r is not implemented by the flat optimizer (only 'full_model'); "
+                          "disable clipping or use full_model" % (get("CLIP_TYPE", "value"),))
 
 
 def _build(cfg, model, kind, **kw):
@@ -148,7 +192,7 @@ def _build(cfg, model, kind, **kw):
         overrides.update(d)  # build.py:226-231 _merge_dict
     segs = param_segments(eng.param_layout, eng.flat_param.numel(), _solver(cfg, "WEIGHT_DECAY", 1e-4), _solver(cfg, "WEIGHT_DECAY_NORM", None),
                           _solver(cfg, "WEIGHT_DECAY_BIAS", None), bias_lr_factor=_solver(cfg, "BIAS_LR_FACTOR", 1.0),
-                          lr_multipliers_overwrite=overrides)
+                          lr_multipliers_overwrite=overrides, norm_param_names=getattr(eng, "norm_param_names", None))
     return FlatOptimizer(eng.flat_param, eng.flat_grad, segs, _solver(cfg, "BASE_LR", 0.001), kind, clip_norm=_clip_norm(cfg), **kw)
 
 
