@@ -248,8 +248,12 @@ extern "C" int yb200_pack_conv_weight_scaled(const float* w_oihw, const float* c
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// lo_delta > 0 selects the STRICT (operand-split) form: activations and weights are (hi, lo) bf16 pairs with x = hi + lo carrying
+// 16 significant bits; x_lo lives lo_delta channels after x_hi in the same NHWC buffer and the weight matrix is [rows][hi taps | lo taps].
+// The product keeps the three leading terms  hi*hi + hi*lo + lo*hi  (the dropped lo*lo is 2^-18 relative) as three taps per spatial
+// tap of the SAME implicit GEMM -- one fp32 accumulator in TMEM, no extra kernel.
 static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int ksize, int stride, ConvGemmParams& p,
-                           cudaStream_t st) {
+                           cudaStream_t st, int lo_delta = 0) {
   YB_REQUIRE(w_fwd != nullptr, YB200_ERR_INVALID, "conv fwd: null weights");
   YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 2 && stride == 2) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
              "conv fwd: ksize=%d stride=%d not implemented", ksize, stride);
@@ -259,6 +263,22 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   const int oh = x->h / stride, ow = x->w / stride;
   set_tiles(p, x->n, oh, ow);
   p.num_taps = fill_fwd_taps(p.taps, *x, ksize, stride, x->c);
+  long long kcols = 1LL * p.num_taps * x->c;
+  if (lo_delta > 0) {
+    YB_REQUIRE(lo_delta % 8 == 0 && x->c_off + lo_delta + x->c <= x->c_pitch, YB200_ERR_INVALID,
+               "conv fwd (split): lo plane [%d, %d) outside the channel pitch %d", x->c_off + lo_delta, x->c_off + lo_delta + x->c, x->c_pitch);
+    const int nt = p.num_taps;
+    const int lo_kb = nt * x->c;
+    for (int t = nt - 1; t >= 0; --t) {
+      const ConvTap b = p.taps[t];
+      ConvTap hl = b, lh = b;
+      hl.kb = lo_kb + b.kb;     // x_hi * w_lo
+      lh.c0 = b.c0 + lo_delta;  // x_lo * w_hi
+      p.taps[3 * t] = b; p.taps[3 * t + 1] = hl; p.taps[3 * t + 2] = lh;
+    }
+    p.num_taps = 3 * nt;
+    kcols *= 2;
+  }
   p.cin_blocks = x->c / bk;
   p.cout = cout;
   const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
@@ -266,7 +286,8 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   int rc = make_act_map(&tmA, *x, stride == 2, bk, tw, th, tn);
   if (rc) return rc;
   // the CTA-pair kernel (column tile 256) loads the weight tile as two 128-row halves, one per CTA
-  rc = make_mat_map(&tmB, w_fwd, cout, 1LL * p.num_taps * x->c, (bn == 256 && use_pair_kernel()) ? 128 : bn, bk);
+  const bool pair = bn == 256 && use_pair_kernel() && !use_v1_kernel() && p.epi_mode != EPI_F32_BIAS;
+  rc = make_mat_map(&tmB, w_fwd, cout, kcols, pair ? 128 : bn, bk);
   if (rc) return rc;
   const int num_kb = p.num_taps * p.cin_blocks;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cout, bn));
@@ -426,6 +447,79 @@ extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// strict (operand-split) forward: fp32 results from bf16 tensor-core products
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_split_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad, int cin_pad,
+                                              __nv_bfloat16* __restrict__ out) {
+  const long long per_plane = 1LL * taps * cin_pad;
+  const long long total = 1LL * cout_pad * per_plane;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = static_cast<int>(i % cin_pad);
+    const int t = static_cast<int>((i / cin_pad) % taps);
+    const int co = static_cast<int>(i / per_plane);
+    const float v = (co < cout && ci < cin) ? w[(1LL * co * cin + ci) * taps + t] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* row = out + 2LL * co * per_plane;
+    row[1LL * t * cin_pad + ci] = hi;
+    row[per_plane + 1LL * t * cin_pad + ci] = lo;
+  }
+}
+
+extern "C" int yb200_pack_conv_weight_split(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, void* w_split,
+                                            void* stream) {
+  YB_REQUIRE(w_oihw && w_split, YB200_ERR_INVALID, "pack_conv_weight_split: null pointer");
+  YB_REQUIRE(cout > 0 && cin > 0 && (ksize >= 1 && ksize <= 3) && cout_pad >= cout && cin_pad >= cin, YB200_ERR_INVALID,
+             "pack_conv_weight_split: bad sizes cout=%d cin=%d k=%d pads=%d,%d", cout, cin, ksize, cout_pad, cin_pad);
+  const long long total = 1LL * cout_pad * ksize * ksize * cin_pad;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
+  pack_conv_weight_split_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, cout_pad, cin_pad,
+                                                                       static_cast<__nv_bfloat16*>(w_split));
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yb200_conv2d_fwd_split(const yb200_act* x, int lo_delta, const void* w_split, int cout, int ksize, int stride, float* z,
+                                      int z_pitch, int z_off, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv2d_fwd_split x"))) return rc;
+  YB_REQUIRE(z && cout > 0 && z_off >= 0 && z_off + cout <= z_pitch && lo_delta > 0, YB200_ERR_INVALID,
+             "conv2d_fwd_split: bad output slice [%d, %d) of %d (lo_delta %d)", z_off, z_off + cout, z_pitch, lo_delta);
+  YB_REQUIRE(stride == 1 || stride == 2, YB200_ERR_UNSUPPORTED, "conv2d_fwd_split: stride %d", stride);
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int oh = x->h / stride, ow = x->w / stride;
+  p.out = z + z_off;  // fp32 NHWC with a channel pitch
+  p.out_sw = z_pitch;
+  p.out_sh = 1LL * z_pitch * ow;
+  p.out_sn = 1LL * z_pitch * ow * oh;
+  p.out_sc = 1;
+  p.out_mh = 1; p.out_mw = 1;
+  p.epi_mode = EPI_F32_BIAS;  // bias == null: staged as zeros
+  return conv_fwd_common(x, w_split, cout, ksize, stride, p, as_stream(stream), lo_delta);
+}
+
+extern "C" int yb200_conv1x1_bias_f32_split(const yb200_act* x, int lo_delta, const void* w_split, const float* bias, int cout, float* out,
+                                            int a_total, int a_off, int c_total, int c_off, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv1x1_bias_f32_split x"))) return rc;
+  YB_REQUIRE(bias && out && cout > 0 && cout <= 128 && lo_delta > 0, YB200_ERR_INVALID, "conv1x1_bias_f32_split: bad arguments (cout=%d)", cout);
+  YB_REQUIRE(a_off >= 0 && a_off + x->h * x->w <= a_total && c_off >= 0 && c_off + cout <= c_total, YB200_ERR_INVALID,
+             "conv1x1_bias_f32_split: slice [%d+%d, %d+%d] outside [%d, %d]", a_off, x->h * x->w, c_off, cout, a_total, c_total);
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = out + 1LL * a_off * c_total + c_off;
+  p.out_sn = 1LL * a_total * c_total;
+  p.out_sh = 1LL * x->w * c_total;
+  p.out_sw = c_total;
+  p.out_sc = 1;
+  p.out_mh = 1; p.out_mw = 1;
+  p.bias = bias;
+  p.epi_mode = EPI_F32_BIAS;
+  return conv_fwd_common(x, w_split, cout, 1, 1, p, as_stream(stream), lo_delta);
+}
+
+// ------------------------------------------------------------------------------------------------
 // data gradient
 // ------------------------------------------------------------------------------------------------
 static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend, int ksize, int stride,
@@ -469,7 +563,7 @@ static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act*
   const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
   CUtensorMap tmA, tmB;
   if ((rc = make_act_map(&tmA, *dz, false, bk, tw, th, tn))) return rc;
-  if ((rc = make_mat_map(&tmB, w_dgrad, cin, 1LL * taps_total * dz->c, (bn == 256 && use_pair_kernel()) ? 128 : bn, bk))) return rc;
+  if ((rc = make_mat_map(&tmB, w_dgrad, cin, 1LL * taps_total * dz->c, (bn == 256 && use_pair_kernel() && !use_v1_kernel()) ? 128 : bn, bk))) return rc;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cin, bn));
 
   if (stride == 1) {

@@ -82,7 +82,7 @@ int grid_for(long long work, int threads) {
 //   (detectron2 ImageList.from_tensors with MODEL.PADDED_VALUE = 114, yolox.py:100-101).
 // ------------------------------------------------------------------------------------------------
 __global__ void preprocess_focus_kernel(const uint8_t* __restrict__ img, int n, int h, int w, const int* __restrict__ hw_valid,
-                                        float pad_value, __nv_bfloat16* __restrict__ out) {
+                                        float pad_value, __nv_bfloat16* __restrict__ out, int pitch) {
   const int oh = h / 2, ow = w / 2;
   const long long total = 1LL * n * oh * ow;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -102,7 +102,7 @@ __global__ void preprocess_focus_kernel(const uint8_t* __restrict__ img, int n, 
         f[patch * 3 + c] = in ? static_cast<float>(img[((1LL * b * 3 + c) * h + yy) * w + xx]) : pad_value;
     }
     f[12] = f[13] = f[14] = f[15] = 0.f;
-    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    uint4* o = reinterpret_cast<uint4*>(out + i * pitch);
     o[0] = pack8(f);
     o[1] = pack8(f + 8);
   }
@@ -556,11 +556,11 @@ extern "C" int yb200_preprocess_focus(const uint8_t* images_nchw, int n, int h, 
                                       const yb200_act* out, void* stream) {
   YB_REQUIRE(images_nchw && out && out->ptr, YB200_ERR_INVALID, "preprocess_focus: null pointer");
   YB_REQUIRE(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, YB200_ERR_INVALID, "preprocess_focus: image %dx%dx%d", n, h, w);
-  YB_REQUIRE(out->n == n && out->h == h / 2 && out->w == w / 2 && out->c == 16 && out->c_pitch == 16 && out->c_off == 0, YB200_ERR_INVALID,
-             "preprocess_focus: output must be a dense [n,h/2,w/2,16] view");
+  YB_REQUIRE(out->n == n && out->h == h / 2 && out->w == w / 2 && out->c == 16 && out->c_pitch >= 16 && out->c_pitch % 8 == 0 && out->c_off == 0,
+             YB200_ERR_INVALID, "preprocess_focus: output must be the first 16 channels of a [n,h/2,w/2,pitch] buffer");
   const long long total = 1LL * n * (h / 2) * (w / 2);
   preprocess_focus_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(images_nchw, n, h, w, hw_valid, pad_value,
-                                                                              static_cast<__nv_bfloat16*>(out->ptr));
+                                                                              static_cast<__nv_bfloat16*>(out->ptr), out->c_pitch);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,6 +12,7 @@ There is no PyTorch fallback: every op is a libyb200.so call.
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -29,9 +30,12 @@ def _ceil(a, b):
 class Buf:
     """NHWC bf16 activation buffer (+ lazily allocated gradient of the same shape)"""
 
-    def __init__(self, name, n, h, w, c, device, dtype=torch.bfloat16):
+    def __init__(self, name, n, h, w, c, device, dtype=torch.bfloat16, split=False):
         self.name, self.n, self.h, self.w, self.c = name, n, h, w, c
-        self.t = torch.zeros(n, h, w, c, dtype=dtype, device=device)
+        # split (strict mode): [hi plane (c) | lo plane (c)] in one NHWC tensor, value = hi + lo (csrc/strict.cu); views address the
+        # hi plane, the lo plane sits self.lo channels further
+        self.lo = c if split else 0
+        self.t = torch.zeros(n, h, w, 2 * c if split else c, dtype=dtype, device=device)
         self.g = None
         self.written = []  # channel ranges of .g already produced in the current backward pass
 
@@ -67,6 +71,11 @@ class View:
     def tensor(self):
         return self.buf.t[..., self.off:self.off + self.c]
 
+    def value(self):
+        """fp32 value of the view (split buffers: hi + lo)"""
+        hi = self.tensor().float()
+        return hi + self.buf.t[..., self.buf.lo + self.off:self.buf.lo + self.off + self.c].float() if self.buf.lo else hi
+
     def grad_tensor(self):
         return self.buf.grad()[..., self.off:self.off + self.c]
 
@@ -99,8 +108,12 @@ class SppOp:
 
 
 class YoloxEngine:
-    def __init__(self, batch, height, width, num_classes=80, width_mul=0.5, depth_mul=0.33, max_gt=100, device="cuda", share_params_of=None):
+    def __init__(self, batch, height, width, num_classes=80, width_mul=0.5, depth_mul=0.33, max_gt=100, device="cuda", share_params_of=None,
+                 strict=None):
+        """strict=True (default: environment YB200_STRICT=1): forward pass in split-bf16 / fp32 arithmetic (csrc/strict.cu) for the
+        1e-3 parity check against the fp32 reference; forward + SimOTA + losses only, no backward."""
         assert height % 32 == 0 and width % 32 == 0, "input must be padded to a multiple of 32 (yolox.py:100-101)"
+        self.strict = (os.environ.get("YB200_STRICT", "0") == "1") if strict is None else bool(strict)
         self.L = capi.lib()
         self.dev = torch.device(device)
         self.n, self.h, self.w, self.nc, self.max_gt = batch, height, width, num_classes, max_gt
@@ -115,7 +128,9 @@ class YoloxEngine:
 
     # ------------------------------------------------------------------ graph construction
     def _buf(self, name, h, w, c, dtype=torch.bfloat16):
-        b = Buf(name, self.n, h, w, c, self.dev, dtype)
+        if self.strict and dtype == torch.float16:
+            dtype = torch.float32  # pre-BatchNorm conv outputs stay fp32 in strict mode
+        b = Buf(name, self.n, h, w, c, self.dev, dtype, split=self.strict and dtype == torch.bfloat16)
         self.bufs[name] = b
         return b
 
@@ -274,12 +289,19 @@ class YoloxEngine:
         for op in self.ops:
             if isinstance(op, ConvOp):
                 kk = op.ksize * op.ksize
-                op.w_fwd = torch.empty(op.cout, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
-                op.w_dgrad = None if op.first else torch.empty(op.cin_pad, kk, op.cout, dtype=torch.bfloat16, device=dev)
+                if self.strict:
+                    op.w_split = torch.empty(op.cout, 2, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
+                    op.w_fwd = op.w_dgrad = None
+                else:
+                    op.w_fwd = torch.empty(op.cout, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
+                    op.w_dgrad = None if op.first else torch.empty(op.cin_pad, kk, op.cout, dtype=torch.bfloat16, device=dev)
                 op.w_src = self.params[op.prefixes[0] + ".conv.weight"]
                 op.g_dst = self.grads[op.prefixes[0] + ".conv.weight"]
             elif isinstance(op, PredOp):
                 k, hc = op.level, self.hc
+                if self.strict:
+                    op.wc_split = torch.empty(self.nc, 2, 1, hc, dtype=torch.bfloat16, device=dev)
+                    op.wr_split = torch.empty(16, 2, 1, hc, dtype=torch.bfloat16, device=dev)
                 op.wc_fwd = torch.empty(self.nc, 1, hc, dtype=torch.bfloat16, device=dev)
                 op.wc_dgrad = torch.empty(hc, 1, self.nc, dtype=torch.bfloat16, device=dev)
                 op.wr_fwd = torch.empty(16, 1, hc, dtype=torch.bfloat16, device=dev)
@@ -378,6 +400,17 @@ class YoloxEngine:
     # ------------------------------------------------------------------ forward
     def pack_weights(self):
         L, sp = self.L, capi.stream_ptr()
+        if self.strict:
+            for op in self.ops:
+                if isinstance(op, ConvOp):
+                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad,
+                                                              capi.ptr(op.w_split), sp), "pack split")
+                    self._count(1, "pack split " + op.prefixes[0])
+                elif isinstance(op, PredOp):
+                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.wc_src), self.nc, self.hc, 1, self.nc, self.hc, capi.ptr(op.wc_split), sp), "pack cls")
+                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, capi.ptr(op.wr_split), sp), "pack reg+obj")
+                    self._count(2, "pack split preds")
+            return
         for op in self.ops:
             if isinstance(op, ConvOp):
                 capi.check(L.yb200_pack_conv_weight(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad, capi.ptr(op.w_fwd),
@@ -396,7 +429,58 @@ class YoloxEngine:
                                                  self.focus.view().act(), capi.stream_ptr()), "preprocess_focus")
         self._count(1, "preprocess")
 
+    def _forward_features_strict(self, training):
+        """the same plan in split-bf16 / fp32 arithmetic: conv (3 operand-split terms on the tensor cores) -> fp32 z -> fp64 batch
+        statistics -> SiLU(BN(z)) (+ shortcut, + upsampled copy) stored as split pairs -> fp32 head outputs"""
+        L, sp = self.L, capi.stream_ptr()
+        nb, f8 = self.nbn, self.flat_stats
+        pf = lambda t, off: ctypes.c_void_p(t.data_ptr() + 4 * off)
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                zb = op.z.buf
+                capi.check(L.yb200_conv2d_fwd_split(op.x.act(), op.x.buf.lo, capi.ptr(op.w_split), op.cout, op.ksize, op.stride, capi.ptr(zb.t), zb.c, 0,
+                                                    sp), "conv split " + op.prefixes[0])
+                o = op.bn_off
+                gamma = self.params[op.prefixes[0] + ".bn.weight"]
+                beta = self.params[op.heads[0].prefix + ".bn.bias"]
+                npix = zb.n * zb.h * zb.w
+                if training:
+                    ssum, ssq = ctypes.c_void_p(f8.data_ptr() + 8 * o), ctypes.c_void_p(f8.data_ptr() + 8 * (nb + o))
+                    capi.check(L.yb200_strict_bn_stats(capi.ptr(zb.t), ctypes.c_int64(npix), zb.c, 0, op.cout, ssum, ssq, sp), "strict_bn_stats")
+                    capi.check(L.yb200_bn_finalize(ssum, ssq, op.cout, ctypes.c_int64(npix), capi.ptr(gamma), capi.ptr(beta), ctypes.c_float(BN_EPS),
+                                                   ctypes.c_float(BN_MOMENTUM), pf(self.flat_rm, o), pf(self.flat_rv, o), None, pf(self.flat_scale, o),
+                                                   pf(self.flat_shift, o), pf(self.flat_mean, o), pf(self.flat_invstd, o), sp), "bn_finalize")
+                else:
+                    capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm, o), pf(self.flat_rv, o),
+                                                      ctypes.c_float(BN_EPS), pf(self.flat_scale, o), pf(self.flat_shift, o), sp), "bn_eval_affine")
+                self._count(3 if training else 2, "strict conv+stats+finalize %s %s" % (op.prefixes[0], self._desc(op)))
+                for hd in op.heads:
+                    capi.check(L.yb200_strict_bn_apply_silu(capi.ptr(zb.t), zb.c, hd.c0, pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
+                                                            hd.residual.act() if hd.residual else None, hd.residual.buf.lo if hd.residual else 0,
+                                                            hd.out.act(), hd.out.buf.lo, hd.up.act() if hd.up else None, hd.up.buf.lo if hd.up else 0, sp),
+                               "strict_bn_apply_silu " + hd.prefix)
+                    self._count(1, "strict bn_apply " + hd.prefix)
+            elif isinstance(op, SppOp):
+                v = op.views
+                capi.check(L.yb200_strict_spp_pool(v[0].act(), v[1].act(), v[2].act(), v[3].act(), v[0].buf.lo, sp), "strict_spp_pool")
+                self._count(1, "strict spp_pool")
+            else:
+                h, w, s, a_off = self.levels[op.level]
+                ch = 5 + self.nc
+                capi.check(L.yb200_conv1x1_bias_f32_split(op.cls_feat.act(), op.cls_feat.buf.lo, capi.ptr(op.wc_split), capi.ptr(op.bc), self.nc,
+                                                          capi.ptr(self.outputs), self.num_anchors, a_off, ch, 5, sp), "cls_pred split")
+                capi.check(L.yb200_conv1x1_bias_f32_split(op.reg_feat.act(), op.reg_feat.buf.lo, capi.ptr(op.wr_split), capi.ptr(op.br), 5,
+                                                          capi.ptr(self.outputs), self.num_anchors, a_off, ch, 0, sp), "reg_obj_pred split")
+                self._count(2, "strict pred convs level %d" % op.level)
+        if training:
+            self.flat_nbt += 1
+        capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
+                                        0 if training else 1, sp), "decode")
+        self._count(1, "decode")
+
     def forward_features(self, training=True):
+        if self.strict:
+            return self._forward_features_strict(training)
         L, sp = self.L, capi.stream_ptr()
         nb = self.nbn
         f8 = self.flat_stats
@@ -522,6 +606,8 @@ class YoloxEngine:
                                             ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad " + label)
 
     def backward(self, accumulate=False):
+        if self.strict:
+            raise capi.Yb200Error("strict mode is a forward / loss verification mode: no backward (use the default engine for training)")
         L, sp = self.L, capi.stream_ptr()
         nb = self.nbn
         f8 = self.flat_stats
@@ -586,8 +672,9 @@ class YoloxEngine:
         self.pack_weights()
         self.preprocess()
         self.forward_features(True)
-        self.assign_and_loss(True)
-        self.backward(accumulate)
+        self.assign_and_loss(not self.strict)
+        if not self.strict:
+            self.backward(accumulate)
         return self.losses
 
     def eval_forward(self):
