@@ -165,6 +165,74 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def library_bar(torch, dev, batch, with_optimizer, steps=5, warmup=3):
+    """Stock PyTorch on the same GPU: the oracle port (plain torch ops: F.conv2d / F.batch_norm / SiLU -> cuDNN, cuBLAS, ATen kernels)
+    under autocast(fp16) with channels_last tensors, the same synthetic batch, forward + SimOTA + losses + backward (+ torch.optim.SGD).
+    A reported baseline, like cpu_baseline: nothing of this repo's kernels runs here, and this repo's path never calls it."""
+    from oracle import yolox_oracle as orc  # baseline being timed (not the product path)
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.to(dev) for k, v in orc.yolox_state_dict(0).items()}
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and "running" not in k:
+            if v.dim() == 4:
+                sd[k] = v = v.contiguous(memory_format=torch.channels_last)
+            v.requires_grad_(True)
+    images, labels = orc.synthetic_batch(batch, 640, 100)
+    x = images.to(dev).float().contiguous(memory_format=torch.channels_last)
+    labels = labels.to(dev)
+    params = [v for v in sd.values() if v.requires_grad]
+    sgd = torch.optim.SGD(params, lr=BENCH_LR, momentum=0.9, weight_decay=5e-4) if with_optimizer else None
+
+    def step():
+        for v in params:
+            v.grad = None
+        with torch.autocast("cuda", dtype=torch.float16):
+            raw = orc.head_raw(orc.pafpn(orc.csp_darknet(x, sd, True), sd, True), sd, True)
+        outputs = orc.decode_train([r.float() for r in raw])
+        xs, ys, ss = orc.anchor_grid([o.shape[-2:] for o in raw], device=dev)
+        loss = orc.yolox_losses(outputs, labels, xs, ys, ss)[0]
+        loss.backward()
+        if sgd is not None:
+            sgd.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # network only (no SimOTA / loss Python loop): forward + backward of a scalar functional of the head outputs
+    def net_step():
+        for v in params:
+            v.grad = None
+        with torch.autocast("cuda", dtype=torch.float16):
+            raw = orc.head_raw(orc.pafpn(orc.csp_darknet(x, sd, True), sd, True), sd, True)
+        sum(r.float().square().mean() for r in raw).backward()
+
+    for _ in range(2):
+        net_step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        net_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_net = e0.elapsed_time(e1) / steps
+    out = {"value": batch / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "network_only_images_per_s": batch / ms_net * 1e3, "network_only_ms": ms_net,
+           "what": "oracle port (plain torch ops) on cuda:0, torch %s / cuDNN %s, autocast fp16 + channels_last, bs=%d 640x640, fwd + SimOTA/loss (per-image "
+                   "Python loop, as the reference) + bwd%s; network_only = conv/BN/SiLU forward+backward without the loss" % (
+                       torch.__version__, torch.backends.cudnn.version(), batch, " + torch.optim.SGD" if with_optimizer else ""),
+           "loss": float(loss)}
+    del sd, params, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,11 +240,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="yb200", choices=["yb200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU (BASELINE.json configs[1]: 64)")
-    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--ref-batch", type=int, default=16, help="images per CPU step of the reference arm / cpu_baseline: enough work per step to use every host core (bs=2 left most of a 128-thread host idle)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-convnext", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: copy each batch inside forward() (serial), as the reference does")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward(+all-reduce) only, without the fused SGD step")
     args = ap.parse_args()
@@ -226,12 +295,6 @@ def main():
             dist.all_reduce(flat_grad)  # the single gradient all-reduce of the path (sum; the 1/world is folded into the update)
         if opt is not None:
             opt.step()
-
-    # probe: CUDA events around the dominant kernel (head 3x3 128->128 @80x80, merged cls|reg: 128->256) on the launch stream
-    probe = {"ev": [], "op": None}
-    for op in eng.ops:
-        if getattr(op, "prefixes", [""])[0] == "head.cls_convs.0.0":
-            probe["op"] = op
 
     for _ in range(max(args.warmup, 3)):
         step_eager()
@@ -292,34 +355,51 @@ def main():
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream (eager launches of the same step) ----
+    # ---- roofline: every C-ABI call of the step timed live with CUDA events on the launch stream (eager launches, weight gradients serialised
+    # on the same stream), grouped into kernel classes; the class with the LARGEST summed time is the one reported ----
     pk = peaks()
-    roof = None
-    op = probe["op"]
-    if op is not None:
-        L = eng.L
-        evs = []
-        for _ in range(max(3, min(args.steps, 10))):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            eng.train_step()  # keeps the cache state of a real step around the probed launch
-            a.record()
-            capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, None, None, capi.stream_ptr()), "probe")
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        t_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
-        n, oh, ow, cout = op.z.shape
-        flops = 2.0 * n * oh * ow * cout * op.cin_pad * op.ksize * op.ksize
-        ach = flops / (t_ms * 1e-3) / 1e12
+    roof, classes = None, None
+    if rank == 0:
+        calls = eng.profile_step(reps=3)
+        agg = {}
+        for c in calls:
+            a = agg.setdefault(c["cls"], dict(ms=0.0, bytes=0.0, flops=0.0, launches=0, roof_ms=0.0))
+            a["ms"] += c["ms"]; a["bytes"] += c["bytes"]; a["flops"] += c["flops"]; a["launches"] += c["launches"]
+            a["roof_ms"] += max(c["bytes"] / (pk["hbm"] * 1e9), c["flops"] / (pk["tf_sust"] * 1e12)) * 1e3  # per call: max(memory, compute) floor
+        serial_ms = sum(a["ms"] for a in agg.values())
+        floor_ms = sum(a["roof_ms"] for a in agg.values())
+        classes = []
+        for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            gbs, tfs = a["bytes"] / a["ms"] / 1e6, a["flops"] / a["ms"] / 1e9
+            classes.append({"class": name, "launches_per_step": a["launches"], "ms_per_step": round(a["ms"], 4), "share": round(a["ms"] / serial_ms, 4),
+                            "algorithmic_GB": round(a["bytes"] / 1e9, 4), "GB_per_s": round(gbs, 1), "TFLOP_per_s": round(tfs, 1),
+                            "frac_of_roofline": round(a["roof_ms"] / a["ms"], 4)})
+        top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+        hbm_bound = top["bytes"] / (pk["hbm"] * 1e9) >= top["flops"] / (pk["tf_sust"] * 1e12)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get("conv_gemm_head3x3_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": "conv_gemm_pair_kernel<64> (cta_group::2, 256x256 tile; head 3x3 128->256 @80x80: implicit GEMM M=%d N=%d K=%d)" % (n * oh * ow, cout, op.cin_pad * 9),
-                "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
-                "peak_source": pk["source"] + " bf16_tflops (burst: kernel timed alone between events)", "us_per_launch": 1e3 * t_ms,
-                "step_frac_of_sustained_peak": value / world * FLOP_PER_IMAGE / 1e12 / pk["tf_sust"]}
+                traffic = json.load(fh).get(top_name)
+        step_ms = ms / args.steps
+        if hbm_bound:
+            ach, peak, unit = top["bytes"] / top["ms"] / 1e6, pk["hbm"], "GB/s"
+        else:
+            ach, peak, unit = top["flops"] / top["ms"] / 1e9, pk["tf_sust"], "TFLOP/s"
+        roof = {"bound": "hbm" if hbm_bound else "tensor",
+                "kernel": "%s: the kernel class with the largest summed time in the step (%d launches per step, %.1f %% of the serialised step)" % (
+                    top_name, top["launches"], 100 * top["ms"] / serial_ms),
+                "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
+                "traffic_note": "dram__bytes read+write of this class summed over one step (ncu --set full, profiles/), null when not captured",
+                "peak_source": pk["source"] + (" hbm_gbs" if hbm_bound else " bf16_tflops_sustained (kernels timed inside a long step)"),
+                "ms_per_step": top["ms"], "algorithmic_bytes_per_step": top["bytes"], "algorithmic_flops_per_step": top["flops"],
+                "how": "sum over the class of (algorithmic bytes or FLOPs of the call: each tensor moved once in 16 bits) / sum of CUDA-event durations, "
+                       "median of 3 eager steps; per-call numbers in `kernel_classes`",
+                "step_serialised_ms": serial_ms,
+                "step_frac_of_layer_roofline": floor_ms / step_ms,
+                "step_frac_of_layer_roofline_note": "sum over calls of max(bytes/HBM peak, FLOPs/sustained bf16 peak) = %.3f ms, divided by the timed step (%.3f ms)" % (floor_ms, step_ms),
+                "step_frac_of_sustained_peak": value / world * FLOP_PER_IMAGE / 1e12 / pk["tf_sust"],
+                "step_frac_of_hbm_peak_on_algorithmic_bytes": value / world * 444e6 / 1e9 / pk["hbm"]}
 
     # ---- end to end through the public API: pinned host uint8 images -> loss.item() ----
     e2e = None
@@ -419,7 +499,8 @@ def main():
         for k, v in csd.items():
             if v.dtype == torch.float32 and "running" not in k:
                 v.requires_grad_(True)
-        ci, cl = orc.synthetic_batch(2, 640, 0)
+        cb = args.ref_batch
+        ci, cl = orc.synthetic_batch(cb, 640, 0)
         cx = ci.float()
 
         copt = None if opt is None else torch.optim.SGD([v for v in csd.values() if v.requires_grad], lr=BENCH_LR, momentum=0.9, weight_decay=5e-4)
@@ -435,12 +516,22 @@ def main():
         threads, avail = pick_cpu_threads(cstep, torch)
         t0 = time.perf_counter()
         iters = 0
-        while iters < 2 or (time.perf_counter() - t0 < 10 and iters < 20):
+        while iters < 2 or (time.perf_counter() - t0 < 15 and iters < 20):
             cstep()
             iters += 1
         cdt = time.perf_counter() - t0
-        cpu = {"value": 2 * iters / cdt, "unit": "images/s", "cores": threads, "cores_available": avail, "kind": "port",
-               "sample": f"{iters} iterations of bs=2 YOLOX-s 640x640 fwd+bwd (BASELINE.json configs[0]) with oracle/yolox_oracle.py, torch CPU fp32"}
+        cpu = {"value": cb * iters / cdt, "unit": "images/s", "cores": threads, "cores_available": avail, "kind": "port",
+               "sample": f"{iters} iterations of bs={cb} YOLOX-s 640x640 fwd+bwd(+SGD) with oracle/yolox_oracle.py, torch CPU fp32, thread count picked "
+                         f"as the fastest of 8..{avail}"}
+
+    # ---- library bar: the same step through stock PyTorch / cuDNN on this GPU (oracle port on cuda, autocast fp16 + channels_last, the
+    # reference's shipped AMP setting configs/coco/yolox_s.yaml:66-68; SimOTA / losses in fp32 as yolox_head.py:350-379 does) ----
+    lib_bar = None
+    if rank == 0 and world == 1 and not args.no_library_bar:
+        try:
+            lib_bar = library_bar(torch, dev, B, opt is not None)
+        except Exception as e:  # noqa: BLE001
+            lib_bar = {"error": str(e)[:300]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -449,7 +540,7 @@ def main():
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                            "optimizer": None if opt is None else "fused SGD step inside the timed step (momentum 0.9, wd 5e-4, lr %g)" % BENCH_LR,
                            "l2": "per-step working set (~%.0f GB of activations and gradients) exceeds the 126 MB L2; no explicit flush" % (0.245 * B)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "cpu_baseline": cpu, "nms": nms, "convnext": cnx_line,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "kernel_classes": classes, "cpu_baseline": cpu, "library_bar": lib_bar, "nms": nms, "convnext": cnx_line,
                 "loss": float(eng.losses[0])}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -133,14 +133,14 @@ def head_raw(fpn_outs, sd, training=True, P="head."):
     return outs
 
 
-def anchor_grid(hw_list, strides=STRIDES, dtype=torch.float32):
+def anchor_grid(hw_list, strides=STRIDES, dtype=torch.float32, device=None):
     """x_shifts, y_shifts, expanded_strides, each [A]   (yolox_head.py:226-245, 295-300)"""
     xs, ys, ss = [], [], []
     for (h, w), s in zip(hw_list, strides):
-        yv, xv = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        yv, xv = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
         xs.append(xv.reshape(-1).to(dtype))
         ys.append(yv.reshape(-1).to(dtype))
-        ss.append(torch.full((h * w,), float(s), dtype=dtype))
+        ss.append(torch.full((h * w,), float(s), dtype=dtype, device=device))
     return torch.cat(xs), torch.cat(ys), torch.cat(ss)
 
 
@@ -150,7 +150,7 @@ def decode_train(raw_levels, strides=STRIDES):
     for o, s in zip(raw_levels, strides):
         b, ch, h, w = o.shape
         o = o.permute(0, 2, 3, 1).reshape(b, h * w, ch)
-        gx, gy, _ = anchor_grid([(h, w)], [s], o.dtype)
+        gx, gy, _ = anchor_grid([(h, w)], [s], o.dtype, o.device)
         grid = torch.stack((gx, gy), 1).unsqueeze(0)
         outs.append(torch.cat([(o[..., :2] + grid) * s, torch.exp(o[..., 2:4]) * s, o[..., 4:]], -1))
     return torch.cat(outs, 1)
@@ -162,7 +162,7 @@ def decode_eval(raw_levels, strides=STRIDES):
     for o, s in zip(raw_levels, strides):
         b, ch, h, w = o.shape
         o = torch.cat([o[:, :4], o[:, 4:].sigmoid()], 1).permute(0, 2, 3, 1).reshape(b, h * w, ch)
-        gx, gy, _ = anchor_grid([(h, w)], [s], o.dtype)
+        gx, gy, _ = anchor_grid([(h, w)], [s], o.dtype, o.device)
         grid = torch.stack((gx, gy), 1).unsqueeze(0)
         outs.append(torch.cat([(o[..., :2] + grid) * s, torch.exp(o[..., 2:4]) * s, o[..., 4:]], -1))
     return torch.cat(outs, 1)
@@ -296,10 +296,10 @@ def yolox_losses(outputs, labels, x_shifts, y_shifts, strides, num_classes=80, l
         g = int(nlabel[b])
         num_gts += g
         if g == 0:
-            fg = torch.zeros(num_anchors, dtype=torch.bool)
+            fg = torch.zeros(num_anchors, dtype=torch.bool, device=outputs.device)
             cls_t.append(outputs.new_zeros((0, num_classes)))
             reg_t.append(outputs.new_zeros((0, 4)))
-            assigns.append((fg, torch.zeros(0, dtype=torch.int64), outputs.new_zeros(0), outputs.new_zeros(0)))
+            assigns.append((fg, torch.zeros(0, dtype=torch.int64, device=outputs.device), outputs.new_zeros(0), outputs.new_zeros(0)))
         else:
             gtb, gtc = labels[b, :g, 1:5], labels[b, :g, 0]
             with torch.no_grad():
@@ -331,7 +331,7 @@ def yolox_forward_train(images, labels, sd, num_classes=80):
     fpn = pafpn(csp_darknet(images, sd, True), sd, True)
     raw = head_raw(fpn, sd, True)
     outputs = decode_train(raw)
-    xs, ys, ss = anchor_grid([o.shape[-2:] for o in raw])
+    xs, ys, ss = anchor_grid([o.shape[-2:] for o in raw], device=outputs.device)
     return yolox_losses(outputs, labels, xs, ys, ss, num_classes) + (outputs,)
 
 

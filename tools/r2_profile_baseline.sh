@@ -12,5 +12,4 @@ run r2base_bn_bwd_reduce 'bn_silu_bwd_reduce_kernel' 73 1
 run r2base_bn_bwd_apply 'bn_silu_bwd_apply_kernel<1>' 71 1
 run r2base_conv1x1 'conv_gemm_persistent_kernel<64, 64' 0 2
 timeout 300 $NCU -k 'regex:nms_' -c 3 -f -o gpurun_out/r2base_nms python tools/profile_nms.py > gpurun_out/r2base_nms.log 2>&1; echo "nms rc=$?"
-YB200_DETR_TRAINING=1 timeout 600 python -m pytest tests/test_detr_gpu.py -m gpu -q -x --timeout=300 2>&1 | tail -30 > gpurun_out/r2_detr_training.log; tail -5 gpurun_out/r2_detr_training.log
 ls -la gpurun_out/*.ncu-rep

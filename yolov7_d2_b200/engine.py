@@ -378,12 +378,56 @@ class YoloxEngine:
         self._side = torch.cuda.Stream(device=dev)
         self._fork_evt = torch.cuda.Event()
         self.trace = None  # set to [] to record (label, launches) per call for tools/summarize_launches.py
+        self._ev = None    # profile_step(): (label, class, launches, bytes, flops, event) per call
 
-    def _count(self, k=1, label=None):
-        """k = number of kernels the preceding C-ABI call(s) launched (memsets excluded); label feeds the per-layer profile"""
+    def _count(self, k=1, label=None, cls=None, nbytes=0.0, flops=0.0):
+        """k = number of kernels the preceding C-ABI call(s) launched (memsets excluded); label feeds the per-layer profile.
+        cls / nbytes / flops: kernel class and ALGORITHMIC bytes / FLOPs of the call (what an ideal fused implementation must move /
+        compute: every tensor read or written once, 16-bit activations) -- the numerators of bench.py's roofline."""
         self.kernel_launches += k
         if self.trace is not None:
             self.trace.append((label or "?", k))
+        if self._ev is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._ev.append((label or "?", cls or "other", k, float(nbytes), float(flops), ev))
+
+    def _alg_conv(self, op):
+        n, h, w, _ = op.x.shape
+        oh, ow = h // op.stride, w // op.stride
+        kk = op.ksize * op.ksize
+        nbytes = 2.0 * n * (h * w * op.cin_pad + oh * ow * op.cout) + 2.0 * op.cout * kk * op.cin_pad
+        return nbytes, 2.0 * n * oh * ow * op.cout * op.cin_real * kk
+
+    def profile_step(self, reps=3):
+        """Warm CUDA-event duration of every C-ABI call of one training step: eager launches on the current stream with the weight
+        gradients serialised on it (no side stream), an event after each call, median over `reps` steps.  Returns a list of dicts
+        (label, cls, launches, bytes, flops, ms).  Tiny kernels include the launch gap in front of them."""
+        import statistics
+        saved = self.overlap_wgrad
+        self.overlap_wgrad = False
+        runs = []
+        try:
+            self.train_step()
+            for _ in range(reps):
+                torch.cuda.synchronize()
+                self._ev = []
+                start = torch.cuda.Event(enable_timing=True)
+                start.record()
+                self.train_step()
+                torch.cuda.synchronize()
+                prev, row = start, []
+                for label, cls, k, nb, fl, ev in self._ev:
+                    row.append((label, cls, k, nb, fl, prev.elapsed_time(ev)))
+                    prev = ev
+                runs.append(row)
+        finally:
+            self._ev = None
+            self.overlap_wgrad = saved
+        out = []
+        for i, (label, cls, k, nb, fl, _) in enumerate(runs[0]):
+            out.append(dict(label=label, cls=cls, launches=k, bytes=nb, flops=fl, ms=statistics.median(r[i][5] for r in runs)))
+        return out
 
     @staticmethod
     def _desc(op):
@@ -415,19 +459,19 @@ class YoloxEngine:
             if isinstance(op, ConvOp):
                 capi.check(L.yb200_pack_conv_weight(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad, capi.ptr(op.w_fwd),
                                                     capi.ptr(op.w_dgrad), sp), "pack")
-                self._count(1, "pack " + op.prefixes[0])
+                self._count(1, "pack " + op.prefixes[0], "pack_weights", 4.0 * op.w_src.numel() * len(op.prefixes) + 2.0 * op.w_fwd.numel() * (1 if op.first else 2))
             elif isinstance(op, PredOp):
                 capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wc_src), self.nc, self.hc, 1, self.nc, self.hc, capi.ptr(op.wc_fwd),
                                                     capi.ptr(op.wc_dgrad), sp), "pack cls")
                 capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, capi.ptr(op.wr_fwd), capi.ptr(op.wr_dgrad),
                                                     sp), "pack reg+obj")
-                self._count(2, "pack preds")
+                self._count(2, "pack preds", "pack_weights", 10.0 * (self.nc + 16) * self.hc)
 
     def preprocess(self):
         """images_u8 [N,3,H,W] (device) -> focus buffer"""
         capi.check(self.L.yb200_preprocess_focus(capi.ptr(self.images_u8), self.n, self.h, self.w, capi.ptr(self.hw_valid), ctypes.c_float(self.pad_value),
                                                  self.focus.view().act(), capi.stream_ptr()), "preprocess_focus")
-        self._count(1, "preprocess")
+        self._count(1, "preprocess", "preprocess_focus", self.n * self.h * self.w * (3.0 + 8.0))
 
     def _forward_features_strict(self, training):
         """the same plan in split-bf16 / fp32 arithmetic: conv (3 operand-split terms on the tensor cores) -> fp32 z -> fp64 batch
@@ -514,17 +558,19 @@ class YoloxEngine:
                 else:
                     capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm), pf(self.flat_rv),
                                                       ctypes.c_float(BN_EPS), pf(self.flat_scale), pf(self.flat_shift), sp), "bn_eval_affine")
-                self._count(2, "conv_fwd+bn_finalize %s %s" % (op.prefixes[0], self._desc(op)))
+                self._count(2, "conv_fwd+bn_finalize %s %s" % (op.prefixes[0], self._desc(op)), "conv_fwd (conv_gemm + bn_finalize)", *self._alg_conv(op))
                 for hd in op.heads:
                     zv = op.z.buf.view(hd.c0, hd.c)
                     capi.check(L.yb200_bn_apply_silu(zv.act(), pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
                                                      hd.residual.act() if hd.residual else None, hd.out.act(), hd.up.act() if hd.up else None, sp),
                                "bn_apply_silu " + hd.prefix)
-                    self._count(1, "bn_apply %s c=%d px=%d" % (hd.prefix, hd.c, op.z.buf.n * op.z.buf.h * op.z.buf.w))
+                    npx = op.z.buf.n * op.z.buf.h * op.z.buf.w
+                    self._count(1, "bn_apply %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_apply_silu",
+                                2.0 * npx * hd.c * (2 + (1 if hd.residual else 0) + (4 if hd.up else 0)))
             elif isinstance(op, SppOp):
                 v = op.views
                 capi.check(L.yb200_spp_pool(v[0].act(), v[1].act(), v[2].act(), v[3].act(), capi.ptr(op.arg) if training else None, sp), "spp_pool")
-                self._count(1, "spp_pool")
+                self._count(1, "spp_pool", "spp_pool", 2.0 * 4 * v[0].buf.n * v[0].buf.h * v[0].buf.w * v[0].c)
             else:
                 h, w, s, a_off = self.levels[op.level]
                 ch = 5 + self.nc
@@ -532,13 +578,14 @@ class YoloxEngine:
                                                     self.num_anchors, a_off, ch, 5, sp), "cls_pred")
                 capi.check(L.yb200_conv1x1_bias_f32(op.reg_feat.act(), capi.ptr(op.wr_fwd), capi.ptr(op.br), 5, capi.ptr(self.outputs),
                                                     self.num_anchors, a_off, ch, 0, sp), "reg_obj_pred")
-                self._count(2, "pred convs level %d" % op.level)
+                self._count(2, "pred convs level %d" % op.level, "pred_conv fwd", self.n * h * w * (2.0 * 2 * self.hc + 4.0 * ch),
+                            2.0 * self.n * h * w * self.hc * ch)
         if training:
             self.flat_nbt += 1
             self._count(1, "num_batches_tracked += 1 (torch)")
         capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
                                         0 if training else 1, sp), "decode")
-        self._count(1, "decode")
+        self._count(1, "decode", "decode", 8.0 * self.n * self.num_anchors * 4)
 
     def assign_and_loss(self, with_grad=True):
         L, sp = self.L, capi.stream_ptr()
@@ -547,13 +594,13 @@ class YoloxEngine:
                                          capi.ptr(self.simota_ws), capi.ptr(self.num_gt), capi.ptr(self.fg_mask), capi.ptr(self.matched_gt),
                                          capi.ptr(self.matched_iou), capi.ptr(self.matched_cls), capi.ptr(self.num_fg_img), capi.ptr(self.totals), sp),
                    "simota_assign")
-        self._count(4, "simota (count_gt, prep, match, resolve)")
+        self._count(4, "simota (count_gt, prep, match, resolve)", "simota_assign", 4.0 * n * a * ch)
         capi.check(L.yb200_yolox_loss(capi.ptr(self.outputs), capi.ptr(self.labels), n, a, ch, self.max_gt, self.lv, len(self.levels),
                                       capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls),
                                       capi.ptr(self.totals), capi.ptr(self.loss_weights) if with_grad else None, capi.ptr(self.loss_acc),
                                       capi.ptr(self.losses), self.p_dcls if with_grad else None, self.p_dro if with_grad else None, None,
                                       capi.ptr(self.bias_acc) if with_grad else None, sp), "yolox_loss")
-        self._count(2, "yolox_loss + finish")
+        self._count(2, "yolox_loss + finish", "yolox_loss", n * a * ch * (4.0 + (2.0 if with_grad else 0.0)))
 
     def loss_grad_only(self):
         """recompute d loss / d head outputs with the current loss_weights (autograd path: upstream gradients arrive late)"""
@@ -628,7 +675,8 @@ class YoloxEngine:
                     self._wgrad(feat.act(), ctypes.byref(dz), 1, 1, self.hc, gdst, acc, "pred")
                     add = self._grad_target(feat)
                     capi.check(L.yb200_conv2d_dgrad(ctypes.byref(dz), capi.ptr(wd), feat.gact(), add.gact() if add else None, 1, 1, sp), "pred dgrad")
-                self._count(7, "pred level %d: bias_grad, 2x(wgrad, reduce, dgrad)" % k)
+                self._count(7, "pred level %d: bias_grad, 2x(wgrad, reduce, dgrad)" % k, "pred_conv bwd", self.n * h * w * 2.0 * (4 * self.hc + self.nc + 16),
+                            4.0 * self.n * h * w * self.hc * (self.nc + 5))
             elif isinstance(op, SppOp):
                 v = op.views
                 if self.spp_scratch is None:
@@ -636,7 +684,7 @@ class YoloxEngine:
                 # in place: the identity slice of the concat gradient receives the pooled gradients
                 capi.check(L.yb200_spp_pool_bwd(v[0].gact(), v[1].gact(), v[2].gact(), v[3].gact(), capi.ptr(op.arg), capi.ptr(self.spp_scratch),
                                                 v[0].gact(), sp), "spp_pool_bwd")
-                self._count(2, "spp_pool_bwd (scatter, finish)")
+                self._count(2, "spp_pool_bwd (scatter, finish)", "spp_pool_bwd", 2.0 * 5 * v[0].buf.n * v[0].buf.h * v[0].buf.w * v[0].c)
             else:
                 dzb = self._dz_buf(op)
                 pf = lambda t, off: ctypes.c_void_p(t.data_ptr() + 4 * off)
@@ -649,12 +697,14 @@ class YoloxEngine:
                                                    ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)), ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)),
                                                    dzv.act(), capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
                                                    acc, sp), "bn_silu_bwd " + hd.prefix)
-                    self._count(3, "bn_bwd (reduce, apply, param) %s c=%d px=%d" % (hd.prefix, hd.c, op.z.buf.n * op.z.buf.h * op.z.buf.w))
+                    npx = op.z.buf.n * op.z.buf.h * op.z.buf.w
+                    self._count(3, "bn_bwd (reduce, apply, param) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd (reduce + apply)",
+                                2.0 * npx * hd.c * (3 + (4 if hd.up else 0)))
                     if hd.residual is not None:
                         pending_res[(id(hd.residual.buf), hd.residual.off)] = hd.out
                 dz = dzb.view()
                 self._wgrad(op.x.act(), dz.act(), op.ksize, op.stride, op.cin_real, op.g_dst, acc, op.prefixes[0])
-                self._count(2, "wgrad+reduce %s %s" % (op.prefixes[0], self._desc(op)))
+                self._count(2, "wgrad+reduce %s %s" % (op.prefixes[0], self._desc(op)), "wgrad (wgrad_gemm + reduce)", *self._alg_conv(op))
                 if not op.first:
                     res = pending_res.pop((id(op.x.buf), op.x.off), None)
                     add = self._grad_target(op.x)
@@ -662,7 +712,7 @@ class YoloxEngine:
                     addend = res.gact() if res is not None else (add.gact() if add is not None else None)
                     capi.check(L.yb200_conv2d_dgrad(dz.act(), capi.ptr(op.w_dgrad), op.x.gact(), addend, op.ksize, op.stride, sp),
                                "dgrad " + op.prefixes[0])
-                    self._count(4 if op.stride == 2 else 1, "dgrad %s %s" % (op.prefixes[0], self._desc(op)))
+                    self._count(4 if op.stride == 2 else 1, "dgrad %s %s" % (op.prefixes[0], self._desc(op)), "dgrad (conv_gemm)", *self._alg_conv(op))
         if self.overlap_wgrad:
             torch.cuda.current_stream().wait_stream(self._side)  # join: gradients are complete when backward() returns
 
