@@ -38,6 +38,19 @@ class Act(ctypes.Structure):
     ]
 
 
+class BnBwdSeg(ctypes.Structure):
+    """mirror of `yb200_bnbwd_seg` (include/yb200.h)"""
+
+    _fields_ = [
+        ("z", Act),
+        ("dx_c_begin", ctypes.c_int32),
+        ("scale", c_void_p),
+        ("shift", c_void_p),
+        ("sum_du", c_void_p),
+        ("sum_duz", c_void_p),
+    ]
+
+
 def declared_symbols(header_path=HEADER_PATH):
     """Every function the public header declares (used by the CPU test that checks the exports)."""
     with open(header_path) as fh:

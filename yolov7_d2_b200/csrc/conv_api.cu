@@ -35,7 +35,7 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
                             cudaStream_t st) {
   using Cfg = ConvGemmCfg<BN, BK>;
   const bool ext = p.epi_mode >= EPI_BF16_AFFINE;  // ConvNeXt / transformer epilogues live in their own instantiations
-  if (use_v1_kernel()) {  // one tile per CTA (kept for A/B comparison)
+  if (use_v1_kernel() && p.num_bnseg == 0) {  // one tile per CTA (kept for A/B comparison)
     static int max_set = 0;
     const int smem = stages * Cfg::kStageBytes + 1024;
     if (smem > max_set) {
@@ -47,7 +47,7 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     return 0;
   }
   if constexpr (BN == 256) {
-    if (use_pair_kernel() && p.epi_mode != EPI_F32_BIAS) {
+    if (use_pair_kernel() && p.epi_mode != EPI_F32_BIAS && p.num_bnseg == 0) {
       // CTA pairs: 2 x 128 pixels x 256 channels per UMMA, one CTA per SM, 32 KB per stage and CTA at BLOCK_K 64
       const int m_tiles = grid.x, n_tiles = grid.y;
       constexpr int stage_bytes = 2 * 128 * BK * 2;
@@ -91,17 +91,27 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   const int smem = pst * kbs * Cfg::kStageBytes + 1024;
   static int max_set_p = 0;
   if (smem > max_set_p) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     max_set_p = smem;
   }
   int groups = (occ * sm_count()) / n_tiles;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
+  if (p.num_bnseg > 0) {  // data gradient with fused BatchNorm-backward statistics
+    if constexpr (BN <= 128) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv_gemm_persistent_kernel<BN, BK, 2><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+      YB_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    } else {
+      return fail(YB200_ERR_UNSUPPORTED, "fused BatchNorm-backward statistics need a column tile <= 128 (gradient tensors of < 256 channels)");
+    }
+  }
   if (ext)
-    conv_gemm_persistent_kernel<BN, BK, true><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+    conv_gemm_persistent_kernel<BN, BK, 1><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
   else
-    conv_gemm_persistent_kernel<BN, BK, false><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+    conv_gemm_persistent_kernel<BN, BK, 0><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -523,7 +533,8 @@ extern "C" int yb200_conv1x1_bias_f32_split(const yb200_act* x, int lo_delta, co
 // data gradient
 // ------------------------------------------------------------------------------------------------
 static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend, int ksize, int stride,
-                      const yb200_act* gelu_u, double* colsum, void* stream, int act_mode = EPI_BF16_GELU_BWD) {
+                      const yb200_act* gelu_u, double* colsum, void* stream, int act_mode = EPI_BF16_GELU_BWD, int num_seg = 0,
+                      const yb200_bnbwd_seg* segs = nullptr) {
   int rc;
   if ((rc = check_act(dz, "conv2d_dgrad dz"))) return rc;
   if ((rc = check_act(dx, "conv2d_dgrad dx"))) return rc;
@@ -559,11 +570,35 @@ static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act*
     p.add_sh = 1LL * addend->c_pitch * addend->w;
     p.add_sn = 1LL * addend->c_pitch * addend->w * addend->h;
   }
+  if (num_seg > 0) {
+    YB_REQUIRE(num_seg <= 2 && segs != nullptr && gelu_u == nullptr, YB200_ERR_INVALID, "conv2d_dgrad_bnbwd: 1 or 2 segments");
+    YB_REQUIRE(bn <= 128, YB200_ERR_UNSUPPORTED, "conv2d_dgrad_bnbwd: gradient tensors of %d channels use a 256-wide column tile (not supported)", cin);
+    p.num_bnseg = num_seg;
+    for (int i = 0; i < num_seg; ++i) {
+      const yb200_bnbwd_seg& sgm = segs[i];
+      const yb200_act& z = sgm.z;
+      YB_REQUIRE(z.ptr && sgm.scale && sgm.shift && sgm.sum_du && sgm.sum_duz, YB200_ERR_INVALID, "conv2d_dgrad_bnbwd: null pointer in segment %d", i);
+      YB_REQUIRE(z.n == dx->n && z.h == dx->h && z.w == dx->w && z.c % 32 == 0 && sgm.dx_c_begin % 32 == 0 && sgm.dx_c_begin >= 0 &&
+                     sgm.dx_c_begin + z.c <= dx->c && z.c_off % 8 == 0 && z.c_pitch % 8 == 0,
+                 YB200_ERR_INVALID, "conv2d_dgrad_bnbwd: segment %d (z %dx%dx%dx%d at dx channel %d) does not fit dx %dx%dx%dx%d", i, z.n, z.h, z.w, z.c,
+                 sgm.dx_c_begin, dx->n, dx->h, dx->w, dx->c);
+      BnBwdSeg& d = p.bnseg[i];
+      d.col_begin = sgm.dx_c_begin;
+      d.col_end = sgm.dx_c_begin + z.c;
+      d.z = static_cast<const __half*>(z.ptr) + z.c_off;
+      d.z_sw = z.c_pitch;
+      d.z_sh = 1LL * z.c_pitch * z.w;
+      d.z_sn = 1LL * z.c_pitch * z.w * z.h;
+      d.scale = sgm.scale; d.shift = sgm.shift; d.sum_du = sgm.sum_du; d.sum_duz = sgm.sum_duz;
+    }
+    YB_REQUIRE(num_seg < 2 || p.bnseg[0].col_end <= p.bnseg[1].col_begin || p.bnseg[1].col_end <= p.bnseg[0].col_begin, YB200_ERR_INVALID,
+               "conv2d_dgrad_bnbwd: overlapping segments");
+  }
   set_tiles(p, dz->n, dz->h, dz->w);  // pixel grid = dz grid (for stride 2: one output-parity class at a time)
   const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
   CUtensorMap tmA, tmB;
   if ((rc = make_act_map(&tmA, *dz, false, bk, tw, th, tn))) return rc;
-  if ((rc = make_mat_map(&tmB, w_dgrad, cin, 1LL * taps_total * dz->c, (bn == 256 && use_pair_kernel() && !use_v1_kernel()) ? 128 : bn, bk))) return rc;
+  if ((rc = make_mat_map(&tmB, w_dgrad, cin, 1LL * taps_total * dz->c, (bn == 256 && use_pair_kernel() && !use_v1_kernel() && num_seg == 0) ? 128 : bn, bk))) return rc;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cin, bn));
 
   if (stride == 1) {
@@ -602,6 +637,12 @@ static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act*
 extern "C" int yb200_conv2d_dgrad(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend,
                                   int ksize, int stride, void* stream) {
   return dgrad_impl(dz, w_dgrad, dx, addend, ksize, stride, nullptr, nullptr, stream);
+}
+
+extern "C" int yb200_conv2d_dgrad_bnbwd(const yb200_act* dz, const void* w_dgrad, const yb200_act* dx, const yb200_act* addend, int ksize, int stride,
+                                        int num_segments, const yb200_bnbwd_seg* segments, void* stream) {
+  YB_REQUIRE(num_segments >= 1, YB200_ERR_INVALID, "conv2d_dgrad_bnbwd: no segments (use yb200_conv2d_dgrad)");
+  return dgrad_impl(dz, w_dgrad, dx, addend, ksize, stride, nullptr, nullptr, stream, EPI_BF16, num_segments, segments);
 }
 
 extern "C" int yb200_linear_dgrad_gelu(const yb200_act* dh_src, const void* w_dgrad, const yb200_act* u, const yb200_act* du, double* bias_grad_sum,

@@ -69,7 +69,23 @@ struct ConvTap {
   int kb;  // column offset of this tap inside the B matrix
 };
 
+// Fused BatchNorm-backward statistics (kernel variant 2, data-gradient launches): the epilogue that produces the FINAL gradient da of an
+// activation a = SiLU(BN(z)) also reads z and accumulates  S1 = sum du,  S2 = sum du * z  with du = da * SiLU'(z*scale + shift)  per channel
+// -- the reduction pass of BatchNorm backward (dbeta = S1, dgamma = invstd * (S2 - mean * S1)) without a second trip of da and z through HBM.
+// Up to two segments: the gradient tensor may be a concat buffer whose channel ranges come from different BatchNorm layers.
+struct BnBwdSeg {
+  int col_begin, col_end;      // columns (channels of the gradient tensor being written) covered by this segment; multiples of 32
+  const __half* z;             // the producer's pre-BN output, pointing at (pixel 0, channel col_begin)
+  long long z_sn, z_sh, z_sw;  // element strides of z over (image, row, column); z has the geometry of the gradient tensor
+  const float* scale;          // BatchNorm scale / shift of the producer, indexed by (column - col_begin)
+  const float* shift;
+  double* sum_du;              // S1 accumulator, indexed by (column - col_begin)
+  double* sum_duz;             // S2 accumulator
+};
+
 struct ConvGemmParams {
+  int num_bnseg;
+  BnBwdSeg bnseg[2];
   int tiles_w, tiles_h, tiles_n;
   int log_tw, log_th;          // tile = (1<<log_tw) x (1<<log_th) x (128 >> (log_tw+log_th)) pixels
   int num_taps, cin_blocks;    // K loop = num_taps * cin_blocks blocks of BLOCK_K
@@ -142,6 +158,36 @@ __device__ __forceinline__ void stage_col_params(const ConvGemmParams& p, int co
   }
 }
 
+__device__ __forceinline__ int bnseg_of(const ConvGemmParams& p, int col) {
+  if (p.num_bnseg > 0 && col >= p.bnseg[0].col_begin && col < p.bnseg[0].col_end) return 0;
+  if (p.num_bnseg > 1 && col >= p.bnseg[1].col_begin && col < p.bnseg[1].col_end) return 1;
+  return -1;
+}
+template <int BLOCK_N>
+__device__ __forceinline__ void stage_col_params_bnseg(const ConvGemmParams& p, int col0, float (*s_col)[BLOCK_N]) {
+  for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) {
+    const int s = bnseg_of(p, col0 + i);
+    s_col[0][i] = s >= 0 ? p.bnseg[s].scale[col0 + i - p.bnseg[s].col_begin] : 1.f;
+    s_col[1][i] = s >= 0 ? p.bnseg[s].shift[col0 + i - p.bnseg[s].col_begin] : 0.f;
+  }
+}
+__device__ __forceinline__ float silu_grad_f(float u, float d) {  // d * d/du [u * sigmoid(u)]
+  const float sg = __fdividef(1.f, 1.f + __expf(-u));
+  return d * sg * (1.f + u * (1.f - sg));
+}
+// fp16 z chunk of one pixel row (CH channels) for the fused BatchNorm-backward statistics
+template <int CH>
+__device__ __forceinline__ void load_z_chunk(const __half* zrow, bool valid, uint4 (&dst)[CH / 8]) {
+#pragma unroll
+  for (int k = 0; k < CH / 8; ++k) {
+    dst[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) {
+      const void* ptr = zrow + 8 * k;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dst[k].x), "=r"(dst[k].y), "=r"(dst[k].z), "=r"(dst[k].w) : "l"(ptr));
+    }
+  }
+}
+
 // The epilogue's per-element side input (GELU_BWD: the pre-activation u; otherwise the addend / residual) is a dependent global load in
 // a warp that has nothing else to do: the persistent kernels fetch it one chunk ahead (before the accumulator barrier for the first
 // chunk of a tile) so that its latency overlaps the TMEM load and the arithmetic of the previous chunk.
@@ -160,7 +206,8 @@ __device__ __forceinline__ void load_side_chunk(const __nv_bfloat16* side_row, b
 template <int CH, bool EXT = true>
 __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, float (&v)[CH], bool valid, long long pix_off, long long add_off,
                                                     int cbase, int lane, float* part_sum, float* part_sq, bool accumulate,
-                                                    const float* col_scale, const float* col_shift, const uint4* side = nullptr) {
+                                                    const float* col_scale, const float* col_shift, const uint4* side = nullptr,
+                                                    const uint4* zq = nullptr) {
   if (p.epi_mode == EPI_F32_BIAS) {
     if (valid) {
       float* o = reinterpret_cast<float*>(p.out) + pix_off;
@@ -280,6 +327,36 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       for (int i = 0; i < CH; i += 8)
         if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
     }
+  }
+  if (zq != nullptr) {
+    // fused BatchNorm-backward statistics on the values just stored (v = rounded da; 0 on masked rows): du -> v, du * z -> zf
+    float zf[CH];
+#pragma unroll
+    for (int k = 0; k < CH / 8; ++k) {
+      const uint32_t w4[4] = {zq[k].x, zq[k].y, zq[k].z, zq[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __half2 h;
+        *reinterpret_cast<uint32_t*>(&h) = w4[j];
+        const float2 f = __half22float2(h);
+        zf[8 * k + 2 * j] = f.x;
+        zf[8 * k + 2 * j + 1] = f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const float du = silu_grad_f(fmaf(zf[i], col_scale[i], col_shift[i]), v[i]);
+      v[i] = du;
+      zf[i] *= du;
+    }
+    float cs, cq;
+    if constexpr (CH == 32) { cs = warp_colsum32(v, lane); cq = warp_colsum32(zf, lane); }
+    else { cs = warp_colsum16(v, lane); cq = warp_colsum16(zf, lane); }
+    if (lane < CH) {
+      part_sum[lane] = accumulate ? part_sum[lane] + cs : cs;
+      part_sq[lane] = accumulate ? part_sq[lane] + cq : cq;
+    }
+    return;
   }
   if (p.epi_mode == EPI_F16_STATS) {
     float sq[CH];
@@ -446,11 +523,15 @@ constexpr int kMaxStagesP = 8;     // ring slots; one slot holds kb_per_slot con
 constexpr int kConvThreadsP = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue: two warps per TMEM lane quadrant, each
                                     // draining half of the accumulator columns (memory-bound layers are epilogue-bound)
 
-template <int BLOCK_N, int BLOCK_K, bool EXT>
+// VAR: 0 = YOLOX training / inference epilogues, 1 = + ConvNeXt / transformer epilogues (EXT), 2 = data gradient with fused
+// BatchNorm-backward statistics (BnBwdSeg; epi_mode EPI_BF16)
+template <int BLOCK_N, int BLOCK_K, int VAR>
 __global__ void __launch_bounds__(kConvThreadsP, BLOCK_N == 256 ? 1 : 2)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ ConvGemmParams p, int num_stages, int kb_per_slot, int n_tiles, int m_tiles) {
   using Cfg = ConvGemmCfg<BLOCK_N, BLOCK_K>;
+  constexpr bool EXT = VAR == 1;
+  constexpr bool BNB = VAR == 2;
   constexpr int kAccCols = Cfg::kTmemCols;          // columns of one accumulator
   constexpr int kTmemAlloc = 2 * kAccCols;          // double buffered (power of two >= 64)
   constexpr int kEpiHalves = BLOCK_N >= 32 ? 2 : 1; // column halves, one epilogue warp group (4 warps) each
@@ -489,7 +570,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 4 * 2 * BLOCK_N; i += blockDim.x) (&s_part[0][0][0])[i] = 0.f;
-  stage_col_params<BLOCK_N>(p, col0, s_col);
+  if constexpr (BNB) stage_col_params_bnseg<BLOCK_N>(p, col0, s_col);
+  else stage_col_params<BLOCK_N>(p, col0, s_col);
   if (warp == 1) tmem_alloc<kTmemAlloc>(smem_u32(&s_tmem));
   tc_fence_before();
   __syncthreads();
@@ -591,6 +673,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       if constexpr (EXT && BLOCK_N == 256) {
         if (side_base != nullptr && cend_live > cbeg) load_side_chunk<CH>(side_row, valid, col0 + cbeg, p.cout, side);  // in flight during the barrier wait
       }
+      // fused BatchNorm-backward statistics: this pixel's row of z in each segment
+      const __half* zrow[2] = {nullptr, nullptr};
+      if constexpr (BNB) {
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg)
+          if (sg < p.num_bnseg)
+            zrow[sg] = p.bnseg[sg].z + (long long)n * p.bnseg[sg].z_sn + (long long)(y * p.out_mh + p.out_ph) * p.bnseg[sg].z_sh +
+                       (long long)(x * p.out_mw + p.out_pw) * p.bnseg[sg].z_sw - p.bnseg[sg].col_begin;
+      }
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       if (cend_live <= cbeg) {  // every column of this warp's share lies beyond cout: nothing to read
@@ -608,6 +699,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         if constexpr (EXT && BLOCK_N == 256) {  // registers to spare (one CTA per SM): fetch the next chunk's side input before using this one
           if (more) load_side_chunk<CH>(side_row, valid, col0 + c + CH, p.cout, side_next);
         }
+        uint4 zq[CH / 8];
+        int zseg = -1;
+        if constexpr (BNB) {
+          zseg = bnseg_of(p, col0 + c);  // warp-uniform: chunks never straddle a segment boundary
+          if (zseg >= 0) load_z_chunk<CH>(zrow[zseg] + col0 + c, valid, zq);  // in flight while the accumulator chunk arrives
+        }
         tmem_ld_wait();
         if (c + CH >= cend_live) {  // this warp's last chunk is in registers: hand its share of the accumulator back
           tc_fence_before();
@@ -619,7 +716,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
         conv_epilogue_chunk<CH, EXT>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
-                                (EXT && BLOCK_N == 256 && side_base) ? side : nullptr);
+                                (EXT && BLOCK_N == 256 && side_base) ? side : nullptr, (BNB && zseg >= 0) ? zq : nullptr);
         if constexpr (EXT && BLOCK_N == 256) {
           if (more) {
 #pragma unroll
@@ -633,6 +730,17 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kTmemAlloc>(tmem_base);
+  if constexpr (BNB) {
+    for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {
+      const int sg = bnseg_of(p, col0 + e);
+      if (sg < 0) continue;
+      const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
+      const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
+      atomicAdd(p.bnseg[sg].sum_du + col0 + e - p.bnseg[sg].col_begin, static_cast<double>(s1));
+      atomicAdd(p.bnseg[sg].sum_duz + col0 + e - p.bnseg[sg].col_begin, static_cast<double>(s2));
+    }
+    return;
+  }
   if (EXT ? epi_has_stats(p.epi_mode, p.stat_sum) : p.epi_mode == EPI_F16_STATS) {
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {  // BLOCK_N may exceed the 192 threads
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);

@@ -340,14 +340,16 @@ template <bool SIMPLE>
 __global__ void __launch_bounds__(kEwThreads, 3)
 bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
-                         const double* __restrict__ dbeta_acc, double inv_count, unsigned npix) {
+                         const double* __restrict__ dbeta_acc, double inv_count, unsigned npix, int raw_sums) {
   const int c8 = threadIdx.x * 8;
   float s[8], t[8], A[8], B[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     s[k] = scale[c8 + k]; t[k] = shift[c8 + k];
     const float is = invstd[c8 + k], mu = mean[c8 + k];
-    const float mg = static_cast<float>(dgamma_acc[c8 + k] * inv_count);
+    // raw_sums: the accumulators hold S2 = sum du*z and S1 = sum du (fused into the data-gradient epilogue): dgamma = invstd * (S2 - mean*S1)
+    const double dg = raw_sums ? static_cast<double>(is) * (dgamma_acc[c8 + k] - static_cast<double>(mu) * dbeta_acc[c8 + k]) : dgamma_acc[c8 + k];
+    const float mg = static_cast<float>(dg * inv_count);
     const float mb = static_cast<float>(dbeta_acc[c8 + k] * inv_count);
     A[k] = -s[k] * is * mg;
     B[k] = -s[k] * mb - A[k] * mu;
@@ -382,10 +384,12 @@ bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ sc
 
 // parameter gradients out of the fp64 accumulators, then re-zero them
 __global__ void bn_param_grad_kernel(double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, int c, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, int accumulate) {
+                                     float* __restrict__ dbeta, int accumulate, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     int raw_sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
-  const float g = static_cast<float>(dgamma_acc[i]), b = static_cast<float>(dbeta_acc[i]);
+  const double dg = raw_sums ? static_cast<double>(invstd[i]) * (dgamma_acc[i] - static_cast<double>(mean[i]) * dbeta_acc[i]) : dgamma_acc[i];
+  const float g = static_cast<float>(dg), b = static_cast<float>(dbeta_acc[i]);
   dgamma[i] = accumulate ? dgamma[i] + g : g;
   dbeta[i] = accumulate ? dbeta[i] + b : b;
   dgamma_acc[i] = 0.0;
@@ -609,9 +613,9 @@ extern "C" int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const
   return 0;
 }
 
-extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const yb200_act* da2, const yb200_act* da_up2x, const float* scale,
-                                 const float* shift, const float* save_mean, const float* save_invstd, double* acc_dgamma, double* acc_dbeta,
-                                 const yb200_act* dz, float* dgamma, float* dbeta, int accumulate, void* stream) {
+static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200_act* da2, const yb200_act* da_up2x, const float* scale,
+                            const float* shift, const float* save_mean, const float* save_invstd, double* acc_dgamma, double* acc_dbeta,
+                            const yb200_act* dz, float* dgamma, float* dbeta, int accumulate, void* stream, int stats_ready) {
   int rc;
   if ((rc = check_view(z, "bn_silu_bwd z")) || (rc = check_view(da, "bn_silu_bwd da")) || (rc = check_view(dz, "bn_silu_bwd dz"))) return rc;
   if (da2 && (rc = check_view(da2, "bn_silu_bwd da2"))) return rc;
@@ -644,20 +648,34 @@ extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const 
     YB_CHECK_CUDA(cudaFuncSetAttribute(bn_silu_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(red_smem)));
     red_smem_set = red_smem;
   }
-  bn_silu_bwd_reduce_kernel<<<grid_r, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                              static_cast<unsigned>(npix), red_iters, l2_order());
-  YB_CHECK_CUDA(cudaGetLastError());
+  if (!stats_ready) {
+    bn_silu_bwd_reduce_kernel<<<grid_r, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                                static_cast<unsigned>(npix), red_iters, l2_order());
+    YB_CHECK_CUDA(cudaGetLastError());
+  }
   const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
   if (!src.has_b && !src.has_up)
     bn_silu_bwd_apply_kernel<true><<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                              1.0 / static_cast<double>(npix), static_cast<unsigned>(npix));
+                                                              1.0 / static_cast<double>(npix), static_cast<unsigned>(npix), stats_ready);
   else
     bn_silu_bwd_apply_kernel<false><<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                               1.0 / static_cast<double>(npix), static_cast<unsigned>(npix));
+                                                               1.0 / static_cast<double>(npix), static_cast<unsigned>(npix), stats_ready);
   YB_CHECK_CUDA(cudaGetLastError());
-  bn_param_grad_kernel<<<ceil_div(z->c, 128), 128, 0, st>>>(acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate);
+  bn_param_grad_kernel<<<ceil_div(z->c, 128), 128, 0, st>>>(acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate, save_mean, save_invstd, stats_ready);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int yb200_bn_silu_bwd(const yb200_act* z, const yb200_act* da, const yb200_act* da2, const yb200_act* da_up2x, const float* scale,
+                                 const float* shift, const float* save_mean, const float* save_invstd, double* acc_dgamma, double* acc_dbeta,
+                                 const yb200_act* dz, float* dgamma, float* dbeta, int accumulate, void* stream) {
+  return bn_silu_bwd_impl(z, da, da2, da_up2x, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta, dz, dgamma, dbeta, accumulate, stream, 0);
+}
+
+extern "C" int yb200_bn_silu_bwd_apply(const yb200_act* z, const yb200_act* da, const float* scale, const float* shift, const float* save_mean,
+                                       const float* save_invstd, double* sum_duz, double* sum_du, const yb200_act* dz, float* dgamma, float* dbeta,
+                                       int accumulate, void* stream) {
+  return bn_silu_bwd_impl(z, da, nullptr, nullptr, scale, shift, save_mean, save_invstd, sum_duz, sum_du, dz, dgamma, dbeta, accumulate, stream, 1);
 }
 
 extern "C" int yb200_spp_pool(const yb200_act* x, const yb200_act* o5, const yb200_act* o9, const yb200_act* o13, uint8_t* argmax, void* stream) {

@@ -125,6 +125,7 @@ class YoloxEngine:
         self._build()
         self._alloc_params(share_params_of)
         self._alloc_runtime()
+        self._plan_bn_fusion()
 
     # ------------------------------------------------------------------ graph construction
     def _buf(self, name, h, w, c, dtype=torch.bfloat16):
@@ -613,6 +614,77 @@ class YoloxEngine:
         self._count(1, "yolox_loss grad")
 
     # ------------------------------------------------------------------ backward
+    def _plan_bn_fusion(self):
+        """Static analysis of the backward pass: for every BatchNorm head, which data-gradient launch writes the FINAL value of the gradient
+        of its output?  That launch's epilogue then also performs the reduction pass of the head's BatchNorm backward
+        (yb200_conv2d_dgrad_bnbwd), and the head only needs the apply pass.  Not fused: heads with an upsampled copy (their gradient has a
+        second, 2x2-pooled source), heads whose gradient is finished by a non-convolution (SPP), gradient tensors of >= 256 channels and
+        more than two heads per launch.  YB200_BN_FUSE=0 disables the fusion (A/B runs)."""
+        self._bn_fuse = {}
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                for hd in op.heads:
+                    hd.fused_stats = False
+        if self.strict or os.environ.get("YB200_BN_FUSE", "1") == "0":
+            return
+        writers = {}  # id(buffer) -> [(lo, hi, key)] in backward order
+        for op in reversed(self.ops):
+            if isinstance(op, PredOp):
+                for which, feat in (("cls", op.cls_feat), ("reg", op.reg_feat)):
+                    writers.setdefault(id(feat.buf), []).append((feat.off, feat.off + feat.c, ("pred", id(op), which)))
+            elif isinstance(op, SppOp):
+                v = op.views[0]
+                writers.setdefault(id(v.buf), []).append((v.off, v.off + v.c, ("spp", id(op), None)))
+            elif not op.first:
+                writers.setdefault(id(op.x.buf), []).append((op.x.off, op.x.off + op.x.c, ("conv", id(op), None)))
+        for op in self.ops:
+            if not isinstance(op, ConvOp):
+                continue
+            for hd in op.heads:
+                v = hd.out
+                if hd.up is not None or hd.c % 32 != 0 or v.off % 32 != 0:
+                    continue
+                ws = [w for w in writers.get(id(v.buf), []) if not (w[1] <= v.off or v.off + v.c <= w[0])]
+                if not ws:
+                    continue
+                lo, hi, key = ws[-1]
+                if key[0] == "spp" or not (lo <= v.off and v.off + v.c <= hi) or hi - lo >= 256 or (v.off - lo) % 32 != 0:
+                    continue
+                segs = self._bn_fuse.setdefault(key, [])
+                if len(segs) < 2:
+                    segs.append((hd, op, v.off - lo))
+                    hd.fused_stats = True
+
+    def _bn_segments(self, key):
+        """ctypes array of yb200_bnbwd_seg for the data-gradient launch `key` (None when nothing is fused into it)"""
+        segs = self._bn_fuse.get(key)
+        if not segs:
+            return None, 0
+        cached = getattr(self, "_bn_seg_cache", None)
+        if cached is None:
+            cached = self._bn_seg_cache = {}
+        if key not in cached:
+            nb, f8 = self.nbn, self.flat_stats
+            arr = (capi.BnBwdSeg * len(segs))()
+            for i, (hd, op, begin) in enumerate(segs):
+                arr[i].z = capi.act(op.z.buf.t, hd.c0, hd.c)
+                arr[i].dx_c_begin = begin
+                arr[i].scale = self.flat_scale.data_ptr() + 4 * hd.bn_off
+                arr[i].shift = self.flat_shift.data_ptr() + 4 * hd.bn_off
+                arr[i].sum_duz = f8.data_ptr() + 8 * (2 * nb + hd.bn_off)
+                arr[i].sum_du = f8.data_ptr() + 8 * (3 * nb + hd.bn_off)
+            cached[key] = arr
+        return cached[key], len(segs)
+
+    def _dgrad(self, dz_act, w_dgrad, dx_view, addend_act, ksize, stride, key, what):
+        L, sp = self.L, capi.stream_ptr()
+        segs, nseg = self._bn_segments(key)
+        if nseg:
+            capi.check(L.yb200_conv2d_dgrad_bnbwd(dz_act, capi.ptr(w_dgrad), dx_view.gact(), addend_act, ksize, stride, nseg, segs, sp), what)
+        else:
+            capi.check(L.yb200_conv2d_dgrad(dz_act, capi.ptr(w_dgrad), dx_view.gact(), addend_act, ksize, stride, sp), what)
+        return nseg
+
     def _dz_buf(self, op):
         b = self._dz.get(id(op))
         if b is None:
@@ -671,10 +743,10 @@ class YoloxEngine:
                 capi.check(L.yb200_head_bias_grad(capi.ptr(self.bias_acc), len(self.levels), 5 + self.nc, k, capi.ptr(self.grads[f"head.reg_preds.{k}.bias"]),
                                                   capi.ptr(self.grads[f"head.obj_preds.{k}.bias"]), capi.ptr(self.grads[f"head.cls_preds.{k}.bias"]),
                                                   acc, sp), "head_bias_grad")
-                for feat, dz, gdst, wd, cr in ((op.cls_feat, dcls, op.gc_dst, op.wc_dgrad, self.nc), (op.reg_feat, dro, op.gr_dst, op.wr_dgrad, 16)):
+                for which, feat, dz, gdst, wd in (("cls", op.cls_feat, dcls, op.gc_dst, op.wc_dgrad), ("reg", op.reg_feat, dro, op.gr_dst, op.wr_dgrad)):
                     self._wgrad(feat.act(), ctypes.byref(dz), 1, 1, self.hc, gdst, acc, "pred")
                     add = self._grad_target(feat)
-                    capi.check(L.yb200_conv2d_dgrad(ctypes.byref(dz), capi.ptr(wd), feat.gact(), add.gact() if add else None, 1, 1, sp), "pred dgrad")
+                    self._dgrad(ctypes.byref(dz), wd, feat, add.gact() if add else None, 1, 1, ("pred", id(op), which), "pred dgrad")
                 self._count(7, "pred level %d: bias_grad, 2x(wgrad, reduce, dgrad)" % k, "pred_conv bwd", self.n * h * w * 2.0 * (4 * self.hc + self.nc + 16),
                             4.0 * self.n * h * w * self.hc * (self.nc + 5))
             elif isinstance(op, SppOp):
@@ -692,14 +764,22 @@ class YoloxEngine:
                     zv = op.z.buf.view(hd.c0, hd.c)
                     dzv = dzb.view(hd.c0, hd.c)
                     o = hd.bn_off
-                    capi.check(L.yb200_bn_silu_bwd(zv.act(), hd.out.gact(), None, hd.up.gact() if hd.up else None, pf(self.flat_scale, o),
-                                                   pf(self.flat_shift, o), pf(self.flat_mean, o), pf(self.flat_invstd, o),
-                                                   ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)), ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)),
-                                                   dzv.act(), capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
-                                                   acc, sp), "bn_silu_bwd " + hd.prefix)
                     npx = op.z.buf.n * op.z.buf.h * op.z.buf.w
-                    self._count(3, "bn_bwd (reduce, apply, param) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd (reduce + apply)",
-                                2.0 * npx * hd.c * (3 + (4 if hd.up else 0)))
+                    if hd.fused_stats:  # the reduction pass ran in the epilogue of the data gradient that produced hd.out's gradient
+                        capi.check(L.yb200_bn_silu_bwd_apply(zv.act(), hd.out.gact(), pf(self.flat_scale, o), pf(self.flat_shift, o), pf(self.flat_mean, o),
+                                                             pf(self.flat_invstd, o), ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)),
+                                                             ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)), dzv.act(),
+                                                             capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
+                                                             acc, sp), "bn_silu_bwd_apply " + hd.prefix)
+                        self._count(2, "bn_bwd (apply, param; reduce fused upstream) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd", 6.0 * npx * hd.c)
+                    else:
+                        capi.check(L.yb200_bn_silu_bwd(zv.act(), hd.out.gact(), None, hd.up.gact() if hd.up else None, pf(self.flat_scale, o),
+                                                       pf(self.flat_shift, o), pf(self.flat_mean, o), pf(self.flat_invstd, o),
+                                                       ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)), ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)),
+                                                       dzv.act(), capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
+                                                       acc, sp), "bn_silu_bwd " + hd.prefix)
+                        self._count(3, "bn_bwd (reduce, apply, param) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd",
+                                    2.0 * npx * hd.c * (3 + (4 if hd.up else 0)))
                     if hd.residual is not None:
                         pending_res[(id(hd.residual.buf), hd.residual.off)] = hd.out
                 dz = dzb.view()
@@ -710,9 +790,9 @@ class YoloxEngine:
                     add = self._grad_target(op.x)
                     assert not (res is not None and add is not None), "residual + fan-out on the same activation"
                     addend = res.gact() if res is not None else (add.gact() if add is not None else None)
-                    capi.check(L.yb200_conv2d_dgrad(dz.act(), capi.ptr(op.w_dgrad), op.x.gact(), addend, op.ksize, op.stride, sp),
-                               "dgrad " + op.prefixes[0])
-                    self._count(4 if op.stride == 2 else 1, "dgrad %s %s" % (op.prefixes[0], self._desc(op)), "dgrad (conv_gemm)", *self._alg_conv(op))
+                    nseg = self._dgrad(dz.act(), op.w_dgrad, op.x, addend, op.ksize, op.stride, ("conv", id(op), None), "dgrad " + op.prefixes[0])
+                    self._count(4 if op.stride == 2 else 1, "dgrad%s %s %s" % (" +bn_stats" if nseg else "", op.prefixes[0], self._desc(op)),
+                                "dgrad (conv_gemm, BN-bwd statistics fused where possible)", *self._alg_conv(op))
         if self.overlap_wgrad:
             torch.cuda.current_stream().wait_stream(self._side)  # join: gradients are complete when backward() returns
 
