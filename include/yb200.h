@@ -174,30 +174,31 @@ int yb200_head_bias_grad(double* bias_acc, int num_levels, int channels, int lev
                          float* grad_obj_bias1, float* grad_cls_bias, int accumulate, void* stream);
 
 /* ---- strict mode: fp32-grade forward on the same tensor-core kernels -------------------------------- */
-/* SPLIT storage: an activation a is the pair hi = bf16(a), lo = bf16(a - hi) (16 significant bits); both planes live in one
- * NHWC bf16 buffer, lo_delta channels apart, so a yb200_act describes the hi plane and (view, lo_delta) the pair.  The
- * convolution keeps hi*hi + hi*lo + lo*hi (three taps per spatial tap of the SAME tcgen05 implicit GEMM, one fp32
- * accumulator); the pre-BatchNorm output z is fp32 NHWC [n][h/stride][w/stride][z_pitch], channels [z_off, z_off+cout).
+/* SPLIT storage: an activation a is the sum of `planes` bf16 values a0 = bf16(a), a1 = bf16(a - a0) [, a2 = bf16(a - a0 - a1)]:
+ * 16 significant bits with planes = 2, the full 24 bits of fp32 with planes = 3.  All planes live in one NHWC bf16 buffer,
+ * lo_delta channels apart, so a yb200_act describes plane 0 and (view, lo_delta, planes) the value.  The convolution keeps
+ * every partial product a_i * w_j with i + j < planes (3 / 6 taps per spatial tap of the SAME tcgen05 implicit GEMM, one
+ * fp32 accumulator); the pre-BatchNorm output z is fp32 NHWC [n][h/stride][w/stride][z_pitch], channels [z_off, z_off+cout).
  * Used to check the reference's fp32 logits / losses to 1e-3 (tests/test_strict_gpu.py); forward only.
- * yb200_pack_conv_weight_split: fp32 OIHW -> [cout_pad][2][k*k][cin_pad] (hi taps | lo taps per row), `nn.Conv2d.weight`
- * of wrappers.py:67-75.  yb200_conv2d_fwd_split: `BaseConv.conv` (wrappers.py:79).  yb200_conv1x1_bias_f32_split: the
- * prediction convolutions (yolox_head.py:103-129,175), same output geometry as yb200_conv1x1_bias_f32.               */
-int yb200_pack_conv_weight_split(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad,
+ * yb200_pack_conv_weight_split: fp32 OIHW -> [cout_pad][planes][k*k][cin_pad], `nn.Conv2d.weight` of wrappers.py:67-75.
+ * yb200_conv2d_fwd_split: `BaseConv.conv` (wrappers.py:79).  yb200_conv1x1_bias_f32_split: the prediction convolutions
+ * (yolox_head.py:103-129,175), same output geometry as yb200_conv1x1_bias_f32.                                           */
+int yb200_pack_conv_weight_split(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, int planes,
                                  void* w_split, void* stream);
-int yb200_conv2d_fwd_split(const yb200_act* x, int lo_delta, const void* w_split, int cout, int ksize, int stride,
-                           float* z, int z_pitch, int z_off, void* stream);
-int yb200_conv1x1_bias_f32_split(const yb200_act* x, int lo_delta, const void* w_split, const float* bias, int cout,
-                                 float* out, int a_total, int a_off, int c_total, int c_off, void* stream);
+int yb200_conv2d_fwd_split(const yb200_act* x, int lo_delta, int planes, const void* w_split, int cout, int ksize,
+                           int stride, float* z, int z_pitch, int z_off, void* stream);
+int yb200_conv1x1_bias_f32_split(const yb200_act* x, int lo_delta, int planes, const void* w_split, const float* bias,
+                                 int cout, float* out, int a_total, int a_off, int c_total, int c_off, void* stream);
 /* BatchNorm batch statistics of an fp32 slice (sum, sum of squares in fp64; feed yb200_bn_finalize), then
- * out = SiLU(z*scale + shift) [+ residual] as a split pair, optionally also 2x nearest-upsampled (wrappers.py:76-80,
+ * out = SiLU(z*scale + shift) [+ residual] as split planes, optionally also 2x nearest-upsampled (wrappers.py:76-80,
  * 119-123; yolo_pafpn.py:96-102); SPP max-pools 5/9/13 on split values (wrappers.py:150-160).                        */
 int yb200_strict_bn_stats(const float* z, int64_t npix, int z_pitch, int z_off, int c, double* stat_sum,
                           double* stat_sqsum, void* stream);
 int yb200_strict_bn_apply_silu(const float* z, int z_pitch, int z_off, const float* scale, const float* shift,
                                const yb200_act* residual, int residual_lo, const yb200_act* out, int out_lo,
-                               const yb200_act* out_up2x, int up_lo, void* stream);
+                               const yb200_act* out_up2x, int up_lo, int planes, void* stream);
 int yb200_strict_spp_pool(const yb200_act* x, const yb200_act* o5, const yb200_act* o9, const yb200_act* o13,
-                          int lo_delta, void* stream);
+                          int lo_delta, int planes, void* stream);
 
 /* ---- post-processing ----------------------------------------------------------------------------- */
 /* `postprocess` (boxes.py:171-210) for the whole batch: prediction [batch][A][5+C] = (cx, cy, w, h, obj, cls...) with

@@ -96,7 +96,6 @@ def test_relu_epilogues(cuda):
     assert (acc.float() - du.float().sum((0, 1, 2))).abs().max() <= 1e-4 * du.float().sum((0, 1, 2)).abs().max() + 1e-4
 
 
-@pytest.mark.skipif(os.environ.get("YB200_DETR_TRAINING", "0") != "1", reason="encoder-layer backward wiring is opt-in until validated on hardware")
 def test_encoder_layer_backward_matches_reference(cuda):
     """training path: gradients w.r.t. the input and every parameter of the encoder layer against the reference layer's autograd
     (tests/golden/detr.npz).  bf16 storage of every saved tensor: cosine > 0.995 and at most 2.5x the error of the oracle's own
@@ -135,7 +134,6 @@ def test_encoder_layer_backward_matches_reference(cuda):
         chk(p.grad, gold["enc_grad/" + name], sde["l." + name].grad, name)
 
 
-@pytest.mark.skipif(os.environ.get("YB200_DETR_TRAINING", "0") != "1", reason="decoder-layer backward wiring is opt-in until validated on hardware")
 def test_decoder_layer_backward_matches_oracle(cuda):
     """training path of the decoder layer against the autograd of the oracle (forward pinned to the reference layer), judged with the oracle's
     bf16-storage emulation as yardstick (see the encoder test)"""

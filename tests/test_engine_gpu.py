@@ -189,3 +189,28 @@ def test_eval_forward_matches_oracle(step):
     e_eng, e_emu = (out - ref).abs()[..., 4:], (emu - ref).abs()[..., 4:]
     print("eval prob error: engine mean %.6f | emulating %.6f" % (e_eng.mean(), e_emu.mean()))
     assert e_eng.mean() <= 1.5 * e_emu.mean() + 1e-5
+
+
+def test_fused_bn_backward_statistics_equal_the_two_pass_path(step, cuda, monkeypatch):
+    """YB200_BN_FUSE=0 (separate reduction kernel for every BatchNorm) vs the default (statistics from the data-gradient epilogue where the
+    plan allows): same step, same gradients up to 16-bit storage noise"""
+    from yolov7_d2_b200.engine import YoloxEngine
+
+    eng, sd0 = step["eng"], step["sd0"]
+    assert sum(hd.fused_stats for op in eng.ops if hasattr(op, "heads") for hd in op.heads) >= 40, "the plan fuses most BatchNorm layers"
+    monkeypatch.setenv("YB200_BN_FUSE", "0")
+    ref = YoloxEngine(eng.n, eng.h, eng.w, device=cuda)
+    assert not any(hd.fused_stats for op in ref.ops if hasattr(op, "heads") for hd in op.heads)
+    grads = []
+    for e in (eng, ref):
+        e.load_state_dict(sd0)
+        e.images_u8.copy_(step["images"].to(cuda))
+        e.labels.copy_(step["labels"].to(cuda))
+        e.train_step()
+        torch.cuda.synchronize()
+        grads.append({n: e.grads[n].clone() for n in e.param_names})
+    assert torch.allclose(eng.losses, ref.losses, rtol=1e-6)
+    for n in eng.param_names:
+        a, b = grads[0][n].flatten().double(), grads[1][n].flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        assert cos >= 0.999 and abs(float(a.norm() / (b.norm() + 1e-30)) - 1) <= 0.02, (n, cos)

@@ -131,3 +131,67 @@ def test_prefetch_gives_identical_steps_and_flat_optimizer_trains(model, cuda):
         opt.step()
         losses.append(float(out["total_loss"].detach()))
     assert not torch.equal(before, w.detach()) and losses[-1] < losses[0]
+
+
+@pytest.mark.gpu
+def test_standalone_backbone_neck_head_like_a_yolov5_caller(model, cuda):
+    """The YOLOV5 / YOLOV7P / YOLOMask architectures build `build_cspdarknetx_backbone` through BACKBONE_REGISTRY and call
+    `backbone(x)["dark3"]` themselves (darknetx.py:165-213, yolo_pafpn.py:79-114, yolox_head.py:197-224).  The registered modules run on
+    their own; chained, they reproduce the fused YOLOX evaluation exactly (same kernels, same 16-bit storage)."""
+    import bench
+    from yolov7_d2_b200 import modeling
+
+    m, sd = model
+    m.eval()
+    cfg = bench.yolox_s_cfg("cuda")
+    bb = modeling.BACKBONE_REGISTRY.get("build_cspdarknetx_backbone")(cfg, None)   # standalone: owns its parameters
+    neck = modeling.YOLOPAFPN(depth=0.33, width=0.5, in_features=["dark3", "dark4", "dark5"])
+    head = modeling.YOLOXHead(80, width=0.5)
+    bb.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=True)
+    neck.load_state_dict({k[len("neck."):]: v for k, v in sd.items() if k.startswith("neck.")}, strict=True)
+    head.load_state_dict({k[len("head."):]: v for k, v in sd.items() if k.startswith("head.")}, strict=True)
+    for mod in (bb, neck, head):
+        mod.eval()
+    images, _ = orc.synthetic_batch(2, 160, 31)
+    x = images.float().to(cuda)
+    feats = bb(x)
+    assert set(feats.keys()) == {"dark3", "dark4", "dark5"}
+    assert tuple(feats["dark3"].shape) == (2, 128, 20, 20) and feats["dark3"].dtype == torch.float32
+    with torch.no_grad():
+        ref = orc.csp_darknet(images.float(), {k: v.clone() for k, v in sd.items()}, False)
+    for k in feats:
+        err = (feats[k].cpu() - ref[k]).abs().mean() / ref[k].abs().mean()
+        assert err < 0.02, (k, float(err))
+    pred = head(neck(feats))
+    eng = m._plan(2, 160, 160)
+    eng.images_u8.copy_(images.to(cuda))
+    fused = eng.eval_forward()
+    assert torch.equal(pred, fused), "standalone backbone -> neck -> head differs from the fused evaluation"
+
+
+@pytest.mark.gpu
+def test_standalone_backbone_trains_through_autograd(cuda):
+    """a caller that owns the loss: gradients reach the backbone's parameters through the partial engine backward"""
+    from yolov7_d2_b200 import modeling
+
+    sd = orc.yolox_state_dict(6)
+    bb = modeling.CSPDarknet(0.33, 0.5)
+    bb.load_state_dict({k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=True)
+    bb.train()
+    images, _ = orc.synthetic_batch(4, 128, 32)
+    x = images.float().to(cuda)
+    g = torch.Generator().manual_seed(1)
+    w3 = torch.randn(4, 128, 16, 16, generator=g).to(cuda) * 1e-2
+    w5 = torch.randn(4, 512, 4, 4, generator=g).to(cuda) * 1e-2
+    feats = bb(x)
+    ((feats["dark3"] * w3).sum() + (feats["dark5"] * w5).sum()).backward()
+    rsd = {k: v.clone().requires_grad_(v.dtype == torch.float32 and "running" not in k) for k, v in sd.items() if k.startswith("backbone.")}
+    rf = orc.csp_darknet(images.float(), rsd, True)
+    ((rf["dark3"] * w3.cpu()).sum() + (rf["dark5"] * w5.cpu()).sum()).backward()
+    worst = 1.0
+    for name, p in bb.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        r = rsd["backbone." + name].grad.flatten().double()
+        gq = p.grad.cpu().flatten().double()
+        worst = min(worst, float((gq @ r) / (gq.norm() * r.norm() + 1e-30)))
+    assert worst >= 0.9, worst

@@ -149,6 +149,7 @@ def test_grad_scaler_drives_the_flat_optimizer(cuda):
     gbuf = torch.zeros(total, device=cuda)
     opt = optim.FlatOptimizer(p, gbuf, segs, 0.1, "sgd", momentum=0.0)
     scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    assert float(scaler.scale(torch.ones(1, device=cuda))) == 1024.0  # scale(loss) is what initialises the scaler's device state
     grad = torch.randn(total, device=cuda, generator=torch.Generator(device=cuda).manual_seed(5))
     p0 = p.clone()
     gbuf.copy_(grad * 1024.0)  # what backward of scaler.scale(loss) leaves in the flat buffer

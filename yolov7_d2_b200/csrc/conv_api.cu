@@ -258,12 +258,13 @@ extern "C" int yb200_pack_conv_weight_scaled(const float* w_oihw, const float* c
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-// lo_delta > 0 selects the STRICT (operand-split) form: activations and weights are (hi, lo) bf16 pairs with x = hi + lo carrying
-// 16 significant bits; x_lo lives lo_delta channels after x_hi in the same NHWC buffer and the weight matrix is [rows][hi taps | lo taps].
-// The product keeps the three leading terms  hi*hi + hi*lo + lo*hi  (the dropped lo*lo is 2^-18 relative) as three taps per spatial
-// tap of the SAME implicit GEMM -- one fp32 accumulator in TMEM, no extra kernel.
+// lo_delta > 0 selects the STRICT (operand-split) form: activations and weights are sums of `planes` bf16 values (x = x0 + x1 [+ x2], 8 more
+// significant bits per plane: 16 bits with two planes, the full 24 of fp32 with three); plane j of an activation lives j * lo_delta channels
+// after plane 0 in the same NHWC buffer and the weight matrix is [rows][plane 0 taps | plane 1 taps | plane 2 taps].  The product keeps every
+// term x_i * w_j with i + j < planes (the dropped ones are below 2^-8planes relative) as extra taps of the SAME implicit GEMM -- one fp32
+// accumulator in TMEM, no extra kernel: 3 taps per spatial tap for two planes, 6 for three.
 static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int ksize, int stride, ConvGemmParams& p,
-                           cudaStream_t st, int lo_delta = 0) {
+                           cudaStream_t st, int lo_delta = 0, int planes = 1) {
   YB_REQUIRE(w_fwd != nullptr, YB200_ERR_INVALID, "conv fwd: null weights");
   YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 2 && stride == 2) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
              "conv fwd: ksize=%d stride=%d not implemented", ksize, stride);
@@ -275,19 +276,26 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   p.num_taps = fill_fwd_taps(p.taps, *x, ksize, stride, x->c);
   long long kcols = 1LL * p.num_taps * x->c;
   if (lo_delta > 0) {
-    YB_REQUIRE(lo_delta % 8 == 0 && x->c_off + lo_delta + x->c <= x->c_pitch, YB200_ERR_INVALID,
-               "conv fwd (split): lo plane [%d, %d) outside the channel pitch %d", x->c_off + lo_delta, x->c_off + lo_delta + x->c, x->c_pitch);
+    YB_REQUIRE(planes == 2 || planes == 3, YB200_ERR_INVALID, "conv fwd (split): %d planes", planes);
+    YB_REQUIRE(lo_delta % 8 == 0 && x->c_off + (planes - 1) * lo_delta + x->c <= x->c_pitch, YB200_ERR_INVALID,
+               "conv fwd (split): plane %d [%d, %d) outside the channel pitch %d", planes - 1, x->c_off + (planes - 1) * lo_delta,
+               x->c_off + (planes - 1) * lo_delta + x->c, x->c_pitch);
     const int nt = p.num_taps;
-    const int lo_kb = nt * x->c;
+    const int plane_kb = nt * x->c;
+    int terms[6][2], nterm = 0;  // (activation plane, weight plane), largest products first
+    for (int sum = 0; sum < planes; ++sum)
+      for (int i = 0; i <= sum; ++i) { terms[nterm][0] = i; terms[nterm][1] = sum - i; ++nterm; }
     for (int t = nt - 1; t >= 0; --t) {
       const ConvTap b = p.taps[t];
-      ConvTap hl = b, lh = b;
-      hl.kb = lo_kb + b.kb;     // x_hi * w_lo
-      lh.c0 = b.c0 + lo_delta;  // x_lo * w_hi
-      p.taps[3 * t] = b; p.taps[3 * t + 1] = hl; p.taps[3 * t + 2] = lh;
+      for (int q = 0; q < nterm; ++q) {
+        ConvTap e = b;
+        e.c0 = b.c0 + terms[q][0] * lo_delta;
+        e.kb = b.kb + terms[q][1] * plane_kb;
+        p.taps[nterm * t + q] = e;
+      }
     }
-    p.num_taps = 3 * nt;
-    kcols *= 2;
+    p.num_taps = nterm * nt;
+    kcols *= planes;
   }
   p.cin_blocks = x->c / bk;
   p.cout = cout;
@@ -459,7 +467,7 @@ extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, con
 // ------------------------------------------------------------------------------------------------
 // strict (operand-split) forward: fp32 results from bf16 tensor-core products
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_conv_weight_split_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad, int cin_pad,
+__global__ void pack_conv_weight_split_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad, int cin_pad, int planes,
                                               __nv_bfloat16* __restrict__ out) {
   const long long per_plane = 1LL * taps * cin_pad;
   const long long total = 1LL * cout_pad * per_plane;
@@ -467,29 +475,30 @@ __global__ void pack_conv_weight_split_kernel(const float* __restrict__ w, int c
     const int ci = static_cast<int>(i % cin_pad);
     const int t = static_cast<int>((i / cin_pad) % taps);
     const int co = static_cast<int>(i / per_plane);
-    const float v = (co < cout && ci < cin) ? w[(1LL * co * cin + ci) * taps + t] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    __nv_bfloat16* row = out + 2LL * co * per_plane;
-    row[1LL * t * cin_pad + ci] = hi;
-    row[per_plane + 1LL * t * cin_pad + ci] = lo;
+    float r = (co < cout && ci < cin) ? w[(1LL * co * cin + ci) * taps + t] : 0.f;
+    __nv_bfloat16* row = out + planes * co * per_plane + 1LL * t * cin_pad + ci;
+    for (int pl = 0; pl < planes; ++pl) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(r);
+      row[pl * per_plane] = h;
+      r -= __bfloat162float(h);  // exact: the residual of a bf16 rounding is representable in fp32
+    }
   }
 }
 
-extern "C" int yb200_pack_conv_weight_split(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, void* w_split,
+extern "C" int yb200_pack_conv_weight_split(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, int planes, void* w_split,
                                             void* stream) {
   YB_REQUIRE(w_oihw && w_split, YB200_ERR_INVALID, "pack_conv_weight_split: null pointer");
-  YB_REQUIRE(cout > 0 && cin > 0 && (ksize >= 1 && ksize <= 3) && cout_pad >= cout && cin_pad >= cin, YB200_ERR_INVALID,
-             "pack_conv_weight_split: bad sizes cout=%d cin=%d k=%d pads=%d,%d", cout, cin, ksize, cout_pad, cin_pad);
+  YB_REQUIRE(cout > 0 && cin > 0 && (ksize >= 1 && ksize <= 3) && cout_pad >= cout && cin_pad >= cin && (planes == 2 || planes == 3), YB200_ERR_INVALID,
+             "pack_conv_weight_split: bad sizes cout=%d cin=%d k=%d pads=%d,%d planes=%d", cout, cin, ksize, cout_pad, cin_pad, planes);
   const long long total = 1LL * cout_pad * ksize * ksize * cin_pad;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
-  pack_conv_weight_split_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, cout_pad, cin_pad,
+  pack_conv_weight_split_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, cout_pad, cin_pad, planes,
                                                                        static_cast<__nv_bfloat16*>(w_split));
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int yb200_conv2d_fwd_split(const yb200_act* x, int lo_delta, const void* w_split, int cout, int ksize, int stride, float* z,
+extern "C" int yb200_conv2d_fwd_split(const yb200_act* x, int lo_delta, int planes, const void* w_split, int cout, int ksize, int stride, float* z,
                                       int z_pitch, int z_off, void* stream) {
   int rc;
   if ((rc = check_act(x, "conv2d_fwd_split x"))) return rc;
@@ -506,10 +515,10 @@ extern "C" int yb200_conv2d_fwd_split(const yb200_act* x, int lo_delta, const vo
   p.out_sc = 1;
   p.out_mh = 1; p.out_mw = 1;
   p.epi_mode = EPI_F32_BIAS;  // bias == null: staged as zeros
-  return conv_fwd_common(x, w_split, cout, ksize, stride, p, as_stream(stream), lo_delta);
+  return conv_fwd_common(x, w_split, cout, ksize, stride, p, as_stream(stream), lo_delta, planes);
 }
 
-extern "C" int yb200_conv1x1_bias_f32_split(const yb200_act* x, int lo_delta, const void* w_split, const float* bias, int cout, float* out,
+extern "C" int yb200_conv1x1_bias_f32_split(const yb200_act* x, int lo_delta, int planes, const void* w_split, const float* bias, int cout, float* out,
                                             int a_total, int a_off, int c_total, int c_off, void* stream) {
   int rc;
   if ((rc = check_act(x, "conv1x1_bias_f32_split x"))) return rc;
@@ -526,7 +535,7 @@ extern "C" int yb200_conv1x1_bias_f32_split(const yb200_act* x, int lo_delta, co
   p.out_mh = 1; p.out_mw = 1;
   p.bias = bias;
   p.epi_mode = EPI_F32_BIAS;
-  return conv_fwd_common(x, w_split, cout, 1, 1, p, as_stream(stream), lo_delta);
+  return conv_fwd_common(x, w_split, cout, 1, 1, p, as_stream(stream), lo_delta, planes);
 }
 
 // ------------------------------------------------------------------------------------------------

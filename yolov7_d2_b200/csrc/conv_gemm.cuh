@@ -18,7 +18,7 @@
 namespace yb {
 
 constexpr int kConvThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
-constexpr int kMaxTaps = 27;  // 9 spatial taps x 3 operand-split terms (strict mode: hi*hi + hi*lo + lo*hi, conv_api.cu)
+constexpr int kMaxTaps = 54;  // 9 spatial taps x up to 6 operand-split terms (strict mode, conv_api.cu)
 constexpr int kMaxStages = 4;
 
 enum EpiMode : int {

@@ -1,9 +1,9 @@
 // STRICT mode (YB200_STRICT / YoloxEngine(strict=True)): the forward pass of the YOLOX path with fp32-grade arithmetic, for the
 // north_star check "fp32 losses and logits within 1e-3 relative" against the fp32 reference.
 //
-// Activations are stored as SPLIT bf16 pairs: a = hi + lo with hi = bf16(a), lo = bf16(a - hi) (16 significant bits, relative error
-// 2^-17), the two planes `lo_delta` channels apart in one NHWC buffer, so every channel-slice view (torch.cat / Focus / upsample
-// fusions of the fast path) keeps working and the SAME tcgen05 implicit-GEMM kernel computes hi*hi + hi*lo + lo*hi into one fp32
+// Activations are stored as SPLIT bf16 planes: a = a0 + a1 [+ a2] with a0 = bf16(a), a1 = bf16(a - a0), a2 = bf16(a - a0 - a1) -- 16 significant
+// bits with two planes, all 24 bits of the fp32 value with three (the default) --, the planes `lo_delta` channels apart in one NHWC buffer, so every channel-slice view (torch.cat / Focus / upsample
+// fusions of the fast path) keeps working and the SAME tcgen05 implicit-GEMM kernel computes the partial products a_i * w_j (i + j < planes) into one fp32
 // TMEM accumulator (conv_api.cu: yb200_conv2d_fwd_split).  The pre-BatchNorm convolution output z stays in fp32.  The kernels here
 // are the element-wise stages around that GEMM; they are a verification mode, written for clarity, not for speed.
 #include <algorithm>
@@ -15,29 +15,34 @@ using namespace yb;
 
 namespace {
 
-struct SplitView {  // device-side view of a split activation: hi plane at p, lo plane at p + lo
+struct SplitView {  // device-side view of a split activation: plane j at p + j * lo, value = sum of the planes
   __nv_bfloat16* p;
-  int n, h, w, c, pitch, lo;
+  int n, h, w, c, pitch, lo, planes;
 };
 
-int mk_split(const yb200_act* a, int lo_delta, const char* name, SplitView* v) {
+int mk_split(const yb200_act* a, int lo_delta, int planes, const char* name, SplitView* v) {
   YB_REQUIRE(a && a->ptr && a->n > 0 && a->h > 0 && a->w > 0 && a->c > 0, YB200_ERR_INVALID, "%s: null / empty view", name);
-  YB_REQUIRE(lo_delta > 0 && a->c_off + lo_delta + a->c <= a->c_pitch, YB200_ERR_INVALID, "%s: lo plane [%d, %d) outside the pitch %d", name,
-             a->c_off + lo_delta, a->c_off + lo_delta + a->c, a->c_pitch);
+  YB_REQUIRE((planes == 2 || planes == 3) && lo_delta > 0 && a->c_off + (planes - 1) * lo_delta + a->c <= a->c_pitch, YB200_ERR_INVALID,
+             "%s: plane %d [%d, %d) outside the pitch %d", name, planes - 1, a->c_off + (planes - 1) * lo_delta,
+             a->c_off + (planes - 1) * lo_delta + a->c, a->c_pitch);
   v->p = static_cast<__nv_bfloat16*>(a->ptr) + a->c_off;
-  v->n = a->n; v->h = a->h; v->w = a->w; v->c = a->c; v->pitch = a->c_pitch; v->lo = lo_delta;
+  v->n = a->n; v->h = a->h; v->w = a->w; v->c = a->c; v->pitch = a->c_pitch; v->lo = lo_delta; v->planes = planes;
   return 0;
 }
 
 __device__ __forceinline__ float split_load(const SplitView& v, long long pix, int ch) {
   const __nv_bfloat16* q = v.p + pix * v.pitch + ch;
-  return __bfloat162float(q[0]) + __bfloat162float(q[v.lo]);
+  float a = __bfloat162float(q[0]) + __bfloat162float(q[v.lo]);  // exact in fp32 (16 significant bits)
+  if (v.planes == 3) a += __bfloat162float(q[2 * v.lo]);          // exact: the three planes are the 24 bits of one fp32 value
+  return a;
 }
 __device__ __forceinline__ void split_store(const SplitView& v, long long pix, int ch, float a) {
   __nv_bfloat16* q = v.p + pix * v.pitch + ch;
-  const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-  q[0] = hi;
-  q[v.lo] = __float2bfloat16_rn(a - __bfloat162float(hi));
+  for (int pl = 0; pl < v.planes; ++pl) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(a);
+    q[pl * v.lo] = h;
+    a -= __bfloat162float(h);
+  }
 }
 
 // per-channel sum / sum of squares of an fp32 NHWC slice, fp64 accumulation (block partials, then one atomic per channel and block)
@@ -136,20 +141,20 @@ extern "C" int yb200_strict_bn_stats(const float* z, int64_t npix, int z_pitch, 
 
 extern "C" int yb200_strict_bn_apply_silu(const float* z, int z_pitch, int z_off, const float* scale, const float* shift,
                                           const yb200_act* residual, int residual_lo, const yb200_act* out, int out_lo,
-                                          const yb200_act* out_up2x, int up_lo, void* stream) {
+                                          const yb200_act* out_up2x, int up_lo, int planes, void* stream) {
   int rc;
   SplitView vo, vr, vu;
   YB_REQUIRE(z && scale && shift && out, YB200_ERR_INVALID, "strict_bn_apply_silu: null pointer");
-  if ((rc = mk_split(out, out_lo, "strict_bn_apply_silu out", &vo))) return rc;
+  if ((rc = mk_split(out, out_lo, planes, "strict_bn_apply_silu out", &vo))) return rc;
   YB_REQUIRE(z_off >= 0 && z_off + out->c <= z_pitch, YB200_ERR_INVALID, "strict_bn_apply_silu: z slice outside its pitch");
   vr = vo; vu = vo;
   if (residual) {
-    if ((rc = mk_split(residual, residual_lo, "strict_bn_apply_silu residual", &vr))) return rc;
+    if ((rc = mk_split(residual, residual_lo, planes, "strict_bn_apply_silu residual", &vr))) return rc;
     YB_REQUIRE(residual->n == out->n && residual->h == out->h && residual->w == out->w && residual->c == out->c, YB200_ERR_INVALID,
                "strict_bn_apply_silu: residual shape mismatch");
   }
   if (out_up2x) {
-    if ((rc = mk_split(out_up2x, up_lo, "strict_bn_apply_silu out_up2x", &vu))) return rc;
+    if ((rc = mk_split(out_up2x, up_lo, planes, "strict_bn_apply_silu out_up2x", &vu))) return rc;
     YB_REQUIRE(out_up2x->n == out->n && out_up2x->h == 2 * out->h && out_up2x->w == 2 * out->w && out_up2x->c == out->c, YB200_ERR_INVALID,
                "strict_bn_apply_silu: upsampled view must be [n,2h,2w,c]");
   }
@@ -160,11 +165,12 @@ extern "C" int yb200_strict_bn_apply_silu(const float* z, int z_pitch, int z_off
   return 0;
 }
 
-extern "C" int yb200_strict_spp_pool(const yb200_act* x, const yb200_act* o5, const yb200_act* o9, const yb200_act* o13, int lo_delta, void* stream) {
+extern "C" int yb200_strict_spp_pool(const yb200_act* x, const yb200_act* o5, const yb200_act* o9, const yb200_act* o13, int lo_delta, int planes,
+                                     void* stream) {
   int rc;
   SplitView vx, v5, v9, v13;
-  if ((rc = mk_split(x, lo_delta, "strict_spp_pool x", &vx)) || (rc = mk_split(o5, lo_delta, "strict_spp_pool o5", &v5)) ||
-      (rc = mk_split(o9, lo_delta, "strict_spp_pool o9", &v9)) || (rc = mk_split(o13, lo_delta, "strict_spp_pool o13", &v13)))
+  if ((rc = mk_split(x, lo_delta, planes, "strict_spp_pool x", &vx)) || (rc = mk_split(o5, lo_delta, planes, "strict_spp_pool o5", &v5)) ||
+      (rc = mk_split(o9, lo_delta, planes, "strict_spp_pool o9", &v9)) || (rc = mk_split(o13, lo_delta, planes, "strict_spp_pool o13", &v13)))
     return rc;
   YB_REQUIRE(o5->c == x->c && o9->c == x->c && o13->c == x->c && o5->h == x->h && o5->w == x->w, YB200_ERR_INVALID, "strict_spp_pool: shape mismatch");
   const long long total = 1LL * x->n * x->h * x->w * x->c;

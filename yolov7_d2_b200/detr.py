@@ -8,10 +8,9 @@ constructor arguments, parameter names / shapes (`self_attn.in_proj_weight` [3E,
     x (+pos) -> in_proj GEMMs (bias epilogue, q|k|v packed in one [B, L, 3E] buffer) -> yb200_attention_fwd (tcgen05, streaming softmax)
       -> out_proj GEMM (+bias +residual epilogue) -> LayerNorm -> linear1 GEMM (+bias +ReLU epilogue) -> linear2 GEMM (+bias +residual) -> LayerNorm
 
-Internally tokens are batch-first bf16 `[B, 1, L, E]` views (yb200_act).  Scope of round 1: the forward pass (inference, and the forward half
-of training) plus the attention-core backward kernel (yb200_attention_bwd, validated).  The encoder layer's full backward (`_EncoderLayerFn`)
-is opt-in (YB200_DETR_TRAINING=1) until its parameter gradients pass tests/test_detr_gpu.py on hardware; by default the modules run under
-no_grad and refuse inputs that require grad.
+Internally tokens are batch-first bf16 `[B, 1, L, E]` views (yb200_act).  Forward and backward: with gradients enabled the layers run as one autograd node each
+(`_EncoderLayerFn` / `_DecoderLayerFn`: attention backward, data / weight gradients and LayerNorm backward on the same kernels), validated on
+hardware against the reference layer's autograd (tests/test_detr_gpu.py, round 2: 6 passed); YB200_DETR_TRAINING=0 forces the inference path.
 Dropout (p = 0.1 in the reference) is identity here: parity runs use eval mode / p = 0.  `attn_mask` (never passed by the
 reference's DETR) and `normalize_before=True` are not supported.  There is no CPU implementation.
 """
@@ -24,9 +23,9 @@ import torch.nn as nn
 from . import capi
 
 LN_EPS = 1e-5
-# The encoder layer's backward wiring (autograd.Function over the attention-backward / dgrad / wgrad / LayerNorm-backward kernels) is
-# opt-in until it has been validated on hardware against tests/golden/detr.npz: YB200_DETR_TRAINING=1
-TRAINING_PATH = os.environ.get("YB200_DETR_TRAINING", "0") == "1"
+# The layers' backward wiring (autograd.Function over the attention-backward / dgrad / wgrad / LayerNorm-backward kernels) is the default
+# whenever autograd is recording; YB200_DETR_TRAINING=0 switches it off (inference-only modules)
+TRAINING_PATH = os.environ.get("YB200_DETR_TRAINING", "1") == "1"
 
 
 def _bl(t):

@@ -30,12 +30,13 @@ def _ceil(a, b):
 class Buf:
     """NHWC bf16 activation buffer (+ lazily allocated gradient of the same shape)"""
 
-    def __init__(self, name, n, h, w, c, device, dtype=torch.bfloat16, split=False):
+    def __init__(self, name, n, h, w, c, device, dtype=torch.bfloat16, split=0):
         self.name, self.n, self.h, self.w, self.c = name, n, h, w, c
-        # split (strict mode): [hi plane (c) | lo plane (c)] in one NHWC tensor, value = hi + lo (csrc/strict.cu); views address the
-        # hi plane, the lo plane sits self.lo channels further
+        # split (strict mode): `split` bf16 planes of c channels each in one NHWC tensor, value = their sum (csrc/strict.cu); views address
+        # plane 0, plane j sits j * self.lo channels further
         self.lo = c if split else 0
-        self.t = torch.zeros(n, h, w, 2 * c if split else c, dtype=dtype, device=device)
+        self.planes = split if split else 1
+        self.t = torch.zeros(n, h, w, self.planes * c, dtype=dtype, device=device)
         self.g = None
         self.written = []  # channel ranges of .g already produced in the current backward pass
 
@@ -73,8 +74,10 @@ class View:
 
     def value(self):
         """fp32 value of the view (split buffers: hi + lo)"""
-        hi = self.tensor().float()
-        return hi + self.buf.t[..., self.buf.lo + self.off:self.buf.lo + self.off + self.c].float() if self.buf.lo else hi
+        v = self.tensor().float()
+        for j in range(1, self.buf.planes):
+            v = v + self.buf.t[..., j * self.buf.lo + self.off:j * self.buf.lo + self.off + self.c].float()
+        return v
 
     def grad_tensor(self):
         return self.buf.grad()[..., self.off:self.off + self.c]
@@ -114,6 +117,8 @@ class YoloxEngine:
         1e-3 parity check against the fp32 reference; forward + SimOTA + losses only, no backward."""
         assert height % 32 == 0 and width % 32 == 0, "input must be padded to a multiple of 32 (yolox.py:100-101)"
         self.strict = (os.environ.get("YB200_STRICT", "0") == "1") if strict is None else bool(strict)
+        self.planes = int(os.environ.get("YB200_STRICT_PLANES", "3"))  # bf16 planes per value in strict mode: 3 = all 24 bits of fp32, 2 = 16 bits
+        assert self.planes in (2, 3)
         self.L = capi.lib()
         self.dev = torch.device(device)
         self.n, self.h, self.w, self.nc, self.max_gt = batch, height, width, num_classes, max_gt
@@ -131,7 +136,7 @@ class YoloxEngine:
     def _buf(self, name, h, w, c, dtype=torch.bfloat16):
         if self.strict and dtype == torch.float16:
             dtype = torch.float32  # pre-BatchNorm conv outputs stay fp32 in strict mode
-        b = Buf(name, self.n, h, w, c, self.dev, dtype, split=self.strict and dtype == torch.bfloat16)
+        b = Buf(name, self.n, h, w, c, self.dev, dtype, split=self.planes if (self.strict and dtype == torch.bfloat16) else 0)
         self.bufs[name] = b
         return b
 
@@ -184,6 +189,7 @@ class YoloxEngine:
         self.ops[-1].first = True
         (x,) = self._conv(["backbone.dark2.0"], x, [bc * 2], 3, 2)
         x = self._csp("backbone.dark2.1", x, bc * 2, bd, True)
+        d2 = x
         (x,) = self._conv(["backbone.dark3.0"], x, [c3], 3, 2)
         d3 = self._csp("backbone.dark3.1", x, c3, bd * 3, True, out=cat_p3.view(c3, c3))
         (x,) = self._conv(["backbone.dark4.0"], d3, [c4], 3, 2)
@@ -195,6 +201,8 @@ class YoloxEngine:
         self.ops.append(SppOp([spp_cat.view(i * c4, c4) for i in range(4)], arg))
         (x,) = self._conv(["backbone.dark5.1.conv2"], spp_cat.view(), [c5], 1, 1)
         d5 = self._csp("backbone.dark5.2", x, c5, bd, False)
+        self.features = {"dark2": d2, "dark3": d3, "dark4": d4, "dark5": d5}  # CSPDarknet.forward outputs (darknetx.py:165-177)
+        n_backbone = len(self.ops)
         # neck (yolo_pafpn.py:79-114)
         self._conv(["neck.lateral_conv0"], d5, [c4], 1, 1, outs=[cat_n4.view(c4, c4)], ups=[cat_p4.view(0, c4)])
         f_out0 = self._csp("neck.C3_p4", cat_p4.view(), c4, nn_, False)
@@ -204,6 +212,8 @@ class YoloxEngine:
         pan1 = self._csp("neck.C3_n3", cat_n3.view(), c4, nn_, False)
         self._conv(["neck.bu_conv1"], pan1, [c4], 3, 2, outs=[cat_n4.view(0, c4)])
         pan0 = self._csp("neck.C3_n4", cat_n4.view(), c5, nn_, False)
+        self.pan = (pan2, pan1, pan0)  # YOLOPAFPN.forward outputs (yolo_pafpn.py:113-114)
+        n_neck = len(self.ops)
         # head (yolox_head.py:151-175)
         hc = int(256 * self.wm)
         self.levels = []
@@ -222,6 +232,7 @@ class YoloxEngine:
             a_off += fh * fw
         self.num_anchors = a_off
         self.hc = hc
+        self.ranges = {"backbone": (0, n_backbone), "neck": (n_backbone, n_neck), "head": (n_neck, len(self.ops))}  # op index ranges
 
     # ------------------------------------------------------------------ parameters
     def _alloc_params(self, share=None):
@@ -291,7 +302,7 @@ class YoloxEngine:
             if isinstance(op, ConvOp):
                 kk = op.ksize * op.ksize
                 if self.strict:
-                    op.w_split = torch.empty(op.cout, 2, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
+                    op.w_split = torch.empty(op.cout, self.planes, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
                     op.w_fwd = op.w_dgrad = None
                 else:
                     op.w_fwd = torch.empty(op.cout, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
@@ -301,8 +312,8 @@ class YoloxEngine:
             elif isinstance(op, PredOp):
                 k, hc = op.level, self.hc
                 if self.strict:
-                    op.wc_split = torch.empty(self.nc, 2, 1, hc, dtype=torch.bfloat16, device=dev)
-                    op.wr_split = torch.empty(16, 2, 1, hc, dtype=torch.bfloat16, device=dev)
+                    op.wc_split = torch.empty(self.nc, self.planes, 1, hc, dtype=torch.bfloat16, device=dev)
+                    op.wr_split = torch.empty(16, self.planes, 1, hc, dtype=torch.bfloat16, device=dev)
                 op.wc_fwd = torch.empty(self.nc, 1, hc, dtype=torch.bfloat16, device=dev)
                 op.wc_dgrad = torch.empty(hc, 1, self.nc, dtype=torch.bfloat16, device=dev)
                 op.wr_fwd = torch.empty(16, 1, hc, dtype=torch.bfloat16, device=dev)
@@ -448,12 +459,12 @@ class YoloxEngine:
         if self.strict:
             for op in self.ops:
                 if isinstance(op, ConvOp):
-                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad,
+                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad, self.planes,
                                                               capi.ptr(op.w_split), sp), "pack split")
                     self._count(1, "pack split " + op.prefixes[0])
                 elif isinstance(op, PredOp):
-                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.wc_src), self.nc, self.hc, 1, self.nc, self.hc, capi.ptr(op.wc_split), sp), "pack cls")
-                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, capi.ptr(op.wr_split), sp), "pack reg+obj")
+                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.wc_src), self.nc, self.hc, 1, self.nc, self.hc, self.planes, capi.ptr(op.wc_split), sp), "pack cls")
+                    capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, self.planes, capi.ptr(op.wr_split), sp), "pack reg+obj")
                     self._count(2, "pack split preds")
             return
         for op in self.ops:
@@ -483,7 +494,7 @@ class YoloxEngine:
         for op in self.ops:
             if isinstance(op, ConvOp):
                 zb = op.z.buf
-                capi.check(L.yb200_conv2d_fwd_split(op.x.act(), op.x.buf.lo, capi.ptr(op.w_split), op.cout, op.ksize, op.stride, capi.ptr(zb.t), zb.c, 0,
+                capi.check(L.yb200_conv2d_fwd_split(op.x.act(), op.x.buf.lo, self.planes, capi.ptr(op.w_split), op.cout, op.ksize, op.stride, capi.ptr(zb.t), zb.c, 0,
                                                     sp), "conv split " + op.prefixes[0])
                 o = op.bn_off
                 gamma = self.params[op.prefixes[0] + ".bn.weight"]
@@ -502,19 +513,19 @@ class YoloxEngine:
                 for hd in op.heads:
                     capi.check(L.yb200_strict_bn_apply_silu(capi.ptr(zb.t), zb.c, hd.c0, pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
                                                             hd.residual.act() if hd.residual else None, hd.residual.buf.lo if hd.residual else 0,
-                                                            hd.out.act(), hd.out.buf.lo, hd.up.act() if hd.up else None, hd.up.buf.lo if hd.up else 0, sp),
+                                                            hd.out.act(), hd.out.buf.lo, hd.up.act() if hd.up else None, hd.up.buf.lo if hd.up else 0, self.planes, sp),
                                "strict_bn_apply_silu " + hd.prefix)
                     self._count(1, "strict bn_apply " + hd.prefix)
             elif isinstance(op, SppOp):
                 v = op.views
-                capi.check(L.yb200_strict_spp_pool(v[0].act(), v[1].act(), v[2].act(), v[3].act(), v[0].buf.lo, sp), "strict_spp_pool")
+                capi.check(L.yb200_strict_spp_pool(v[0].act(), v[1].act(), v[2].act(), v[3].act(), v[0].buf.lo, self.planes, sp), "strict_spp_pool")
                 self._count(1, "strict spp_pool")
             else:
                 h, w, s, a_off = self.levels[op.level]
                 ch = 5 + self.nc
-                capi.check(L.yb200_conv1x1_bias_f32_split(op.cls_feat.act(), op.cls_feat.buf.lo, capi.ptr(op.wc_split), capi.ptr(op.bc), self.nc,
+                capi.check(L.yb200_conv1x1_bias_f32_split(op.cls_feat.act(), op.cls_feat.buf.lo, self.planes, capi.ptr(op.wc_split), capi.ptr(op.bc), self.nc,
                                                           capi.ptr(self.outputs), self.num_anchors, a_off, ch, 5, sp), "cls_pred split")
-                capi.check(L.yb200_conv1x1_bias_f32_split(op.reg_feat.act(), op.reg_feat.buf.lo, capi.ptr(op.wr_split), capi.ptr(op.br), 5,
+                capi.check(L.yb200_conv1x1_bias_f32_split(op.reg_feat.act(), op.reg_feat.buf.lo, self.planes, capi.ptr(op.wr_split), capi.ptr(op.br), 5,
                                                           capi.ptr(self.outputs), self.num_anchors, a_off, ch, 0, sp), "reg_obj_pred split")
                 self._count(2, "strict pred convs level %d" % op.level)
         if training:
@@ -523,13 +534,17 @@ class YoloxEngine:
                                         0 if training else 1, sp), "decode")
         self._count(1, "decode")
 
-    def forward_features(self, training=True):
+    def forward_features(self, training=True, op_range=None):
+        """op_range = (lo, hi): run only self.ops[lo:hi] (standalone backbone / neck / head execution, modeling.py); the head decode
+        runs when the range reaches the end of the plan"""
         if self.strict:
+            assert op_range is None
             return self._forward_features_strict(training)
         L, sp = self.L, capi.stream_ptr()
         nb = self.nbn
         f8 = self.flat_stats
-        for op in self.ops:
+        lo_i, hi_i = op_range if op_range is not None else (0, len(self.ops))
+        for op in self.ops[lo_i:hi_i]:
             if isinstance(op, ConvOp):
                 o = op.bn_off
                 gamma = self.params[op.prefixes[0] + ".bn.weight"]
@@ -582,8 +597,15 @@ class YoloxEngine:
                 self._count(2, "pred convs level %d" % op.level, "pred_conv fwd", self.n * h * w * (2.0 * 2 * self.hc + 4.0 * ch),
                             2.0 * self.n * h * w * self.hc * ch)
         if training:
-            self.flat_nbt += 1
+            if op_range is None:
+                self.flat_nbt += 1
+            else:  # only the BatchNorm layers that ran
+                i0 = sum(len(o.heads) for o in self.ops[:lo_i] if isinstance(o, ConvOp))
+                i1 = i0 + sum(len(o.heads) for o in self.ops[lo_i:hi_i] if isinstance(o, ConvOp))
+                self.flat_nbt[i0:i1] += 1
             self._count(1, "num_batches_tracked += 1 (torch)")
+        if hi_i < len(self.ops):
+            return
         capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
                                         0 if training else 1, sp), "decode")
         self._count(1, "decode", "decode", 8.0 * self.n * self.num_anchors * 4)
@@ -657,7 +679,7 @@ class YoloxEngine:
 
     def _bn_segments(self, key):
         """ctypes array of yb200_bnbwd_seg for the data-gradient launch `key` (None when nothing is fused into it)"""
-        segs = self._bn_fuse.get(key)
+        segs = self._bn_fuse.get(key) if getattr(self, "_fuse_active", True) else None
         if not segs:
             return None, 0
         cached = getattr(self, "_bn_seg_cache", None)
@@ -724,7 +746,10 @@ class YoloxEngine:
             capi.check(L.yb200_conv2d_wgrad(x_act, dz_act, ksize, stride, cin_real, capi.ptr(gdst), acc, capi.ptr(self.ws),
                                             ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad " + label)
 
-    def backward(self, accumulate=False):
+    def backward(self, accumulate=False, op_range=None, seeded=()):
+        """op_range = (lo, hi): backward of self.ops[lo:hi] only, from gradients the caller has already stored in the gradient buffers of
+        the `seeded` views (standalone backbone / neck / head, modeling.py).  Partial passes run every BatchNorm backward in two passes:
+        the fused-statistics plan assumes the whole network."""
         if self.strict:
             raise capi.Yb200Error("strict mode is a forward / loss verification mode: no backward (use the default engine for training)")
         L, sp = self.L, capi.stream_ptr()
@@ -733,8 +758,12 @@ class YoloxEngine:
         acc = 1 if accumulate else 0
         for b in self.bufs.values():
             b.written = []
+        for v in seeded:
+            v.buf.written.append((v.off, v.off + v.c))
+        self._fuse_active = op_range is None
+        lo_i, hi_i = op_range if op_range is not None else (0, len(self.ops))
         pending_res = {}  # id(view.buf), off -> gradient view of the residual sum
-        for op in reversed(self.ops):
+        for op in reversed(self.ops[lo_i:hi_i]):
             if isinstance(op, PredOp):
                 k = op.level
                 h, w, s, a_off = self.levels[k]
@@ -765,7 +794,7 @@ class YoloxEngine:
                     dzv = dzb.view(hd.c0, hd.c)
                     o = hd.bn_off
                     npx = op.z.buf.n * op.z.buf.h * op.z.buf.w
-                    if hd.fused_stats:  # the reduction pass ran in the epilogue of the data gradient that produced hd.out's gradient
+                    if hd.fused_stats and self._fuse_active:  # the reduction pass ran in the epilogue of the data gradient that produced hd.out's gradient
                         capi.check(L.yb200_bn_silu_bwd_apply(zv.act(), hd.out.gact(), pf(self.flat_scale, o), pf(self.flat_shift, o), pf(self.flat_mean, o),
                                                              pf(self.flat_invstd, o), ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)),
                                                              ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)), dzv.act(),

@@ -158,8 +158,88 @@ class _ParamTree(nn.Module):
             mod.register_parameter(parts[-1], value)
 
 
-class CSPDarknet(Backbone, _ParamTree):
-    """YOLOX CSPDarknet (darknetx.py:103-191).  Parameters live in the engine of the owning YOLOX model."""
+_ADOPTING = [False]  # True while YOLOX.__init__ builds its sub-modules: they adopt YOLOX's parameter storage instead of creating their own
+
+
+class _PartFn(torch.autograd.Function):
+    """One of the three parts of the plan (backbone / neck / head-train) executed on its own: forward = the engine ops of that range,
+    backward = the same range of the engine backward, seeded with the gradients autograd delivers for the part's outputs."""
+
+    @staticmethod
+    def forward(ctx, eng, part, training, in_views, out_views, n_in, *tensors):
+        inputs = tensors[:n_in]
+        eng.pack_weights()
+        for v, t in zip(in_views, inputs):
+            v.tensor().copy_(t.detach().permute(0, 2, 3, 1))
+        eng.forward_features(training, eng.ranges[part])
+        ctx.eng, ctx.part, ctx.in_views, ctx.out_views, ctx.n_in = eng, part, in_views, out_views, n_in
+        ctx.need_in = [t.requires_grad for t in inputs]
+        return tuple(v.tensor().permute(0, 3, 1, 2).float().contiguous() for v in out_views)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        eng = ctx.eng
+        for v, g in zip(ctx.out_views, grads):
+            gt = v.grad_tensor()
+            if g is None:
+                gt.zero_()
+            else:
+                gt.copy_(g.permute(0, 2, 3, 1))
+        eng.backward(False, eng.ranges[ctx.part], seeded=ctx.out_views)
+        gin = [v.grad_tensor().permute(0, 3, 1, 2).float().contiguous() if need else None for v, need in zip(ctx.in_views, ctx.need_in)]
+        prefix = ctx.part + "."
+        gpar = [eng.grads[n].clone() for n in eng.param_names if n.startswith(prefix)]
+        return (None,) * 6 + tuple(gin) + tuple(gpar)
+
+
+class _Part(_ParamTree):
+    """shared machinery of the standalone modules: own parameter storage (a root plan) unless adopted by YOLOX, one plan per input shape"""
+
+    _part = None
+
+    def _init_storage(self, num_classes, width, depth, device=None):
+        self._root, self._plans = None, {}
+        self._cfg = (num_classes, width, depth)
+        if not _ADOPTING[0]:
+            dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self._root = YoloxEngine(1, 32, 32, num_classes, width, depth, 100, dev)
+            self._root.init_weights(0)
+            self._adopt(self._root, self._part + ".")
+
+    def _adopt_root(self, root):
+        self._root, self._plans = root, {}
+        self._adopt(root, self._part + ".")
+
+    def _plan(self, batch, h, w):
+        if self._root is None:
+            raise capi.Yb200Error(f"{type(self).__name__} has no parameter storage (constructed inside YOLOX but never adopted)")
+        key = (batch, h, w)
+        if key not in self._plans:
+            nc, wm, dm = self._cfg
+            self._plans[key] = YoloxEngine(batch, h, w, nc, wm, dm, 100, self._root.dev, share_params_of=self._root)
+        return self._plans[key]
+
+    def _params_of_part(self, eng):
+        by_name = dict(self.named_parameters())
+        pre = self._part + "."
+        return [by_name[n[len(pre):]] for n in eng.param_names if n.startswith(pre)]
+
+    def _run(self, eng, in_views, out_views, inputs):
+        for t in inputs:
+            if not (t.is_cuda and t.dim() == 4):
+                raise capi.Yb200Error(f"{type(self).__name__}.forward expects CUDA NCHW tensors (no CPU fallback)")
+        if torch.is_grad_enabled() and self.training:
+            return _PartFn.apply(eng, self._part, True, in_views, out_views, len(inputs), *inputs, *self._params_of_part(eng))
+        with torch.no_grad():
+            return _PartFn.apply(eng, self._part, self.training, in_views, out_views, len(inputs), *inputs)
+
+
+class CSPDarknet(Backbone, _Part):
+    """YOLOX CSPDarknet (darknetx.py:103-191).  Inside YOLOX the parameters live in the model's engine and execution is fused into
+    YOLOX.forward; used on its own (the YOLOV5 / YOLOV7P / YOLOMask architectures build it through BACKBONE_REGISTRY and call
+    `backbone(x)`), `forward(x)` runs the backbone range of the plan and returns the reference's dict of NCHW fp32 features."""
+
+    _part = "backbone"
 
     def __init__(self, dep_mul, wid_mul, out_features=("dark3", "dark4", "dark5"), depthwise=False, act="silu"):
         Backbone.__init__(self)
@@ -171,7 +251,7 @@ class CSPDarknet(Backbone, _ParamTree):
         self.dep_mul, self.wid_mul, self.out_features = dep_mul, wid_mul, out_features
         bc = int(wid_mul * 64)
         self.output_shape_dict = {f"dark{i + 2}": ShapeSpec(channels=bc * 2 ** (i + 1)) for i in range(4)}
-        self._engine = None
+        self._init_storage(80, wid_mul, dep_mul)
 
     def output_shape(self):
         return self.output_shape_dict
@@ -181,21 +261,49 @@ class CSPDarknet(Backbone, _ParamTree):
         return 32
 
     def forward(self, x):
-        raise capi.Yb200Error("CSPDarknet runs fused inside YOLOX.forward; standalone execution is not exposed in this build")
+        """x: [B, 3, H, W] float (H, W multiples of 32) -> {name: [B, C, H/s, W/s] fp32 for name in out_features}   (darknetx.py:165-177).
+        The Focus slice (wrappers.py:210-220) is laid out by torch indexing; everything after it runs in libyb200.so.  Activations are
+        stored in bf16 (the input image too), as in YOLOX.forward."""
+        b, c, h, w = x.shape
+        if c != 3 or h % 32 or w % 32:
+            raise capi.Yb200Error(f"CSPDarknet.forward: input {tuple(x.shape)} must be [B, 3, H, W] with H, W multiples of 32")
+        eng = self._plan(b, h, w)
+        focus = torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), 1)  # [B, 12, H/2, W/2]
+        eng.focus.t[..., :12].copy_(focus.detach().permute(0, 2, 3, 1))
+        names = [k for k in ("dark2", "dark3", "dark4", "dark5") if k in self.out_features]
+        outs = self._run(eng, (), tuple(eng.features[k] for k in names), ())
+        return dict(zip(names, outs))
 
 
-class YOLOPAFPN(_ParamTree):
+class YOLOPAFPN(_Part):
+    """yolo_pafpn.py:13-114: forward(dict of backbone features) -> (pan_out2, pan_out1, pan_out0), NCHW fp32"""
+
+    _part = "neck"
+
     def __init__(self, depth=1.0, width=1.0, in_features=("dark3", "dark4", "dark5"), in_channels=[256, 512, 1024], depthwise=False, act="silu"):
         super().__init__()
         if depthwise:
             raise capi.Yb200Error("depthwise YOLOPAFPN is not implemented by the B200 path")
         self.in_features, self.in_channels = in_features, in_channels
+        self._init_storage(80, width, depth)
 
     def forward(self, out_features):
-        raise capi.Yb200Error("YOLOPAFPN runs fused inside YOLOX.forward; standalone execution is not exposed in this build")
+        feats = [out_features[f] for f in self.in_features]
+        b, _, h8, w8 = feats[0].shape
+        eng = self._plan(b, 8 * h8, 8 * w8)
+        in_views = tuple(eng.features[k] for k in ("dark3", "dark4", "dark5"))
+        for v, t in zip(in_views, feats):
+            if tuple(t.shape) != (v.shape[0], v.shape[3], v.shape[1], v.shape[2]):
+                raise capi.Yb200Error(f"YOLOPAFPN.forward: feature {tuple(t.shape)} does not match the plan {v.shape}")
+        return self._run(eng, in_views, eng.pan, tuple(feats))
 
 
-class YOLOXHead(_ParamTree):
+class YOLOXHead(_Part):
+    """yolox_head.py:24-272.  Evaluation: forward(xin) -> [B, A, 5+C] decoded predictions (sigmoid applied).  Training with labels runs
+    inside YOLOX.forward (one fused autograd node); the standalone module covers the inference call of the other architectures."""
+
+    _part = "head"
+
     def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu", depthwise=False):
         super().__init__()
         if depthwise:
@@ -206,6 +314,7 @@ class YOLOXHead(_ParamTree):
         self.strides = strides
         self.onnx_export = False
         self.hw = None
+        self._init_storage(num_classes, width, 0.33)
 
     def initialize_biases(self, prior_prob):
         """yolox_head.py:140-149"""
@@ -216,7 +325,19 @@ class YOLOXHead(_ParamTree):
                     p.fill_(v)
 
     def forward(self, xin, labels=None, imgs=None):
-        raise capi.Yb200Error("YOLOXHead runs fused inside YOLOX.forward; standalone execution is not exposed in this build")
+        if self.training or labels is not None:
+            raise capi.Yb200Error("YOLOXHead training (SimOTA + losses) runs fused inside YOLOX.forward; the standalone head is the "
+                                  "inference path: call .eval() and forward(xin)")
+        feats = list(xin)
+        b, _, h8, w8 = feats[0].shape
+        eng = self._plan(b, 8 * h8, 8 * w8)
+        self.hw = [tuple(f.shape[-2:]) for f in feats]
+        with torch.no_grad():
+            eng.pack_weights()
+            for v, t in zip(eng.pan, feats):
+                v.tensor().copy_(t.permute(0, 2, 3, 1))
+            eng.forward_features(False, eng.ranges["head"])
+            return eng.outputs.clone()
 
 
 @BACKBONE_REGISTRY.register()
@@ -284,12 +405,16 @@ class YOLOX(nn.Module):
         self._root = YoloxEngine(1, 32, 32, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device)
         self._root.init_weights(0)
         self._plans = {}
-        self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, None)
-        self.neck = YOLOPAFPN(depth=self.depth_mul, width=self.width_mul, in_features=self.in_features)
-        self.head = YOLOXHead(self.num_classes, width=self.width_mul)
-        self.backbone._adopt(self._root, "backbone.")
-        self.neck._adopt(self._root, "neck.")
-        self.head._adopt(self._root, "head.")
+        _ADOPTING[0] = True  # the sub-modules share this model's parameter storage instead of allocating their own
+        try:
+            self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, None)
+            self.neck = YOLOPAFPN(depth=self.depth_mul, width=self.width_mul, in_features=self.in_features)
+            self.head = YOLOXHead(self.num_classes, width=self.width_mul)
+        finally:
+            _ADOPTING[0] = False
+        for part in (self.backbone, self.neck, self.head):
+            part._cfg = (self.num_classes, self.width_mul, self.depth_mul)
+            part._adopt_root(self._root)
         self.head.initialize_biases(1e-2)
         self._param_list = None
         self._flat_grads = False
