@@ -233,6 +233,93 @@ def library_bar(torch, dev, batch, with_optimizer, steps=5, warmup=3):
     return out
 
 
+def yolox_convnext_step(torch, dist, dev, rank, world, batch, steps, warmup, with_optimizer, use_graph):
+    """BASELINE.json configs[2]: YOLOX on a ConvNeXt-T backbone (corrected wiring, yolov7_d2_b200/yolox_convnext.py), `batch` images of 640x640 per
+    GPU: forward, SimOTA + losses, backward, (N > 1: all-reduce of the two flat gradient buffers), fused SGD step.  Returns the result dict."""
+    from yolov7_d2_b200 import optim as yopt, synth
+    from yolov7_d2_b200.yolox_convnext import YoloxConvNeXtEngine
+
+    eng = YoloxConvNeXtEngine(batch, 640, 640, device=dev)
+    eng.init_weights(0)
+    for pname in eng.cn.param_names:  # a trained-like layer scale instead of the 1e-6 initial value, so the residual branches carry signal
+        if pname.endswith("gamma"):
+            eng.cn.params[pname].fill_(0.1)
+    images, labels = synth.synthetic_batch(batch, 640, seed=200 + rank)
+    eng.images_u8.copy_(images.to(dev))
+    eng.labels.copy_(labels.to(dev))
+    cfg = yolox_s_cfg("cuda")
+    opt = yopt.build_optimizer_mapper(cfg, eng) if with_optimizer else None
+    if opt is not None:
+        opt.grad_scale = 1.0 / world
+    grads = [g for _, g, _, _ in eng.flat_buffers()]
+
+    def fb():
+        eng.train_step()
+        if opt is not None and world == 1:
+            opt.step()
+
+    def eager():
+        eng.train_step()
+        if world > 1:
+            for g in grads:
+                dist.all_reduce(g)
+        if opt is not None:
+            opt.step()
+
+    for _ in range(max(warmup, 3)):
+        eager()
+    torch.cuda.synchronize()
+    launches = eng.kernel_launches // max(warmup, 3)
+    graph = None
+    if use_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                fb()
+            graph = g
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[bench] yolox_convnext graph capture failed ({e}); eager launches\n")
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is None:
+            return eager()
+        graph.replay()
+        if world > 1:
+            for g in grads:
+                dist.all_reduce(g)
+            if opt is not None:
+                opt.step()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    ips = world * batch * steps / (ms / 1e3)
+    out = {"workload": "YOLOX-ConvNeXt-T (ConvNeXt-T stages 1-3 -> PAFPN / head width 0.75), %d x 640x640 per GPU, fwd + SimOTA/loss + bwd%s%s" % (
+               batch, " + all-reduce" if world > 1 else "", " + fused SGD" if opt is not None else ""),
+           "images_per_s": ips, "ms_per_step": ms / steps, "n_gpus": world, "global_batch": world * batch, "cuda_graph": graph is not None,
+           "launches_per_step": launches, "loss": float(eng.losses[0])}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +333,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-convnext", action="store_true")
     ap.add_argument("--no-library-bar", action="store_true")
+    ap.add_argument("--workload", default="yolox_s", choices=["yolox_s", "yolox_convnext"],
+                    help="yolox_s = the headline metric (BASELINE.json configs[1]); yolox_convnext = configs[2] (32 images per GPU; `--gpus 8` = bs 256)")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: copy each batch inside forward() (serial), as the reference does")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward(+all-reduce) only, without the fused SGD step")
     args = ap.parse_args()
@@ -268,6 +357,18 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "yolox_convnext":
+        res = yolox_convnext_step(torch, dist, dev, rank, world, 32, args.steps, args.warmup, not args.no_optimizer, not args.no_graph)
+        if rank == 0:
+            print(json.dumps({"metric": "images/sec (640x640) YOLOX-ConvNeXt-T fwd+bwd", "value": res["images_per_s"], "unit": "images/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                              "config": {"workload": res["workload"] + " (BASELINE.json configs[2])", "global_batch": res["global_batch"],
+                                         "parallelism": f"dp{world}", "cuda_graph": res["cuda_graph"]},
+                              "gpu_launches": res["launches_per_step"] * args.steps, "loss": res["loss"]}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     B = args.batch
 
     cfg = yolox_s_cfg("cuda")
@@ -460,34 +561,12 @@ def main():
         nms = {"value": cand * len(clones) / (e0.elapsed_time(e1) / 1e3), "unit": "boxes/s", "candidates_per_call": cand,
                "workload": "postprocess on [%d,8400,85] clustered stress set, conf 0.001, IoU 0.65" % B}
 
-    # ---- secondary workload (BASELINE.json configs[2], per-GPU share): ConvNeXt-T backbone fwd+bwd, 32 x 640x640 ----
+    final_loss = float(eng.losses[0])
+    # ---- secondary workload (BASELINE.json configs[2], per-GPU share): YOLOX-ConvNeXt-T training step, 32 x 640x640 ----
     cnx_line = None
     if rank == 0 and world == 1 and not args.no_convnext:
         try:
-            from yolov7_d2_b200.convnext import ConvNeXtEngine
-            ce = ConvNeXtEngine(32, 640, 640, device=dev)
-            ce.init_weights(0)
-            for pname in ce.param_names:  # a trained-like layer scale instead of the 1e-6 initial value, so the residual branches carry signal
-                if pname.endswith("gamma"):
-                    ce.params[pname].fill_(0.1)
-            ce.images_u8.copy_(synth.synthetic_images(32, 640, 1).to(dev))
-            gen = torch.Generator(device=dev).manual_seed(2)
-            for st in ce.stage:
-                st.gout.t.copy_(torch.randn(st.gout.t.shape, generator=gen, device=dev) * 1e-2)
-            for _ in range(3):
-                ce.train_step()
-            torch.cuda.synchronize()
-            cl = ce.kernel_launches // 3
-            e0.record()
-            for _ in range(5):
-                ce.train_step()
-            e1.record()
-            torch.cuda.synchronize()
-            cms = e0.elapsed_time(e1) / 5
-            cnx_line = {"workload": "ConvNeXt-T backbone fwd+bwd, 32 x 640x640 (BASELINE.json configs[2] per-GPU share), eager launches", "images_per_s": 32 / cms * 1e3,
-                        "ms_per_step": cms, "tflops": 3 * 72.7 * 32 / cms, "launches_per_step": cl}
-            del ce
-            torch.cuda.empty_cache()
+            cnx_line = yolox_convnext_step(torch, None, dev, 0, 1, 32, 5, 3, not args.no_optimizer, not args.no_graph)
         except Exception as e:  # noqa: BLE001
             cnx_line = {"error": str(e)[:200]}
 
@@ -541,7 +620,7 @@ def main():
                            "optimizer": None if opt is None else "fused SGD step inside the timed step (momentum 0.9, wd 5e-4, lr %g)" % BENCH_LR,
                            "l2": "per-step working set (~%.0f GB of activations and gradients) exceeds the 126 MB L2; no explicit flush" % (0.245 * B)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "kernel_classes": classes, "cpu_baseline": cpu, "library_bar": lib_bar, "nms": nms, "convnext": cnx_line,
-                "loss": float(eng.losses[0])}
+                "loss": final_loss}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -304,18 +304,23 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
       }
     }
   }
-  // lanes sharing a channel vector (same threadIdx.x) sit blockDim.x apart inside the warp (blockDim.x is a power of two)
+  // blockDim.x a power of two below 32: lanes sharing a channel vector (same threadIdx.x) sit blockDim.x apart inside the warp and are folded
+  // by shuffles first; otherwise (wide or non-power-of-two channel counts, e.g. 96 / 192 / 384 / 768 of the width-0.75 plans) every thread
+  // row goes to shared memory
   const int cvx = blockDim.x;
-  for (int off = 16; off >= cvx; off >>= 1) {
+  const bool shuf = cvx < 32 && (cvx & (cvx - 1)) == 0;
+  if (shuf) {
+    for (int off = 16; off >= cvx; off >>= 1) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
-      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+        s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+      }
     }
   }
-  const int rows = cvx < 32 ? nthreads / 32 : blockDim.y;
-  const int row = cvx < 32 ? tid / 32 : threadIdx.y;
-  if (cvx >= 32 || (tid & 31) < cvx) {
+  const int rows = shuf ? nthreads / 32 : blockDim.y;
+  const int row = shuf ? tid / 32 : threadIdx.y;
+  if (!shuf || (tid & 31) < cvx) {
     float* dst = sm + static_cast<size_t>(row) * 2 * z.c;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -626,8 +631,7 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
              "bn_silu_bwd: upsampled gradient view must be [n,2h,2w,c]");
   const long long npix = 1LL * z->n * z->h * z->w;
   const int cv = z->c / 8;
-  YB_REQUIRE(cv <= kEwThreads && (cv & (cv - 1)) == 0 && npix < (1LL << 31), YB200_ERR_UNSUPPORTED,
-             "bn_silu_bwd: %d channels (need 8 * 2^k <= 2048) / %lld pixels", z->c, npix);
+  YB_REQUIRE(cv <= kEwThreads && npix < (1LL << 31), YB200_ERR_UNSUPPORTED, "bn_silu_bwd: %d channels (at most 2048) / %lld pixels", z->c, npix);
   cudaStream_t st = as_stream(stream);
   DaSrc src;
   src.a = mk(da);
@@ -641,7 +645,8 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
   int red_iters = static_cast<int>(npix / (static_cast<long long>(block.y) * 6 * sm_count()));
   red_iters = red_iters < 4 ? 4 : (red_iters > kBnRedIters ? kBnRedIters : red_iters);
   const unsigned grid_r = static_cast<unsigned>((npix + block.y * red_iters - 1) / (block.y * red_iters));
-  const int red_rows = cv < 32 ? kEwThreads / 32 : static_cast<int>(block.y);
+  const bool red_shuffle = cv < 32 && (cv & (cv - 1)) == 0;
+  const int red_rows = red_shuffle ? static_cast<int>(block.x * block.y) / 32 : static_cast<int>(block.y);
   const size_t red_smem = static_cast<size_t>(red_rows) * 2 * z->c * sizeof(float);
   static size_t red_smem_set = 48 * 1024;
   if (red_smem > red_smem_set) {

@@ -643,6 +643,8 @@ class YoloxEngine:
         second, 2x2-pooled source), heads whose gradient is finished by a non-convolution (SPP), gradient tensors of >= 256 channels and
         more than two heads per launch.  YB200_BN_FUSE=0 disables the fusion (A/B runs)."""
         self._bn_fuse = {}
+        self._bn_fuse_idx = {}  # key -> (index of the writing op, [indices of the producing ops])
+        op_index = {id(op): i for i, op in enumerate(self.ops)}
         for op in self.ops:
             if isinstance(op, ConvOp):
                 for hd in op.heads:
@@ -676,6 +678,17 @@ class YoloxEngine:
                 if len(segs) < 2:
                     segs.append((hd, op, v.off - lo))
                     hd.fused_stats = True
+                    self._bn_fuse_idx.setdefault(key, (op_index[key[1]], []))[1].append(op_index[id(op)])
+
+    def _range_fusable(self, op_range):
+        """a partial backward may keep the fused statistics when it runs to the end of the plan and no fused launch inside the range feeds
+        the accumulators of a BatchNorm outside it"""
+        if op_range is None:
+            return True
+        lo, hi = op_range
+        if hi != len(self.ops):
+            return False
+        return all(min(prods) >= lo for w, prods in self._bn_fuse_idx.values() if w >= lo)
 
     def _bn_segments(self, key):
         """ctypes array of yb200_bnbwd_seg for the data-gradient launch `key` (None when nothing is fused into it)"""
@@ -760,7 +773,7 @@ class YoloxEngine:
             b.written = []
         for v in seeded:
             v.buf.written.append((v.off, v.off + v.c))
-        self._fuse_active = op_range is None
+        self._fuse_active = self._range_fusable(op_range)
         lo_i, hi_i = op_range if op_range is not None else (0, len(self.ops))
         pending_res = {}  # id(view.buf), off -> gradient view of the residual sum
         for op in reversed(self.ops[lo_i:hi_i]):

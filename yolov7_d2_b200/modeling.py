@@ -402,19 +402,39 @@ class YOLOX(nn.Module):
         self.onnx_export = False
 
         # parameter storage lives in a tiny "root" plan; execution plans per (batch, H, W) share it
-        self._root = YoloxEngine(1, 32, 32, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device)
-        self._root.init_weights(0)
+        self._convnext = cfg.MODEL.BACKBONE.NAME == "build_convnext_backbone"
         self._plans = {}
-        _ADOPTING[0] = True  # the sub-modules share this model's parameter storage instead of allocating their own
-        try:
-            self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, None)
-            self.neck = YOLOPAFPN(depth=self.depth_mul, width=self.width_mul, in_features=self.in_features)
-            self.head = YOLOXHead(self.num_classes, width=self.width_mul)
-        finally:
-            _ADOPTING[0] = False
-        for part in (self.backbone, self.neck, self.head):
-            part._cfg = (self.num_classes, self.width_mul, self.depth_mul)
-            part._adopt_root(self._root)
+        if self._convnext:
+            # configs/coco/yolox/yolox_convnext.yaml with the corrected wiring of yolox_convnext.py (the shipped one does not run: SURVEY.md par.0.2):
+            # ConvNeXt-T stages 1-3 -> PAFPN / head of width 0.75
+            from .yolox_convnext import DEPTH, WIDTH, YoloxConvNeXtEngine
+            self.width_mul, self.depth_mul = WIDTH, DEPTH
+            self._root = YoloxConvNeXtEngine(1, 32, 32, self.num_classes, self.max_boxes_num, self.device)
+            self._root.init_weights(0)
+            _ADOPTING[0] = True
+            try:
+                self.backbone = _Part()
+                self.neck = YOLOPAFPN(depth=DEPTH, width=WIDTH, in_features=self.in_features)
+                self.head = YOLOXHead(self.num_classes, width=WIDTH)
+            finally:
+                _ADOPTING[0] = False
+            self.backbone._adopt(self._root, "backbone.")
+            for part in (self.neck, self.head):
+                part._cfg = (self.num_classes, WIDTH, DEPTH)
+                part._adopt_root(self._root.yx)
+        else:
+            self._root = YoloxEngine(1, 32, 32, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device)
+            self._root.init_weights(0)
+            _ADOPTING[0] = True  # the sub-modules share this model's parameter storage instead of allocating their own
+            try:
+                self.backbone = BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, None)
+                self.neck = YOLOPAFPN(depth=self.depth_mul, width=self.width_mul, in_features=self.in_features)
+                self.head = YOLOXHead(self.num_classes, width=self.width_mul)
+            finally:
+                _ADOPTING[0] = False
+            for part in (self.backbone, self.neck, self.head):
+                part._cfg = (self.num_classes, self.width_mul, self.depth_mul)
+                part._adopt_root(self._root)
         self.head.initialize_biases(1e-2)
         self._param_list = None
         self._flat_grads = False
@@ -447,6 +467,9 @@ class YOLOX(nn.Module):
     # -- helpers ---------------------------------------------------------------------------------
     def _plan(self, batch, h, w):
         key = (batch, h, w)
+        if key not in self._plans and self._convnext:
+            from .yolox_convnext import YoloxConvNeXtEngine
+            self._plans[key] = YoloxConvNeXtEngine(batch, h, w, self.num_classes, self.max_boxes_num, self.device, share_params_of=self._root)
         if key not in self._plans:
             self._plans[key] = YoloxEngine(batch, h, w, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device,
                                            share_params_of=self._root)
@@ -493,6 +516,8 @@ class YOLOX(nn.Module):
             if not contiguous_run:
                 eng._stage_evt.record()
         else:
+            if not getattr(eng, "device_pad", True):  # a plan that reads images_u8 as is: the padding value goes in here
+                images_dst.fill_(int(round(self.padded_value)))
             for k, im in enumerate(imgs):
                 images_dst[k, :, :im.shape[-2], :im.shape[-1]].copy_(im if im.dtype == torch.uint8 else im.round().clamp_(0, 255).to(torch.uint8), non_blocking=True)  # pixel values are integers 0..255 (detectron2 mappers emit uint8); a float image is rounded, never truncated
         hw_dst.copy_(torch.tensor([[i.shape[-2], i.shape[-1]] for i in imgs], dtype=torch.int32), non_blocking=True)

@@ -157,9 +157,51 @@ class FlatOptimizer(torch.optim.Optimizer):
         st["step"] = int(st.get("step", 0))
 
 
+class FlatOptimizerGroup(torch.optim.Optimizer):
+    """Several flat buffers (e.g. ConvNeXt backbone + YOLOX neck / head plans) behind ONE torch.optim.Optimizer: param group i is buffer i, so LR
+    schedulers drive every buffer through `param_groups[i]["lr"]`; step() is one fused launch per buffer."""
+
+    def __init__(self, children):
+        self.children = list(children)
+        d = dict(self.children[0].defaults)
+        super().__init__([{"params": [c.flat_param]} for c in self.children], d)
+        for c, g in zip(self.children, self.param_groups):
+            g.update({k: v for k, v in c.param_groups[0].items() if k != "params"})
+
+    @property
+    def grad_scale(self):
+        return self.children[0].grad_scale
+
+    @grad_scale.setter
+    def grad_scale(self, v):
+        for c in self.children:
+            c.grad_scale = float(v)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for c, g in zip(self.children, self.param_groups):
+            c.param_groups[0].update({k: v for k, v in g.items() if k != "params"})
+            c.step()
+        return loss
+
+    def zero_grad(self, set_to_none=False):
+        for c in self.children:
+            c.zero_grad()
+
+    def state_dict(self):
+        return {"children": [c.state_dict() for c in self.children]}
+
+    def load_state_dict(self, sd):
+        for c, d in zip(self.children, sd["children"]):
+            c.load_state_dict(d)
+        for c, g in zip(self.children, self.param_groups):
+            g.update({k: v for k, v in c.param_groups[0].items() if k != "params"})
+
+
 def _flat_buffers(model):
     eng = getattr(model, "engine", None) or getattr(getattr(model, "module", None), "engine", None) or model
-    if not hasattr(eng, "flat_param"):
+    if not hasattr(eng, "flat_param") and not hasattr(eng, "flat_buffers"):
         raise capi.Yb200Error("optimizer needs a model that exposes the engine's flat_param / flat_grad / param_layout")
     if type(model).__name__ == "DistributedDataParallel":
         raise capi.Yb200Error("the flat optimizer writes gradients straight into the flat buffer, so torch DDP's per-parameter reducer hooks never "
@@ -190,10 +232,19 @@ def _build(cfg, model, kind, **kw):
     overrides = {}
     for d in _solver(cfg, "LR_MULTIPLIER_OVERWRITE", None) or []:
         overrides.update(d)  # build.py:226-231 _merge_dict
-    segs = param_segments(eng.param_layout, eng.flat_param.numel(), _solver(cfg, "WEIGHT_DECAY", 1e-4), _solver(cfg, "WEIGHT_DECAY_NORM", None),
-                          _solver(cfg, "WEIGHT_DECAY_BIAS", None), bias_lr_factor=_solver(cfg, "BIAS_LR_FACTOR", 1.0),
-                          lr_multipliers_overwrite=overrides, norm_param_names=getattr(eng, "norm_param_names", None))
-    return FlatOptimizer(eng.flat_param, eng.flat_grad, segs, _solver(cfg, "BASE_LR", 0.001), kind, clip_norm=_clip_norm(cfg), **kw)
+    if hasattr(eng, "flat_buffers"):
+        bufs = eng.flat_buffers()
+    else:
+        bufs = [(eng.flat_param, eng.flat_grad, eng.param_layout, getattr(eng, "norm_param_names", None))]
+    if len(bufs) > 1 and _clip_norm(cfg) > 0:
+        raise capi.Yb200Error("full-model gradient clipping over several flat buffers is not implemented")
+    opts = []
+    for flat_param, flat_grad, layout, norm_names in bufs:
+        segs = param_segments(layout, flat_param.numel(), _solver(cfg, "WEIGHT_DECAY", 1e-4), _solver(cfg, "WEIGHT_DECAY_NORM", None),
+                              _solver(cfg, "WEIGHT_DECAY_BIAS", None), bias_lr_factor=_solver(cfg, "BIAS_LR_FACTOR", 1.0),
+                              lr_multipliers_overwrite=overrides, norm_param_names=norm_names)
+        opts.append(FlatOptimizer(flat_param, flat_grad, segs, _solver(cfg, "BASE_LR", 0.001), kind, clip_norm=_clip_norm(cfg), **kw))
+    return opts[0] if len(opts) == 1 else FlatOptimizerGroup(opts)
 
 
 def sgd(cfg, model):
