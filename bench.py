@@ -385,55 +385,71 @@ def main():
         opt = yopt.build_optimizer_mapper(cfg, model)  # one fused SGD launch over the flat buffers (optimizer/build.py:234-245)
         opt.grad_scale = 1.0 / world                    # the mean of DDP, folded into the update
 
-    def train_step():
-        eng.train_step()
-        if opt is not None and world == 1:
-            opt.step()
+    # N = 1: the whole step (forward, backward, optimizer) is ONE CUDA graph.
+    # N > 1: the step is three graphs -- [forward + loss + head backward], [neck backward], [backbone backward] -- and the gradient bucket of
+    # each finished range is all-reduced (NCCL, communication stream) while the next graph runs (yolov7_d2_b200.dist.GradientBuckets);
+    # the optimizer step follows the last reduction.
+    from yolov7_d2_b200.dist import GradientBuckets
+    gb = GradientBuckets(eng) if world > 1 else None
+    n_seg = 3 if world > 1 else 1
 
-    def step_eager():
-        eng.train_step()
-        if world > 1:
-            dist.all_reduce(flat_grad)  # the single gradient all-reduce of the path (sum; the 1/world is folded into the update)
-        if opt is not None:
-            opt.step()
+    def segment(i):
+        if world == 1:
+            eng.train_step()
+            if opt is not None:
+                opt.step()
+            return
+        if i == 0:
+            eng.pack_weights()
+            eng.preprocess()
+            eng.forward_features(True)
+            eng.assign_and_loss(True)
+        eng.backward(False, eng.ranges[gb.PARTS[i]], fresh=(i == 0))
+
+    graphs = None
+
+    def step():
+        for i in range(n_seg):
+            if graphs is not None:
+                graphs[i].replay()
+            else:
+                segment(i)
+            if gb is not None:
+                gb.reduce_part(i)
+        if gb is not None:
+            gb.wait()
+            if opt is not None:
+                opt.step()
 
     for _ in range(max(args.warmup, 3)):
-        step_eager()
+        step()
     torch.cuda.synchronize()
     launches_per_step = eng.kernel_launches // max(args.warmup, 3)
 
-    graph = None
     if not args.no_graph:
-        # N = 1: the whole step (forward, backward, optimizer) is one graph.  N > 1: forward + backward are replayed as a graph, the NCCL
-        # all-reduce and the optimizer step follow on the same stream (capture is thread-local: NCCL's watchdog thread polls CUDA events)
         try:
-            g = torch.cuda.CUDAGraph()
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                train_step()
+                for i in range(n_seg):
+                    segment(i)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                train_step()
-            graph = g
+            gs = []
+            for i in range(n_seg):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    segment(i)
+                gs.append(g)
+            graphs = gs
             for _ in range(2):
-                graph.replay()
+                step()
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); timing eager launches\n")
-            graph = None
+            graphs = None
             torch.cuda.synchronize()
-
-    def step():
-        if graph is not None:
-            graph.replay()
-            if world > 1:
-                dist.all_reduce(flat_grad)
-                if opt is not None:
-                    opt.step()
-        else:
-            step_eager()
+    graph = graphs
 
     def barrier():
         if world > 1:
@@ -618,6 +634,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": graph is not None,
                            "optimizer": None if opt is None else "fused SGD step inside the timed step (momentum 0.9, wd 5e-4, lr %g)" % BENCH_LR,
+                           "allreduce": None if world == 1 else "3 gradient buckets (head / neck / backbone+BN), NCCL all-reduce of each overlapped with the backward of the next range",
                            "l2": "per-step working set (~%.0f GB of activations and gradients) exceeds the 126 MB L2; no explicit flush" % (0.245 * B)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "kernel_classes": classes, "cpu_baseline": cpu, "library_bar": lib_bar, "nms": nms, "convnext": cnx_line,
                 "loss": final_loss}

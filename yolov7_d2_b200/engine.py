@@ -681,14 +681,13 @@ class YoloxEngine:
                     self._bn_fuse_idx.setdefault(key, (op_index[key[1]], []))[1].append(op_index[id(op)])
 
     def _range_fusable(self, op_range):
-        """a partial backward may keep the fused statistics when it runs to the end of the plan and no fused launch inside the range feeds
-        the accumulators of a BatchNorm outside it"""
+        """a partial backward keeps the fused statistics when every fused launch has its writer and its producers on the same side of the
+        range boundaries (otherwise accumulators would be fed without being consumed, or consumed without being fed)"""
         if op_range is None:
             return True
         lo, hi = op_range
-        if hi != len(self.ops):
-            return False
-        return all(min(prods) >= lo for w, prods in self._bn_fuse_idx.values() if w >= lo)
+        inside = lambda i: lo <= i < hi
+        return all(all(inside(p) == inside(w) for p in prods) for w, prods in self._bn_fuse_idx.values())
 
     def _bn_segments(self, key):
         """ctypes array of yb200_bnbwd_seg for the data-gradient launch `key` (None when nothing is fused into it)"""
@@ -759,18 +758,20 @@ class YoloxEngine:
             capi.check(L.yb200_conv2d_wgrad(x_act, dz_act, ksize, stride, cin_real, capi.ptr(gdst), acc, capi.ptr(self.ws),
                                             ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad " + label)
 
-    def backward(self, accumulate=False, op_range=None, seeded=()):
+    def backward(self, accumulate=False, op_range=None, seeded=(), fresh=True):
         """op_range = (lo, hi): backward of self.ops[lo:hi] only, from gradients the caller has already stored in the gradient buffers of
-        the `seeded` views (standalone backbone / neck / head, modeling.py).  Partial passes run every BatchNorm backward in two passes:
-        the fused-statistics plan assumes the whole network."""
+        the `seeded` views (standalone backbone / neck / head, modeling.py), or -- fresh=False -- continuing a backward pass that earlier
+        calls ran over the later ranges (dist.GradientBuckets: the gradient bucket of a finished range is all-reduced while the next range
+        computes).  A range keeps the fused BatchNorm statistics only if no fused launch pairs an op inside it with one outside."""
         if self.strict:
             raise capi.Yb200Error("strict mode is a forward / loss verification mode: no backward (use the default engine for training)")
         L, sp = self.L, capi.stream_ptr()
         nb = self.nbn
         f8 = self.flat_stats
         acc = 1 if accumulate else 0
-        for b in self.bufs.values():
-            b.written = []
+        if fresh:
+            for b in self.bufs.values():
+                b.written = []
         for v in seeded:
             v.buf.written.append((v.off, v.off + v.c))
         self._fuse_active = self._range_fusable(op_range)
