@@ -177,3 +177,44 @@ def test_decoder_layer_backward_matches_oracle(cuda):
         chk(a.grad, r.grad, m.grad, k + " gradient")
     for name, p in layer.named_parameters():
         chk(p.grad, ref_sd["l." + name].grad, emu_sd["l." + name].grad, name)
+
+
+def test_transformer_stack_forward_and_backward(cuda):
+    """`Transformer` (detr_backbone.py:25-126): encoder stack -> decoder stack with the final LayerNorm and return_intermediate, against
+    the composed oracle layers (oracle/detr_oracle.py, pinned to the reference layers by tests/golden/detr.npz); gradients flow to every
+    parameter and to the inputs."""
+    from yolov7_d2_b200.detr import Transformer
+
+    d, nhead, ffn, bs, h, w, nq = 256, 8, 512, 2, 6, 9, 20
+    torch.manual_seed(0)
+    model = Transformer(d, nhead, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=ffn, dropout=0.0, return_intermediate_dec=True)
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(bs, d, h, w, generator=g).to(cuda).requires_grad_(True)
+    pos = torch.randn(bs, d, h, w, generator=g).to(cuda)
+    mask = torch.zeros(bs, h, w, dtype=torch.bool)
+    mask[1, :, 6:] = True
+    query = torch.randn(nq, d, generator=g).to(cuda)
+    hs, memory = model(src, mask.to(cuda), query, pos)
+    assert tuple(hs.shape) == (2, bs, nq, d) and tuple(memory.shape) == (bs, d, h, w)
+    # oracle composition with the same parameters
+    sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
+    s = src.detach().cpu().flatten(2).permute(2, 0, 1)
+    p = pos.cpu().flatten(2).permute(2, 0, 1)
+    q = query.cpu().unsqueeze(1).repeat(1, bs, 1)
+    m = mask.flatten(1)
+    mem = s
+    for i in range(2):
+        mem = dto.encoder_layer_post(mem, sd, f"encoder.layers.{i}.", nhead, m, p)
+    out, inter = torch.zeros_like(q), []
+    for i in range(2):
+        out = dto.decoder_layer_post(out, mem, sd, f"decoder.layers.{i}.", nhead, m, p, q)
+        inter.append(torch.nn.functional.layer_norm(out, (d,), sd["decoder.norm.weight"], sd["decoder.norm.bias"]))
+    ref_hs = torch.stack(inter).transpose(1, 2)
+    err = (hs.detach().cpu() - ref_hs).abs().max().item() / ref_hs.abs().max().item()
+    assert err <= 0.05, err  # bf16 storage through 4 layers
+    merr = (memory.detach().cpu() - mem.permute(1, 2, 0).view(bs, d, h, w)).abs().max().item() / mem.abs().max().item()
+    assert merr <= 0.05, merr
+    (hs.float().square().mean() + memory.float().mean()).backward()
+    assert src.grad is not None and torch.isfinite(src.grad).all() and float(src.grad.abs().sum()) > 0
+    missing = [n for n, prm in model.named_parameters() if prm.grad is None or not torch.isfinite(prm.grad).all()]
+    assert not missing, missing[:5]

@@ -237,6 +237,7 @@ class _LayerBase(nn.Module):
         if normalize_before:
             raise capi.Yb200Error("normalize_before=True (forward_pre) is not implemented")
         self.d_model, self.nhead = d_model, nhead
+        self._ctor = (d_model, nhead, dim_feedforward, dropout, activation, normalize_before, device)
         self.linear1 = _Lin(d_model, dim_feedforward, device)
         self.linear2 = _Lin(dim_feedforward, d_model, device)
         self.k = _Kernels()
@@ -504,3 +505,129 @@ class TransformerDecoderLayer(_LayerBase):
         a = kn.attention((q, 0, e), (kv, 0, e), (kv, e, e), _mask_u8(memory_key_padding_mask), self.nhead)
         x = kn.layernorm(kn.linear(a, att.out_proj.weight, att.out_proj.bias, residual=x), self.norm2.weight, self.norm2.bias)
         return _lb(self._ffn(x, self.norm3))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# the stack: Transformer / TransformerEncoder / TransformerDecoder   (detr_backbone.py:25-126)
+# ------------------------------------------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension of a seq-first [L, B, E] fp32 tensor on the LayerNorm kernels (forward + backward)"""
+
+    @staticmethod
+    def forward(ctx, k, x, weight, bias):
+        xb = _bl(x)
+        y, stats = k.layernorm_train(xb, weight, bias)
+        ctx.k = k
+        ctx.save_for_backward(xb, stats, weight)
+        return _lb(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, stats, weight = ctx.saved_tensors
+        dx, gw, gb = ctx.k.layernorm_bwd(_bl(g), xb, stats, weight)
+        return None, _lb(dx), gw, gb
+
+
+class LayerNorm(nn.Module):
+    """`nn.LayerNorm(d_model)` of the stack (the decoder's final / intermediate norm, detr_backbone.py:37-41,118-124)"""
+
+    def __init__(self, d_model, device="cuda"):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d_model, device=device))
+        self.bias = nn.Parameter(torch.zeros(d_model, device=device))
+        self.k = _Kernels()
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise capi.Yb200Error("DETR layers: inputs must be CUDA tensors (no CPU path)")
+        if TRAINING_PATH and torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return _LayerNormFn.apply(self.k, x, self.weight, self.bias)
+        with torch.no_grad():
+            return _lb(self.k.layernorm(_bl(x), self.weight, self.bias))
+
+
+def _clone_layer(layer):
+    """`_get_clones` (detr_backbone.py:281-282): a new layer of the same shape carrying a copy of the prototype's parameters"""
+    new = type(layer)(*layer._ctor)
+    new.load_state_dict(layer.state_dict())
+    return new
+
+
+class TransformerEncoder(nn.Module):
+    """detr_backbone.py:69-90; `layers` are independent TransformerEncoderLayer modules (the reference deep-copies one prototype)"""
+
+    def __init__(self, encoder_layer, num_layers, norm=None):
+        super().__init__()
+        self.layers = nn.ModuleList([encoder_layer] + [_clone_layer(encoder_layer) for _ in range(num_layers - 1)])
+        self.num_layers = num_layers
+        self.norm = norm
+
+    def forward(self, src, mask=None, src_key_padding_mask=None, pos=None):
+        output = src
+        for layer in self.layers:
+            output = layer(output, src_mask=mask, src_key_padding_mask=src_key_padding_mask, pos=pos)
+        if self.norm is not None:
+            output = self.norm(output)
+        return output
+
+
+class TransformerDecoder(nn.Module):
+    """detr_backbone.py:93-126: optional stack of the normalised intermediate outputs (auxiliary losses of DETR)"""
+
+    def __init__(self, decoder_layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        self.layers = nn.ModuleList([decoder_layer] + [_clone_layer(decoder_layer) for _ in range(num_layers - 1)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.return_intermediate = return_intermediate
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
+        output = tgt
+        intermediate = []
+        for layer in self.layers:
+            output = layer(output, memory, tgt_mask=tgt_mask, memory_mask=memory_mask, tgt_key_padding_mask=tgt_key_padding_mask,
+                           memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos)
+            if self.return_intermediate:
+                intermediate.append(self.norm(output))
+        if self.norm is not None:
+            output = self.norm(output)
+            if self.return_intermediate:
+                intermediate.pop()
+                intermediate.append(output)
+        if self.return_intermediate:
+            return torch.stack(intermediate)
+        return output.unsqueeze(0)
+
+
+class Transformer(nn.Module):
+    """detr_backbone.py:25-66: encoder stack over the flattened feature map, decoder stack over the object queries.
+    forward(src [B,C,H,W], mask [B,H,W] bool, query_embed [Q,C], pos_embed [B,C,H,W]) -> (hs [layers or 1, B, Q, C], memory [B,C,H,W]).
+    Dropout (0.1 in the reference) is the identity in these layers (module docstring); normalize_before is not supported."""
+
+    def __init__(self, d_model=512, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048, dropout=0.1, activation="relu",
+                 normalize_before=False, return_intermediate_dec=False, device="cuda"):
+        super().__init__()
+        if normalize_before:
+            raise capi.Yb200Error("normalize_before=True (pre-norm) is not implemented by the B200 DETR layers")
+        enc = TransformerEncoderLayer(d_model, nhead, dim_feedforward, dropout, activation, normalize_before, device)
+        self.encoder = TransformerEncoder(enc, num_encoder_layers, None)
+        dec = TransformerDecoderLayer(d_model, nhead, dim_feedforward, dropout, activation, normalize_before, device)
+        self.decoder = TransformerDecoder(dec, num_decoder_layers, LayerNorm(d_model, device), return_intermediate=return_intermediate_dec)
+        self._reset_parameters()
+        self.d_model, self.nhead = d_model, nhead
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, src, mask, query_embed, pos_embed):
+        bs, c, h, w = src.shape
+        src = src.flatten(2).permute(2, 0, 1)
+        pos_embed = pos_embed.flatten(2).permute(2, 0, 1)
+        query_embed = query_embed.unsqueeze(1).repeat(1, bs, 1)
+        mask = mask.flatten(1)
+        tgt = torch.zeros_like(query_embed)
+        memory = self.encoder(src, src_key_padding_mask=mask, pos=pos_embed)
+        hs = self.decoder(tgt, memory, memory_key_padding_mask=mask, pos=pos_embed, query_pos=query_embed)
+        return hs.transpose(1, 2), memory.permute(1, 2, 0).view(bs, c, h, w)
