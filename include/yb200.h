@@ -173,6 +173,16 @@ int yb200_yolox_loss(const float* outputs, const float* labels, int batch, int n
 int yb200_head_bias_grad(double* bias_acc, int num_levels, int channels, int level, float* grad_reg_bias4,
                          float* grad_obj_bias1, float* grad_cls_bias, int accumulate, void* stream);
 
+/* All convolution weights of a plan repacked in ONE launch (same result as n calls of yb200_pack_conv_weight).  table / prefix live in
+ * DEVICE memory and are built once per plan: prefix[i] = sum of cout_pad*k*k*cin_pad over layers < i, prefix[n] = total.               */
+typedef struct yb200_pack_desc {
+  const float* w_oihw;
+  void* w_fwd;      /* [cout_pad][k*k][cin_pad] bf16, may be NULL */
+  void* w_dgrad;    /* [cin_pad][k*k][cout_pad] bf16, may be NULL */
+  int32_t cout, cin, ksize, cout_pad, cin_pad, reserved;
+} yb200_pack_desc;
+int yb200_pack_conv_weights_batched(const yb200_pack_desc* table_dev, const int64_t* prefix_dev, int n, int64_t total, void* stream);
+
 /* ---- strict mode: fp32-grade forward on the same tensor-core kernels -------------------------------- */
 /* SPLIT storage: an activation a is the sum of `planes` bf16 values a0 = bf16(a), a1 = bf16(a - a0) [, a2 = bf16(a - a0 - a1)]:
  * 16 significant bits with planes = 2, the full 24 bits of fp32 with planes = 3.  All planes live in one NHWC bf16 buffer,

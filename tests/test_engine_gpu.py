@@ -192,11 +192,13 @@ def test_eval_forward_matches_oracle(step):
 
 
 def test_fused_bn_backward_statistics_equal_the_two_pass_path(step, cuda, monkeypatch):
-    """YB200_BN_FUSE=0 (separate reduction kernel for every BatchNorm) vs the default (statistics from the data-gradient epilogue where the
-    plan allows): same step, same gradients up to 16-bit storage noise"""
+    """YB200_BN_FUSE=1 (BatchNorm-backward statistics from the data-gradient epilogue where the plan allows) vs the default two-pass kernels:
+    same step, same gradients up to 16-bit storage noise"""
     from yolov7_d2_b200.engine import YoloxEngine
 
-    eng, sd0 = step["eng"], step["sd0"]
+    sd0 = step["sd0"]
+    monkeypatch.setenv("YB200_BN_FUSE", "1")
+    eng = YoloxEngine(step["eng"].n, step["eng"].h, step["eng"].w, device=cuda)
     assert sum(hd.fused_stats for op in eng.ops if hasattr(op, "heads") for hd in op.heads) >= 40, "the plan fuses most BatchNorm layers"
     monkeypatch.setenv("YB200_BN_FUSE", "0")
     ref = YoloxEngine(eng.n, eng.h, eng.w, device=cuda)

@@ -51,6 +51,13 @@ class BnBwdSeg(ctypes.Structure):
     ]
 
 
+class PackDesc(ctypes.Structure):
+    """mirror of `yb200_pack_desc` (include/yb200.h)"""
+
+    _fields_ = [("w_oihw", c_void_p), ("w_fwd", c_void_p), ("w_dgrad", c_void_p), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32),
+                ("ksize", ctypes.c_int32), ("cout_pad", ctypes.c_int32), ("cin_pad", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 def declared_symbols(header_path=HEADER_PATH):
     """Every function the public header declares (used by the CPU test that checks the exports)."""
     with open(header_path) as fh:

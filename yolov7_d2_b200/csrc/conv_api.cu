@@ -237,6 +237,38 @@ static int pack_weight_impl(const float* w_oihw, const float* cout_scale, int co
   return 0;
 }
 
+// every convolution of a plan in ONE launch: the per-layer kernels are a few microseconds of work each, so ~70 launches per step are pure
+// launch latency at the head of the step.  `table` (device memory, built once per plan) lists the layers; `prefix[i]` = padded elements of
+// layers 0..i-1 (prefix[n] = total), so a thread finds its layer by binary search.
+__global__ void pack_conv_weights_batched_kernel(const yb200_pack_desc* __restrict__ table, const long long* __restrict__ prefix, int n) {
+  const long long total = prefix[n];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const yb200_pack_desc d = table[lo];
+    const long long e = i - prefix[lo];
+    const int taps = d.ksize * d.ksize;
+    const int ci = static_cast<int>(e % d.cin_pad);
+    const int t = static_cast<int>((e / d.cin_pad) % taps);
+    const int co = static_cast<int>(e / (1LL * d.cin_pad * taps));
+    const float v = (co < d.cout && ci < d.cin) ? d.w_oihw[(1LL * co * d.cin + ci) * taps + t] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    if (d.w_fwd) static_cast<__nv_bfloat16*>(d.w_fwd)[e] = b;
+    if (d.w_dgrad) static_cast<__nv_bfloat16*>(d.w_dgrad)[(1LL * ci * taps + t) * d.cout_pad + co] = b;
+  }
+}
+
+extern "C" int yb200_pack_conv_weights_batched(const yb200_pack_desc* table_dev, const int64_t* prefix_dev, int n, int64_t total, void* stream) {
+  YB_REQUIRE(table_dev && prefix_dev && n > 0 && total > 0, YB200_ERR_INVALID, "pack_conv_weights_batched: bad arguments");
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * sm_count()));
+  pack_conv_weights_batched_kernel<<<blocks, 256, 0, as_stream(stream)>>>(table_dev, reinterpret_cast<const long long*>(prefix_dev), n);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, void* w_fwd,
                                       void* w_dgrad, void* stream) {
   return pack_weight_impl(w_oihw, nullptr, cout, cin, ksize, cout_pad, cin_pad, w_fwd, w_dgrad, stream);

@@ -262,7 +262,8 @@ __device__ __forceinline__ float silu_grad(float u, float d) {  // d * d/du [u *
 // pass 1: per channel  S1 = sum du,  S2 = sum du * z   (dgamma = invstd * (S2 - mean * S1), dbeta = S1)
 // Block reduction in a fixed order (warp shuffles, then one shared-memory row per warp summed sequentially): two runs on
 // the same data produce the same fp32 block partials; only the final fp64 atomics are unordered.
-__global__ void __launch_bounds__(kEwThreads, 3)
+template <int U, int MINB, bool SIMPLE>
+__global__ void __launch_bounds__(kEwThreads, MINB)
 bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, unsigned npix,
                           int iters, int rev) {
@@ -276,8 +277,7 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // rev: start at the tail (written last by the data-gradient kernel, still in L2) and finish at the head, which the apply pass reads first
   const unsigned p0 = (rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.y * iters) + threadIdx.y;
-  const bool simple = !da.has_b && !da.has_up;
-  constexpr int U = 2;
+  constexpr bool simple = SIMPLE;  // one gradient source (the common case): leaner code, more resident blocks
 #pragma unroll 1
   for (int it0 = 0; it0 < iters; it0 += U) {
     uint4 zq[U], dq[U];
@@ -648,14 +648,32 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
   const bool red_shuffle = cv < 32 && (cv & (cv - 1)) == 0;
   const int red_rows = red_shuffle ? static_cast<int>(block.x * block.y) / 32 : static_cast<int>(block.y);
   const size_t red_smem = static_cast<size_t>(red_rows) * 2 * z->c * sizeof(float);
-  static size_t red_smem_set = 48 * 1024;
-  if (red_smem > red_smem_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(bn_silu_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(red_smem)));
-    red_smem_set = red_smem;
+  // tuning knob (tools/bench_bn.py): YB200_BN_RED = "U:MINB:ITERS" -- loads in flight per thread, resident blocks per SM, pixels per thread
+  static int red_u = -1, red_minb = 3, red_it = 0;
+  if (red_u < 0) {
+    red_u = 2;
+    const char* e = getenv("YB200_BN_RED");
+    if (e) sscanf(e, "%d:%d:%d", &red_u, &red_minb, &red_it);
   }
+  if (red_it > 0) red_iters = red_it;
+  const unsigned grid_r2 = static_cast<unsigned>((npix + block.y * red_iters - 1) / (block.y * red_iters));
   if (!stats_ready) {
-    bn_silu_bwd_reduce_kernel<<<grid_r, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
-                                                                static_cast<unsigned>(npix), red_iters, l2_order());
+    if (src.has_b || src.has_up) {  // fan-out / upsampled gradient sources: the general kernel
+      if (red_smem > 48 * 1024)
+        YB_CHECK_CUDA(cudaFuncSetAttribute(bn_silu_bwd_reduce_kernel<2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(red_smem)));
+      bn_silu_bwd_reduce_kernel<2, 3, false><<<grid_r2, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+                                                                               static_cast<unsigned>(npix), red_iters, l2_order());
+    } else
+#define YB_RED(UU, MB)                                                                                                                     \
+  if (red_u == UU && red_minb == MB) {                                                                                                     \
+    if (red_smem > 48 * 1024)                                                                                                              \
+      YB_CHECK_CUDA(cudaFuncSetAttribute(bn_silu_bwd_reduce_kernel<UU, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(red_smem))); \
+    bn_silu_bwd_reduce_kernel<UU, MB, true><<<grid_r2, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,   \
+                                                                        static_cast<unsigned>(npix), red_iters, l2_order());                \
+  } else
+    YB_RED(1, 3) YB_RED(2, 3) YB_RED(4, 3) YB_RED(1, 4) YB_RED(2, 4) YB_RED(4, 4) YB_RED(2, 2) YB_RED(4, 2) YB_RED(1, 6) YB_RED(2, 6)
+    return fail(YB200_ERR_INVALID, "YB200_BN_RED: no reduce variant U=%d MINB=%d", red_u, red_minb);
+#undef YB_RED
     YB_CHECK_CUDA(cudaGetLastError());
   }
   const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));

@@ -391,6 +391,7 @@ class YoloxEngine:
         self._fork_evt = torch.cuda.Event()
         self.trace = None  # set to [] to record (label, launches) per call for tools/summarize_launches.py
         self._ev = None    # profile_step(): (label, class, launches, bytes, flops, event) per call
+        self._pack_table = None
 
     def _count(self, k=1, label=None, cls=None, nbytes=0.0, flops=0.0):
         """k = number of kernels the preceding C-ABI call(s) launched (memsets excluded); label feeds the per-layer profile.
@@ -467,17 +468,27 @@ class YoloxEngine:
                     capi.check(L.yb200_pack_conv_weight_split(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, self.planes, capi.ptr(op.wr_split), sp), "pack reg+obj")
                     self._count(2, "pack split preds")
             return
-        for op in self.ops:
-            if isinstance(op, ConvOp):
-                capi.check(L.yb200_pack_conv_weight(capi.ptr(op.w_src), op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad, capi.ptr(op.w_fwd),
-                                                    capi.ptr(op.w_dgrad), sp), "pack")
-                self._count(1, "pack " + op.prefixes[0], "pack_weights", 4.0 * op.w_src.numel() * len(op.prefixes) + 2.0 * op.w_fwd.numel() * (1 if op.first else 2))
-            elif isinstance(op, PredOp):
-                capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wc_src), self.nc, self.hc, 1, self.nc, self.hc, capi.ptr(op.wc_fwd),
-                                                    capi.ptr(op.wc_dgrad), sp), "pack cls")
-                capi.check(L.yb200_pack_conv_weight(capi.ptr(op.wr_src), 5, self.hc, 1, 16, self.hc, capi.ptr(op.wr_fwd), capi.ptr(op.wr_dgrad),
-                                                    sp), "pack reg+obj")
-                self._count(2, "pack preds", "pack_weights", 10.0 * (self.nc + 16) * self.hc)
+        if self._pack_table is None:
+            # one launch for every layer of the plan: the layer table lives in device memory (built once; the pointers are plan constants)
+            rows = []
+            for op in self.ops:
+                if isinstance(op, ConvOp):
+                    rows.append((op.w_src, op.w_fwd, op.w_dgrad, op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad))
+                elif isinstance(op, PredOp):
+                    rows.append((op.wc_src, op.wc_fwd, op.wc_dgrad, self.nc, self.hc, 1, self.nc, self.hc))
+                    rows.append((op.wr_src, op.wr_fwd, op.wr_dgrad, 5, self.hc, 1, 16, self.hc))
+            arr = (capi.PackDesc * len(rows))()
+            prefix = [0]
+            for d, (src, wf, wd, cout, cin, k, cop, cip) in zip(arr, rows):
+                d.w_oihw, d.w_fwd, d.w_dgrad = src.data_ptr(), wf.data_ptr(), (wd.data_ptr() if wd is not None else None)
+                d.cout, d.cin, d.ksize, d.cout_pad, d.cin_pad = cout, cin, k, cop, cip
+                prefix.append(prefix[-1] + cop * k * k * cip)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+            self._pack_table = (raw, torch.tensor(prefix, dtype=torch.int64, device=self.dev), len(rows), prefix[-1],
+                                4.0 * sum(r[0].numel() for r in rows) + 2.0 * sum(prefix[-1:]) * 2)
+        raw, prefix, n, total, nbytes = self._pack_table
+        capi.check(L.yb200_pack_conv_weights_batched(capi.ptr(raw), capi.ptr(prefix), n, ctypes.c_int64(total), sp), "pack weights")
+        self._count(1, "pack all weights", "pack_weights", nbytes)
 
     def preprocess(self):
         """images_u8 [N,3,H,W] (device) -> focus buffer"""
@@ -641,7 +652,8 @@ class YoloxEngine:
         of its output?  That launch's epilogue then also performs the reduction pass of the head's BatchNorm backward
         (yb200_conv2d_dgrad_bnbwd), and the head only needs the apply pass.  Not fused: heads with an upsampled copy (their gradient has a
         second, 2x2-pooled source), heads whose gradient is finished by a non-convolution (SPP), gradient tensors of >= 256 channels and
-        more than two heads per launch.  YB200_BN_FUSE=0 disables the fusion (A/B runs)."""
+        more than two heads per launch.  Opt-in (YB200_BN_FUSE=1): measured on B200 (profiles/r2_bn_fusion_ab.md) the statistics cost the
+        epilogue-bound data-gradient kernels more (+3.4 ms per step) than the removed reduction pass saves (-2.4 ms), until z is staged by TMA."""
         self._bn_fuse = {}
         self._bn_fuse_idx = {}  # key -> (index of the writing op, [indices of the producing ops])
         op_index = {id(op): i for i, op in enumerate(self.ops)}
@@ -649,7 +661,7 @@ class YoloxEngine:
             if isinstance(op, ConvOp):
                 for hd in op.heads:
                     hd.fused_stats = False
-        if self.strict or os.environ.get("YB200_BN_FUSE", "1") == "0":
+        if self.strict or os.environ.get("YB200_BN_FUSE", "0") != "1":
             return
         writers = {}  # id(buffer) -> [(lo, hi, key)] in backward order
         for op in reversed(self.ops):
