@@ -475,7 +475,7 @@ def main():
     # ---- roofline: every C-ABI call of the step timed live with CUDA events on the launch stream (eager launches, weight gradients serialised
     # on the same stream), grouped into kernel classes; the class with the LARGEST summed time is the one reported ----
     pk = peaks()
-    roof, classes = None, None
+    roof, classes, top_calls = None, None, None
     if rank == 0:
         calls = eng.profile_step(reps=3)
         agg = {}
@@ -491,6 +491,10 @@ def main():
             classes.append({"class": name, "launches_per_step": a["launches"], "ms_per_step": round(a["ms"], 4), "share": round(a["ms"] / serial_ms, 4),
                             "algorithmic_GB": round(a["bytes"] / 1e9, 4), "GB_per_s": round(gbs, 1), "TFLOP_per_s": round(tfs, 1),
                             "frac_of_roofline": round(a["roof_ms"] / a["ms"], 4)})
+        top_calls = []
+        for c in sorted(calls, key=lambda c: -c["ms"])[:14]:
+            fl = max(c["bytes"] / (pk["hbm"] * 1e9), c["flops"] / (pk["tf_sust"] * 1e12)) * 1e3
+            top_calls.append({"call": c["label"], "ms": round(c["ms"], 4), "floor_ms": round(fl, 4), "frac_of_roofline": round(fl / c["ms"], 3) if c["ms"] > 0 else None})
         top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         hbm_bound = top["bytes"] / (pk["hbm"] * 1e9) >= top["flops"] / (pk["tf_sust"] * 1e12)
         traffic = None
@@ -636,7 +640,7 @@ def main():
                            "optimizer": None if opt is None else "fused SGD step inside the timed step (momentum 0.9, wd 5e-4, lr %g)" % BENCH_LR,
                            "allreduce": None if world == 1 else "3 gradient buckets (head / neck / backbone+BN), NCCL all-reduce of each overlapped with the backward of the next range",
                            "l2": "per-step working set (~%.0f GB of activations and gradients) exceeds the 126 MB L2; no explicit flush" % (0.245 * B)},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "kernel_classes": classes, "cpu_baseline": cpu, "library_bar": lib_bar, "nms": nms, "convnext": cnx_line,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step + (1 if opt is not None else 0)) * args.steps, "roofline": roof, "kernel_classes": classes, "slowest_calls": top_calls if rank == 0 else None, "cpu_baseline": cpu, "library_bar": lib_bar, "nms": nms, "convnext": cnx_line,
                 "loss": final_loss}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -117,6 +117,13 @@ int yb200_bn_eval_affine(int c, const float* gamma, const float* beta, const flo
  * result is also written nearest-upsampled x2 into that view (nn.Upsample + torch.cat of yolo_pafpn.py:96-102). */
 int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const float* shift, const yb200_act* residual,
                         const yb200_act* out, const yb200_act* out_up2x, void* stream);
+/* yb200_bn_finalize + yb200_bn_apply_silu in ONE launch (training): every block derives scale / shift of its channels from the batch
+ * sums, block 0 publishes scale / shift / save_mean / save_invstd (read by the backward pass) and updates the running statistics.
+ * All pointers are per-channel arrays of this view's channels.  stat_sum / stat_sqsum are NOT cleared (clear them once per step).      */
+int yb200_bn_train_apply_silu(const yb200_act* z, const double* stat_sum, const double* stat_sqsum, int64_t count,
+                              const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                              float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                              const yb200_act* residual, const yb200_act* out, const yb200_act* out_up2x, void* stream);
 /* Backward of SiLU(BN(z)) in training mode.  The incoming gradient is da [+ da2] [+ 2x2 sum-pool of da_up2x]
  * (fan-out of the activation / backward of the upsample).  Writes dz (bf16) and dgamma / dbeta (fp32, optionally
  * accumulated).  acc_dgamma / acc_dbeta: fp64 scratch [c], must be zero on entry, are zero on exit.          */

@@ -11,4 +11,10 @@ run r2_conv_128_64 "conv_gemm_persistent_kernel<${I}128, ${I}64, ${I}0>" 0 2
 run r2_stem_wgrad "wgrad_gemm_kernel<${I}64>" 6 1
 run r2_bn_bwd_reduce "bn_silu_bwd_reduce_kernel" 73 1
 run r2_bn_bwd_apply "bn_silu_bwd_apply_kernel" 73 1
-ls -la gpurun_out/r2_*.ncu-rep
+# keep gpurun_out small (64 MiB cap): export the metric tables as CSV and drop the reports
+for f in gpurun_out/r2_*.ncu-rep; do
+  ncu -i $f --page raw --csv > ${f%.ncu-rep}.raw.csv 2>/dev/null
+  ncu -i $f --page details --csv > ${f%.ncu-rep}.details.csv 2>/dev/null
+  rm -f $f
+done
+ls -la gpurun_out/ | head -40

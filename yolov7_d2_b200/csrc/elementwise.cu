@@ -165,13 +165,54 @@ __device__ __forceinline__ PixXY decode_pix(unsigned pix, int w, int h) {
 }
 
 // a = SiLU(z*scale + shift) [+ residual];  optionally also written 2x nearest-upsampled into a second view
+// Training-mode finalize folded into the apply pass (fin.ssum != nullptr): every block derives scale / shift of its channels from the batch
+// sums (a dozen fp64 operations per channel), block 0 additionally publishes scale / shift / mean / invstd for the backward pass and updates the
+// running statistics -- one launch per BatchNorm instead of two.  The sums are NOT cleared here (the plan clears all accumulators once per step).
+struct BnFinalize {
+  const double* ssum;
+  const double* ssq;
+  double count;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  float* scale_out;
+  float* shift_out;
+  float* mean_out;
+  float* invstd_out;
+};
+
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift, int has_res,
-                     int has_up, unsigned npix, int rev) {
+                     int has_up, unsigned npix, int rev, BnFinalize fin) {
   const int c8 = threadIdx.x * 8;
   float s[8], t[8];
+  if (fin.ssum != nullptr) {
+    const bool publish = blockIdx.x == 0 && threadIdx.y == 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 + k;
+      const double mean = fin.ssum[c] / fin.count;
+      double var = fin.ssq[c] / fin.count - mean * mean;  // biased variance, used for normalisation (ATen batch_norm)
+      if (var < 0) var = 0;
+      const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(fin.eps)));
+      const float g = fin.gamma[c];
+      s[k] = g * invstd;
+      t[k] = fin.beta[c] - static_cast<float>(mean) * g * invstd;
+      if (publish) {
+        fin.scale_out[c] = s[k]; fin.shift_out[c] = t[k]; fin.mean_out[c] = static_cast<float>(mean); fin.invstd_out[c] = invstd;
+        if (fin.running_mean) {
+          const double unbiased = fin.count > 1 ? var * fin.count / (fin.count - 1) : var;
+          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * static_cast<float>(mean);
+          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * static_cast<float>(unbiased);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
+  }
   // rev: walk the tensor from its end -- the convolution that produced z wrote its tail last, so the tail is what the L2 still holds
   const unsigned p0 = (rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.y * kEwIters) + threadIdx.y;
   constexpr int U = 4;  // loads of U pixels are issued before any of them is consumed
@@ -596,13 +637,13 @@ extern "C" int yb200_bn_eval_affine(int c, const float* gamma, const float* beta
   return 0;
 }
 
-extern "C" int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const float* shift, const yb200_act* residual, const yb200_act* out,
-                                   const yb200_act* out_up2x, void* stream) {
+static int bn_apply_impl(const yb200_act* z, const float* scale, const float* shift, const yb200_act* residual, const yb200_act* out,
+                         const yb200_act* out_up2x, const BnFinalize& fin, void* stream) {
   int rc;
   if ((rc = check_view(z, "bn_apply_silu z")) || (rc = check_view(out, "bn_apply_silu out"))) return rc;
   if (residual && (rc = check_view(residual, "bn_apply_silu residual"))) return rc;
   if (out_up2x && (rc = check_view(out_up2x, "bn_apply_silu out_up2x"))) return rc;
-  YB_REQUIRE(scale && shift, YB200_ERR_INVALID, "bn_apply_silu: null scale/shift");
+  YB_REQUIRE((scale && shift) || fin.ssum, YB200_ERR_INVALID, "bn_apply_silu: null scale/shift");
   YB_REQUIRE(same_shape(z, out) && (!residual || same_shape(z, residual)), YB200_ERR_INVALID, "bn_apply_silu: shape mismatch");
   YB_REQUIRE(!out_up2x || (out_up2x->n == z->n && out_up2x->h == 2 * z->h && out_up2x->w == 2 * z->w && out_up2x->c == z->c), YB200_ERR_INVALID,
              "bn_apply_silu: upsampled view must be [n,2h,2w,c]");
@@ -613,9 +654,30 @@ extern "C" int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const
   dim3 block(cv, kEwThreads / cv);
   const unsigned grid = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
   bn_apply_silu_kernel<<<grid, block, 0, as_stream(stream)>>>(vz, vo, vr, vu, scale, shift, residual != nullptr, out_up2x != nullptr,
-                                                             static_cast<unsigned>(npix), l2_order());
+                                                             static_cast<unsigned>(npix), l2_order(), fin);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int yb200_bn_apply_silu(const yb200_act* z, const float* scale, const float* shift, const yb200_act* residual, const yb200_act* out,
+                                   const yb200_act* out_up2x, void* stream) {
+  BnFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  return bn_apply_impl(z, scale, shift, residual, out, out_up2x, fin, stream);
+}
+
+extern "C" int yb200_bn_train_apply_silu(const yb200_act* z, const double* stat_sum, const double* stat_sqsum, int64_t count, const float* gamma,
+                                         const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                                         float* shift, float* save_mean, float* save_invstd, const yb200_act* residual, const yb200_act* out,
+                                         const yb200_act* out_up2x, void* stream) {
+  YB_REQUIRE(stat_sum && stat_sqsum && gamma && beta && scale && shift && save_mean && save_invstd && count > 0, YB200_ERR_INVALID,
+             "bn_train_apply_silu: null pointer / empty batch");
+  YB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), YB200_ERR_INVALID, "bn_train_apply_silu: running stats must come in pairs");
+  BnFinalize fin;
+  fin.ssum = stat_sum; fin.ssq = stat_sqsum; fin.count = static_cast<double>(count); fin.gamma = gamma; fin.beta = beta; fin.eps = eps;
+  fin.momentum = momentum; fin.running_mean = running_mean; fin.running_var = running_var; fin.scale_out = scale; fin.shift_out = shift;
+  fin.mean_out = save_mean; fin.invstd_out = save_invstd;
+  return bn_apply_impl(z, nullptr, nullptr, residual, out, out_up2x, fin, stream);
 }
 
 static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200_act* da2, const yb200_act* da_up2x, const float* scale,
@@ -649,7 +711,7 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
   const int red_rows = red_shuffle ? static_cast<int>(block.x * block.y) / 32 : static_cast<int>(block.y);
   const size_t red_smem = static_cast<size_t>(red_rows) * 2 * z->c * sizeof(float);
   // tuning knob (tools/bench_bn.py): YB200_BN_RED = "U:MINB:ITERS" -- loads in flight per thread, resident blocks per SM, pixels per thread
-  static int red_u = -1, red_minb = 3, red_it = 0;
+  static int red_u = -1, red_minb = 4, red_it = 0;  // measured best of the sweep in profiles/r2_bn_backward_sweep.md: U=2, 4 blocks / SM
   if (red_u < 0) {
     red_u = 2;
     const char* e = getenv("YB200_BN_RED");

@@ -555,6 +555,9 @@ class YoloxEngine:
         nb = self.nbn
         f8 = self.flat_stats
         lo_i, hi_i = op_range if op_range is not None else (0, len(self.ops))
+        if training:
+            f8[:2 * nb].zero_()  # BatchNorm sum / sum-of-squares accumulators of every layer: cleared once per forward (one memset)
+            self._count(1, "clear BatchNorm accumulators (memset)")
         for op in self.ops[lo_i:hi_i]:
             if isinstance(op, ConvOp):
                 o = op.bn_off
@@ -577,22 +580,27 @@ class YoloxEngine:
                 ssum = ctypes.c_void_p(f8.data_ptr() + 8 * o) if training else None
                 ssq = ctypes.c_void_p(f8.data_ptr() + 8 * (nb + o)) if training else None
                 capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, ssum, ssq, sp), op.prefixes[0])
-                if training:
-                    cnt = op.z.buf.n * op.z.buf.h * op.z.buf.w
-                    capi.check(L.yb200_bn_finalize(ssum, ssq, op.cout, ctypes.c_int64(cnt), capi.ptr(gamma), capi.ptr(beta), ctypes.c_float(BN_EPS),
-                                                   ctypes.c_float(BN_MOMENTUM), pf(self.flat_rm), pf(self.flat_rv), None, pf(self.flat_scale),
-                                                   pf(self.flat_shift), pf(self.flat_mean), pf(self.flat_invstd), sp), "bn_finalize")
-                else:
+                npx = op.z.buf.n * op.z.buf.h * op.z.buf.w
+                if not training:
                     capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm), pf(self.flat_rv),
                                                       ctypes.c_float(BN_EPS), pf(self.flat_scale), pf(self.flat_shift), sp), "bn_eval_affine")
-                self._count(2, "conv_fwd+bn_finalize %s %s" % (op.prefixes[0], self._desc(op)), "conv_fwd (conv_gemm + bn_finalize)", *self._alg_conv(op))
+                self._count(1 if training else 2, "conv_fwd %s %s" % (op.prefixes[0], self._desc(op)), "conv_fwd (conv_gemm, BN statistics in the epilogue)",
+                            *self._alg_conv(op))
                 for hd in op.heads:
                     zv = op.z.buf.view(hd.c0, hd.c)
-                    capi.check(L.yb200_bn_apply_silu(zv.act(), pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
-                                                     hd.residual.act() if hd.residual else None, hd.out.act(), hd.up.act() if hd.up else None, sp),
-                               "bn_apply_silu " + hd.prefix)
-                    npx = op.z.buf.n * op.z.buf.h * op.z.buf.w
-                    self._count(1, "bn_apply %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_apply_silu",
+                    if training:  # finalize (scale / shift, running statistics, saved mean / invstd) folded into the apply pass: one launch
+                        ho = hd.bn_off
+                        capi.check(L.yb200_bn_train_apply_silu(zv.act(), ctypes.c_void_p(f8.data_ptr() + 8 * ho), ctypes.c_void_p(f8.data_ptr() + 8 * (nb + ho)),
+                                                               ctypes.c_int64(npx), pf(gamma, hd.c0), pf(beta, hd.c0), ctypes.c_float(BN_EPS),
+                                                               ctypes.c_float(BN_MOMENTUM), pf(self.flat_rm, ho), pf(self.flat_rv, ho), pf(self.flat_scale, ho),
+                                                               pf(self.flat_shift, ho), pf(self.flat_mean, ho), pf(self.flat_invstd, ho),
+                                                               hd.residual.act() if hd.residual else None, hd.out.act(), hd.up.act() if hd.up else None, sp),
+                                   "bn_train_apply_silu " + hd.prefix)
+                    else:
+                        capi.check(L.yb200_bn_apply_silu(zv.act(), pf(self.flat_scale, hd.bn_off), pf(self.flat_shift, hd.bn_off),
+                                                         hd.residual.act() if hd.residual else None, hd.out.act(), hd.up.act() if hd.up else None, sp),
+                                   "bn_apply_silu " + hd.prefix)
+                    self._count(1, "bn_apply %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_apply_silu (+ finalize)",
                                 2.0 * npx * hd.c * (2 + (1 if hd.residual else 0) + (4 if hd.up else 0)))
             elif isinstance(op, SppOp):
                 v = op.views
