@@ -71,6 +71,22 @@ def main():
            "pred_kernel": kernel.numpy(), "iam": iam.numpy(), "dims": np.array([dim, nm, kd, nc, convs, cin])}
     np.savez_compressed(OUT, **res)
     print("wrote", OUT, "%.1f KB" % (os.path.getsize(OUT) / 1e3))
+    # GroupIAMDecoder (decoder_sparseinst.py:172-250): 4 groups
+    groups = 4
+    cfg.MODEL.SPARSE_INST.DECODER.GROUPS = groups
+    gdec = mod.GroupIAMDecoder(cfg)
+    gsd = sio.decoder_state_dict(7, in_channels=cin, dim=dim, num_masks=nm, kernel_dim=kd, num_classes=nc, num_convs=convs, groups=groups)
+    gdec.load_state_dict(gsd, strict=True)
+    gdec.eval()
+    with torch.no_grad():
+        gout = gdec(feat)
+        x = torch.cat([gdec.compute_coordinates(feat), feat], 1)
+        _, gkernel, _, giam = gdec.inst_branch(x)
+    gres = {"feat": feat.numpy(), "pred_logits": gout["pred_logits"].numpy(), "pred_masks": gout["pred_masks"].numpy(), "pred_scores": gout["pred_scores"].numpy(),
+            "pred_kernel": gkernel.numpy(), "iam": giam.numpy(), "dims": np.array([dim, nm, kd, nc, convs, cin, groups])}
+    gpath = OUT.replace("sparseinst.npz", "sparseinst_group.npz")
+    np.savez_compressed(gpath, **gres)
+    print("wrote", gpath, "%.1f KB" % (os.path.getsize(gpath) / 1e3))
 
 
 if __name__ == "__main__":

@@ -41,16 +41,39 @@ def instance_branch(features, sd, prefix="inst_branch.", num_convs=4):
     return logits, kernel, scores, iam
 
 
+def group_instance_branch(features, sd, prefix="inst_branch.", num_convs=4, groups=4):
+    """GroupInstanceBranch.forward, decoder_sparseinst.py:212-242: grouped IAM convolution (N masks per group), aggregation, the four groups of
+    one instance concatenated along the channels, fc + ReLU, then the heads"""
+    f = _stack(features, sd, prefix + "inst_convs.", num_convs)
+    iam = F.conv2d(f, sd[prefix + "iam_conv.weight"], sd[prefix + "iam_conv.bias"], padding=1, groups=groups)   # :215
+    prob = iam.sigmoid()
+    b, n = prob.shape[:2]
+    c = f.shape[1]
+    prob = prob.view(b, n, -1)
+    inst = torch.bmm(prob, f.view(b, c, -1).permute(0, 2, 1))                                                # :224
+    inst = inst / prob.sum(-1).clamp(min=1e-6, max=1e5)[:, :, None]                                         # :225-227
+    d4 = n // 4                                                                                              # :230
+    inst = inst.reshape(b, 4, d4, -1).transpose(1, 2).reshape(b, d4, -1)                                     # :231-235
+    inst = F.relu(F.linear(inst, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"]))                        # :237
+    logits = F.linear(inst, sd[prefix + "cls_score.weight"], sd[prefix + "cls_score.bias"])
+    kernel = F.linear(inst, sd[prefix + "mask_kernel.weight"], sd[prefix + "mask_kernel.bias"])
+    scores = F.linear(inst, sd[prefix + "objectness.weight"], sd[prefix + "objectness.bias"])
+    return logits, kernel, scores, iam
+
+
 def mask_branch(features, sd, prefix="mask_branch.", num_convs=4):
     """MaskBranch.forward, decoder_sparseinst.py:101-104"""
     f = _stack(features, sd, prefix + "mask_convs.", num_convs)
     return F.conv2d(f, sd[prefix + "projection.weight"], sd[prefix + "projection.bias"])
 
 
-def decoder_forward(features, sd, scale_factor=2.0, num_convs=4):
-    """BaseIAMDecoder.forward, decoder_sparseinst.py:130-169"""
+def decoder_forward(features, sd, scale_factor=2.0, num_convs=4, groups=0):
+    """BaseIAMDecoder.forward, decoder_sparseinst.py:130-169 (groups > 0: GroupIAMDecoder :245-250, the same forward with the group branch)"""
     x = torch.cat([coordinates(features), features], 1)                                                    # :131-132
-    logits, kernel, scores, iam = instance_branch(x, sd, num_convs=num_convs)
+    if groups:
+        logits, kernel, scores, iam = group_instance_branch(x, sd, num_convs=num_convs, groups=groups)
+    else:
+        logits, kernel, scores, iam = instance_branch(x, sd, num_convs=num_convs)
     mf = mask_branch(x, sd, num_convs=num_convs)
     b, c, h, w = mf.shape
     masks = torch.bmm(kernel, mf.view(b, c, h * w)).view(b, kernel.shape[1], h, w)                         # :143-146
@@ -58,7 +81,7 @@ def decoder_forward(features, sd, scale_factor=2.0, num_convs=4):
     return {"pred_logits": logits, "pred_masks": masks, "pred_scores": scores, "pred_kernel": kernel, "iam": iam, "masks_lowres": torch.bmm(kernel, mf.view(b, c, h * w)).view(b, -1, h, w)}
 
 
-def decoder_state_dict(seed=0, in_channels=256, dim=256, num_masks=100, kernel_dim=128, num_classes=80, num_convs=4, trained_like=True):
+def decoder_state_dict(seed=0, in_channels=256, dim=256, num_masks=100, kernel_dim=128, num_classes=80, num_convs=4, trained_like=True, groups=0):
     g = torch.Generator().manual_seed(seed)
 
     def rn(*s, std):
@@ -72,10 +95,13 @@ def decoder_state_dict(seed=0, in_channels=256, dim=256, num_masks=100, kernel_d
             sd[f"{br}{2 * i}.weight"] = rn(d, c, 3, 3, std=(2.0 / (9 * c)) ** 0.5)
             sd[f"{br}{2 * i}.bias"] = rn(d, std=0.05) if trained_like else torch.zeros(d)
             c = d
-    sd["inst_branch.iam_conv.weight"] = rn(num_masks, dim, 3, 3, std=0.02 if trained_like else 0.01)
-    sd["inst_branch.iam_conv.bias"] = torch.full((num_masks,), -2.0 if trained_like else -4.595) + (rn(num_masks, std=0.5) if trained_like else 0)
-    sd["inst_branch.cls_score.weight"], sd["inst_branch.cls_score.bias"] = rn(num_classes, dim, std=0.05), rn(num_classes, std=0.5) - 2.0
-    sd["inst_branch.mask_kernel.weight"], sd["inst_branch.mask_kernel.bias"] = rn(kernel_dim, dim, std=0.05), rn(kernel_dim, std=0.1)
-    sd["inst_branch.objectness.weight"], sd["inst_branch.objectness.bias"] = rn(1, dim, std=0.05), rn(1, std=0.1)
+    nm_all, hd = (num_masks * groups, dim * groups) if groups else (num_masks, dim)  # GroupInstanceBranch :182-193
+    sd["inst_branch.iam_conv.weight"] = rn(nm_all, dim // groups if groups else dim, 3, 3, std=0.02 if trained_like else 0.01)
+    sd["inst_branch.iam_conv.bias"] = torch.full((nm_all,), -2.0 if trained_like else -4.595) + (rn(nm_all, std=0.5) if trained_like else 0)
+    if groups:
+        sd["inst_branch.fc.weight"], sd["inst_branch.fc.bias"] = rn(hd, hd, std=(1.0 / hd) ** 0.5), rn(hd, std=0.05)
+    sd["inst_branch.cls_score.weight"], sd["inst_branch.cls_score.bias"] = rn(num_classes, hd, std=0.05), rn(num_classes, std=0.5) - 2.0
+    sd["inst_branch.mask_kernel.weight"], sd["inst_branch.mask_kernel.bias"] = rn(kernel_dim, hd, std=0.05), rn(kernel_dim, std=0.1)
+    sd["inst_branch.objectness.weight"], sd["inst_branch.objectness.bias"] = rn(1, hd, std=0.05), rn(1, std=0.1)
     sd["mask_branch.projection.weight"], sd["mask_branch.projection.bias"] = rn(kernel_dim, dim, 1, 1, std=(2.0 / dim) ** 0.5), rn(kernel_dim, std=0.05)
     return sd

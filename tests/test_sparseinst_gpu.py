@@ -63,3 +63,42 @@ def test_decoder_full_size_against_oracle(cuda):
     _check(out["pred_scores"], ref["pred_scores"], "objectness")
     _check(dec.last["masks_lowres"], ref["masks_lowres"], "masks before up-sampling")
     _check(out["pred_masks"], ref["pred_masks"], "masks")
+
+
+def test_group_decoder_matches_reference(cuda):
+    """GroupIAMDecoder (grouped IAM convolution, N*G maps, fc + ReLU: decoder_sparseinst.py:172-250) against the unmodified reference
+    (tests/golden/sparseinst_group.npz)"""
+    from yolov7_d2_b200.sparseinst import GroupIAMDecoder
+
+    gold = np.load(GOLD.replace("sparseinst.npz", "sparseinst_group.npz"), allow_pickle=False)
+    dim, nm, kd, nc, convs, cin, groups = (int(v) for v in gold["dims"])
+    cfg = _cfg(dim, nm, kd, nc, convs, cin, iam=True)
+    cfg.MODEL.SPARSE_INST.DECODER.GROUPS = groups
+    dec = GroupIAMDecoder(cfg)
+    sd = sio.decoder_state_dict(7, in_channels=cin, dim=dim, num_masks=nm, kernel_dim=kd, num_classes=nc, num_convs=convs, groups=groups)
+    dec.load_state_dict({k: v.to(cuda) for k, v in sd.items()}, strict=True)
+    out = dec(torch.tensor(gold["feat"]).to(cuda))
+    _check(dec.last["iam"].permute(0, 3, 1, 2), gold["iam"], "grouped instance activation maps")
+    _check(dec.last["pred_kernel"], gold["pred_kernel"], "mask kernels")
+    _check(out["pred_logits"], gold["pred_logits"], "class logits")
+    _check(out["pred_scores"], gold["pred_scores"], "objectness")
+    _check(out["pred_masks"], gold["pred_masks"], "masks")
+    assert out["pred_iam"].shape == (2, nm * groups, 24, 40)
+
+
+def test_group_decoder_full_size_against_oracle(cuda):
+    """the shipped Group-IAM configuration: 4 groups x 100 masks, dim 256 -> 1024-wide instance features, 40x40 map"""
+    from yolov7_d2_b200.sparseinst import GroupIAMDecoder
+
+    cfg = _cfg(256, 100, 128, 80, 4, 256)
+    cfg.MODEL.SPARSE_INST.DECODER.GROUPS = 4
+    dec = GroupIAMDecoder(cfg)
+    sd = sio.decoder_state_dict(11, groups=4)
+    dec.load_state_dict({k: v.to(cuda) for k, v in sd.items()}, strict=True)
+    feat = torch.randn(2, 256, 40, 40, generator=torch.Generator().manual_seed(12))
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    ref = sio.decoder_forward(feat, sd, groups=4)
+    out = dec(feat.to(cuda))
+    _check(out["pred_logits"], ref["pred_logits"], "class logits")
+    _check(out["pred_scores"], ref["pred_scores"], "objectness")
+    _check(out["pred_masks"], ref["pred_masks"], "masks")

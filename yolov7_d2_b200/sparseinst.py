@@ -67,16 +67,21 @@ class BaseIAMDecoder(nn.Module):
         prior = -4.59511985013459  # -log((1 - 0.01) / 0.01)   (:45, :54)
         self.inst_branch = nn.Module()
         self.inst_branch.inst_convs = _stack(self.num_convs, self.in_channels, self.dim, dev)
-        self.inst_branch.iam_conv = _Conv(self.dim, self.num_masks, 3, dev, 0.01)
-        with torch.no_grad():
-            self.inst_branch.iam_conv.bias.fill_(prior)
-        self.inst_branch.cls_score = _Linear(self.dim, self.num_classes, dev, bias=prior)
-        self.inst_branch.mask_kernel = _Linear(self.dim, self.kernel_dim, dev)
-        self.inst_branch.objectness = _Linear(self.dim, 1, dev)
+        self.head_dim = self._build_iam(dev, prior)  # width of the per-instance feature the heads read
+        self.inst_branch.cls_score = _Linear(self.head_dim, self.num_classes, dev, bias=prior)
+        self.inst_branch.mask_kernel = _Linear(self.head_dim, self.kernel_dim, dev)
+        self.inst_branch.objectness = _Linear(self.head_dim, 1, dev)
         self.mask_branch = nn.Module()
         self.mask_branch.mask_convs = _stack(self.mask_convs_n, self.in_channels, self.mask_dim, dev)
         self.mask_branch.projection = _Conv(self.mask_dim, self.kernel_dim, 1, dev, (2.0 / self.kernel_dim) ** 0.5)
         self.L = capi.lib()
+
+    def _build_iam(self, dev, prior):
+        """InstanceBranch (:27-60): one 3x3 convolution dim -> num_masks"""
+        self.inst_branch.iam_conv = _Conv(self.dim, self.num_masks, 3, dev, 0.01)
+        with torch.no_grad():
+            self.inst_branch.iam_conv.bias.fill_(prior)
+        return self.dim
 
     # ---- helpers -----------------------------------------------------------------------------------------------------------------
     def _pack(self, w, cout_pad, cin_pad):
@@ -111,6 +116,42 @@ class BaseIAMDecoder(nn.Module):
                                                  npad, 0, cout, 0, capi.stream_ptr()), "head")
         return out
 
+    def _aggregate(self, f, prob):
+        """inst[b] = prob[b]^T f[b] / clamp(sum prob[b], 1e-6)   (:70-76): the pixel contraction is the weight-gradient GEMM (MN-major UMMA
+        descriptors on the NHWC tiles), per image; returns bf16 [B, 1, C_prob, dim]"""
+        L, sp = self.L, capi.stream_ptr()
+        b, dev, npad = f.shape[0], f.device, prob.shape[-1]
+        inst = torch.empty(b, 1, npad, self.dim, dtype=torch.bfloat16, device=dev)
+        raw = torch.empty(npad, self.dim, device=dev)
+        norm = torch.empty(npad, device=dev)
+        f1, p1 = capi.act(f[0:1]), capi.act(prob[0:1])
+        ws_g = torch.empty(max(int(L.yb200_conv2d_wgrad_workspace(ctypes.byref(f1), ctypes.byref(p1), 1, 1)), 16), dtype=torch.uint8, device=dev)
+        ws_c = torch.empty(max(int(L.yb200_colsum_workspace(ctypes.byref(p1))), 16), dtype=torch.uint8, device=dev)
+        for i in range(b):
+            fi, pi, oi = capi.act(f[i:i + 1]), capi.act(prob[i:i + 1]), capi.act(inst[i:i + 1])
+            capi.check(L.yb200_conv2d_wgrad(ctypes.byref(fi), ctypes.byref(pi), 1, 1, self.dim, capi.ptr(raw), 0, capi.ptr(ws_g), ctypes.c_int64(ws_g.numel()), sp), "iam bmm")
+            capi.check(L.yb200_colsum(ctypes.byref(pi), ctypes.c_float(1.0), capi.ptr(norm), 0, capi.ptr(ws_c), sp), "iam normaliser")
+            capi.check(L.yb200_iam_normalize(capi.ptr(raw), capi.ptr(norm), npad, self.dim, ctypes.byref(oi), sp), "iam normalise")
+        return inst
+
+    def _instances(self, f):
+        """InstanceBranch.forward (:62-81) up to the aggregated instance features"""
+        L, sp = self.L, capi.stream_ptr()
+        b, h, w, _ = f.shape
+        dev = f.device
+        n, npad = self.num_masks, _pad16(self.num_masks)
+        iam_conv = self.inst_branch.iam_conv
+        bias = torch.full((npad,), -30.0, device=dev)
+        bias[:n] = iam_conv.bias.detach()
+        iam = torch.empty(b, h, w, npad, dtype=torch.bfloat16, device=dev)
+        fa, ia = capi.act(f), capi.act(iam)
+        capi.check(L.yb200_conv2d_affine_fwd(ctypes.byref(fa), capi.ptr(self._pack(iam_conv.weight, npad, self.dim)), None, capi.ptr(bias), None, ctypes.byref(ia), 3, 1, sp),
+                   "iam_conv")
+        prob = torch.empty_like(iam)
+        pa = capi.act(prob)
+        capi.check(L.yb200_sigmoid(ctypes.byref(ia), ctypes.byref(pa), sp), "sigmoid")
+        return self._aggregate(f, prob), iam[..., :n]
+
     # ---- forward -----------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, features):
@@ -128,28 +169,9 @@ class BaseIAMDecoder(nn.Module):
         x[..., 2:2 + c] = features.detach().permute(0, 2, 3, 1)
         # instance branch
         f = self._branch(x, self.inst_branch.inst_convs, self.num_convs)
-        n, npad = self.num_masks, _pad16(self.num_masks)
-        iam_conv = self.inst_branch.iam_conv
-        bias = torch.full((npad,), -30.0, device=dev)
-        bias[:n] = iam_conv.bias.detach()
-        iam = torch.empty(b, h, w, npad, dtype=torch.bfloat16, device=dev)
-        fa, ia = capi.act(f), capi.act(iam)
-        capi.check(L.yb200_conv2d_affine_fwd(ctypes.byref(fa), capi.ptr(self._pack(iam_conv.weight, npad, self.dim)), None, capi.ptr(bias), None, ctypes.byref(ia), 3, 1, sp),
-                   "iam_conv")
-        prob = torch.empty_like(iam)
-        pa = capi.act(prob)
-        capi.check(L.yb200_sigmoid(ctypes.byref(ia), ctypes.byref(pa), sp), "sigmoid")
-        inst = torch.empty(b, 1, npad, self.dim, dtype=torch.bfloat16, device=dev)
-        raw = torch.empty(npad, self.dim, device=dev)
-        norm = torch.empty(npad, device=dev)
-        f1, p1 = capi.act(f[0:1]), capi.act(prob[0:1])
-        ws_g = torch.empty(max(int(L.yb200_conv2d_wgrad_workspace(ctypes.byref(f1), ctypes.byref(p1), 1, 1)), 16), dtype=torch.uint8, device=dev)
-        ws_c = torch.empty(max(int(L.yb200_colsum_workspace(ctypes.byref(p1))), 16), dtype=torch.uint8, device=dev)
-        for i in range(b):  # aggregation per image (:70-76): iam_prob^T [N, HW] x features [HW, C]
-            fi, pi, oi = capi.act(f[i:i + 1]), capi.act(prob[i:i + 1]), capi.act(inst[i:i + 1])
-            capi.check(L.yb200_conv2d_wgrad(ctypes.byref(fi), ctypes.byref(pi), 1, 1, self.dim, capi.ptr(raw), 0, capi.ptr(ws_g), ctypes.c_int64(ws_g.numel()), sp), "iam bmm")
-            capi.check(L.yb200_colsum(ctypes.byref(pi), ctypes.c_float(1.0), capi.ptr(norm), 0, capi.ptr(ws_c), sp), "iam normaliser")
-            capi.check(L.yb200_iam_normalize(capi.ptr(raw), capi.ptr(norm), npad, self.dim, ctypes.byref(oi), sp), "iam normalise")
+        n = self.num_masks
+        inst, iam = self._instances(f)  # [B, 1, Npad, head_dim] bf16 instance features; iam logits [B, n, H, W]-shaped source (NHWC slice)
+        npad = inst.shape[2]
         ib = self.inst_branch
         logits = self._heads_f32(inst, ib.cls_score, self.num_classes)[:, :n]
         kernel = self._heads_f32(inst, ib.mask_kernel, self.kernel_dim)            # [B, Npad, kernel_dim] (padded instances: bias only)
@@ -168,10 +190,67 @@ class BaseIAMDecoder(nn.Module):
         pred_masks = F.interpolate(masks[:, :n], scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
         out = {"pred_logits": logits, "pred_masks": pred_masks, "pred_scores": scores}
         if self.output_iam:
-            out["pred_iam"] = F.interpolate(iam[..., :n].permute(0, 3, 1, 2).float(), scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
+            out["pred_iam"] = F.interpolate(iam.permute(0, 3, 1, 2).float(), scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
         # kept for tests / callers that want the un-interpolated tensors
-        self.last = {"pred_kernel": kernel[:, :n], "iam": iam[..., :n], "masks_lowres": masks[:, :n]}
+        self.last = {"pred_kernel": kernel[:, :n], "iam": iam, "masks_lowres": masks[:, :n]}
         return out
+
+
+class GroupIAMDecoder(BaseIAMDecoder):
+    """decoder_sparseinst.py:172-250: `GroupInstanceBranch` -- a GROUPED 3x3 IAM convolution (G groups of dim/G input channels, N maps each), the
+    aggregation over all N*G maps, the G features of one instance concatenated ([B, N, G*dim]), fc + ReLU, then the heads.  Extra cfg key
+    MODEL.SPARSE_INST.DECODER.GROUPS.  The grouped convolution is G implicit-GEMM launches on channel-slice views of the same tensors
+    (each group padded to a multiple of 8 maps with bias -30, i.e. probability 0)."""
+
+    def _build_iam(self, dev, prior):
+        self.groups = int(self._cfg_groups)
+        if self.dim % (16 * self.groups):
+            raise capi.Yb200Error("GroupIAMDecoder: INST.DIM / GROUPS must be a multiple of 16")
+        self.inst_branch.iam_conv = _Conv(self.dim // self.groups, self.num_masks * self.groups, 3, dev, 0.01)
+        with torch.no_grad():
+            self.inst_branch.iam_conv.bias.fill_(prior)
+        expand = self.dim * self.groups
+        self.inst_branch.fc = _Linear(expand, expand, dev, std=(1.0 / expand) ** 0.5)
+        return expand
+
+    def __init__(self, cfg, device="cuda"):
+        self._cfg_groups = cfg.MODEL.SPARSE_INST.DECODER.GROUPS
+        super().__init__(cfg, device)
+
+    def _instances(self, f):
+        L, sp = self.L, capi.stream_ptr()
+        b, h, w, _ = f.shape
+        dev = f.device
+        n, g = self.num_masks, self.groups
+        np8 = (n + 7) // 8 * 8                   # maps per group, padded
+        ctot = _pad16(np8 * g)
+        cg = self.dim // g
+        conv = self.inst_branch.iam_conv
+        iam = torch.zeros(b, h, w, ctot, dtype=torch.bfloat16, device=dev)
+        for k in range(g):                       # nn.Conv2d(dim, N*G, 3, padding=1, groups=G) (:186-188): group k reads channels [k*cg, (k+1)*cg)
+            bias = torch.full((np8,), -30.0, device=dev)
+            bias[:n] = conv.bias.detach()[k * n:(k + 1) * n]
+            wk = self._pack(conv.weight[k * n:(k + 1) * n], np8, cg)
+            fa, ia = capi.act(f, k * cg, cg), capi.act(iam, k * np8, np8)
+            capi.check(L.yb200_conv2d_affine_fwd(ctypes.byref(fa), capi.ptr(wk), None, capi.ptr(bias), None, ctypes.byref(ia), 3, 1, sp), "grouped iam_conv")
+        if ctot > np8 * g:
+            iam[..., np8 * g:] = -30.0           # alignment padding of the channel count: probability 0
+        prob = torch.empty_like(iam)
+        ia, pa = capi.act(iam), capi.act(prob)
+        capi.check(L.yb200_sigmoid(ctypes.byref(ia), ctypes.byref(pa), sp), "sigmoid")
+        inst = self._aggregate(f, prob)          # [B, 1, ctot, dim]; row k*np8 + i = map i of group k
+        # reshape(B, 4, N, C).transpose(1, 2).reshape(B, N, 4C) (:231-235): the G features of instance i side by side
+        v = inst[:, 0, :np8 * g].view(b, g, np8, self.dim)[:, :, :n].permute(0, 2, 1, 3).reshape(b, n, g * self.dim)
+        npad = _pad16(n)
+        x = torch.zeros(b, 1, npad, g * self.dim, dtype=torch.bfloat16, device=dev)
+        x[:, 0, :n] = v
+        fc = self.inst_branch.fc
+        y = torch.empty_like(x)
+        xa, ya = capi.act(x), capi.act(y)
+        capi.check(L.yb200_conv2d_relu_fwd(ctypes.byref(xa), capi.ptr(self._pack(fc.weight, fc.weight.shape[0], x.shape[-1])), capi.ptr(fc.bias.detach()), ctypes.byref(ya),
+                                           1, 1, sp), "fc + relu")
+        iam_out = torch.cat([iam[..., k * np8:k * np8 + n] for k in range(g)], -1)  # the reference's channel order: group-major, N per group
+        return y, iam_out
 
 
 def _register():
@@ -182,6 +261,7 @@ def _register():
     try:  # pragma: no cover
         from yolov7.modeling.transcoders.decoder_sparseinst import SPARSE_INST_DECODER_REGISTRY
         SPARSE_INST_DECODER_REGISTRY._obj_map["BaseIAMDecoder"] = BaseIAMDecoder
+        SPARSE_INST_DECODER_REGISTRY._obj_map["GroupIAMDecoder"] = GroupIAMDecoder
     except Exception:  # noqa: BLE001
         pass
 
