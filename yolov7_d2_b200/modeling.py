@@ -370,7 +370,12 @@ class _TrainStep(torch.autograd.Function):
         eng.loss_grad_only()
         if ctx.flat_grads:
             # every parameter's .grad already is its slice of the flat gradient buffer (YOLOX.attach_flat_grads): accumulate in place
-            eng.backward(accumulate=True)
+            gb = getattr(eng, "_grad_buckets", None)
+            if gb is not None:  # data parallel: backward range by range, each bucket's all-reduce overlapping the next range (dist.py)
+                gb.step_backward(accumulate=True)
+                gb.wait()
+            else:
+                eng.backward(accumulate=True)
             return (None, None) + (None,) * len(eng.param_names)
         eng.backward()
         return (None, None) + tuple(eng.grads[n].clone() for n in eng.param_names)
@@ -461,6 +466,20 @@ class YOLOX(nn.Module):
                 view.zero_()
                 p.grad = view
 
+    def enable_overlapped_allreduce(self, group=None):
+        """Data-parallel training on the flat buffers without DistributedDataParallel: after attach_flat_grads(), every backward reduces the
+        gradient in three buckets (head / neck / backbone + BatchNorm) over `group`, each NCCL all-reduce overlapping the backward of the next
+        range (yolov7_d2_b200.dist.GradientBuckets).  The SUM is left in the buffer; set optimizer.grad_scale = 1 / world_size for DDP's mean."""
+        if self._convnext:
+            raise capi.Yb200Error("enable_overlapped_allreduce: only the CSPDarknet plan is bucketed; all-reduce engine.flat_buffers() for ConvNeXt")
+        self._dp_group = (group,)
+        for eng in self._plans.values():
+            self._attach_buckets(eng)
+
+    def _attach_buckets(self, eng):
+        from .dist import GradientBuckets
+        eng._grad_buckets = GradientBuckets(eng, self._dp_group[0])
+
     def update_iter(self, i):
         self.iter = i
 
@@ -474,6 +493,8 @@ class YOLOX(nn.Module):
             self._plans[key] = YoloxEngine(batch, h, w, self.num_classes, self.width_mul, self.depth_mul, self.max_boxes_num, self.device,
                                            share_params_of=self._root)
             self._plans[key].pad_value = float(self.padded_value)  # cfg.MODEL.PADDED_VALUE (yolox.py:55, ImageList.from_tensors pad_value)
+            if getattr(self, "_dp_group", None) is not None:
+                self._attach_buckets(self._plans[key])
         return self._plans[key]
 
     def _params_in_engine_order(self):
