@@ -216,3 +216,31 @@ def test_fused_bn_backward_statistics_equal_the_two_pass_path(step, cuda, monkey
         a, b = grads[0][n].flatten().double(), grads[1][n].flatten().double()
         cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
         assert cos >= 0.999 and abs(float(a.norm() / (b.norm() + 1e-30)) - 1) <= 0.02, (n, cos)
+
+
+def test_pixel_grouped_stem_equals_plain_stem(step, cuda, monkeypatch):
+    """YB200_STEM_GROUP4 (default on): the stem convolution and its weight gradient run on [N, H, W/4, 64] views (128-byte TMA rows) with an
+    expanded weight matrix; same pre-BatchNorm output, statistics and parameter gradient as the plain 16-channel formulation"""
+    from yolov7_d2_b200.engine import YoloxEngine
+
+    sd0 = step["sd0"]
+    engs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("YB200_STEM_GROUP4", flag)
+        e = YoloxEngine(step["eng"].n, step["eng"].h, step["eng"].w, device=cuda)
+        assert e.group4 == (flag == "1")
+        e.load_state_dict(sd0)
+        e.images_u8.copy_(step["images"].to(cuda))
+        e.labels.copy_(step["labels"].to(cuda))
+        e.train_step()
+        torch.cuda.synchronize()
+        engs.append(e)
+    a, b = engs
+    za, zb = a.ops[0].z.buf.t.float(), b.ops[0].z.buf.t.float()
+    assert (za - zb).abs().max() <= 2.0 ** -9 * zb.abs().max(), "stem pre-BN output"
+    n = a.ops[0].cout
+    assert torch.allclose(a.flat_mean[:n], b.flat_mean[:n], rtol=1e-4, atol=1e-4) and torch.allclose(a.flat_invstd[:n], b.flat_invstd[:n], rtol=1e-3)
+    ga, gb = a.grads["backbone.stem.conv.conv.weight"].flatten().double(), b.grads["backbone.stem.conv.conv.weight"].flatten().double()
+    cos = float((ga @ gb) / (ga.norm() * gb.norm()))
+    assert cos >= 0.9995 and abs(float(ga.norm() / gb.norm()) - 1) <= 0.01, (cos, float(ga.norm() / gb.norm()))
+    assert torch.allclose(a.losses, b.losses, rtol=2e-3)

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-t() { eval timeout ${2:-600} python -m pytest $1 -m gpu -q -x --timeout=500 -p no:cacheprovider -s 2>&1 | tail -60 | cut -c1-500 > gpurun_out/r2_$3.log; echo "== $3: $(tail -1 gpurun_out/r2_$3.log)"; }
+t() { eval timeout ${2:-600} python -m pytest $1 -m gpu -q -x --timeout=500 -p no:cacheprovider -s 2>&1 | tail -90 | cut -c1-700 > gpurun_out/r2_$3.log; echo "== $3: $(tail -1 gpurun_out/r2_$3.log)"; }
 t "tests/test_conv_gpu.py -k 'fwd or dgrad'" 600 conv
 t "tests/test_engine_gpu.py tests/test_elementwise_gpu.py" 600 engine
 t tests/test_yolox_convnext_gpu.py 600 cnx_yolox

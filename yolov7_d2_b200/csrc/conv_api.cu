@@ -383,8 +383,22 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, num_kb), st, out_act);
 }
 
+static int conv2d_fwd_impl(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride, double* stat_sum, double* stat_sqsum,
+                           int stat_fold, void* stream);
+
 extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride,
                                 double* stat_sum, double* stat_sqsum, void* stream) {
+  return conv2d_fwd_impl(x, w_fwd, z, ksize, stride, stat_sum, stat_sqsum, 0, stream);
+}
+
+extern "C" int yb200_conv2d_fwd_fold(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride, double* stat_sum,
+                                     double* stat_sqsum, int stat_fold, void* stream) {
+  YB_REQUIRE(stat_fold > 0 && z && z->c % stat_fold == 0, YB200_ERR_INVALID, "conv2d_fwd_fold: output channels must be a multiple of stat_fold");
+  return conv2d_fwd_impl(x, w_fwd, z, ksize, stride, stat_sum, stat_sqsum, stat_fold, stream);
+}
+
+static int conv2d_fwd_impl(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride, double* stat_sum, double* stat_sqsum,
+                           int stat_fold, void* stream) {
   int rc;
   if ((rc = check_act(x, "conv2d_fwd x"))) return rc;
   if ((rc = check_act(z, "conv2d_fwd z"))) return rc;
@@ -398,6 +412,7 @@ extern "C" int yb200_conv2d_fwd(const yb200_act* x, const void* w_fwd, const yb2
   p.epi_mode = stat_sum ? EPI_F16_STATS : EPI_F16;
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sqsum;
+  p.stat_fold = stat_fold;
   return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream), 0, 1, z);
 }
 

@@ -103,6 +103,7 @@ struct ConvGemmParams {
   const float* shift;
   double* stat_sum;
   double* stat_sq;
+  int stat_fold;  // > 0: column c accumulates into statistic c % stat_fold (pixel-grouped views: several columns are the same channel)
   const __nv_bfloat16* aux_in;  // EPI_BF16_GELU_BWD: pre-activation u, same geometry as `out`
   __nv_bfloat16* aux_out;       // EPI_BF16_BIAS_GELU: where u is stored (may be null), same geometry as `out`
   ConvTap taps[kMaxTaps];
@@ -772,8 +773,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {  // BLOCK_N may exceed the 192 threads
       const float s1 = (s_part[0][0][e] + s_part[1][0][e]) + (s_part[2][0][e] + s_part[3][0][e]);
       const float s2 = (s_part[0][1][e] + s_part[1][1][e]) + (s_part[2][1][e] + s_part[3][1][e]);
-      atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s1));
-      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s2));
+      const int ch = p.stat_fold > 0 ? (col0 + e) % p.stat_fold : col0 + e;
+      atomicAdd(p.stat_sum + ch, static_cast<double>(s1));
+      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + ch, static_cast<double>(s2));
     }
   }
 }
@@ -1021,8 +1023,9 @@ conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 1) tmem_dealloc<kTmemAlloc>(tmem_base);
   if (stats && group < m_tiles) {
     for (int e = threadIdx.x; e < BLOCK_N && col0 + e < p.cout; e += blockDim.x) {
-      atomicAdd(p.stat_sum + col0 + e, static_cast<double>(s_stat[0][e]));
-      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col0 + e, static_cast<double>(s_stat[1][e]));
+      const int ch = p.stat_fold > 0 ? (col0 + e) % p.stat_fold : col0 + e;
+      atomicAdd(p.stat_sum + ch, static_cast<double>(s_stat[0][e]));
+      if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + ch, static_cast<double>(s_stat[1][e]));
     }
   }
 }

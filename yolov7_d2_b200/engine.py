@@ -117,6 +117,7 @@ class YoloxEngine:
         1e-3 parity check against the fp32 reference; forward + SimOTA + losses only, no backward."""
         assert height % 32 == 0 and width % 32 == 0, "input must be padded to a multiple of 32 (yolox.py:100-101)"
         self.strict = (os.environ.get("YB200_STRICT", "0") == "1") if strict is None else bool(strict)
+        self.group4 = os.environ.get("YB200_STEM_GROUP4", "1") == "1" and not self.strict and (width // 2) % 4 == 0
         self.planes = int(os.environ.get("YB200_STRICT_PLANES", "3"))  # bf16 planes per value in strict mode: 3 = all 24 bits of fp32, 2 = 16 bits
         assert self.planes in (2, 3)
         self.L = capi.lib()
@@ -304,6 +305,28 @@ class YoloxEngine:
                 if self.strict:
                     op.w_split = torch.empty(op.cout, self.planes, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
                     op.w_fwd = op.w_dgrad = None
+                elif op.first and self.group4:
+                    # Stem on a pixel-grouped view (yb200_conv2d_fwd_fold): 4 horizontally adjacent Focus pixels = one pixel of 64 channels
+                    # (128-byte rows for TMA instead of 32-byte ones), 4 x 32 output columns.  Expanded weight W'[(e, c)][(f, ci)][kh][t]:
+                    # output pixel 4j+e reads input pixel 4(j+t-1)+f through the original tap kw = 4(t-1) + f - e + 1 when 0 <= kw <= 2.
+                    g, co, ci_pad, ci_real = 4, op.cout, op.cin_pad, op.cin_real
+                    idx = torch.zeros(g * co, g * ci_pad, 3, 3, dtype=torch.int64)
+                    msk = torch.zeros(g * co, g * ci_pad, 3, 3)
+                    for e in range(g):
+                        for f in range(g):
+                            for t in range(3):
+                                kw = 4 * (t - 1) + f - e + 1
+                                if 0 <= kw <= 2:
+                                    c_i, ci_i, kh_i = torch.meshgrid(torch.arange(co), torch.arange(ci_real), torch.arange(3), indexing="ij")
+                                    idx[e * co:(e + 1) * co, f * ci_pad:f * ci_pad + ci_real, :, t] = ((c_i * ci_real + ci_i) * 3 + kh_i) * 3 + kw
+                                    msk[e * co:(e + 1) * co, f * ci_pad:f * ci_pad + ci_real, :, t] = 1.0
+                    op.exp_idx, op.exp_mask = idx.to(dev), msk.to(dev)
+                    op.exp_valid = torch.nonzero(msk.flatten()).flatten().to(dev)       # positions of W' that map to a real weight
+                    op.exp_target = idx.flatten()[op.exp_valid.cpu()].to(dev)            # ... and the flat index of that weight
+                    op.w_exp = torch.zeros(g * co, g * ci_pad, 3, 3, device=dev)         # fp32 OIHW of the grouped convolution
+                    op.g_exp = torch.zeros_like(op.w_exp)
+                    op.w_fwd = torch.empty(g * co, kk, g * ci_pad, dtype=torch.bfloat16, device=dev)
+                    op.w_dgrad = None
                 else:
                     op.w_fwd = torch.empty(op.cout, kk, op.cin_pad, dtype=torch.bfloat16, device=dev)
                     op.w_dgrad = None if op.first else torch.empty(op.cin_pad, kk, op.cout, dtype=torch.bfloat16, device=dev)
@@ -472,7 +495,9 @@ class YoloxEngine:
             # one launch for every layer of the plan: the layer table lives in device memory (built once; the pointers are plan constants)
             rows = []
             for op in self.ops:
-                if isinstance(op, ConvOp):
+                if isinstance(op, ConvOp) and op.first and self.group4:
+                    rows.append((op.w_exp, op.w_fwd, None, 4 * op.cout, 4 * op.cin_pad, 3, 4 * op.cout, 4 * op.cin_pad))
+                elif isinstance(op, ConvOp):
                     rows.append((op.w_src, op.w_fwd, op.w_dgrad, op.cout, op.cin_real, op.ksize, op.cout, op.cin_pad))
                 elif isinstance(op, PredOp):
                     rows.append((op.wc_src, op.wc_fwd, op.wc_dgrad, self.nc, self.hc, 1, self.nc, self.hc))
@@ -487,6 +512,10 @@ class YoloxEngine:
             self._pack_table = (raw, torch.tensor(prefix, dtype=torch.int64, device=self.dev), len(rows), prefix[-1],
                                 4.0 * sum(r[0].numel() for r in rows) + 2.0 * sum(prefix[-1:]) * 2)
         raw, prefix, n, total, nbytes = self._pack_table
+        if self.group4:  # refresh the expanded stem weights from the parameter (two tiny torch kernels)
+            st = self.ops[0]
+            torch.mul(st.w_src.reshape(-1)[st.exp_idx], st.exp_mask, out=st.w_exp)
+            self._count(2, "expand stem weights (torch gather, mul)", "pack_weights")
         capi.check(L.yb200_pack_conv_weights_batched(capi.ptr(raw), capi.ptr(prefix), n, ctypes.c_int64(total), sp), "pack weights")
         self._count(1, "pack all weights", "pack_weights", nbytes)
 
@@ -564,7 +593,7 @@ class YoloxEngine:
                 gamma = self.params[op.prefixes[0] + ".bn.weight"]
                 beta = self.params[op.heads[0].prefix + ".bn.bias"]
                 pf = lambda t, off=o: ctypes.c_void_p(t.data_ptr() + 4 * off)
-                if not training and all(hd.up is None for hd in op.heads):
+                if not training and all(hd.up is None for hd in op.heads) and not (op.first and self.group4):
                     # eval: BatchNorm (running statistics) + SiLU + shortcut folded into the convolution's epilogue
                     capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm), pf(self.flat_rv),
                                                       ctypes.c_float(BN_EPS), pf(self.flat_scale), pf(self.flat_shift), sp), "bn_eval_affine")
@@ -579,7 +608,14 @@ class YoloxEngine:
                     continue
                 ssum = ctypes.c_void_p(f8.data_ptr() + 8 * o) if training else None
                 ssq = ctypes.c_void_p(f8.data_ptr() + 8 * (nb + o)) if training else None
-                capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, ssum, ssq, sp), op.prefixes[0])
+                if op.first and self.group4:
+                    xg, zg = self._grouped_views(op)
+                    if training:
+                        capi.check(L.yb200_conv2d_fwd_fold(ctypes.byref(xg), capi.ptr(op.w_fwd), ctypes.byref(zg), 3, 1, ssum, ssq, op.cout, sp), op.prefixes[0])
+                    else:
+                        capi.check(L.yb200_conv2d_fwd(ctypes.byref(xg), capi.ptr(op.w_fwd), ctypes.byref(zg), 3, 1, None, None, sp), op.prefixes[0])
+                else:
+                    capi.check(L.yb200_conv2d_fwd(op.x.act(), capi.ptr(op.w_fwd), op.z.act(), op.ksize, op.stride, ssum, ssq, sp), op.prefixes[0])
                 npx = op.z.buf.n * op.z.buf.h * op.z.buf.w
                 if not training:
                     capi.check(L.yb200_bn_eval_affine(op.cout, capi.ptr(gamma), capi.ptr(beta), pf(self.flat_rm), pf(self.flat_rv),
@@ -739,6 +775,39 @@ class YoloxEngine:
             capi.check(L.yb200_conv2d_dgrad(dz_act, capi.ptr(w_dgrad), dx_view.gact(), addend_act, ksize, stride, sp), what)
         return nseg
 
+    def _grouped_views(self, op, dz=None):
+        """the stem's input / output (or output gradient) seen as [N, H, W/4, 4C]: same memory, 4 pixels per row"""
+        xb = op.x.buf
+        xg = capi.act(xb.t.view(xb.n, xb.h, xb.w // 4, 4 * xb.c))
+        zt = op.z.buf.t if dz is None else dz
+        zg = capi.act(zt.view(zt.shape[0], zt.shape[1], zt.shape[2] // 4, 4 * zt.shape[3]))
+        return xg, zg
+
+    def _wgrad_stem_grouped(self, op, dz_t, acc):
+        """weight gradient of the grouped stem convolution, folded back onto the [32, 12, 3, 3] parameter (side stream)"""
+        L = self.L
+        xg, dzg = self._grouped_views(op, dz_t)
+        need = L.yb200_conv2d_wgrad_workspace(ctypes.byref(xg), ctypes.byref(dzg), 3, 1)
+        assert need > 0, L.yb200_last_error()
+        self._ensure_ws(need)
+
+        def run():
+            capi.check(L.yb200_conv2d_wgrad(ctypes.byref(xg), ctypes.byref(dzg), 3, 1, 4 * op.cin_pad, capi.ptr(op.g_exp), 0, capi.ptr(self.ws),
+                                            ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad stem (grouped)")
+            g = op.g_dst.reshape(-1)
+            if not acc:
+                g.zero_()
+            g.index_add_(0, op.exp_target, op.g_exp.reshape(-1)[op.exp_valid])  # every real weight appears in several (e, f, t) positions
+
+        if self.overlap_wgrad:
+            main = torch.cuda.current_stream()
+            self._fork_evt.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._fork_evt)
+                run()
+        else:
+            run()
+
     def _dz_buf(self, op):
         b = self._dz.get(id(op))
         if b is None:
@@ -846,7 +915,10 @@ class YoloxEngine:
                     if hd.residual is not None:
                         pending_res[(id(hd.residual.buf), hd.residual.off)] = hd.out
                 dz = dzb.view()
-                self._wgrad(op.x.act(), dz.act(), op.ksize, op.stride, op.cin_real, op.g_dst, acc, op.prefixes[0])
+                if op.first and self.group4:
+                    self._wgrad_stem_grouped(op, dzb.t, acc)
+                else:
+                    self._wgrad(op.x.act(), dz.act(), op.ksize, op.stride, op.cin_real, op.g_dst, acc, op.prefixes[0])
                 self._count(2, "wgrad+reduce %s %s" % (op.prefixes[0], self._desc(op)), "wgrad (wgrad_gemm + reduce)", *self._alg_conv(op))
                 if not op.first:
                     res = pending_res.pop((id(op.x.buf), op.x.off), None)
