@@ -1,4 +1,5 @@
 """The drop-in surface: registry entries, state_dict layout, YOLOX.forward contract in training and eval mode."""
+import numpy as np
 import pytest
 import torch
 
@@ -196,3 +197,40 @@ def test_standalone_backbone_trains_through_autograd(cuda):
         gq = p.grad.cpu().flatten().double()
         worst = min(worst, float((gq @ r) / (gq.norm() * r.norm() + 1e-30)))
     assert worst >= 0.9, worst
+
+
+@pytest.mark.gpu
+def test_api_cuda_graphs_reproduce_eager_training(cuda, monkeypatch):
+    """YOLOX.forward / backward replay CUDA graphs after two eager calls (YB200_API_GRAPHS, default on): same losses and parameters as eager
+    launches over several optimizer steps, including a prefetched batch"""
+    import bench
+    from yolov7_d2_b200 import optim
+    from yolov7_d2_b200.modeling import YOLOX
+
+    images, labels = orc.synthetic_batch(2, 128, 61, max_gt=4)
+    batches = [bench.batched_inputs_from(images, labels), bench.batched_inputs_from(images.flip(0).contiguous(), labels.flip(0).contiguous())]
+    results = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("YB200_API_GRAPHS", flag)
+        m = YOLOX(bench.yolox_s_cfg("cuda"))
+        m.load_state_dict(orc.yolox_state_dict(8), strict=True)
+        m.train()
+        cfg = bench.yolox_s_cfg("cuda")
+        cfg.SOLVER.BASE_LR = 1e-3
+        opt = optim.build_optimizer_mapper(cfg, m)
+        losses = []
+        for it in range(6):
+            opt.zero_grad()
+            out = m(batches[it & 1])
+            if it == 3:
+                m.prefetch(batches[(it + 1) & 1])
+            sum(out.values()).backward()
+            opt.step()
+            losses.append(float(out["total_loss"].detach()))
+        plan = m._plan(2, 128, 128)
+        graphed = bool(getattr(plan, "_api_graphs", {}).get("backward", {}).get("graph"))
+        assert graphed == (flag == "1"), "graph capture state"
+        results.append((losses, m.engine.flat_param.clone()))
+    (la, pa), (lb, pb) = results
+    assert np.allclose(la, lb, rtol=2e-3), (la, lb)
+    assert float((pa - pb).abs().max()) <= 1e-3 * float(pb.abs().max())

@@ -18,7 +18,9 @@ def _state(seed):
     return sd
 
 
-def _oracle(sd, images, labels, emulate):
+def _oracle(sd, images, labels, emulate, g_raw):
+    """head outputs and loss of the composed oracles; parameter gradients of the LINEAR functional sum(g_raw * raw head outputs) -- no discrete
+    decision (SimOTA) between parameters and objective, as in tests/test_engine_gpu.py::test_backward_against_oracle"""
     orc.EMULATE_STORAGE = cno.EMULATE_STORAGE = emulate
     try:
         sd = {k: v.clone() for k, v in sd.items()}
@@ -27,10 +29,11 @@ def _oracle(sd, images, labels, emulate):
                 v.requires_grad_(True)
         f1, f2, f3 = cno.forward_features(images.float(), sd, out_indices=(1, 2, 3), prefix="backbone.")
         raw = orc.head_raw(orc.pafpn({"dark3": f1, "dark4": f2, "dark5": f3}, sd, True), sd, True)
-        outputs = orc.decode_train(raw)
+        outputs = orc.decode_train([r.detach() for r in raw])
         xs, ys, ss = orc.anchor_grid([o.shape[-2:] for o in raw])
         total = orc.yolox_losses(outputs, labels, xs, ys, ss)[0]
-        total.backward()
+        flat = torch.cat([r.permute(0, 2, 3, 1).reshape(r.shape[0], -1, r.shape[1]) for r in raw], 1)
+        (flat * g_raw).sum().backward()
     finally:
         orc.EMULATE_STORAGE = cno.EMULATE_STORAGE = False
     return outputs.detach(), {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}, float(total)
@@ -49,8 +52,10 @@ def test_yolox_convnext_step_against_oracles(cuda):
     eng.train_step()
     torch.cuda.synchronize()
     out = eng.outputs.cpu()
-    ref_out, ref_g, ref_loss = _oracle(sd, images, labels, False)
-    emu_out, emu_g, emu_loss = _oracle(sd, images, labels, True)
+    n, a, ch = out.shape
+    g_raw = (torch.randn(n, a, ch, generator=torch.Generator().manual_seed(43)) * 1e-2).to(torch.bfloat16).float()
+    ref_out, ref_g, ref_loss = _oracle(sd, images, labels, False, g_raw)
+    emu_out, emu_g, emu_loss = _oracle(sd, images, labels, True, g_raw)
     e_eng, e_emu = (out - ref_out).abs()[..., 4:].mean(), (emu_out - ref_out).abs()[..., 4:].mean()
     print("YOLOX-ConvNeXt logits vs fp32 oracles: engine mean err %.5f, 16-bit-storage oracles %.5f; loss %.4f / %.4f / %.4f" %
           (e_eng, e_emu, float(eng.losses[0]), ref_loss, emu_loss))
@@ -63,7 +68,18 @@ def test_yolox_convnext_step_against_oracles(cuda):
         assert torch.equal(fg[b], rfg) and torch.equal(eng.matched_gt.cpu()[b][rfg].long(), mgt)
     got = eng.losses.cpu().double().numpy()
     assert np.allclose(got[:4], [float(total), float(iou5), float(lobj), float(lcls)], rtol=1e-4, atol=1e-5)
-    # gradients reach every parameter of both plans
+    # backward of both plans for the fixed upstream gradient g_raw on the raw head outputs
+    yx = eng.yx
+    eng.pack_weights()
+    eng.forward_features(True)
+    for k, (h, w, s_, a_off) in enumerate(yx.levels):
+        gl = g_raw[:, a_off:a_off + h * w]
+        yx.d_cls[k].copy_(gl[..., 5:].reshape(n, h, w, ch - 5).to(cuda))
+        yx.d_ro[k].zero_()
+        yx.d_ro[k][..., :5].copy_(gl[..., :5].reshape(n, h, w, 5).to(cuda))
+        yx.bias_acc[k].copy_(gl.double().sum((0, 1)).to(cuda))
+    eng.backward()
+    torch.cuda.synchronize()
     worst = []
     for name in eng.param_names:
         if name not in ref_g:

@@ -787,8 +787,9 @@ int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, W
   p.kc_a = dz->c >= 64 ? 64 : (dz->c >= 32 ? 32 : 16);
   YB_REQUIRE(dz->c % p.kc_a == 0 || dz->c == dz->c_pitch, YB200_ERR_UNSUPPORTED,
              "conv2d_wgrad: dz channel slice %d not a multiple of %d", dz->c, p.kc_a);
-  p.ma = dz->c >= 128 ? 2 : 1;
-  if (dz->c > 64 && dz->c < 128) p.ma = 2;  // e.g. 80 classes: second box is partly out of bounds (zero filled)
+  // boxes of kc_a channels per 128-row tile; a box that overshoots the slice (48 -> 2 x 32, 80 -> 2 x 64, 96 -> 2 x 64) is legal only when
+  // the slice ends at the channel pitch (required above): the overshoot is then out of bounds for TMA and zero filled
+  p.ma = ceil_div(dz->c < 128 ? dz->c : 128, p.kc_a);
   p.cout_tiles = ceil_div(dz->c, 128);
   p.kc_b = x->c % 64 == 0 ? 64 : (x->c % 32 == 0 ? 32 : 16);
   p.bn = x->c % 128 == 0 ? 128 : (x->c % 64 == 0 ? 64 : p.kc_b);
