@@ -495,6 +495,11 @@ def main():
         for c in sorted(calls, key=lambda c: -c["ms"])[:14]:
             fl = max(c["bytes"] / (pk["hbm"] * 1e9), c["flops"] / (pk["tf_sust"] * 1e12)) * 1e3
             top_calls.append({"call": c["label"], "ms": round(c["ms"], 4), "floor_ms": round(fl, 4), "frac_of_roofline": round(fl / c["ms"], 3) if c["ms"] > 0 else None})
+        if os.environ.get("YB200_DUMP_CALLS"):  # every call of the step (label, class, ms, floor) for profiles/
+            with open(os.environ["YB200_DUMP_CALLS"], "w") as f:
+                for c in calls:
+                    fl = max(c["bytes"] / (pk["hbm"] * 1e9), c["flops"] / (pk["tf_sust"] * 1e12)) * 1e3
+                    f.write(json.dumps({"call": c["label"], "cls": c["cls"], "launches": c["launches"], "ms": round(c["ms"], 4), "floor_ms": round(fl, 4)}) + "\n")
         top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         hbm_bound = top["bytes"] / (pk["hbm"] * 1e9) >= top["flops"] / (pk["tf_sust"] * 1e12)
         traffic = None
@@ -546,7 +551,7 @@ def main():
                 opt.step()
             return float(losses["total_loss"].detach())  # device -> host read of the step's result
 
-        for _ in range(2):
+        for _ in range(max(3, args.warmup)):  # call 1 eager, call 2 captures the forward / backward graphs, then replays
             api_step()
         barrier()
         e0.record()

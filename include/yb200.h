@@ -145,6 +145,14 @@ int yb200_bn_silu_bwd_apply(const yb200_act* z, const yb200_act* da, const float
                             const float* save_mean, const float* save_invstd, double* sum_duz, double* sum_du,
                             const yb200_act* dz, float* dgamma, float* dbeta, int accumulate, void* stream);
 
+/* yb200_bn_silu_bwd / _apply with dgamma == dbeta == NULL leave their sums in the fp64 accumulators; this call converts the accumulators of a
+ * run of c channels (several layers) in one launch: grad_base[gamma_off[i]] (+)= dgamma_i, grad_base[beta_off[i]] (+)= dbeta_i, accumulators
+ * zeroed.  raw_sums (may be NULL): per channel, 1 where the accumulators hold S2 / S1 of yb200_conv2d_dgrad_bnbwd (then save_mean / save_invstd
+ * are read).  Replaces the tail of torch's batch_norm backward for every BaseConv of a plan (wrappers.py:60-80).                        */
+int yb200_bn_param_grads(double* acc_dgamma, double* acc_dbeta, int c, const int32_t* gamma_off, const int32_t* beta_off,
+                         float* grad_base, const float* save_mean, const float* save_invstd, const uint8_t* raw_sums,
+                         int accumulate, void* stream);
+
 /* ---- SPP / concat helpers ------------------------------------------------------------------------ */
 /* nn.MaxPool2d(k, 1, k//2) for k = 5, 9, 13 written into three channel slices (SPPBottleneck, wrappers.py:150-160).
  * argmax (may be NULL): uint8 [3][n][h][w][c] window offsets for the backward.                                */

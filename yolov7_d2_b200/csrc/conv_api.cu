@@ -115,7 +115,9 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   // of shared memory allows
   const int m_tiles = grid.x, n_tiles = grid.y;
   const int occ = BN == 256 ? 1 : 2;
-  const int budget = (occ == 1 ? 216 : 110) * 1024 - 1024;
+  // fp32 rows with channel stride 1 and an odd pitch ([B, A, 85]): chunks go through a per-warp transpose scratch behind the ring
+  const bool xpose = p.epi_mode == EPI_F32_BIAS && p.out_sc == 1 && BN <= 128 && p.num_bnseg == 0;
+  const int budget = (occ == 1 ? 216 : 110) * 1024 - 1024 - (xpose ? kXposeBytes : 0);
   int slots_kb = budget / Cfg::kStageBytes;  // k-blocks that fit in the ring
   // narrow layers (BLOCK_K 16 / 32) would spend their time on mbarrier round trips: put several k-blocks (up to 144
   // channels-taps) behind one barrier, keeping at least two ring slots
@@ -127,7 +129,7 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   int pst = slots_kb / kbs;
   if (pst > kMaxStagesP) pst = kMaxStagesP;
   if (pst < 2) pst = 2;
-  const int smem = pst * kbs * Cfg::kStageBytes + 1024;
+  const int smem = pst * kbs * Cfg::kStageBytes + 1024 + (xpose ? kXposeBytes : 0);
   static int max_set_p = 0;
   if (smem > max_set_p) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -147,10 +149,12 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
       return fail(YB200_ERR_UNSUPPORTED, "fused BatchNorm-backward statistics need a column tile <= 128 (gradient tensors of < 256 channels)");
     }
   }
+  ConvGemmParams pp = p;
+  pp.xpose = xpose ? 1 : 0;
   if (ext)
-    conv_gemm_persistent_kernel<BN, BK, 1><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+    conv_gemm_persistent_kernel<BN, BK, 1><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, pp, pst, kbs, n_tiles, m_tiles);
   else
-    conv_gemm_persistent_kernel<BN, BK, 0><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+    conv_gemm_persistent_kernel<BN, BK, 0><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, pp, pst, kbs, n_tiles, m_tiles);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -280,29 +284,36 @@ static int pack_weight_impl(const float* w_oihw, const float* cout_scale, int co
 // launch latency at the head of the step.  `table` (device memory, built once per plan) lists the layers; `prefix[i]` = padded elements of
 // layers 0..i-1 (prefix[n] = total), so a thread finds its layer by binary search.
 __global__ void pack_conv_weights_batched_kernel(const yb200_pack_desc* __restrict__ table, const long long* __restrict__ prefix, int n) {
+  // index space [0, total): forward operands in their own order; [total, 2 total): data-gradient operands in THEIR order -- both outputs are
+  // written with consecutive 2-byte stores, the fp32 source is gathered (9 MB of parameters: L2 resident)
   const long long total = prefix[n];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i2 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i2 < 2 * total; i2 += (long long)gridDim.x * blockDim.x) {
+    const bool second = i2 >= total;
+    const long long i = second ? i2 - total : i2;
     int lo = 0, hi = n - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (prefix[mid] <= i) lo = mid; else hi = mid - 1;
     }
     const yb200_pack_desc d = table[lo];
-    const long long e = i - prefix[lo];
-    const int taps = d.ksize * d.ksize;
-    const int ci = static_cast<int>(e % d.cin_pad);
-    const int t = static_cast<int>((e / d.cin_pad) % taps);
-    const int co = static_cast<int>(e / (1LL * d.cin_pad * taps));
-    const float v = (co < d.cout && ci < d.cin) ? d.w_oihw[(1LL * co * d.cin + ci) * taps + t] : 0.f;
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    if (d.w_fwd) static_cast<__nv_bfloat16*>(d.w_fwd)[e] = b;
-    if (d.w_dgrad) static_cast<__nv_bfloat16*>(d.w_dgrad)[(1LL * ci * taps + t) * d.cout_pad + co] = b;
+    const unsigned e = static_cast<unsigned>(i - prefix[lo]);  // one layer holds < 2^31 padded elements
+    const unsigned taps = d.ksize * d.ksize;
+    unsigned ci, t, co;
+    if (!second) {
+      if (!d.w_fwd) continue;
+      ci = e % d.cin_pad; t = (e / d.cin_pad) % taps; co = e / (d.cin_pad * taps);
+    } else {
+      if (!d.w_dgrad) continue;
+      co = e % d.cout_pad; t = (e / d.cout_pad) % taps; ci = e / (d.cout_pad * taps);
+    }
+    const float v = (co < static_cast<unsigned>(d.cout) && ci < static_cast<unsigned>(d.cin)) ? d.w_oihw[(1LL * co * d.cin + ci) * taps + t] : 0.f;
+    static_cast<__nv_bfloat16*>(second ? d.w_dgrad : d.w_fwd)[e] = __float2bfloat16_rn(v);
   }
 }
 
 extern "C" int yb200_pack_conv_weights_batched(const yb200_pack_desc* table_dev, const int64_t* prefix_dev, int n, int64_t total, void* stream) {
   YB_REQUIRE(table_dev && prefix_dev && n > 0 && total > 0, YB200_ERR_INVALID, "pack_conv_weights_batched: bad arguments");
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * sm_count()));
+  const int blocks = static_cast<int>(std::min<long long>((2 * total + 255) / 256, 16LL * sm_count()));
   pack_conv_weights_batched_kernel<<<blocks, 256, 0, as_stream(stream)>>>(table_dev, reinterpret_cast<const long long*>(prefix_dev), n);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;

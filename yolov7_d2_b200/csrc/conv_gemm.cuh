@@ -104,6 +104,7 @@ struct ConvGemmParams {
   double* stat_sum;
   double* stat_sq;
   int stat_fold;  // > 0: column c accumulates into statistic c % stat_fold (pixel-grouped views: several columns are the same channel)
+  int xpose;      // EPI_F32_BIAS with channel-contiguous rows: transpose each 32 x 32 chunk through shared memory (kXposeBytes behind the ring)
   const __nv_bfloat16* aux_in;  // EPI_BF16_GELU_BWD: pre-activation u, same geometry as `out`
   __nv_bfloat16* aux_out;       // EPI_BF16_BIAS_GELU: where u is stored (may be null), same geometry as `out`
   ConvTap taps[kMaxTaps];
@@ -206,12 +207,33 @@ __device__ __forceinline__ void load_side_chunk(const __nv_bfloat16* side_row, b
 // EXT = false: the YOLOX training / inference modes only (EPI_BF16 .. EPI_BF16_BN_SILU); EXT = true adds the ConvNeXt / transformer
 // modes and the prefetched side input.  Two instantiations per kernel keep the hot YOLOX kernels as small as they were before the
 // extra modes existed (the combined epilogue cost the 3x3 kernels 2-13 % through registers and code size).
+// fp32 rows with a pitch that is not a multiple of 16 bytes (the [B, A, 85] prediction tensor): a lane-per-pixel store touches 32 different
+// sectors per instruction.  With the per-warp scratch each store instruction writes 32 consecutive floats of ONE pixel row instead.
+constexpr int kXposeWarpFloats = 32 * 33 + 64;              // 32 x 32 chunk (pitch 33: conflict free both ways) + 32 row offsets (8 B each)
+constexpr int kXposeBytes = 8 * kXposeWarpFloats * 4;       // eight epilogue warps
+
 template <int CH, bool EXT = true>
 __device__ __forceinline__ void conv_epilogue_chunk(const ConvGemmParams& p, float (&v)[CH], bool valid, long long pix_off, long long add_off,
                                                     int cbase, int lane, float* part_sum, float* part_sq, bool accumulate,
                                                     const float* col_scale, const float* col_shift, const uint4* side = nullptr,
-                                                    const uint4* zq = nullptr) {
+                                                    const uint4* zq = nullptr, float* xp = nullptr) {
   if (p.epi_mode == EPI_F32_BIAS) {
+    if (xp != nullptr) {
+      long long* s_off = reinterpret_cast<long long*>(xp + 32 * 33);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) xp[lane * 33 + i] = v[i] + col_shift[i];
+      s_off[lane] = valid ? pix_off : -1;
+      __syncwarp();
+      float* o = reinterpret_cast<float*>(p.out) + cbase + lane;
+      const bool colok = lane < CH && cbase + lane < p.cout;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const long long off = s_off[r];
+        if (off >= 0 && colok) o[off] = xp[r * 33 + lane];
+      }
+      __syncwarp();
+      return;
+    }
     if (valid) {
       float* o = reinterpret_cast<float*>(p.out) + pix_off;
 #pragma unroll
@@ -682,6 +704,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int xl = mrow & ((1 << log_tw) - 1);
     const int yl = (mrow >> log_tw) & ((1 << log_th) - 1);
     const int nl = mrow >> (log_tw + log_th);
+    float* xp = nullptr;
+    if (!BNB && p.xpose)
+      xp = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + num_stages * kb_per_slot * Cfg::kStageBytes) + (warp - 2) * kXposeWarpFloats;
     int it = 0;
     for (int m = group; m < m_tiles; m += groups, ++it) {
       int t = m;
@@ -744,7 +769,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
         const int cbase = col0 + c;
         conv_epilogue_chunk<CH, EXT>(p, v, valid, pix_off, add_off, cbase, lane, &s_part[q][0][c], &s_part[q][1][c], true, &s_col[0][c], &s_col[1][c],
-                                (EXT && BLOCK_N == 256 && side_base) ? side : nullptr, (BNB && zseg >= 0) ? zq : nullptr);
+                                (EXT && BLOCK_N == 256 && side_base) ? side : nullptr, (BNB && zseg >= 0) ? zq : nullptr, xp);
         if constexpr (EXT && BLOCK_N == 256) {
           if (more) {
 #pragma unroll

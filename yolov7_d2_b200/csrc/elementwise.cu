@@ -531,31 +531,32 @@ __global__ void spp_pool_kernel(View x, View o5, View o9, View o13, uint8_t* __r
 // separable max with argmax -- row pass keeps (max, first column) per pixel, column pass picks the first row with the
 // largest row-max, which is exactly the first maximum of the 2-D window in row-major order.
 // The low 16 bits of the packed word carry the column code so one 4-byte shared-memory read serves value and index.
+template <int CG>  // channels per block: 16 keeps four blocks (32 warps) resident per SM at 20 x 20 -- the loops are shared-memory-latency bound
 __global__ void __launch_bounds__(256)
 spp_pool_tiled_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ arg) {
-  extern __shared__ uint32_t sp[];  // [hw][32] input (bf16 bits << 16), then [hw][32] row results (bf16 bits << 16 | column code)
+  extern __shared__ uint32_t sp[];  // [hw][CG] input (bf16 bits << 16), then [hw][CG] row results (bf16 bits << 16 | column code)
   const int hw = x.h * x.w;
   uint32_t* sin = sp;
-  uint32_t* srow = sp + hw * 32;
-  const int cg = blockIdx.x * 32;
+  uint32_t* srow = sp + hw * CG;
+  const int cg = blockIdx.x * CG;
   const int b = blockIdx.y;
   const __nv_bfloat16* src = x.p + static_cast<size_t>(b) * hw * x.pitch + cg;
-  for (int e = threadIdx.x; e < hw * 32; e += blockDim.x) {
-    const int ch = e & 31, p = e >> 5;
+  for (int e = threadIdx.x; e < hw * CG; e += blockDim.x) {
+    const int ch = e % CG, p = e / CG;
     sin[e] = static_cast<uint32_t>(__bfloat16_as_ushort(src[static_cast<size_t>(p) * x.pitch + ch])) << 16;
   }
   __syncthreads();
 #pragma unroll 1
   for (int j = 0; j < 3; ++j) {
     const int r = 2 + 2 * j;  // k = 5, 9, 13
-    for (int e = threadIdx.x; e < hw * 32; e += blockDim.x) {
-      const int ch = e & 31, p = e >> 5;
+    for (int e = threadIdx.x; e < hw * CG; e += blockDim.x) {
+      const int ch = e % CG, p = e / CG;
       const int px = p % x.w, rowbase = p - px;
       float best = -INFINITY;
       uint32_t bw = 0;
       const int x0 = max(px - r, 0), x1 = min(px + r, x.w - 1);
       for (int xx = x0; xx <= x1; ++xx) {
-        const uint32_t wv = sin[(rowbase + xx) * 32 + ch];
+        const uint32_t wv = sin[(rowbase + xx) * CG + ch];
         const float v = __uint_as_float(wv);
         if (v > best) { best = v; bw = wv | static_cast<uint32_t>(xx - px + 6); }
       }
@@ -565,15 +566,15 @@ spp_pool_tiled_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ 
     const View& o = j == 0 ? o5 : (j == 1 ? o9 : o13);
     __nv_bfloat16* dst = o.p + static_cast<size_t>(b) * hw * o.pitch + cg;
     uint8_t* adst = arg ? arg + (static_cast<size_t>(j) * x.n + b) * hw * x.c + cg : nullptr;
-    for (int e = threadIdx.x; e < hw * 32; e += blockDim.x) {
-      const int ch = e & 31, p = e >> 5;
+    for (int e = threadIdx.x; e < hw * CG; e += blockDim.x) {
+      const int ch = e % CG, p = e / CG;
       const int py = p / x.w, px = p - py * x.w;
       float best = -INFINITY;
       uint32_t bw = 0;
       int bdy = 0;
       const int y0 = max(py - r, 0), y1 = min(py + r, x.h - 1);
       for (int yy = y0; yy <= y1; ++yy) {
-        const uint32_t wv = srow[(yy * x.w + px) * 32 + ch];
+        const uint32_t wv = srow[(yy * x.w + px) * CG + ch];
         const float v = __uint_as_float(wv & 0xFFFF0000u);
         if (v > best) { best = v; bw = wv; bdy = yy - py; }
       }
@@ -719,7 +720,8 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
   if ((rc = check_view(z, "bn_silu_bwd z")) || (rc = check_view(da, "bn_silu_bwd da")) || (rc = check_view(dz, "bn_silu_bwd dz"))) return rc;
   if (da2 && (rc = check_view(da2, "bn_silu_bwd da2"))) return rc;
   if (da_up2x && (rc = check_view(da_up2x, "bn_silu_bwd da_up2x"))) return rc;
-  YB_REQUIRE(scale && shift && save_mean && save_invstd && acc_dgamma && acc_dbeta && dgamma && dbeta, YB200_ERR_INVALID, "bn_silu_bwd: null pointer");
+  YB_REQUIRE(scale && shift && save_mean && save_invstd && acc_dgamma && acc_dbeta && (dgamma != nullptr) == (dbeta != nullptr), YB200_ERR_INVALID,
+             "bn_silu_bwd: null pointer");
   YB_REQUIRE(same_shape(z, da) && same_shape(z, dz) && (!da2 || same_shape(z, da2)), YB200_ERR_INVALID, "bn_silu_bwd: shape mismatch");
   YB_REQUIRE(!da_up2x || (da_up2x->n == z->n && da_up2x->h == 2 * z->h && da_up2x->w == 2 * z->w && da_up2x->c == z->c), YB200_ERR_INVALID,
              "bn_silu_bwd: upsampled gradient view must be [n,2h,2w,c]");
@@ -778,7 +780,35 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
     bn_silu_bwd_apply_kernel<false><<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
                                                                1.0 / static_cast<double>(npix), static_cast<unsigned>(npix), stats_ready);
   YB_CHECK_CUDA(cudaGetLastError());
+  if (dgamma == nullptr) return 0;  // deferred: yb200_bn_param_grads turns the accumulators of many layers into parameter gradients in one launch
   bn_param_grad_kernel<<<ceil_div(z->c, 128), 128, 0, st>>>(acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate, save_mean, save_invstd, stats_ready);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// the same for a run of layers: channel i of the run writes grad_base[gamma_off[i]] / grad_base[beta_off[i]]
+__global__ void bn_param_grads_table_kernel(double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, int c, const int* __restrict__ gamma_off,
+                                            const int* __restrict__ beta_off, float* __restrict__ grad_base, int accumulate,
+                                            const float* __restrict__ mean, const float* __restrict__ invstd, const uint8_t* __restrict__ raw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const bool is_raw = raw != nullptr && raw[i] != 0;
+  const double dg = is_raw ? static_cast<double>(invstd[i]) * (dgamma_acc[i] - static_cast<double>(mean[i]) * dbeta_acc[i]) : dgamma_acc[i];
+  const float g = static_cast<float>(dg), b = static_cast<float>(dbeta_acc[i]);
+  float* pg = grad_base + gamma_off[i];
+  float* pb = grad_base + beta_off[i];
+  *pg = accumulate ? *pg + g : g;
+  *pb = accumulate ? *pb + b : b;
+  dgamma_acc[i] = 0.0;
+  dbeta_acc[i] = 0.0;
+}
+
+extern "C" int yb200_bn_param_grads(double* acc_dgamma, double* acc_dbeta, int c, const int32_t* gamma_off, const int32_t* beta_off, float* grad_base,
+                                    const float* save_mean, const float* save_invstd, const uint8_t* raw_sums, int accumulate, void* stream) {
+  YB_REQUIRE(acc_dgamma && acc_dbeta && gamma_off && beta_off && grad_base && c > 0 && (!raw_sums || (save_mean && save_invstd)), YB200_ERR_INVALID,
+             "bn_param_grads: bad arguments");
+  bn_param_grads_table_kernel<<<ceil_div(c, 128), 128, 0, as_stream(stream)>>>(acc_dgamma, acc_dbeta, c, gamma_off, beta_off, grad_base, accumulate,
+                                                                               save_mean, save_invstd, raw_sums);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -801,14 +831,15 @@ extern "C" int yb200_spp_pool(const yb200_act* x, const yb200_act* o5, const yb2
       (rc = check_view(o13, "spp_pool o13")))
     return rc;
   YB_REQUIRE(same_shape(x, o5) && same_shape(x, o9) && same_shape(x, o13), YB200_ERR_INVALID, "spp_pool: shape mismatch");
-  const size_t tiled_smem = static_cast<size_t>(x->h) * x->w * 32 * 2 * sizeof(uint32_t);
-  if (x->c % 32 == 0 && tiled_smem <= 200 * 1024) {
+  constexpr int kCg = 16;
+  const size_t tiled_smem = static_cast<size_t>(x->h) * x->w * kCg * 2 * sizeof(uint32_t);
+  if (x->c % kCg == 0 && tiled_smem <= 200 * 1024) {
     static size_t smem_set = 48 * 1024;
     if (tiled_smem > smem_set) {
-      YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tiled_smem)));
+      YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_tiled_kernel<kCg>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tiled_smem)));
       smem_set = tiled_smem;
     }
-    spp_pool_tiled_kernel<<<dim3(x->c / 32, x->n), 256, tiled_smem, as_stream(stream)>>>(mk(x), mk(o5), mk(o9), mk(o13), argmax);
+    spp_pool_tiled_kernel<kCg><<<dim3(x->c / kCg, x->n), 256, tiled_smem, as_stream(stream)>>>(mk(x), mk(o5), mk(o9), mk(o13), argmax);
     YB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }

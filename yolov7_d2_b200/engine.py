@@ -295,6 +295,16 @@ class YoloxEngine:
                 hd.bn_off = o
                 o += hd.c
         self.nbn = nbn
+        # destination of every BatchNorm channel's weight / bias gradient in the flat gradient buffer (yb200_bn_param_grads: one launch per range)
+        g_off, b_off = torch.empty(nbn, dtype=torch.int32), torch.empty(nbn, dtype=torch.int32)
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                for hd in op.heads:
+                    for dst, leaf in ((g_off, ".bn.weight"), (b_off, ".bn.bias")):
+                        base = (self.grads[hd.prefix + leaf].data_ptr() - self.flat_grad.data_ptr()) // 4
+                        dst[hd.bn_off:hd.bn_off + hd.c] = torch.arange(base, base + hd.c, dtype=torch.int32)
+        self.bn_goff, self.bn_boff = g_off.to(dev), b_off.to(dev)
+        self._bn_raw = None
         self.flat_nbt = share.flat_nbt if share is not None else torch.zeros(len(nbt), dtype=torch.int64, device=dev)
         for i, name in enumerate(nbt):
             self.buffers[name] = self.flat_nbt[i]
@@ -735,6 +745,13 @@ class YoloxEngine:
                     segs.append((hd, op, v.off - lo))
                     hd.fused_stats = True
                     self._bn_fuse_idx.setdefault(key, (op_index[key[1]], []))[1].append(op_index[id(op)])
+        raw = torch.zeros(self.nbn, dtype=torch.uint8)  # channels whose accumulators hold the raw sums S2 / S1 of the fused epilogue
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                for hd in op.heads:
+                    if hd.fused_stats:
+                        raw[hd.bn_off:hd.bn_off + hd.c] = 1
+        self._bn_raw = raw.to(self.dev) if bool(raw.any()) else None
 
     def _range_fusable(self, op_range):
         """a partial backward keeps the fused statistics when every fused launch has its writer and its producers on the same side of the
@@ -900,17 +917,15 @@ class YoloxEngine:
                     if hd.fused_stats and self._fuse_active:  # the reduction pass ran in the epilogue of the data gradient that produced hd.out's gradient
                         capi.check(L.yb200_bn_silu_bwd_apply(zv.act(), hd.out.gact(), pf(self.flat_scale, o), pf(self.flat_shift, o), pf(self.flat_mean, o),
                                                              pf(self.flat_invstd, o), ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)),
-                                                             ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)), dzv.act(),
-                                                             capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
+                                                             ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)), dzv.act(), None, None,
                                                              acc, sp), "bn_silu_bwd_apply " + hd.prefix)
-                        self._count(2, "bn_bwd (apply, param; reduce fused upstream) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd", 6.0 * npx * hd.c)
+                        self._count(1, "bn_bwd (apply; reduce fused upstream) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd", 6.0 * npx * hd.c)
                     else:
                         capi.check(L.yb200_bn_silu_bwd(zv.act(), hd.out.gact(), None, hd.up.gact() if hd.up else None, pf(self.flat_scale, o),
                                                        pf(self.flat_shift, o), pf(self.flat_mean, o), pf(self.flat_invstd, o),
                                                        ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + o)), ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + o)),
-                                                       dzv.act(), capi.ptr(self.grads[hd.prefix + ".bn.weight"]), capi.ptr(self.grads[hd.prefix + ".bn.bias"]),
-                                                       acc, sp), "bn_silu_bwd " + hd.prefix)
-                        self._count(3, "bn_bwd (reduce, apply, param) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd",
+                                                       dzv.act(), None, None, acc, sp), "bn_silu_bwd " + hd.prefix)
+                        self._count(2, "bn_bwd (reduce, apply) %s c=%d px=%d" % (hd.prefix, hd.c, npx), "bn_silu_bwd",
                                     2.0 * npx * hd.c * (3 + (4 if hd.up else 0)))
                     if hd.residual is not None:
                         pending_res[(id(hd.residual.buf), hd.residual.off)] = hd.out
@@ -928,6 +943,17 @@ class YoloxEngine:
                     nseg = self._dgrad(dz.act(), op.w_dgrad, op.x, addend, op.ksize, op.stride, ("conv", id(op), None), "dgrad " + op.prefixes[0])
                     self._count(4 if op.stride == 2 else 1, "dgrad%s %s %s" % (" +bn_stats" if nseg else "", op.prefixes[0], self._desc(op)),
                                 "dgrad (conv_gemm, BN-bwd statistics fused where possible)", *self._alg_conv(op))
+        # BatchNorm weight / bias gradients of the whole range out of the fp64 accumulators: one launch (the per-layer kernels left them there)
+        heads = [hd for op in self.ops[lo_i:hi_i] if isinstance(op, ConvOp) for hd in op.heads]
+        if heads:
+            b0, b1 = min(hd.bn_off for hd in heads), max(hd.bn_off + hd.c for hd in heads)
+            assert b1 - b0 == sum(hd.c for hd in heads), "BatchNorm channels of an op range are one run of the flat statistics buffers"
+            raw = self._bn_raw if (self._fuse_active and self._bn_raw is not None) else None
+            i4 = lambda t: ctypes.c_void_p(t.data_ptr() + 4 * b0)
+            capi.check(L.yb200_bn_param_grads(ctypes.c_void_p(f8.data_ptr() + 8 * (2 * nb + b0)), ctypes.c_void_p(f8.data_ptr() + 8 * (3 * nb + b0)), b1 - b0,
+                                              i4(self.bn_goff), i4(self.bn_boff), capi.ptr(self.flat_grad), i4(self.flat_mean), i4(self.flat_invstd),
+                                              ctypes.c_void_p(raw.data_ptr() + b0) if raw is not None else None, acc, sp), "bn_param_grads")
+            self._count(1, "bn param grads of %d layers" % len(heads), "bn_silu_bwd")
         if self.overlap_wgrad:
             torch.cuda.current_stream().wait_stream(self._side)  # join: gradients are complete when backward() returns
 

@@ -348,7 +348,7 @@ def build_cspdarknetx_backbone(cfg, input_shape=None):
 
 
 def _run_graphed(eng, key, fn):
-    """Run `fn` (a fixed sequence of launches on the plan's static buffers) -- eagerly for the first calls (lazy allocations, autotuned state),
+    """Run `fn` (a fixed sequence of launches on the plan's static buffers) -- eagerly for the first call (lazy allocations),
     then captured once into a CUDA graph and replayed: the public API then costs one graph launch per pass instead of ~250 kernel launches."""
     if not getattr(eng, "use_graphs", False):
         return fn()
@@ -356,7 +356,7 @@ def _run_graphed(eng, key, fn):
     ent = st.setdefault(key, {"calls": 0, "graph": None})
     if ent["graph"] is None:
         ent["calls"] += 1
-        if ent["calls"] <= 2:
+        if ent["calls"] <= 1:
             return fn()
         try:
             torch.cuda.synchronize()
