@@ -69,7 +69,7 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
       int groups = (2 * sm_count()) / n_tiles;
       if (groups < 1) groups = 1;
       if (groups > m_tiles) groups = m_tiles;
-      conv_gemm_staged_kernel<BN, BK><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, tmOut, p, pst, kbs, n_tiles, m_tiles, out_act->c_off);
+      launch_k(conv_gemm_staged_kernel<BN, BK>, groups * n_tiles, kConvThreadsP, smem, st, tmA, tmB, tmOut, p, pst, kbs, n_tiles, m_tiles, out_act->c_off);
       YB_CHECK_CUDA(cudaGetLastError());
       return 0;
     }
@@ -81,12 +81,12 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
       YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       max_set = smem;
     }
-    conv_gemm_kernel<BN, BK><<<grid, kConvThreads, smem, st>>>(tmA, tmB, p, stages);
+    launch_k(conv_gemm_kernel<BN, BK>, grid, kConvThreads, smem, st, tmA, tmB, p, stages);
     YB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
   if constexpr (BN == 256) {
-    if (use_pair_kernel() && p.epi_mode != EPI_F32_BIAS && p.num_bnseg == 0) {
+    if (use_pair_kernel() && p.epi_mode != EPI_F32_BIAS && p.num_bnseg == 0 && p.num_phases == 0) {
       // CTA pairs: 2 x 128 pixels x 256 channels per UMMA, one CTA per SM, 32 KB per stage and CTA at BLOCK_K 64
       const int m_tiles = grid.x, n_tiles = grid.y;
       constexpr int stage_bytes = 2 * 128 * BK * 2;
@@ -104,16 +104,17 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
       if (groups < 1) groups = 1;
       if (groups > pair_tiles) groups = pair_tiles;
       if (ext)
-        conv_gemm_pair_kernel<BK, true><<<2 * groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
+        launch_k(conv_gemm_pair_kernel<BK, true>, 2 * groups * n_tiles, kConvThreadsP, smem, st, tmA, tmB, p, pst, n_tiles, m_tiles);
       else
-        conv_gemm_pair_kernel<BK, false><<<2 * groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, n_tiles, m_tiles);
+        launch_k(conv_gemm_pair_kernel<BK, false>, 2 * groups * n_tiles, kConvThreadsP, smem, st, tmA, tmB, p, pst, n_tiles, m_tiles);
       YB_CHECK_CUDA(cudaGetLastError());
       return 0;
     }
   }
   // persistent kernel: two CTAs per SM (2 x 2 x BN TMEM columns <= 512; one CTA for BN = 256), ring as deep as the CTA's share
   // of shared memory allows
-  const int m_tiles = grid.x, n_tiles = grid.y;
+  const int phases = p.num_phases == 4 ? 4 : 1;
+  const int m_tiles = grid.x * phases, n_tiles = grid.y;  // work items of one column tile (pixel tiles x output-parity phases)
   const int occ = BN == 256 ? 1 : 2;
   // fp32 rows with channel stride 1 and an odd pitch ([B, A, 85]): chunks go through a per-warp transpose scratch behind the ring
   const bool xpose = p.epi_mode == EPI_F32_BIAS && p.out_sc == 1 && BN <= 128 && p.num_bnseg == 0;
@@ -121,7 +122,7 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   int slots_kb = budget / Cfg::kStageBytes;  // k-blocks that fit in the ring
   // narrow layers (BLOCK_K 16 / 32) would spend their time on mbarrier round trips: put several k-blocks (up to 144
   // channels-taps) behind one barrier, keeping at least two ring slots
-  const int num_kb = p.num_taps * p.cin_blocks;
+  const int num_kb = phases == 4 ? p.cin_blocks : p.num_taps * p.cin_blocks;  // phases: 1 / 2 / 2 / 4 (or 1 each) taps -- slots must divide all
   int kbs = 1;
   if (BK <= 32)
     for (int t = 1; t <= num_kb; ++t)
@@ -139,10 +140,11 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   int groups = (occ * sm_count()) / n_tiles;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
+  if (phases == 4 && groups > 1 && groups % 2 == 0) --groups;  // odd stride through the work items: every CTA cycles through all four phases (1 / 2 / 2 / 4 taps)
   if (p.num_bnseg > 0) {  // data gradient with fused BatchNorm-backward statistics
     if constexpr (BN <= 128) {
       YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv_gemm_persistent_kernel<BN, BK, 2><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
+      launch_k(conv_gemm_persistent_kernel<BN, BK, 2>, groups * n_tiles, kConvThreadsP, smem, st, tmA, tmB, p, pst, kbs, n_tiles, m_tiles);
       YB_CHECK_CUDA(cudaGetLastError());
       return 0;
     } else {
@@ -152,9 +154,9 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   ConvGemmParams pp = p;
   pp.xpose = xpose ? 1 : 0;
   if (ext)
-    conv_gemm_persistent_kernel<BN, BK, 1><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, pp, pst, kbs, n_tiles, m_tiles);
+    launch_k(conv_gemm_persistent_kernel<BN, BK, 1>, groups * n_tiles, kConvThreadsP, smem, st, tmA, tmB, pp, pst, kbs, n_tiles, m_tiles);
   else
-    conv_gemm_persistent_kernel<BN, BK, 0><<<groups * n_tiles, kConvThreadsP, smem, st>>>(tmA, tmB, pp, pst, kbs, n_tiles, m_tiles);
+    launch_k(conv_gemm_persistent_kernel<BN, BK, 0>, groups * n_tiles, kConvThreadsP, smem, st, tmA, tmB, pp, pst, kbs, n_tiles, m_tiles);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -253,6 +255,7 @@ using namespace yb;
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, const float* __restrict__ cout_scale, int cout, int cin, int taps, int cout_pad,
                                         int cin_pad, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  pdl_sync();
   const long long total = 1LL * cout_pad * taps * cin_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = static_cast<int>(i % cin_pad);
@@ -273,7 +276,7 @@ static int pack_weight_impl(const float* w_oihw, const float* cout_scale, int co
              "pack_conv_weight: bad sizes cout=%d cin=%d k=%d pads=%d,%d", cout, cin, ksize, cout_pad, cin_pad);
   const long long total = 1LL * cout_pad * ksize * ksize * cin_pad;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
-  pack_conv_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout_scale, cout, cin, ksize * ksize, cout_pad, cin_pad,
+  launch_k(pack_conv_weight_kernel, blocks, 256, 0, as_stream(stream), w_oihw, cout_scale, cout, cin, ksize * ksize, cout_pad, cin_pad,
                                                                  static_cast<__nv_bfloat16*>(w_fwd),
                                                                  static_cast<__nv_bfloat16*>(w_dgrad));
   YB_CHECK_CUDA(cudaGetLastError());
@@ -284,6 +287,7 @@ static int pack_weight_impl(const float* w_oihw, const float* cout_scale, int co
 // launch latency at the head of the step.  `table` (device memory, built once per plan) lists the layers; `prefix[i]` = padded elements of
 // layers 0..i-1 (prefix[n] = total), so a thread finds its layer by binary search.
 __global__ void pack_conv_weights_batched_kernel(const yb200_pack_desc* __restrict__ table, const long long* __restrict__ prefix, int n) {
+  pdl_sync();
   // index space [0, total): forward operands in their own order; [total, 2 total): data-gradient operands in THEIR order -- both outputs are
   // written with consecutive 2-byte stores, the fp32 source is gathered (9 MB of parameters: L2 resident)
   const long long total = prefix[n];
@@ -314,7 +318,7 @@ __global__ void pack_conv_weights_batched_kernel(const yb200_pack_desc* __restri
 extern "C" int yb200_pack_conv_weights_batched(const yb200_pack_desc* table_dev, const int64_t* prefix_dev, int n, int64_t total, void* stream) {
   YB_REQUIRE(table_dev && prefix_dev && n > 0 && total > 0, YB200_ERR_INVALID, "pack_conv_weights_batched: bad arguments");
   const int blocks = static_cast<int>(std::min<long long>((2 * total + 255) / 256, 16LL * sm_count()));
-  pack_conv_weights_batched_kernel<<<blocks, 256, 0, as_stream(stream)>>>(table_dev, reinterpret_cast<const long long*>(prefix_dev), n);
+  launch_k(pack_conv_weights_batched_kernel, blocks, 256, 0, as_stream(stream), table_dev, reinterpret_cast<const long long*>(prefix_dev), n);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -325,6 +329,7 @@ extern "C" int yb200_pack_conv_weight(const float* w_oihw, int cout, int cin, in
 }
 
 __global__ void scale_bias_kernel(const float* __restrict__ scale, const float* __restrict__ bias, int n, float* __restrict__ out) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = scale[i] * bias[i];
 }
@@ -333,7 +338,7 @@ extern "C" int yb200_pack_conv_weight_scaled(const float* w_oihw, const float* c
                                              int cout_pad, int cin_pad, void* w_fwd, void* w_dgrad, float* scaled_bias, void* stream) {
   YB_REQUIRE(cout_scale != nullptr, YB200_ERR_INVALID, "pack_conv_weight_scaled: null scale");
   YB_REQUIRE((bias == nullptr) == (scaled_bias == nullptr), YB200_ERR_INVALID, "pack_conv_weight_scaled: pass both bias and scaled_bias or neither");
-  if (bias) scale_bias_kernel<<<ceil_div(cout, 256), 256, 0, as_stream(stream)>>>(cout_scale, bias, cout, scaled_bias);
+  if (bias) launch_k(scale_bias_kernel, ceil_div(cout, 256), 256, 0, as_stream(stream), cout_scale, bias, cout, scaled_bias);
   return pack_weight_impl(w_oihw, cout_scale, cout, cin, ksize, cout_pad, cin_pad, w_fwd, w_dgrad, stream);
 }
 
@@ -566,6 +571,7 @@ extern "C" int yb200_conv1x1_bias_f32(const yb200_act* x, const void* w_fwd, con
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_split_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cout_pad, int cin_pad, int planes,
                                               __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   const long long per_plane = 1LL * taps * cin_pad;
   const long long total = 1LL * cout_pad * per_plane;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -589,7 +595,7 @@ extern "C" int yb200_pack_conv_weight_split(const float* w_oihw, int cout, int c
              "pack_conv_weight_split: bad sizes cout=%d cin=%d k=%d pads=%d,%d planes=%d", cout, cin, ksize, cout_pad, cin_pad, planes);
   const long long total = 1LL * cout_pad * ksize * ksize * cin_pad;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
-  pack_conv_weight_split_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, cout_pad, cin_pad, planes,
+  launch_k(pack_conv_weight_split_kernel, blocks, 256, 0, as_stream(stream), w_oihw, cout, cin, ksize * ksize, cout_pad, cin_pad, planes,
                                                                        static_cast<__nv_bfloat16*>(w_split));
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -720,21 +726,45 @@ static int dgrad_impl(const yb200_act* dz, const void* w_dgrad, const yb200_act*
     return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, nt * p.cin_blocks), st, (gelu_u == nullptr && addend == nullptr) ? dx : nullptr);
   }
   // stride 2: input pixel (2i+ph, 2j+pw) receives  kh with (ph + 1 - kh) even:  ph=0 -> kh=1 (row i);  ph=1 -> kh=0 (row i+1), kh=2 (row i)
+  auto phase_taps = [&](int ph, int pw, ConvTap* out) {
+    int nt = 0;
+    if (ksize == 2) out[nt++] = ConvTap{dz->c_off, 0, 0, 0, (ph * 2 + pw) * dz->c};  // 2x2 s2: input pixel (2i+ph, 2j+pw) sees only tap (ph, pw)
+    for (int kh = 0; kh < 3 && ksize == 3; ++kh) {
+      if (((ph + 1 - kh) & 1) != 0) continue;
+      const int dh = (ph + 1 - kh) / 2;
+      for (int kw = 0; kw < 3; ++kw) {
+        if (((pw + 1 - kw) & 1) != 0) continue;
+        const int dw = (pw + 1 - kw) / 2;
+        out[nt++] = ConvTap{dz->c_off, dw, 0, dh, (kh * 3 + kw) * dz->c};
+      }
+    }
+    return nt;
+  };
+  p.out_mh = 2; p.out_mw = 2;
+  static int one_launch = -1;  // YB200_DGRAD_PHASES=4 restores one launch per output-parity class (A/B runs)
+  if (one_launch < 0) {
+    const char* e = getenv("YB200_DGRAD_PHASES");
+    one_launch = (e && e[0] == '4') ? 0 : 1;
+  }
+  const bool pair = bn == 256 && use_pair_kernel() && num_seg == 0;  // the CTA-pair kernel keeps the per-phase launches
+  if (one_launch && !use_v1_kernel() && !pair) {
+    // all four phases in ONE persistent launch: the phases of a pixel tile run back to back on neighbouring CTAs and share its dz tile in L2
+    int nt = 0;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        p.phase_tap[ph * 2 + pw] = nt;
+        nt += phase_taps(ph, pw, p.taps + nt);
+      }
+    p.phase_tap[4] = nt;
+    p.num_taps = nt;
+    p.num_phases = 4;
+    return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, p.cin_blocks), st);
+  }
   for (int ph = 0; ph < 2; ++ph)
     for (int pw = 0; pw < 2; ++pw) {
-      int nt = 0;
-      if (ksize == 2) p.taps[nt++] = ConvTap{dz->c_off, 0, 0, 0, (ph * 2 + pw) * dz->c};  // 2x2 s2: input pixel (2i+ph, 2j+pw) sees only tap (ph, pw)
-      for (int kh = 0; kh < 3 && ksize == 3; ++kh) {
-        if (((ph + 1 - kh) & 1) != 0) continue;
-        const int dh = (ph + 1 - kh) / 2;
-        for (int kw = 0; kw < 3; ++kw) {
-          if (((pw + 1 - kw) & 1) != 0) continue;
-          const int dw = (pw + 1 - kw) / 2;
-          p.taps[nt++] = ConvTap{dz->c_off, dw, 0, dh, (kh * 3 + kw) * dz->c};
-        }
-      }
+      const int nt = phase_taps(ph, pw, p.taps);
       p.num_taps = nt;
-      p.out_mh = 2; p.out_ph = ph; p.out_mw = 2; p.out_pw = pw;
+      p.out_ph = ph; p.out_pw = pw;
       if ((rc = launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, nt * p.cin_blocks), st))) return rc;
     }
   return 0;
@@ -851,7 +881,7 @@ static int launch_wgrad_inst(const CUtensorMap& tmDz, const CUtensorMap& tmX, co
     YB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     max_set = pl.smem;
   }
-  wgrad_gemm_kernel<TC><<<grid, kConvThreads, pl.smem, st>>>(tmDz, tmX, pl.p);
+  launch_k(wgrad_gemm_kernel<TC>, grid, kConvThreads, pl.smem, st, tmDz, tmX, pl.p);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -883,7 +913,7 @@ extern "C" int yb200_conv2d_wgrad(const yb200_act* x, const yb200_act* dz, int k
   if (rc) return rc;
   const long long total = 1LL * pl.p.cout * pl.p.num_taps * pl.p.cin;
   const int blocks = static_cast<int>(std::min<long long>((total + 31) / 32, 16 * sm_count()));
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(pl.p.ws, grad_oihw, pl.splits, pl.p.cout, pl.p.num_taps, pl.p.cin, cin_real, accumulate);
+  launch_k(wgrad_reduce_kernel, blocks, 256, 0, st, pl.p.ws, grad_oihw, pl.splits, pl.p.cout, pl.p.num_taps, pl.p.cin, cin_real, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

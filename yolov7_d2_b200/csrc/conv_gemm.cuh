@@ -104,11 +104,30 @@ struct ConvGemmParams {
   double* stat_sum;
   double* stat_sq;
   int stat_fold;  // > 0: column c accumulates into statistic c % stat_fold (pixel-grouped views: several columns are the same channel)
+  // num_phases == 4: ONE launch computes the four output-parity classes of a stride-2 data gradient.  Work item wi = 4 * tile + phase;
+  // phase (ph, pw) = (wi >> 1 & 1, wi & 1) uses taps[phase_tap[phase] .. phase_tap[phase + 1]) and writes pixel (2y + ph, 2x + pw).  The four
+  // phases of a tile run on neighbouring CTAs at about the same time, so the gradient tile they share comes from HBM once (four separate
+  // launches read the whole tensor four times).
+  int num_phases;
+  int phase_tap[5];
   int xpose;      // EPI_F32_BIAS with channel-contiguous rows: transpose each 32 x 32 chunk through shared memory (kXposeBytes behind the ring)
   const __nv_bfloat16* aux_in;  // EPI_BF16_GELU_BWD: pre-activation u, same geometry as `out`
   __nv_bfloat16* aux_out;       // EPI_BF16_BIAS_GELU: where u is stored (may be null), same geometry as `out`
   ConvTap taps[kMaxTaps];
 };
+
+__device__ __forceinline__ void conv_decode_work(const ConvGemmParams& p, int wi, int& m, int& tap0, int& ntaps, int& oph, int& opw) {
+  if (p.num_phases == 4) {
+    m = wi >> 2;
+    const int ph = wi & 3;
+    tap0 = p.phase_tap[ph];
+    ntaps = p.phase_tap[ph + 1] - tap0;
+    oph = ph >> 1;
+    opw = ph & 1;
+  } else {
+    m = wi; tap0 = 0; ntaps = p.num_taps; oph = p.out_ph; opw = p.out_pw;
+  }
+}
 
 template <int BLOCK_N, int BLOCK_K>
 struct ConvGemmCfg {
@@ -431,6 +450,7 @@ template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(kConvThreads)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvGemmParams p, int num_stages) {
+  pdl_sync();
   using Cfg = ConvGemmCfg<BLOCK_N, BLOCK_K>;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[2 * kMaxStages + 1];
@@ -606,7 +626,6 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   const int groups = gridDim.x / n_tiles;
   const int col0 = n_tile * BLOCK_N;
   const int log_tw = p.log_tw, log_th = p.log_th;
-  const int num_kb = p.num_taps * p.cin_blocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) {
@@ -620,9 +639,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 4 * 2 * BLOCK_N; i += blockDim.x) (&s_part[0][0][0])[i] = 0.f;
+  if (warp == 1) tmem_alloc<kTmemAlloc>(smem_u32(&s_tmem));
+  pdl_sync();  // everything above touches only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel
   if constexpr (BNB) stage_col_params_bnseg<BLOCK_N>(p, col0, s_col);
   else stage_col_params<BLOCK_N>(p, col0, s_col);
-  if (warp == 1) tmem_alloc<kTmemAlloc>(smem_u32(&s_tmem));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -635,14 +655,17 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       tma_prefetch_desc(&tmB);
       int stage = 0;
       uint32_t phase = 0;
-      for (int m = group; m < m_tiles; m += groups) {
+      for (int wi = group; wi < m_tiles; wi += groups) {  // m_tiles counts work items (pixel tiles x phases)
+        int m, tap, ntaps, oph, opw;
+        conv_decode_work(p, wi, m, tap, ntaps, oph, opw);
+        const int num_kb = ntaps * p.cin_blocks;
         int t = m;
         const int tw = t % p.tiles_w;
         t /= p.tiles_w;
         const int th = t % p.tiles_h;
         const int tn = t / p.tiles_h;
         const int w0 = tw << log_tw, h0 = th << log_th, n0 = tn << (7 - log_tw - log_th);
-        int tap = 0, cb = 0;
+        int cb = 0;
         for (int kb = 0; kb < num_kb; kb += kb_per_slot) {  // num_kb is a multiple of kb_per_slot
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8 * stage;
@@ -667,7 +690,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int m = group; m < m_tiles; m += groups, ++it) {
+      for (int wi = group; wi < m_tiles; wi += groups, ++it) {
+        int m, tap0, ntaps, oph, opw;
+        conv_decode_work(p, wi, m, tap0, ntaps, oph, opw);
+        const int num_kb = ntaps * p.cin_blocks;
         const int acc = it & 1;
         mbar_wait(bar_acc_empty + 8 * acc, ((it >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -708,7 +734,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     if (!BNB && p.xpose)
       xp = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + num_stages * kb_per_slot * Cfg::kStageBytes) + (warp - 2) * kXposeWarpFloats;
     int it = 0;
-    for (int m = group; m < m_tiles; m += groups, ++it) {
+    for (int wi = group; wi < m_tiles; wi += groups, ++it) {
+      int m, tap0, ntaps, oph, opw;
+      conv_decode_work(p, wi, m, tap0, ntaps, oph, opw);
       int t = m;
       const int tw = t % p.tiles_w;
       t /= p.tiles_w;
@@ -716,10 +744,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int tn = t / p.tiles_h;
       const int x = (tw << log_tw) + xl, y = (th << log_th) + yl, n = (tn << (7 - log_tw - log_th)) + nl;
       const bool valid = (x < p.w_valid) && (y < p.h_valid) && (n < p.n_valid);
-      const long long pix_off = (long long)n * p.out_sn + (long long)(y * p.out_mh + p.out_ph) * p.out_sh +
-                                (long long)(x * p.out_mw + p.out_pw) * p.out_sw;
-      const long long add_off = (long long)n * p.add_sn + (long long)(y * p.out_mh + p.out_ph) * p.add_sh +
-                                (long long)(x * p.out_mw + p.out_pw) * p.add_sw;
+      const long long pix_off = (long long)n * p.out_sn + (long long)(y * p.out_mh + oph) * p.out_sh +
+                                (long long)(x * p.out_mw + opw) * p.out_sw;
+      const long long add_off = (long long)n * p.add_sn + (long long)(y * p.out_mh + oph) * p.add_sh +
+                                (long long)(x * p.out_mw + opw) * p.add_sw;
       const int acc = it & 1;
       const __nv_bfloat16* side_row = side_base ? side_base + (side_is_aux ? pix_off : add_off) : nullptr;
       uint4 side[CH / 8];
@@ -732,8 +760,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg)
           if (sg < p.num_bnseg)
-            zrow[sg] = p.bnseg[sg].z + (long long)n * p.bnseg[sg].z_sn + (long long)(y * p.out_mh + p.out_ph) * p.bnseg[sg].z_sh +
-                       (long long)(x * p.out_mw + p.out_pw) * p.bnseg[sg].z_sw - p.bnseg[sg].col_begin;
+            zrow[sg] = p.bnseg[sg].z + (long long)n * p.bnseg[sg].z_sn + (long long)(y * p.out_mh + oph) * p.bnseg[sg].z_sh +
+                       (long long)(x * p.out_mw + opw) * p.bnseg[sg].z_sw - p.bnseg[sg].col_begin;
       }
       mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
@@ -874,6 +902,7 @@ conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   fence_proxy_async_smem();
   if (warp == 1) tmem_alloc<kTmemAlloc>(smem_u32(&s_tmem));
+  pdl_sync();  // the set-up above touches only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1068,6 +1097,7 @@ template <int BLOCK_K, bool EXT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreadsP, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ ConvGemmParams p, int num_stages, int n_tiles, int m_tiles) {
+  pdl_sync();
   constexpr int BLOCK_N = 256;
   constexpr int kSwizzle = BLOCK_K * 2;
   constexpr int kABytes = 128 * BLOCK_K * 2;

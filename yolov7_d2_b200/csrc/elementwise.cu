@@ -91,6 +91,7 @@ int grid_for(long long work, int threads) {
 // ------------------------------------------------------------------------------------------------
 __global__ void preprocess_focus_kernel(const uint8_t* __restrict__ img, int n, int h, int w, const int* __restrict__ hw_valid,
                                         float pad_value, __nv_bfloat16* __restrict__ out, int pitch) {
+  pdl_sync();
   const int oh = h / 2, ow = w / 2;
   const long long total = 1LL * n * oh * ow;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -123,6 +124,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ ssum, double* __restrict
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, long long* __restrict__ num_batches, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && num_batches) *num_batches += 1;
   if (i >= c) return;
@@ -147,6 +149,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ ssum, double* __restrict
 // eval mode: scale/shift from the running statistics (the fold of utils/checkpoint.py:11-43 applied as an epilogue)
 __global__ void bn_eval_affine_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
                                       const float* __restrict__ rv, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   const float s = gamma[i] / sqrtf(rv[i] + eps);
@@ -195,6 +198,7 @@ struct BnFinalize {
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_silu_kernel(View z, View a, View res, View up, const float* __restrict__ scale, const float* __restrict__ shift, int has_res,
                      int has_up, unsigned npix, int rev, BnFinalize fin) {
+  pdl_sync();
   const int c8 = threadIdx.x * 8;
   float s[8], t[8];
   if (fin.ssum != nullptr) {
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(kEwThreads, MINB)
 bn_silu_bwd_reduce_kernel(View z, DaSrc da, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, unsigned npix,
                           int iters, int rev) {
+  pdl_sync();
   extern __shared__ float sm[];  // [rows][2][c], rows = warps (c < 256) or blockDim.y (c >= 256)
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthreads = blockDim.x * blockDim.y;
@@ -418,6 +423,7 @@ __global__ void __launch_bounds__(kEwThreads, 3)
 bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ dgamma_acc,
                          const double* __restrict__ dbeta_acc, double inv_count, unsigned npix, int raw_sums) {
+  pdl_sync();
   const int c8 = threadIdx.x * 8;
   float s[8], t[8], A[8], B[8];
 #pragma unroll
@@ -463,6 +469,7 @@ bn_silu_bwd_apply_kernel(View z, DaSrc da, View dz, const float* __restrict__ sc
 __global__ void bn_param_grad_kernel(double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, int c, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int accumulate, const float* __restrict__ mean, const float* __restrict__ invstd,
                                      int raw_sums) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   const double dg = raw_sums ? static_cast<double>(invstd[i]) * (dgamma_acc[i] - static_cast<double>(mean[i]) * dbeta_acc[i]) : dgamma_acc[i];
@@ -478,6 +485,7 @@ __global__ void bn_param_grad_kernel(double* __restrict__ dgamma_acc, double* __
 // for the backward (first maximum in row-major window order, as ATen max_pool2d_with_indices).
 // ------------------------------------------------------------------------------------------------
 __global__ void spp_pool_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ arg) {
+  pdl_sync();
   const int cv = x.c / 8;
   const long long total = 1LL * x.n * x.h * x.w * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -534,6 +542,7 @@ __global__ void spp_pool_kernel(View x, View o5, View o9, View o13, uint8_t* __r
 template <int CG>  // channels per block: 16 keeps four blocks (32 warps) resident per SM at 20 x 20 -- the loops are shared-memory-latency bound
 __global__ void __launch_bounds__(256)
 spp_pool_tiled_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ arg) {
+  pdl_sync();
   extern __shared__ uint32_t sp[];  // [hw][CG] input (bf16 bits << 16), then [hw][CG] row results (bf16 bits << 16 | column code)
   const int hw = x.h * x.w;
   uint32_t* sin = sp;
@@ -588,6 +597,7 @@ spp_pool_tiled_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ 
 // backward: scatter the three pooled gradients to their argmax positions (fp32 atomics into a zeroed scratch), ...
 __global__ void spp_pool_bwd_scatter_kernel(View d5, View d9, View d13, const uint8_t* __restrict__ arg, float* __restrict__ scratch, int n,
                                             int h, int w, int c) {
+  pdl_sync();
   const long long total = 3LL * n * h * w * c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = static_cast<int>(i % c);
@@ -604,6 +614,7 @@ __global__ void spp_pool_bwd_scatter_kernel(View d5, View d9, View d13, const ui
 }
 // ... then dx = identity-branch gradient + scattered sums
 __global__ void spp_pool_bwd_finish_kernel(View d0, const float* __restrict__ scratch, View dx) {
+  pdl_sync();
   const int cv = dx.c / 8;
   const long long total = 1LL * dx.n * dx.h * dx.w * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -620,6 +631,7 @@ __global__ void spp_pool_bwd_finish_kernel(View d0, const float* __restrict__ sc
 
 // plain copy between views (used to place an activation into a concat slice when it cannot be produced there)
 __global__ void copy_view_kernel(View s, View d) {
+  pdl_sync();
   const int cv = s.c / 8;
   const long long total = 1LL * s.n * s.h * s.w * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -641,7 +653,7 @@ extern "C" int yb200_preprocess_focus(const uint8_t* images_nchw, int n, int h, 
   YB_REQUIRE(out->n == n && out->h == h / 2 && out->w == w / 2 && out->c == 16 && out->c_pitch >= 16 && out->c_pitch % 8 == 0 && out->c_off == 0,
              YB200_ERR_INVALID, "preprocess_focus: output must be the first 16 channels of a [n,h/2,w/2,pitch] buffer");
   const long long total = 1LL * n * (h / 2) * (w / 2);
-  preprocess_focus_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(images_nchw, n, h, w, hw_valid, pad_value,
+  launch_k(preprocess_focus_kernel, grid_for(total, 256), 256, 0, as_stream(stream), images_nchw, n, h, w, hw_valid, pad_value,
                                                                               static_cast<__nv_bfloat16*>(out->ptr), out->c_pitch);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -653,7 +665,7 @@ extern "C" int yb200_bn_finalize(double* stat_sum, double* stat_sqsum, int c, in
   YB_REQUIRE(stat_sum && stat_sqsum && gamma && beta && scale && shift && save_mean && save_invstd, YB200_ERR_INVALID, "bn_finalize: null pointer");
   YB_REQUIRE(c > 0 && count > 0, YB200_ERR_INVALID, "bn_finalize: c=%d count=%lld", c, (long long)count);
   YB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), YB200_ERR_INVALID, "bn_finalize: running stats must come in pairs");
-  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, as_stream(stream)>>>(stat_sum, stat_sqsum, c, static_cast<double>(count), gamma, beta, eps,
+  launch_k(bn_finalize_kernel, ceil_div(c, 128), 128, 0, as_stream(stream), stat_sum, stat_sqsum, c, static_cast<double>(count), gamma, beta, eps,
                                                                       momentum, running_mean, running_var,
                                                                       reinterpret_cast<long long*>(num_batches_tracked), scale, shift,
                                                                       save_mean, save_invstd);
@@ -664,7 +676,7 @@ extern "C" int yb200_bn_finalize(double* stat_sum, double* stat_sqsum, int c, in
 extern "C" int yb200_bn_eval_affine(int c, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
                                     float* scale, float* shift, void* stream) {
   YB_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && c > 0, YB200_ERR_INVALID, "bn_eval_affine: bad arguments");
-  bn_eval_affine_kernel<<<ceil_div(c, 128), 128, 0, as_stream(stream)>>>(c, gamma, beta, running_mean, running_var, eps, scale, shift);
+  launch_k(bn_eval_affine_kernel, ceil_div(c, 128), 128, 0, as_stream(stream), c, gamma, beta, running_mean, running_var, eps, scale, shift);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -685,7 +697,7 @@ static int bn_apply_impl(const yb200_act* z, const float* scale, const float* sh
   YB_REQUIRE(cv <= kEwThreads && npix < (1LL << 31), YB200_ERR_UNSUPPORTED, "bn_apply_silu: %d channels / %lld pixels", z->c, npix);
   dim3 block(cv, kEwThreads / cv);
   const unsigned grid = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
-  bn_apply_silu_kernel<<<grid, block, 0, as_stream(stream)>>>(vz, vo, vr, vu, scale, shift, residual != nullptr, out_up2x != nullptr,
+  launch_k(bn_apply_silu_kernel, grid, block, 0, as_stream(stream), vz, vo, vr, vu, scale, shift, residual != nullptr, out_up2x != nullptr,
                                                              static_cast<unsigned>(npix), l2_order(), fin);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -757,14 +769,14 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
     if (src.has_b || src.has_up) {  // fan-out / upsampled gradient sources: the general kernel
       if (red_smem > 48 * 1024)
         YB_CHECK_CUDA(cudaFuncSetAttribute(bn_silu_bwd_reduce_kernel<2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(red_smem)));
-      bn_silu_bwd_reduce_kernel<2, 3, false><<<grid_r2, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+      launch_k(bn_silu_bwd_reduce_kernel<2, 3, false>, grid_r2, block, red_smem, st, vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
                                                                                static_cast<unsigned>(npix), red_iters, l2_order());
     } else
 #define YB_RED(UU, MB)                                                                                                                     \
   if (red_u == UU && red_minb == MB) {                                                                                                     \
     if (red_smem > 48 * 1024)                                                                                                              \
       YB_CHECK_CUDA(cudaFuncSetAttribute(bn_silu_bwd_reduce_kernel<UU, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(red_smem))); \
-    bn_silu_bwd_reduce_kernel<UU, MB, true><<<grid_r2, block, red_smem, st>>>(vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,   \
+    launch_k(bn_silu_bwd_reduce_kernel<UU, MB, true>, grid_r2, block, red_smem, st, vz, src, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,   \
                                                                         static_cast<unsigned>(npix), red_iters, l2_order());                \
   } else
     YB_RED(1, 3) YB_RED(2, 3) YB_RED(4, 3) YB_RED(1, 4) YB_RED(2, 4) YB_RED(4, 4) YB_RED(2, 2) YB_RED(4, 2) YB_RED(1, 6) YB_RED(2, 6)
@@ -774,14 +786,14 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
   }
   const unsigned grid_a = static_cast<unsigned>((npix + block.y * kEwIters - 1) / (block.y * kEwIters));
   if (!src.has_b && !src.has_up)
-    bn_silu_bwd_apply_kernel<true><<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+    launch_k(bn_silu_bwd_apply_kernel<true>, grid_a, block, 0, st, vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
                                                               1.0 / static_cast<double>(npix), static_cast<unsigned>(npix), stats_ready);
   else
-    bn_silu_bwd_apply_kernel<false><<<grid_a, block, 0, st>>>(vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
+    launch_k(bn_silu_bwd_apply_kernel<false>, grid_a, block, 0, st, vz, src, vdz, scale, shift, save_mean, save_invstd, acc_dgamma, acc_dbeta,
                                                                1.0 / static_cast<double>(npix), static_cast<unsigned>(npix), stats_ready);
   YB_CHECK_CUDA(cudaGetLastError());
   if (dgamma == nullptr) return 0;  // deferred: yb200_bn_param_grads turns the accumulators of many layers into parameter gradients in one launch
-  bn_param_grad_kernel<<<ceil_div(z->c, 128), 128, 0, st>>>(acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate, save_mean, save_invstd, stats_ready);
+  launch_k(bn_param_grad_kernel, ceil_div(z->c, 128), 128, 0, st, acc_dgamma, acc_dbeta, z->c, dgamma, dbeta, accumulate, save_mean, save_invstd, stats_ready);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -790,6 +802,7 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
 __global__ void bn_param_grads_table_kernel(double* __restrict__ dgamma_acc, double* __restrict__ dbeta_acc, int c, const int* __restrict__ gamma_off,
                                             const int* __restrict__ beta_off, float* __restrict__ grad_base, int accumulate,
                                             const float* __restrict__ mean, const float* __restrict__ invstd, const uint8_t* __restrict__ raw) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   const bool is_raw = raw != nullptr && raw[i] != 0;
@@ -807,7 +820,7 @@ extern "C" int yb200_bn_param_grads(double* acc_dgamma, double* acc_dbeta, int c
                                     const float* save_mean, const float* save_invstd, const uint8_t* raw_sums, int accumulate, void* stream) {
   YB_REQUIRE(acc_dgamma && acc_dbeta && gamma_off && beta_off && grad_base && c > 0 && (!raw_sums || (save_mean && save_invstd)), YB200_ERR_INVALID,
              "bn_param_grads: bad arguments");
-  bn_param_grads_table_kernel<<<ceil_div(c, 128), 128, 0, as_stream(stream)>>>(acc_dgamma, acc_dbeta, c, gamma_off, beta_off, grad_base, accumulate,
+  launch_k(bn_param_grads_table_kernel, ceil_div(c, 128), 128, 0, as_stream(stream), acc_dgamma, acc_dbeta, c, gamma_off, beta_off, grad_base, accumulate,
                                                                                save_mean, save_invstd, raw_sums);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -839,12 +852,12 @@ extern "C" int yb200_spp_pool(const yb200_act* x, const yb200_act* o5, const yb2
       YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_tiled_kernel<kCg>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tiled_smem)));
       smem_set = tiled_smem;
     }
-    spp_pool_tiled_kernel<kCg><<<dim3(x->c / kCg, x->n), 256, tiled_smem, as_stream(stream)>>>(mk(x), mk(o5), mk(o9), mk(o13), argmax);
+    launch_k(spp_pool_tiled_kernel<kCg>, dim3(x->c / kCg, x->n), 256, tiled_smem, as_stream(stream), mk(x), mk(o5), mk(o9), mk(o13), argmax);
     YB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
   const long long total = 1LL * x->n * x->h * x->w * (x->c / 8);
-  spp_pool_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(mk(x), mk(o5), mk(o9), mk(o13), argmax);
+  launch_k(spp_pool_kernel, grid_for(total, 128), 128, 0, as_stream(stream), mk(x), mk(o5), mk(o9), mk(o13), argmax);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -860,9 +873,9 @@ extern "C" int yb200_spp_pool_bwd(const yb200_act* d0, const yb200_act* d5, cons
   cudaStream_t st = as_stream(stream);
   const long long elems = 1LL * dx->n * dx->h * dx->w * dx->c;
   YB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, elems * sizeof(float), st));
-  spp_pool_bwd_scatter_kernel<<<grid_for(3 * elems, 256), 256, 0, st>>>(mk(d5), mk(d9), mk(d13), argmax, scratch, dx->n, dx->h, dx->w, dx->c);
+  launch_k(spp_pool_bwd_scatter_kernel, grid_for(3 * elems, 256), 256, 0, st, mk(d5), mk(d9), mk(d13), argmax, scratch, dx->n, dx->h, dx->w, dx->c);
   YB_CHECK_CUDA(cudaGetLastError());
-  spp_pool_bwd_finish_kernel<<<grid_for(elems / 8, 256), 256, 0, st>>>(mk(d0), scratch, mk(dx));
+  launch_k(spp_pool_bwd_finish_kernel, grid_for(elems / 8, 256), 256, 0, st, mk(d0), scratch, mk(dx));
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -872,7 +885,7 @@ extern "C" int yb200_copy_view(const yb200_act* src, const yb200_act* dst, void*
   if ((rc = check_view(src, "copy_view src")) || (rc = check_view(dst, "copy_view dst"))) return rc;
   YB_REQUIRE(same_shape(src, dst), YB200_ERR_INVALID, "copy_view: shape mismatch");
   const long long total = 1LL * src->n * src->h * src->w * (src->c / 8);
-  copy_view_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(mk(src), mk(dst));
+  launch_k(copy_view_kernel, grid_for(total, 256), 256, 0, as_stream(stream), mk(src), mk(dst));
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,5 +1,7 @@
 #include "host_common.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace yb {
@@ -14,6 +16,15 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int sm_count() {

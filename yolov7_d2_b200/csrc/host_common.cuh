@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
+
 #include "../../include/yb200.h"
 
 namespace yb {
@@ -36,6 +38,26 @@ int make_mat_map(CUtensorMap* m, const void* ptr, long long rows, long long cols
 
 // pick (tw, th, tn) with tw*th*tn == npix (power of two) minimising padded pixels for an (n,h,w) grid
 void choose_tile(int n, int h, int w, int npix, int* log_tw, int* log_th);
+
+// Programmatic dependent launch: every kernel of the YOLOX path starts with pdl_sync() (griddepcontrol.wait, then launch_dependents) and is
+// launched through launch_k with the programmatic-stream-serialization attribute.  The next kernel of the stream (or of the captured graph) is
+// then scheduled while this one drains: its CTAs take the SM slots that free up and park at their own griddepcontrol.wait until this grid has
+// completed and flushed -- launch latency and block scheduling of ~540 launches per step leave the critical path.  YB200_PDL=0 launches plainly.
+bool use_pdl();
+template <typename... K, typename... A>
+inline cudaError_t launch_k(void (*kernel)(K...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }

@@ -34,6 +34,7 @@ __device__ __forceinline__ float clip_coef(const float* total_norm, float max_no
 
 // deterministic sum of squares: fixed grid, fixed in-block order, second stage in one block
 __global__ void __launch_bounds__(kOptThreads) sqnorm_partial_kernel(const float* __restrict__ g, int64_t n, float scale, double* __restrict__ partial) {
+  pdl_sync();
   __shared__ double s_w[kOptThreads / 32];
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * kOptThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kOptThreads) {
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(kOptThreads) sqnorm_partial_kernel(const float
   }
 }
 __global__ void sqnorm_final_kernel(const double* __restrict__ partial, int nparts, float* __restrict__ out_norm) {
+  pdl_sync();
   __shared__ double s_w[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += partial[i];
@@ -74,6 +76,7 @@ template <bool NESTEROV>
 __global__ void __launch_bounds__(kOptThreads) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, int64_t n, SegTable st,
                                                            float lr, float momentum, float dampening, int first_step, float grad_scale,
                                                            const float* __restrict__ total_norm, float max_norm) {
+  pdl_sync();
   const long long i0 = ((long long)blockIdx.x * kOptThreads + threadIdx.x) * 4;
   if (i0 >= n) return;
   const float gs = grad_scale * clip_coef(total_norm, max_norm);
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(kOptThreads) sgd_kernel(float* __restrict__ p,
 __global__ void __launch_bounds__(kOptThreads) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                              int64_t n, SegTable st, float lr, float beta1, float beta2, float eps, float bc1,
                                                              float bc2_sqrt, float grad_scale, const float* __restrict__ total_norm, float max_norm) {
+  pdl_sync();
   const long long i0 = ((long long)blockIdx.x * kOptThreads + threadIdx.x) * 4;
   if (i0 >= n) return;
   const float gs = grad_scale * clip_coef(total_norm, max_norm);
@@ -155,8 +159,8 @@ extern "C" int64_t yb200_grad_norm_workspace(void) { return kNormBlocks * sizeof
 extern "C" int yb200_grad_norm(const float* grad, int64_t n, float grad_scale, void* workspace, float* out_norm, void* stream) {
   YB_REQUIRE(grad && workspace && out_norm && n >= 0, YB200_ERR_INVALID, "grad_norm: null pointer");
   cudaStream_t st = as_stream(stream);
-  sqnorm_partial_kernel<<<kNormBlocks, kOptThreads, 0, st>>>(grad, n, grad_scale, static_cast<double*>(workspace));
-  sqnorm_final_kernel<<<1, 256, 0, st>>>(static_cast<const double*>(workspace), kNormBlocks, out_norm);
+  launch_k(sqnorm_partial_kernel, kNormBlocks, kOptThreads, 0, st, grad, n, grad_scale, static_cast<double*>(workspace));
+  launch_k(sqnorm_final_kernel, 1, 256, 0, st, static_cast<const double*>(workspace), kNormBlocks, out_norm);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -174,9 +178,9 @@ extern "C" int yb200_sgd_step(float* param, const float* grad, float* momentum_b
   const long long threads = (n + 3) / 4;
   const int blocks = static_cast<int>((threads + kOptThreads - 1) / kOptThreads);
   if (nesterov)
-    sgd_kernel<true><<<blocks, kOptThreads, 0, as_stream(stream)>>>(param, grad, momentum_buf, n, st, lr, momentum, dampening, first_step, grad_scale, total_norm, max_norm);
+    launch_k(sgd_kernel<true>, blocks, kOptThreads, 0, as_stream(stream), param, grad, momentum_buf, n, st, lr, momentum, dampening, first_step, grad_scale, total_norm, max_norm);
   else
-    sgd_kernel<false><<<blocks, kOptThreads, 0, as_stream(stream)>>>(param, grad, momentum_buf, n, st, lr, momentum, dampening, first_step, grad_scale, total_norm, max_norm);
+    launch_k(sgd_kernel<false>, blocks, kOptThreads, 0, as_stream(stream), param, grad, momentum_buf, n, st, lr, momentum, dampening, first_step, grad_scale, total_norm, max_norm);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -193,7 +197,7 @@ extern "C" int yb200_adamw_step(float* param, const float* grad, float* exp_avg,
   const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow((double)beta2, (double)step)));
   const long long threads = (n + 3) / 4;
   const int blocks = static_cast<int>((threads + kOptThreads - 1) / kOptThreads);
-  adamw_kernel<<<blocks, kOptThreads, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, st, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale,
+  launch_k(adamw_kernel, blocks, kOptThreads, 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, st, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale,
                                                                total_norm, max_norm);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;

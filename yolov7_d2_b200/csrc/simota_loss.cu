@@ -53,6 +53,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 //   yolox_head.py:226-245 (train), 197-224 + 247-272 (eval)
 // ------------------------------------------------------------------------------------------------
 __global__ void decode_kernel(float* __restrict__ out, int batch, int num_anchors, int ch, Levels L, int eval_mode) {
+  pdl_sync();
   const long long total = 1LL * batch * num_anchors;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int a = static_cast<int>(i % num_anchors);
@@ -123,6 +124,7 @@ __device__ __forceinline__ float pair_cost(float s_all, float p_gt, float iou, b
 // kernel 1: number of gts per image, candidate anchors and their class-cost base
 // ------------------------------------------------------------------------------------------------
 __global__ void simota_count_gt_kernel(const float* __restrict__ labels, int batch, int gmax, int* __restrict__ num_gt, int* __restrict__ totals) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) { totals[0] = 0; totals[1] = 0; }
   if (b >= batch) return;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(kPrepAnchors)
 simota_prep_kernel(const float* __restrict__ outputs, const float* __restrict__ labels, const int* __restrict__ num_gt, int num_anchors, int ch,
                    int gmax, Levels L, uint8_t* __restrict__ cand, float* __restrict__ s_all, int* __restrict__ match_count,
                    int* __restrict__ totals) {
+  pdl_sync();
   extern __shared__ __align__(16) float tile[];  // [kPrepAnchors][ch]
   __shared__ Gt gts[kMaxGt];
   const int b = blockIdx.y;
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(kMatchThreads)
 simota_match_kernel(const float* __restrict__ outputs, const float* __restrict__ labels, const int* __restrict__ num_gt, int num_anchors, int ch,
                     int gmax, Levels L, const uint8_t* __restrict__ cand, const float* __restrict__ s_all, int* __restrict__ match_count,
                     int* __restrict__ matched_gt) {
+  pdl_sync();
   const int b = blockIdx.y, g = blockIdx.x;
   if (g >= num_gt[b]) return;
   const Gt gt = load_gt(labels, b, gmax, g);
@@ -348,6 +352,7 @@ __global__ void simota_resolve_kernel(const float* __restrict__ outputs, const f
                                       const int* __restrict__ match_count, int* __restrict__ matched_gt, float* __restrict__ matched_iou,
                                       int* __restrict__ matched_cls, uint8_t* __restrict__ fg_mask, int* __restrict__ num_fg_img,
                                       int* __restrict__ totals) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   int fg = 0;
@@ -419,6 +424,7 @@ yolox_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ l
                   const uint8_t* __restrict__ fg_mask, const int* __restrict__ matched_gt, const float* __restrict__ matched_iou,
                   const int* __restrict__ matched_cls, const int* __restrict__ totals, const float* __restrict__ weights, LossOut out,
                   int want_loss, int want_grad) {
+  pdl_sync();
   extern __shared__ __align__(16) float tile[];  // [kLossAnchors][ch] outputs, reused for gradients
   __shared__ double s_loss[3];
   const int b = blockIdx.y;
@@ -538,6 +544,7 @@ yolox_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ l
 
 // (total, 5*iou, obj, cls, l1 = 0, num_fg / max(num_gts, 1))  --  the 6-tuple get_losses returns (yolox_head.py:433-441)
 __global__ void yolox_loss_finish_kernel(double* __restrict__ loss_acc, const int* __restrict__ totals, float* __restrict__ out6) {
+  pdl_sync();
   const float nfg = fmaxf(static_cast<float>(totals[0]), 1.f);
   const float li = static_cast<float>(loss_acc[0]) / nfg, lo = static_cast<float>(loss_acc[1]) / nfg, lc = static_cast<float>(loss_acc[2]) / nfg;
   out6[0] = 5.f * li + lo + lc;
@@ -585,7 +592,7 @@ extern "C" int yb200_yolox_decode(float* outputs, int batch, int num_anchors, in
   if (rc) return rc;
   const long long total = 1LL * batch * num_anchors;
   const int blocks = static_cast<int>(std::min<long long>((total + 127) / 128, 16LL * sm_count()));
-  decode_kernel<<<blocks, 128, 0, as_stream(stream)>>>(outputs, batch, num_anchors, channels, L, eval_mode);
+  launch_k(decode_kernel, blocks, 128, 0, as_stream(stream), outputs, batch, num_anchors, channels, L, eval_mode);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -617,7 +624,7 @@ extern "C" int yb200_simota_assign(const float* outputs, const float* labels, in
   float* s_all = reinterpret_cast<float*>(ws + pad(ba));
   int* match_count = reinterpret_cast<int*>(ws + pad(ba) + pad(4 * ba));
   YB_CHECK_CUDA(cudaMemsetAsync(num_fg_img, 0, sizeof(int) * batch, st));
-  simota_count_gt_kernel<<<ceil_div(batch, 64), 64, 0, st>>>(labels, batch, max_gt, num_gt, totals);
+  launch_k(simota_count_gt_kernel, ceil_div(batch, 64), 64, 0, st, labels, batch, max_gt, num_gt, totals);
   YB_CHECK_CUDA(cudaGetLastError());
   const size_t tile = static_cast<size_t>(kPrepAnchors) * channels * sizeof(float);
   static size_t prep_smem = 0;
@@ -625,13 +632,13 @@ extern "C" int yb200_simota_assign(const float* outputs, const float* labels, in
     YB_CHECK_CUDA(cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile)));
     prep_smem = tile;
   }
-  simota_prep_kernel<<<dim3(ceil_div(num_anchors, kPrepAnchors), batch), kPrepAnchors, tile, st>>>(outputs, labels, num_gt, num_anchors, channels,
+  launch_k(simota_prep_kernel, dim3(ceil_div(num_anchors, kPrepAnchors), batch), kPrepAnchors, tile, st, outputs, labels, num_gt, num_anchors, channels,
                                                                                                   max_gt, L, cand, s_all, match_count, totals);
   YB_CHECK_CUDA(cudaGetLastError());
-  simota_match_kernel<<<dim3(max_gt, batch), kMatchThreads, 0, st>>>(outputs, labels, num_gt, num_anchors, channels, max_gt, L, cand, s_all,
+  launch_k(simota_match_kernel, dim3(max_gt, batch), kMatchThreads, 0, st, outputs, labels, num_gt, num_anchors, channels, max_gt, L, cand, s_all,
                                                                      match_count, matched_gt);
   YB_CHECK_CUDA(cudaGetLastError());
-  simota_resolve_kernel<<<dim3(ceil_div(num_anchors, 128), batch), 128, 0, st>>>(outputs, labels, num_gt, num_anchors, channels, max_gt, L, s_all,
+  launch_k(simota_resolve_kernel, dim3(ceil_div(num_anchors, 128), batch), 128, 0, st, outputs, labels, num_gt, num_anchors, channels, max_gt, L, s_all,
                                                                                  match_count, matched_gt, matched_iou, matched_cls, fg_mask,
                                                                                  num_fg_img, totals);
   YB_CHECK_CUDA(cudaGetLastError());
@@ -670,11 +677,11 @@ extern "C" int yb200_yolox_loss(const float* outputs, const float* labels, int b
     loss_smem = tile;
   }
   static_assert(kLossAnchors == 128, "Levels::blk_off assumes 128-anchor blocks");
-  yolox_loss_kernel<<<dim3(L.blk_off[kMaxLevels], batch), kLossAnchors, tile, st>>>(
+  launch_k(yolox_loss_kernel, dim3(L.blk_off[kMaxLevels], batch), kLossAnchors, tile, st, 
       outputs, labels, num_anchors, channels, max_gt, L, fg_mask, matched_gt, matched_iou, matched_cls, totals, weights3, out, want_loss, want_grad);
   YB_CHECK_CUDA(cudaGetLastError());
   if (want_loss) {
-    yolox_loss_finish_kernel<<<1, 1, 0, st>>>(loss_acc3, totals, losses6);
+    launch_k(yolox_loss_finish_kernel, 1, 1, 0, st, loss_acc3, totals, losses6);
     YB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -683,6 +690,7 @@ extern "C" int yb200_yolox_loss(const float* outputs, const float* labels, int b
 // sum over anchors of the raw-output gradients = bias gradients of cls_preds / reg_preds / obj_preds (yolox_head.py:103-129)
 __global__ void head_bias_grad_kernel(double* __restrict__ bias_acc, int num_levels, int ch, float* __restrict__ g_reg, float* __restrict__ g_obj,
                                       float* __restrict__ g_cls, int level, int accumulate) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ch) return;
   const float v = static_cast<float>(bias_acc[level * ch + c]);
@@ -695,7 +703,7 @@ extern "C" int yb200_head_bias_grad(double* bias_acc, int num_levels, int channe
                                     float* grad_cls_bias, int accumulate, void* stream) {
   YB_REQUIRE(bias_acc && grad_reg_bias4 && grad_obj_bias1 && grad_cls_bias && level >= 0 && level < num_levels && channels > 5, YB200_ERR_INVALID,
              "head_bias_grad: bad arguments");
-  head_bias_grad_kernel<<<ceil_div(channels, 128), 128, 0, as_stream(stream)>>>(bias_acc, num_levels, channels, grad_reg_bias4, grad_obj_bias1,
+  launch_k(head_bias_grad_kernel, ceil_div(channels, 128), 128, 0, as_stream(stream), bias_acc, num_levels, channels, grad_reg_bias4, grad_obj_bias1,
                                                                                grad_cls_bias, level, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;

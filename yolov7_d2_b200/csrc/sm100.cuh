@@ -12,6 +12,13 @@
 
 namespace yb {
 
+// Programmatic dependent launch (host side: launch_k in host_common.cuh).  Must precede the first global-memory access of the kernel (reads of
+// predecessors' results AND writes to buffers they may still read); without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -38,6 +38,7 @@ template <int TMEM_COLS>
 __global__ void __launch_bounds__(kConvThreads)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX,
                   const __grid_constant__ WgradParams p) {
+  pdl_sync();
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[2 * kWgStages + 1];
   __shared__ uint32_t s_tmem;
@@ -184,6 +185,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad_oihw, int splits, int cout, int num_taps, int cin_pad,
                     int cin_real, int accumulate) {
+  pdl_sync();
   __shared__ float part[8][33];
   const unsigned total = static_cast<unsigned>(cout) * num_taps * cin_pad;
   const unsigned tc = static_cast<unsigned>(num_taps) * cin_pad;
