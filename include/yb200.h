@@ -63,7 +63,8 @@ int yb200_conv2d_bn_silu_fwd(const yb200_act* x, const void* w_fwd, const float*
 
 /* yb200_conv2d_fwd on a PIXEL-GROUPED view: when g horizontally adjacent pixels are viewed as one pixel of g*C channels (same memory), a
  * convolution becomes a convolution of the grouped tensors with an expanded weight matrix; output column k is channel k % stat_fold of one of
- * the g pixels, and the BatchNorm sums accumulate per channel.  Used for the stem (12 -> 32 channels at 320x320: 32-byte pixel rows are bound by
+ * the g pixels, and the BatchNorm sums accumulate per channel.  For ksize 3 the weights MUST be such an expansion: the kernel skips the products of
+ * the left / right neighbour group that the expansion makes zero (all but its last / first pixel).  Used for the stem (12 -> 32 channels at 320x320: 32-byte pixel rows are bound by
  * the TMA row rate; grouped by 4 they are 128-byte rows), `BaseConv` of `backbone.stem.conv` (darknetx.py:117, wrappers.py:60-80).            */
 int yb200_conv2d_fwd_fold(const yb200_act* x, const void* w_fwd, const yb200_act* z, int ksize, int stride,
                           double* stat_sum, double* stat_sqsum, int stat_fold, void* stream);

@@ -98,13 +98,21 @@ def test_bn_finalize_apply_and_backward(cuda, c, hw, res, up):
     assert (acc1 == 0).all() and (acc2 == 0).all()
 
 
-def test_spp_pool_fwd_bwd(cuda):
+@pytest.mark.parametrize("levels", [0, 2], ids=["random", "many_ties"])
+def test_spp_pool_fwd_bwd(cuda, levels):
+    """levels > 0: values quantised to multiples of 1/levels -- every window holds several equal maxima, so the gradient routing checks the
+    first-maximum (row-major) rule of ATen's max_pool2d_with_indices, through the 5 -> 9 -> 13 cascade of the kernel"""
     from yolov7_d2_b200 import capi
 
     L = capi.lib()
     n, c, hw = 3, 64, 20
     g = torch.Generator().manual_seed(3)
-    x = torch.randn(n, c, hw, hw, generator=g).to(torch.bfloat16)
+    x = torch.randn(n, c, hw, hw, generator=g)
+    if levels:
+        x = torch.round(x * levels) / levels
+        x[0, :8] = 0.0  # constant planes, +0 / -0 mixed
+        x[0, :4, ::2] = -0.0
+    x = x.to(torch.bfloat16)
     cat = torch.zeros(n, hw, hw, 4 * c, dtype=torch.bfloat16, device=cuda)
     cat[..., :c] = nhwc(x).to(cuda)
     arg = torch.empty(3, n, hw, hw, c, dtype=torch.uint8, device=cuda)

@@ -214,7 +214,7 @@ static int fill_fwd_taps(ConvTap* taps, const yb200_act& x, int ksize, int strid
   } else {
     for (int kh = 0; kh < 3; ++kh)
       for (int kw = 0; kw < 3; ++kw) {
-        ConvTap t;
+        ConvTap t{};
         if (stride == 1) {
           t.c0 = x.c_off; t.dw = kw - 1; t.p = 0; t.dh = kh - 1;
         } else {  // input row 2*o + kh - 1: kh=0 -> (parity 1, o-1), kh=1 -> (0, o), kh=2 -> (1, o)
@@ -286,37 +286,57 @@ static int pack_weight_impl(const float* w_oihw, const float* cout_scale, int co
 // every convolution of a plan in ONE launch: the per-layer kernels are a few microseconds of work each, so ~70 launches per step are pure
 // launch latency at the head of the step.  `table` (device memory, built once per plan) lists the layers; `prefix[i]` = padded elements of
 // layers 0..i-1 (prefix[n] = total), so a thread finds its layer by binary search.
-__global__ void pack_conv_weights_batched_kernel(const yb200_pack_desc* __restrict__ table, const long long* __restrict__ prefix, int n) {
+constexpr int kPackMaxLayers = 256;
+__global__ void __launch_bounds__(256)
+pack_conv_weights_batched_kernel(const yb200_pack_desc* __restrict__ table, const long long* __restrict__ prefix, int n) {
   pdl_sync();
-  // index space [0, total): forward operands in their own order; [total, 2 total): data-gradient operands in THEIR order -- both outputs are
-  // written with consecutive 2-byte stores, the fp32 source is gathered (9 MB of parameters: L2 resident)
-  const long long total = prefix[n];
-  for (long long i2 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i2 < 2 * total; i2 += (long long)gridDim.x * blockDim.x) {
-    const bool second = i2 >= total;
-    const long long i = second ? i2 - total : i2;
+  // Work unit = one ROW of a packed operand, one warp per row: forward rows (co, tap) run over ci, data-gradient rows (ci, tap) over co, so both
+  // outputs are written with consecutive 2-byte stores; the fp32 source is gathered (9 M parameters: L2 resident).  Row r of the launch belongs
+  // to layer l with rows_before[l] <= r: the row prefix is rebuilt per block in shared memory (n <= 256 layers), one binary search per row.
+  __shared__ int s_rows[kPackMaxLayers + 1];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < n; ++l) {
+      s_rows[l] = acc;
+      const yb200_pack_desc d = table[l];
+      const int taps = d.ksize * d.ksize;
+      acc += (d.w_fwd ? d.cout_pad * taps : 0) + (d.w_dgrad ? d.cin_pad * taps : 0);
+    }
+    s_rows[n] = acc;
+  }
+  __syncthreads();
+  const int total_rows = s_rows[n];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < total_rows; r += warps) {
     int lo = 0, hi = n - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (prefix[mid] <= i) lo = mid; else hi = mid - 1;
+      if (s_rows[mid] <= r) lo = mid; else hi = mid - 1;
     }
     const yb200_pack_desc d = table[lo];
-    const unsigned e = static_cast<unsigned>(i - prefix[lo]);  // one layer holds < 2^31 padded elements
-    const unsigned taps = d.ksize * d.ksize;
-    unsigned ci, t, co;
-    if (!second) {
-      if (!d.w_fwd) continue;
-      ci = e % d.cin_pad; t = (e / d.cin_pad) % taps; co = e / (d.cin_pad * taps);
-    } else {
-      if (!d.w_dgrad) continue;
-      co = e % d.cout_pad; t = (e / d.cout_pad) % taps; ci = e / (d.cout_pad * taps);
+    const int taps = d.ksize * d.ksize;
+    int q = r - s_rows[lo];
+    const int fwd_rows = d.w_fwd ? d.cout_pad * taps : 0;
+    if (q < fwd_rows) {  // forward operand [cout_pad][taps][cin_pad]
+      const int co = q / taps, t = q - co * taps;
+      __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(d.w_fwd) + static_cast<size_t>(q) * d.cin_pad;
+      const float* src = d.w_oihw + static_cast<size_t>(co) * d.cin * taps + t;
+      for (int ci = lane; ci < d.cin_pad; ci += 32)
+        dst[ci] = __float2bfloat16_rn((co < d.cout && ci < d.cin) ? src[static_cast<size_t>(ci) * taps] : 0.f);
+    } else {             // data-gradient operand [cin_pad][taps][cout_pad]
+      q -= fwd_rows;
+      const int ci = q / taps, t = q - ci * taps;
+      __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(d.w_dgrad) + static_cast<size_t>(q) * d.cout_pad;
+      const float* src = d.w_oihw + static_cast<size_t>(ci) * taps + t;
+      for (int co = lane; co < d.cout_pad; co += 32)
+        dst[co] = __float2bfloat16_rn((co < d.cout && ci < d.cin) ? src[static_cast<size_t>(co) * d.cin * taps] : 0.f);
     }
-    const float v = (co < static_cast<unsigned>(d.cout) && ci < static_cast<unsigned>(d.cin)) ? d.w_oihw[(1LL * co * d.cin + ci) * taps + t] : 0.f;
-    static_cast<__nv_bfloat16*>(second ? d.w_dgrad : d.w_fwd)[e] = __float2bfloat16_rn(v);
   }
 }
 
 extern "C" int yb200_pack_conv_weights_batched(const yb200_pack_desc* table_dev, const int64_t* prefix_dev, int n, int64_t total, void* stream) {
-  YB_REQUIRE(table_dev && prefix_dev && n > 0 && total > 0, YB200_ERR_INVALID, "pack_conv_weights_batched: bad arguments");
+  YB_REQUIRE(table_dev && prefix_dev && n > 0 && n <= kPackMaxLayers && total > 0, YB200_ERR_INVALID, "pack_conv_weights_batched: bad arguments (n=%d)", n);
   const int blocks = static_cast<int>(std::min<long long>((2 * total + 255) / 256, 16LL * sm_count()));
   launch_k(pack_conv_weights_batched_kernel, blocks, 256, 0, as_stream(stream), table_dev, reinterpret_cast<const long long*>(prefix_dev), n);
   YB_CHECK_CUDA(cudaGetLastError());
@@ -351,7 +371,7 @@ extern "C" int yb200_pack_conv_weight_scaled(const float* w_oihw, const float* c
 // term x_i * w_j with i + j < planes (the dropped ones are below 2^-8planes relative) as extra taps of the SAME implicit GEMM -- one fp32
 // accumulator in TMEM, no extra kernel: 3 taps per spatial tap for two planes, 6 for three.
 static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int ksize, int stride, ConvGemmParams& p,
-                           cudaStream_t st, int lo_delta = 0, int planes = 1, const yb200_act* out_act = nullptr) {
+                           cudaStream_t st, int lo_delta = 0, int planes = 1, const yb200_act* out_act = nullptr, int group = 0) {
   YB_REQUIRE(w_fwd != nullptr, YB200_ERR_INVALID, "conv fwd: null weights");
   YB_REQUIRE((ksize == 1 && stride == 1) || (ksize == 2 && stride == 2) || (ksize == 3 && (stride == 1 || stride == 2)), YB200_ERR_UNSUPPORTED,
              "conv fwd: ksize=%d stride=%d not implemented", ksize, stride);
@@ -386,6 +406,24 @@ static int conv_fwd_common(const yb200_act* x, const void* w_fwd, int cout, int 
   }
   p.cin_blocks = x->c / bk;
   p.cout = cout;
+  if (group > 1 && ksize == 3 && stride == 1 && lo_delta == 0 && p.cin_blocks == 1 && x->c_off == 0 && x->c == x->c_pitch && (x->c / group) % 16 == 0) {
+    // pixel-grouped 3x3 convolution (yb200_conv2d_fwd_fold): of the left neighbour GROUP only its last pixel reaches this group's outputs, of the
+    // right neighbour only its first.  The side taps therefore load / multiply `cpp` channels instead of group * cpp: their activation box starts
+    // at the needed pixel (the rest of the box lies beyond the channel extent: TMA zero fill, no L2 traffic), the weight box at the matching
+    // columns, and the persistent kernel issues only the first cpp / 16 K steps.  Correct in every kernel variant (the skipped products are
+    // zero either way); YB200_STEM_SPARSE=0 keeps the dense taps for A/B runs.
+    static int sparse = -1;
+    if (sparse < 0) {
+      const char* e = getenv("YB200_STEM_SPARSE");
+      sparse = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int cpp = x->c / group;
+    for (int t = 0; t < p.num_taps && sparse; ++t) {
+      ConvTap& tp = p.taps[t];
+      if (tp.dw == -1) { tp.c0 += (group - 1) * cpp; tp.kb += (group - 1) * cpp; tp.ks = cpp / 16; }
+      if (tp.dw == 1) tp.ks = cpp / 16;
+    }
+  }
   const int tw = 1 << p.log_tw, th = 1 << p.log_th, tn = 128 >> (p.log_tw + p.log_th);
   CUtensorMap tmA, tmB;
   int rc = make_act_map(&tmA, *x, stride == 2, bk, tw, th, tn);
@@ -429,7 +467,7 @@ static int conv2d_fwd_impl(const yb200_act* x, const void* w_fwd, const yb200_ac
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sqsum;
   p.stat_fold = stat_fold;
-  return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream), 0, 1, z);
+  return conv_fwd_common(x, w_fwd, z->c, ksize, stride, p, as_stream(stream), 0, 1, z, stat_fold > 0 ? z->c / stat_fold : 0);
 }
 
 extern "C" int yb200_conv2d_bn_silu_fwd(const yb200_act* x, const void* w_fwd, const float* scale, const float* shift,

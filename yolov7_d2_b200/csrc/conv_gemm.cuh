@@ -67,6 +67,7 @@ struct ConvTap {
   int p;   // coordinate in the parity dimension
   int dh;  // offset in h
   int kb;  // column offset of this tap inside the B matrix
+  int ks;  // > 0: only the first ks 16-wide K steps of each k-block of this tap carry non-zero operands (persistent kernel: the rest is skipped)
 };
 
 // Fused BatchNorm-backward statistics (kernel variant 2, data-gradient launches): the epilogue that produces the FINAL gradient da of an
@@ -698,18 +699,23 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         mbar_wait(bar_acc_empty + 8 * acc, ((it >> 1) & 1) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * kAccCols;
+        int tap = tap0, cb = 0;
         for (int kb = 0; kb < num_kb; kb += kb_per_slot) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           for (int j = 0; j < kb_per_slot; ++j) {
             const uint32_t sa = smem_base + (stage * kb_per_slot + j) * Cfg::kStageBytes;
             const uint32_t sb = sa + Cfg::kABytes;
+            const int ks = p.taps[tap].ks > 0 ? p.taps[tap].ks : BLOCK_K / 16;
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
-              const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
-              const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
-              umma_f16(tacc, da, db, idesc, (kb | j | k) != 0 ? 1u : 0u);
+              if (k < ks) {
+                const uint64_t da = umma_smem_desc(sa + k * 32, 16, sbo, lcode);
+                const uint64_t db = umma_smem_desc(sb + k * 32, 16, sbo, lcode);
+                umma_f16(tacc, da, db, idesc, (kb | j | k) != 0 ? 1u : 0u);
+              }
             }
+            if (++cb == p.cin_blocks) { cb = 0; ++tap; }
           }
           umma_commit(bar_empty + 8 * stage);
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }

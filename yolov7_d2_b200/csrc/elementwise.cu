@@ -535,62 +535,105 @@ __global__ void spp_pool_kernel(View x, View o5, View o9, View o13, uint8_t* __r
   }
 }
 
-// Shared-memory version for maps that fit in one SM (the usual case: 20x20 at 640 px): one block per (32 channels, image),
-// separable max with argmax -- row pass keeps (max, first column) per pixel, column pass picks the first row with the
-// largest row-max, which is exactly the first maximum of the 2-D window in row-major order.
-// The low 16 bits of the packed word carry the column code so one 4-byte shared-memory read serves value and index.
-template <int CG>  // channels per block: 16 keeps four blocks (32 warps) resident per SM at 20 x 20 -- the loops are shared-memory-latency bound
+// Shared-memory version for maps that fit in one SM (the usual case: 20x20 at 640 px): one block per (CG channels, image).
+// Every element becomes a 32-bit KEY = (order-preserving code of the bf16 value) << 16 | (0xFFFF - pixel index): the unsigned maximum of keys is
+// the maximum value and, among equal values, the SMALLEST pixel index = the first maximum of the window in row-major order (ATen's rule), whatever
+// the order in which the candidates are combined.  Max-pooling of keys is therefore separable (row pass, column pass: 5 + 5 reads) and cascades:
+// pool9 = pool5(pool5), pool13 = pool5(pool9), exactly, borders included (windows clipped to the map = -inf padding).  30 shared-memory reads and
+// 30 integer maxima per element for the three sizes instead of 54 compare / select chains.
+__device__ __forceinline__ uint32_t spp_key(unsigned short bits, int pix) {
+  if (bits == 0x8000u) bits = 0;  // -0 == +0
+  const uint32_t ord = (bits & 0x8000u) ? (~static_cast<uint32_t>(bits) & 0xFFFFu) : (static_cast<uint32_t>(bits) | 0x8000u);
+  return (ord << 16) | static_cast<uint32_t>(0xFFFF - pix);
+}
+__device__ __forceinline__ unsigned short spp_key_bits(uint32_t key) {
+  const uint32_t ord = key >> 16;
+  return static_cast<unsigned short>((ord & 0x8000u) ? (ord & 0x7FFFu) : (~ord & 0xFFFFu));
+}
+
+template <int CG>
 __global__ void __launch_bounds__(256)
 spp_pool_tiled_kernel(View x, View o5, View o9, View o13, uint8_t* __restrict__ arg) {
   pdl_sync();
-  extern __shared__ uint32_t sp[];  // [hw][CG] input (bf16 bits << 16), then [hw][CG] row results (bf16 bits << 16 | column code)
+  extern __shared__ uint32_t sp[];  // two [hw][CG] key planes
   const int hw = x.h * x.w;
-  uint32_t* sin = sp;
-  uint32_t* srow = sp + hw * CG;
+  uint32_t* ka = sp;
+  uint32_t* kb = sp + hw * CG;
   const int cg = blockIdx.x * CG;
   const int b = blockIdx.y;
+  const int total = hw * CG;
   const __nv_bfloat16* src = x.p + static_cast<size_t>(b) * hw * x.pitch + cg;
-  for (int e = threadIdx.x; e < hw * CG; e += blockDim.x) {
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int ch = e % CG, p = e / CG;
-    sin[e] = static_cast<uint32_t>(__bfloat16_as_ushort(src[static_cast<size_t>(p) * x.pitch + ch])) << 16;
+    ka[e] = spp_key(__bfloat16_as_ushort(src[static_cast<size_t>(p) * x.pitch + ch]), p);
   }
   __syncthreads();
 #pragma unroll 1
   for (int j = 0; j < 3; ++j) {
-    const int r = 2 + 2 * j;  // k = 5, 9, 13
-    for (int e = threadIdx.x; e < hw * CG; e += blockDim.x) {
-      const int ch = e % CG, p = e / CG;
-      const int px = p % x.w, rowbase = p - px;
-      float best = -INFINITY;
-      uint32_t bw = 0;
-      const int x0 = max(px - r, 0), x1 = min(px + r, x.w - 1);
-      for (int xx = x0; xx <= x1; ++xx) {
-        const uint32_t wv = sin[(rowbase + xx) * CG + ch];
-        const float v = __uint_as_float(wv);
-        if (v > best) { best = v; bw = wv | static_cast<uint32_t>(xx - px + 6); }
-      }
-      srow[e] = bw;
+    // ka holds the keys pooled with window 4j + 1 (j = 0: the input): one more 5x5 pass -> window 4j + 5
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int p = e / CG;
+      const int px = p % x.w;
+      const int lo = max(px - 2, 0) - px, hi = min(px + 2, x.w - 1) - px;
+      uint32_t m = 0;
+      for (int d = lo; d <= hi; ++d) m = max(m, ka[e + d * CG]);
+      kb[e] = m;
     }
     __syncthreads();
     const View& o = j == 0 ? o5 : (j == 1 ? o9 : o13);
     __nv_bfloat16* dst = o.p + static_cast<size_t>(b) * hw * o.pitch + cg;
     uint8_t* adst = arg ? arg + (static_cast<size_t>(j) * x.n + b) * hw * x.c + cg : nullptr;
-    for (int e = threadIdx.x; e < hw * CG; e += blockDim.x) {
+    const int rowstride = x.w * CG;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
       const int ch = e % CG, p = e / CG;
       const int py = p / x.w, px = p - py * x.w;
-      float best = -INFINITY;
-      uint32_t bw = 0;
-      int bdy = 0;
-      const int y0 = max(py - r, 0), y1 = min(py + r, x.h - 1);
-      for (int yy = y0; yy <= y1; ++yy) {
-        const uint32_t wv = srow[(yy * x.w + px) * CG + ch];
-        const float v = __uint_as_float(wv & 0xFFFF0000u);
-        if (v > best) { best = v; bw = wv; bdy = yy - py; }
+      const int lo = max(py - 2, 0) - py, hi = min(py + 2, x.h - 1) - py;
+      uint32_t m = 0;
+      for (int d = lo; d <= hi; ++d) m = max(m, kb[e + d * rowstride]);
+      ka[e] = m;  // each thread rewrites only its own elements of ka; the row pass of the next round starts after the barrier below
+      dst[static_cast<size_t>(p) * o.pitch + ch] = __ushort_as_bfloat16(spp_key_bits(m));
+      if (adst) {
+        const int q = 0xFFFF - static_cast<int>(m & 0xFFFFu);  // pixel index of the first maximum
+        const int qy = q / x.w, qx = q - qy * x.w;
+        adst[static_cast<size_t>(p) * x.c + ch] = static_cast<uint8_t>((qy - py + 6) * 13 + (qx - px + 6));
       }
-      dst[static_cast<size_t>(p) * o.pitch + ch] = __ushort_as_bfloat16(static_cast<unsigned short>(bw >> 16));
-      if (adst) adst[static_cast<size_t>(p) * x.c + ch] = static_cast<uint8_t>((bdy + 6) * 13 + (bw & 0xFFFFu));
     }
     __syncthreads();
+  }
+}
+
+// backward for the same maps: one block per (CG channels, image) scatters the three pooled gradients to their argmax positions in SHARED memory
+// (fp32 atomics on a [hw][CG] plane) and adds the identity-branch gradient -- no scratch plane in HBM, no global atomics
+template <int CG>
+__global__ void __launch_bounds__(256)
+spp_pool_bwd_tiled_kernel(View d0, View d5, View d9, View d13, const uint8_t* __restrict__ arg, View dx) {
+  pdl_sync();
+  extern __shared__ float sacc[];  // [hw][CG]
+  const int hw = dx.h * dx.w;
+  const int cg = blockIdx.x * CG;
+  const int b = blockIdx.y;
+  const int total = hw * CG;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int ch = e % CG, p = e / CG;
+    sacc[e] = __bfloat162float(d0.p[(static_cast<size_t>(b) * hw + p) * d0.pitch + cg + ch]);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int j = 0; j < 3; ++j) {
+    const View& d = j == 0 ? d5 : (j == 1 ? d9 : d13);
+    const uint8_t* a = arg + (static_cast<size_t>(j) * dx.n + b) * hw * dx.c + cg;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int ch = e % CG, p = e / CG;
+      const float g = __bfloat162float(d.p[(static_cast<size_t>(b) * hw + p) * d.pitch + cg + ch]);
+      const int code = a[static_cast<size_t>(p) * dx.c + ch];
+      const int q = p + (code / 13 - 6) * dx.w + (code % 13 - 6);
+      atomicAdd(&sacc[q * CG + ch], g);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int ch = e % CG, p = e / CG;
+    dx.p[(static_cast<size_t>(b) * hw + p) * dx.pitch + cg + ch] = __float2bfloat16_rn(sacc[e]);
   }
 }
 
@@ -872,6 +915,18 @@ extern "C" int yb200_spp_pool_bwd(const yb200_act* d0, const yb200_act* d5, cons
   YB_REQUIRE(same_shape(dx, d0) && same_shape(dx, d5) && same_shape(dx, d9) && same_shape(dx, d13), YB200_ERR_INVALID, "spp_pool_bwd: shape mismatch");
   cudaStream_t st = as_stream(stream);
   const long long elems = 1LL * dx->n * dx->h * dx->w * dx->c;
+  constexpr int kCg = 16;
+  const size_t tiled_smem = static_cast<size_t>(dx->h) * dx->w * kCg * sizeof(float);
+  if (dx->c % kCg == 0 && tiled_smem <= 200 * 1024) {  // same condition as the forward: the argmax codes stay inside the map
+    static size_t smem_set = 48 * 1024;
+    if (tiled_smem > smem_set) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_bwd_tiled_kernel<kCg>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tiled_smem)));
+      smem_set = tiled_smem;
+    }
+    launch_k(spp_pool_bwd_tiled_kernel<kCg>, dim3(dx->c / kCg, dx->n), 256, tiled_smem, st, mk(d0), mk(d5), mk(d9), mk(d13), argmax, mk(dx));
+    YB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   YB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, elems * sizeof(float), st));
   launch_k(spp_pool_bwd_scatter_kernel, grid_for(3 * elems, 256), 256, 0, st, mk(d5), mk(d9), mk(d13), argmax, scratch, dx->n, dx->h, dx->w, dx->c);
   YB_CHECK_CUDA(cudaGetLastError());
