@@ -68,6 +68,12 @@ def test_attention_and_pair_kernels_use_tensor_memory():
     assert pair and all("UTCHMMA.2CTA" in b for b in pair), "CTA-pair kernels must issue cta_group::2 MMAs"
     wg = [b for n, b in funcs.items() if "wgrad_gemm_kernel" in n]
     assert wg and all("UTCHMMA" in b for b in wg)
+    staged = [b for n, b in funcs.items() if "conv_gemm_staged_kernel" in n]
+    assert staged and all("UTMASTG" in b for b in staged), "the staged epilogue must store its tile through the TMA unit"
+    # programmatic dependent launch: every kernel of the library waits for its predecessor (griddepcontrol.wait = ACQBULK) and releases its
+    # dependents (launch_dependents = PREEXIT)
+    missing = [n for n, b in funcs.items() if "ACQBULK" not in b or "PREEXIT" not in b]
+    assert not missing, missing[:5]
 
 
 def test_extended_entry_points_validate_arguments_without_gpu():
@@ -150,3 +156,36 @@ def test_product_never_imports_the_oracle():
     for h, fn in zip(hits[:2], ("def run_reference", "def library_bar")):  # inside the two baseline functions
         assert src.rfind(fn, 0, h) == src.rfind("\ndef ", 0, h) + 1, fn
     assert "no_cpu_baseline" in src[src.rfind("\n    if ", 0, hits[2]):hits[2]]  # third one inside the cpu_baseline block
+
+
+def test_every_pdl_launched_kernel_waits_for_its_predecessor():
+    """launch_k (csrc/host_common.cuh) gives kernels the programmatic-stream-serialization attribute: such a kernel may be scheduled while its
+    predecessor is still running, so it MUST execute griddepcontrol.wait (pdl_sync) before touching global memory.  Static check over the sources."""
+    import glob
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolov7_d2_b200", "csrc")
+    src = {f: open(f).read() for f in glob.glob(os.path.join(root, "*.cu*"))}
+    names = set()
+    for s in src.values():
+        names.update(m.group(1) for m in re.finditer(r"launch_k\(\s*([A-Za-z_]\w*)", s))
+    names.discard("void")  # the declaration of launch_k itself
+    assert len(names) >= 50
+    for n in sorted(names):
+        bodies = []
+        for s in src.values():
+            for m in re.finditer(r"__global__[^;{]*?\b" + n + r"\s*\(", s, re.S):
+                i, depth = m.end(), 1
+                while depth:
+                    depth += (s[i] == "(") - (s[i] == ")")
+                    i += 1
+                j = s.index("{", i)
+                if s[i:j].strip():
+                    continue
+                k, d = j + 1, 1
+                while d:
+                    d += (s[k] == "{") - (s[k] == "}")
+                    k += 1
+                bodies.append(s[j:k])
+        assert bodies, f"definition of kernel {n} not found"
+        assert all("pdl_sync()" in b for b in bodies), f"kernel {n} is launched through launch_k but never calls pdl_sync()"

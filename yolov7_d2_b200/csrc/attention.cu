@@ -47,6 +47,7 @@ struct AttnParams {
 __global__ void __launch_bounds__(kAttThreads)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ AttnParams p) {
+  pdl_sync();
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[8];  // q_full, kv_full[2], kv_empty[2], s_full, p_ready, o_full
   __shared__ uint32_t s_tmem;
@@ -259,6 +260,7 @@ constexpr int kBwdSmemQ = 2 * kQBytes + 4 * kKVBytes + kPBytes + 1024;       // 
 // D[b][h][q] = sum_d dO[b][q][h][d] * O[b][q][h][d]
 __global__ void attention_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int o_pitch, int o_coff, const __nv_bfloat16* __restrict__ d_o, int do_pitch,
                                           int do_coff, int batch, int lq, int heads, float* __restrict__ dsum) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(batch) * lq * heads) return;
   const int h = static_cast<int>(i % heads);
@@ -322,6 +324,7 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (
 __global__ void __launch_bounds__(kAttThreads)
 attention_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ AttnBwdParams p) {
+  pdl_sync();
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[8];  // kv_full, qdo_full[2], qdo_empty[2], sdp_full, pds_ready, mma_done
   __shared__ uint32_t s_tmem;
@@ -438,6 +441,7 @@ attention_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 __global__ void __launch_bounds__(kAttThreads)
 attention_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ AttnBwdParams p) {
+  pdl_sync();
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t s_bar[8];  // qdo_full, kv_full[2], kv_empty[2], sdp_full, ds_ready, mma_done
   __shared__ uint32_t s_tmem;
@@ -583,7 +587,7 @@ extern "C" int yb200_attention_fwd(const yb200_act* q, const yb200_act* k, const
     attr_set = true;
   }
   dim3 grid(ceil_div(p.lq, kAttTile), p.heads, q->n);
-  attention_fwd_kernel<<<grid, kAttThreads, kAttSmem, as_stream(stream)>>>(tmQ, tmK, tmV, p);
+  launch_k(attention_fwd_kernel, grid, kAttThreads, kAttSmem, as_stream(stream), tmQ, tmK, tmV, p);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -630,11 +634,11 @@ extern "C" int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const
   }
   cudaStream_t st = as_stream(stream);
   const long long rows = 1LL * q->n * q->w * p.heads;
-  attention_bwd_prep_kernel<<<static_cast<int>((rows + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out->ptr), out->c_pitch, out->c_off,
+  launch_k(attention_bwd_prep_kernel, static_cast<int>((rows + 255) / 256), 256, 0, st, static_cast<const __nv_bfloat16*>(out->ptr), out->c_pitch, out->c_off,
                                                                                   static_cast<const __nv_bfloat16*>(dout->ptr), dout->c_pitch, dout->c_off, q->n,
                                                                                   q->w, p.heads, static_cast<float*>(workspace));
-  attention_bwd_kv_kernel<<<dim3(ceil_div(p.lk, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemKV, st>>>(tmQ, tmK, tmV, tmDO, p);
-  attention_bwd_q_kernel<<<dim3(ceil_div(p.lq, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemQ, st>>>(tmQ, tmK, tmV, tmDO, p);
+  launch_k(attention_bwd_kv_kernel, dim3(ceil_div(p.lk, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemKV, st, tmQ, tmK, tmV, tmDO, p);
+  launch_k(attention_bwd_q_kernel, dim3(ceil_div(p.lq, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemQ, st, tmQ, tmK, tmV, tmDO, p);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -56,6 +56,7 @@ __device__ __forceinline__ void dw_load_halo(uint32_t* s_x, const ActV& x, int n
 template <bool FLIP>
 __global__ void __launch_bounds__(256) dwconv7_kernel(ActV x, const float* __restrict__ w, const float* __restrict__ bias, ActV addend, ActV out_v,
                                                       __nv_bfloat16* __restrict__ out, int tiles_w, int tiles_h) {
+  pdl_sync();
   __shared__ __align__(16) uint32_t s_x[kDwHH * kDwRow * kDwPixWords];
   __shared__ float2 s_w[49][kDwC / 2];
   int t = blockIdx.x;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(ActV x, const float* __res
 constexpr int kDwgThreads = 128;
 __global__ void __launch_bounds__(kDwgThreads) dwconv7_wgrad_kernel(ActV x, ActV dy, float* __restrict__ partial, int tiles_w, int tiles_h, int tiles_total,
                                                                      int ctas_per_slice) {
+  pdl_sync();
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t* s_x = s_dyn;                                  // halo tile of x
   uint32_t* s_d = s_dyn + kDwHH * kDwRow * kDwPixWords;   // dy tile
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(kDwgThreads) dwconv7_wgrad_kernel(ActV x, ActV
 }
 __global__ void dwconv7_wgrad_reduce_kernel(const float* __restrict__ partial, int ctas_per_slice, int channels, float* __restrict__ dw,
                                             float* __restrict__ db, int accumulate) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over channels * 50
   if (i >= channels * 50) return;
   const int c = i / 50, tap = i - c * 50;
@@ -231,6 +234,7 @@ template <int STEPS>
 __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(ActV x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                                        __nv_bfloat16* __restrict__ y, int y_pitch, float2* __restrict__ stats,
                                                                        long long npix) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = x.c >> 2;  // 4-channel groups
   float g[STEPS][4], b[STEPS][4];
@@ -292,6 +296,7 @@ template <int STEPS>
 __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(ActV dy, ActV x, const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                                        ActV addend, __nv_bfloat16* __restrict__ dx, int dx_pitch,
                                                                        float* __restrict__ partial, long long npix) {
+  pdl_sync();
   extern __shared__ float s_red[];  // [kLnWarps][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = x.c >> 2;
@@ -371,6 +376,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(ActV dy, A
 }
 __global__ void layernorm_param_grad_kernel(const float* __restrict__ partial, int blocks, int C, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                             int accumulate) {
+  pdl_sync();
   // one warp per output element (2C of them): lanes stride over blocks, then a fixed-order shuffle tree
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -389,6 +395,7 @@ __global__ void layernorm_param_grad_kernel(const float* __restrict__ partial, i
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int kCsBlocks = 592;
 __global__ void __launch_bounds__(256) colsum_partial_kernel(ActV x, long long npix, float* __restrict__ partial) {
+  pdl_sync();
   // thread = (8-channel group, pixel lane); block covers all channel groups when c/8 <= 256
   extern __shared__ float s_cs[];  // [rows][c]
   const int groups = x.c >> 3;
@@ -414,6 +421,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(ActV x, long long n
   }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int blocks, int C, float scale, float* __restrict__ out, int accumulate) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
@@ -431,6 +439,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int block
 __global__ void layer_scale_grad_kernel(const float* __restrict__ G, const float* __restrict__ W2, const float* __restrict__ b2,
                                         const float* __restrict__ gamma, const float* __restrict__ s, int C, int K, float* __restrict__ dW2,
                                         float* __restrict__ dgamma, float* __restrict__ db2, int accumulate) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
@@ -457,6 +466,7 @@ __global__ void layer_scale_grad_kernel(const float* __restrict__ G, const float
 template <typename T>
 __global__ void __launch_bounds__(256) patchify4_kernel(const T* __restrict__ img, int n, int h, int w, __nv_bfloat16* __restrict__ out, int out_pitch,
                                                         int out_coff) {
+  pdl_sync();
   const int ow = w >> 2, oh = h >> 2;
   const long long total = static_cast<long long>(n) * oh * ow * 12;  // one thread per (patch, c, kh): 4 pixels in, 4 bf16 out
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -484,6 +494,7 @@ __global__ void __launch_bounds__(256) patchify4_kernel(const T* __restrict__ im
 }
 
 __global__ void f64_to_f32_kernel(double* __restrict__ src, int n, float* __restrict__ dst, int accumulate, int zero_src) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = static_cast<float>(src[i]);
@@ -493,6 +504,7 @@ __global__ void f64_to_f32_kernel(double* __restrict__ src, int n, float* __rest
 
 // out = a + b on bf16 views of equal shape (tensor + positional embedding, detr_backbone.py:154-155)
 __global__ void __launch_bounds__(256) add_bf16_kernel(ActV a, ActV b, __nv_bfloat16* __restrict__ out, int out_pitch, long long npix) {
+  pdl_sync();
   const int groups = a.c >> 3;
   const long long total = npix * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -510,6 +522,7 @@ __global__ void __launch_bounds__(256) add_bf16_kernel(ActV a, ActV b, __nv_bflo
 
 // out = sigmoid(x) on bf16 views (instance activation maps, decoder_sparseinst.py:67)
 __global__ void __launch_bounds__(256) sigmoid_bf16_kernel(ActV a, __nv_bfloat16* __restrict__ out, int out_pitch, long long npix) {
+  pdl_sync();
   const int groups = a.c >> 3;
   const long long total = npix * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -527,6 +540,7 @@ __global__ void __launch_bounds__(256) sigmoid_bf16_kernel(ActV a, __nv_bfloat16
 }
 // inst[r][c] = raw[r][c] / max(norm[r], 1e-6) -> bf16 (decoder_sparseinst.py:75-76)
 __global__ void iam_normalize_kernel(const float* __restrict__ raw, const float* __restrict__ norm, int rows, int cols, __nv_bfloat16* __restrict__ out, int out_pitch) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int r = i / cols, c = i - r * cols;
@@ -572,9 +586,9 @@ extern "C" int yb200_dwconv7(const yb200_act* x, const float* w_c49, const float
   ActV ov = viewc(out);
   __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out->ptr) + out->c_off;
   if (flip)
-    dwconv7_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(viewc(x), w_c49, bias, av, ov, op, tiles_w, tiles_h);
+    launch_k(dwconv7_kernel<true>, grid, 256, 0, as_stream(stream), viewc(x), w_c49, bias, av, ov, op, tiles_w, tiles_h);
   else
-    dwconv7_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(viewc(x), w_c49, bias, av, ov, op, tiles_w, tiles_h);
+    launch_k(dwconv7_kernel<false>, grid, 256, 0, as_stream(stream), viewc(x), w_c49, bias, av, ov, op, tiles_w, tiles_h);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -609,9 +623,9 @@ extern "C" int yb200_dwconv7_wgrad(const yb200_act* x, const yb200_act* dy, floa
     YB_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
-  dwconv7_wgrad_kernel<<<slices * per, kDwgThreads, kSmem, st>>>(viewc(x), viewc(dy), static_cast<float*>(workspace), tiles_w, tiles_h,
+  launch_k(dwconv7_wgrad_kernel, slices * per, kDwgThreads, kSmem, st, viewc(x), viewc(dy), static_cast<float*>(workspace), tiles_w, tiles_h,
                                                              tiles_w * tiles_h * x->n, per);
-  dwconv7_wgrad_reduce_kernel<<<ceil_div(x->c * 50, 256), 256, 0, st>>>(static_cast<const float*>(workspace), per, x->c, grad_w_c49, grad_bias, accumulate);
+  launch_k(dwconv7_wgrad_reduce_kernel, ceil_div(x->c * 50, 256), 256, 0, st, static_cast<const float*>(workspace), per, x->c, grad_w_c49, grad_bias, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -626,8 +640,8 @@ extern "C" int yb200_layernorm_fwd(const yb200_act* x, const float* gamma, const
   cudaStream_t st = as_stream(stream);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y->ptr) + y->c_off;
   rc = dispatch_steps(x->c, [&](auto steps) {
-    layernorm_fwd_kernel<decltype(steps)::value><<<ln_grid(npix), kLnWarps * 32, 0, st>>>(viewc(x), gamma, beta, eps, yp, y->c_pitch,
-                                                                                          reinterpret_cast<float2*>(stats_mean_rstd), npix);
+    launch_k(layernorm_fwd_kernel<decltype(steps)::value>, ln_grid(npix), kLnWarps * 32, 0, st, viewc(x), gamma, beta, eps, yp, y->c_pitch,
+             reinterpret_cast<float2*>(stats_mean_rstd), npix);
     return 0;
   });
   if (rc) return rc;
@@ -663,12 +677,12 @@ extern "C" int yb200_layernorm_bwd(const yb200_act* dy, const yb200_act* x, cons
       if (e != cudaSuccess) return fail(YB200_ERR_CUDA, "layernorm_bwd: %s", cudaGetErrorString(e));
       attr_set = true;
     }
-    layernorm_bwd_kernel<S><<<blocks, kLnWarps * 32, smem, st>>>(viewc(dy), viewc(x), reinterpret_cast<const float2*>(stats_mean_rstd), gamma, av, dxp,
+    launch_k(layernorm_bwd_kernel<S>, blocks, kLnWarps * 32, smem, st, viewc(dy), viewc(x), reinterpret_cast<const float2*>(stats_mean_rstd), gamma, av, dxp,
                                                                  dx->c_pitch, static_cast<float*>(workspace), npix);
     return 0;
   });
   if (rc) return rc;
-  layernorm_param_grad_kernel<<<ceil_div(2 * x->c * 32, 256), 256, 0, st>>>(static_cast<const float*>(workspace), blocks, x->c, grad_gamma, grad_beta,
+  launch_k(layernorm_param_grad_kernel, ceil_div(2 * x->c * 32, 256), 256, 0, st, static_cast<const float*>(workspace), blocks, x->c, grad_gamma, grad_beta,
                                                                             accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -688,8 +702,8 @@ extern "C" int yb200_colsum(const yb200_act* x, float scale, float* out, int acc
   const int groups = x->c / 8, rows = 256 / groups;
   const int smem = rows * x->c * 4;
   cudaStream_t st = as_stream(stream);
-  colsum_partial_kernel<<<kCsBlocks, 256, smem, st>>>(viewc(x), npix, static_cast<float*>(workspace));
-  colsum_final_kernel<<<ceil_div(x->c * 32, 256), 256, 0, st>>>(static_cast<const float*>(workspace), kCsBlocks, x->c, scale, out, accumulate);
+  launch_k(colsum_partial_kernel, kCsBlocks, 256, smem, st, viewc(x), npix, static_cast<float*>(workspace));
+  launch_k(colsum_final_kernel, ceil_div(x->c * 32, 256), 256, 0, st, static_cast<const float*>(workspace), kCsBlocks, x->c, scale, out, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -698,7 +712,7 @@ extern "C" int yb200_layer_scale_grad(const float* raw_wgrad, const float* w2, c
                                       int hidden, float* grad_w2, float* grad_gamma, float* grad_b2, int accumulate, void* stream) {
   YB_REQUIRE(raw_wgrad && w2 && b2 && gamma && gout_colsum && grad_w2 && grad_gamma && grad_b2 && channels > 0 && hidden > 0, YB200_ERR_INVALID,
              "layer_scale_grad: bad arguments");
-  layer_scale_grad_kernel<<<ceil_div(channels * 32, 256), 256, 0, as_stream(stream)>>>(raw_wgrad, w2, b2, gamma, gout_colsum, channels, hidden, grad_w2,
+  launch_k(layer_scale_grad_kernel, ceil_div(channels * 32, 256), 256, 0, as_stream(stream), raw_wgrad, w2, b2, gamma, gout_colsum, channels, hidden, grad_w2,
                                                                                        grad_gamma, grad_b2, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -714,9 +728,9 @@ extern "C" int yb200_patchify4(const void* images_nchw, int is_f32, int n, int h
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
   __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out->ptr);
   if (is_f32)
-    patchify4_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(images_nchw), n, h, w, op, out->c_pitch, out->c_off);
+    launch_k(patchify4_kernel<float>, blocks, 256, 0, as_stream(stream), static_cast<const float*>(images_nchw), n, h, w, op, out->c_pitch, out->c_off);
   else
-    patchify4_kernel<uint8_t><<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(images_nchw), n, h, w, op, out->c_pitch, out->c_off);
+    launch_k(patchify4_kernel<uint8_t>, blocks, 256, 0, as_stream(stream), static_cast<const uint8_t*>(images_nchw), n, h, w, op, out->c_pitch, out->c_off);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -724,7 +738,7 @@ extern "C" int yb200_patchify4(const void* images_nchw, int is_f32, int n, int h
 extern "C" int yb200_f64_to_f32(double* src, int n, float* dst, int accumulate, int zero_src, void* stream) {
   YB_REQUIRE(src && dst && n >= 0, YB200_ERR_INVALID, "f64_to_f32: null pointer");
   if (n == 0) return 0;
-  f64_to_f32_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(src, n, dst, accumulate, zero_src);
+  launch_k(f64_to_f32_kernel, ceil_div(n, 256), 256, 0, as_stream(stream), src, n, dst, accumulate, zero_src);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -738,7 +752,7 @@ extern "C" int yb200_add(const yb200_act* a, const yb200_act* b, const yb200_act
   const long long npix = 1LL * a->n * a->h * a->w;
   const long long total = npix * (a->c / 8);
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
-  add_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewc(a), viewc(b), static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, npix);
+  launch_k(add_bf16_kernel, blocks, 256, 0, as_stream(stream), viewc(a), viewc(b), static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, npix);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -751,7 +765,7 @@ extern "C" int yb200_sigmoid(const yb200_act* x, const yb200_act* out, void* str
   const long long npix = 1LL * x->n * x->h * x->w;
   const long long total = npix * (x->c / 8);
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
-  sigmoid_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewc(x), static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, npix);
+  launch_k(sigmoid_bf16_kernel, blocks, 256, 0, as_stream(stream), viewc(x), static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, npix);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -761,7 +775,7 @@ extern "C" int yb200_iam_normalize(const float* raw, const float* normalizer, in
   if ((rc = check_view(out, "iam_normalize out", 8))) return rc;
   YB_REQUIRE(raw && normalizer && rows > 0 && cols > 0, YB200_ERR_INVALID, "iam_normalize: bad arguments");
   YB_REQUIRE(out->n == 1 && out->h == 1 && out->w == rows && out->c == cols, YB200_ERR_INVALID, "iam_normalize: output must be a [1][1][%d][%d] view", rows, cols);
-  iam_normalize_kernel<<<ceil_div(rows * cols, 256), 256, 0, as_stream(stream)>>>(raw, normalizer, rows, cols, static_cast<__nv_bfloat16*>(out->ptr) + out->c_off,
+  launch_k(iam_normalize_kernel, ceil_div(rows * cols, 256), 256, 0, as_stream(stream), raw, normalizer, rows, cols, static_cast<__nv_bfloat16*>(out->ptr) + out->c_off,
                                                                                   out->c_pitch);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;

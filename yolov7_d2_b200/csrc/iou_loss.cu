@@ -49,6 +49,7 @@ __device__ __forceinline__ D4 datan(const D4& a) {
 
 __global__ void iou_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int n, int mode, float* __restrict__ loss,
                                 float* __restrict__ dpred) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const D4 px = var(pred[4 * i], 0), py = var(pred[4 * i + 1], 1), pw = var(pred[4 * i + 2], 2), ph = var(pred[4 * i + 3], 3);
@@ -113,7 +114,7 @@ extern "C" int yb200_iou_loss(const float* pred_cxcywh, const float* target_cxcy
   YB_REQUIRE(pred_cxcywh && target_cxcywh && loss, YB200_ERR_INVALID, "iou_loss: null pointer");
   YB_REQUIRE(n >= 0 && mode >= 0 && mode <= 4, YB200_ERR_INVALID, "iou_loss: n=%d mode=%d", n, mode);
   if (n == 0) return 0;
-  iou_loss_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(pred_cxcywh, target_cxcywh, n, mode, loss, dloss_dpred);
+  launch_k(iou_loss_kernel, ceil_div(n, 128), 128, 0, as_stream(stream), pred_cxcywh, target_cxcywh, n, mode, loss, dloss_dpred);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -21,6 +21,7 @@ constexpr int kIdxBits = 16;  // anchors per image < 65536
 // ---- stage 1: per anchor class max / score / filter, xyxy conversion, sort keys ----
 __global__ void nms_prepare_kernel(float* __restrict__ pred, int num_anchors, int ch, int apad, float conf_thre, int mutate,
                                    float4* __restrict__ boxes, float4* __restrict__ meta, unsigned long long* __restrict__ keys) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= apad) return;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kNmsThreads)
 nms_suppress_kernel(const unsigned long long* __restrict__ keys_in, const float4* __restrict__ boxes, const float4* __restrict__ meta,
                     int num_anchors, int num_classes, int apad, float nms_thre, float* __restrict__ det, int* __restrict__ det_count,
                     int* __restrict__ det_anchor, int* __restrict__ tie_count) {
+  pdl_sync();
   extern __shared__ unsigned long long sk[];                          // [apad]
   unsigned char* sup = reinterpret_cast<unsigned char*>(sk + apad);   // [apad]
   __shared__ int s_n, s_keep, s_ties;
@@ -182,11 +184,11 @@ extern "C" int yb200_postprocess_nms_indexed(float* prediction, int batch, int n
   float4* meta = reinterpret_cast<float4*>(ws + pad256(16 * ba));
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + 2 * pad256(16 * ba));
   cudaStream_t st = as_stream(stream);
-  nms_prepare_kernel<<<dim3(ceil_div(apad, 256), batch), 256, 0, st>>>(prediction, num_anchors, 5 + num_classes, apad, conf_thre, mutate_prediction,
+  launch_k(nms_prepare_kernel, dim3(ceil_div(apad, 256), batch), 256, 0, st, prediction, num_anchors, 5 + num_classes, apad, conf_thre, mutate_prediction,
                                                                       boxes, meta, keys);
   YB_CHECK_CUDA(cudaGetLastError());
   YB_CHECK_CUDA(cudaFuncSetAttribute(nms_suppress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));  // per device, cheap
-  nms_suppress_kernel<<<batch, kNmsThreads, smem, st>>>(keys, boxes, meta, num_anchors, num_classes, apad, nms_thre, detections, det_count,
+  launch_k(nms_suppress_kernel, batch, kNmsThreads, smem, st, keys, boxes, meta, num_anchors, num_classes, apad, nms_thre, detections, det_count,
                                                         det_anchor, tie_count);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;

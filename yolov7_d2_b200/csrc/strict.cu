@@ -48,6 +48,7 @@ __device__ __forceinline__ void split_store(const SplitView& v, long long pix, i
 // per-channel sum / sum of squares of an fp32 NHWC slice, fp64 accumulation (block partials, then one atomic per channel and block)
 __global__ void strict_bn_stats_kernel(const float* __restrict__ z, long long npix, int pitch, int c, double* __restrict__ sum,
                                        double* __restrict__ sq) {
+  pdl_sync();
   // blockDim = (32 channels, 8 pixel rows); grid = (channel groups, pixel blocks)
   const int ch = blockIdx.x * 32 + threadIdx.x;
   __shared__ double s1[8][32], s2[8][32];
@@ -72,6 +73,7 @@ __global__ void strict_bn_stats_kernel(const float* __restrict__ z, long long np
 // a = SiLU(z*scale + shift) [+ residual], written as a split pair; optionally also 2x nearest-upsampled into `up`
 __global__ void strict_bn_apply_silu_kernel(const float* __restrict__ z, int z_pitch, const float* __restrict__ scale,
                                             const float* __restrict__ shift, SplitView res, int has_res, SplitView out, SplitView up, int has_up) {
+  pdl_sync();
   const long long total = 1LL * out.n * out.h * out.w * out.c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = static_cast<int>(i % out.c);
@@ -95,6 +97,7 @@ __global__ void strict_bn_apply_silu_kernel(const float* __restrict__ z, int z_p
 
 // SPP max-pools k = 5, 9, 13 (stride 1, -inf padding) on the reconstructed fp32 values
 __global__ void strict_spp_pool_kernel(SplitView x, SplitView o5, SplitView o9, SplitView o13) {
+  pdl_sync();
   const long long total = 1LL * x.n * x.h * x.w * x.c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = static_cast<int>(i % x.c);
@@ -134,7 +137,7 @@ extern "C" int yb200_strict_bn_stats(const float* z, int64_t npix, int z_pitch, 
   YB_REQUIRE(z && stat_sum && stat_sqsum && npix > 0 && c > 0 && z_off >= 0 && z_off + c <= z_pitch, YB200_ERR_INVALID,
              "strict_bn_stats: bad arguments (npix=%lld c=%d off=%d pitch=%d)", (long long)npix, c, z_off, z_pitch);
   const int gy = static_cast<int>(std::min<long long>((npix + 7) / 8, 8LL * sm_count()));
-  strict_bn_stats_kernel<<<dim3(ceil_div(c, 32), gy), dim3(32, 8), 0, as_stream(stream)>>>(z + z_off, npix, z_pitch, c, stat_sum, stat_sqsum);
+  launch_k(strict_bn_stats_kernel, dim3(ceil_div(c, 32), gy), dim3(32, 8), 0, as_stream(stream), z + z_off, npix, z_pitch, c, stat_sum, stat_sqsum);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -159,7 +162,7 @@ extern "C" int yb200_strict_bn_apply_silu(const float* z, int z_pitch, int z_off
                "strict_bn_apply_silu: upsampled view must be [n,2h,2w,c]");
   }
   const long long total = 1LL * out->n * out->h * out->w * out->c;
-  strict_bn_apply_silu_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(z + z_off, z_pitch, scale, shift, vr, residual != nullptr, vo, vu,
+  launch_k(strict_bn_apply_silu_kernel, grid_for(total, 256), 256, 0, as_stream(stream), z + z_off, z_pitch, scale, shift, vr, residual != nullptr, vo, vu,
                                                                                   out_up2x != nullptr);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -174,7 +177,7 @@ extern "C" int yb200_strict_spp_pool(const yb200_act* x, const yb200_act* o5, co
     return rc;
   YB_REQUIRE(o5->c == x->c && o9->c == x->c && o13->c == x->c && o5->h == x->h && o5->w == x->w, YB200_ERR_INVALID, "strict_spp_pool: shape mismatch");
   const long long total = 1LL * x->n * x->h * x->w * x->c;
-  strict_spp_pool_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(vx, v5, v9, v13);
+  launch_k(strict_spp_pool_kernel, grid_for(total, 128), 128, 0, as_stream(stream), vx, v5, v9, v13);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
