@@ -347,6 +347,12 @@ int yb200_conv2d_relu_fwd(const yb200_act* x, const void* w_fwd, const float* bi
 /* 1x1 convolution with fp32 NCHW output [N][cout][H][W] (+ bias, may be NULL): with per-image weights = pred_kernel[b] this is
  * `torch.bmm(pred_kernel, mask_features.view(B, C, HW))` (:143-146); cout <= 128                                                            */
 int yb200_conv1x1_nchw_f32(const yb200_act* x, const void* w_fwd, const float* bias, int cout, float* out_nchw, void* stream);
+/* The same for a whole batch with ONE WEIGHT MATRIX PER IMAGE (w_fwd: [x->n][cout][x->c] bf16 = the batch's predicted kernels): the batched
+ * `torch.bmm` of :143-146 in one launch.  h * w must be a multiple of 128 pixels arranged so that a tile stays inside one image.            */
+int yb200_conv1x1_nchw_f32_batched(const yb200_act* x, const void* w_fwd, int cout, float* out_nchw, void* stream);
+/* F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) on fp32 planes [planes][h][w] -> [planes][2h][2w]: the mask logits
+ * (:148-153)                                                                                                                                  */
+int yb200_upsample_bilinear2x_f32(const float* in, float* out, int64_t planes, int h, int w, void* stream);
 /* out = sigmoid(x): instance activation maps (:67)                                                                                           */
 int yb200_sigmoid(const yb200_act* x, const yb200_act* out, void* stream);
 /* inst[r][c] = raw[r][c] / max(normalizer[r], 1e-6) -> bf16 [1][1][rows][cols] view (:75-76).  raw = iam_prob^T features of one image is

@@ -102,3 +102,20 @@ def test_group_decoder_full_size_against_oracle(cuda):
     _check(out["pred_logits"], ref["pred_logits"], "class logits")
     _check(out["pred_scores"], ref["pred_scores"], "objectness")
     _check(out["pred_masks"], ref["pred_masks"], "masks")
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 7), (200, 80, 80), (1, 1, 1)], ids=str)
+def test_bilinear_x2_matches_torch(cuda, shape):
+    """yb200_upsample_bilinear2x_f32 == F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) (decoder_sparseinst.py:148-153)"""
+    import ctypes
+
+    import torch.nn.functional as F
+
+    from yolov7_d2_b200 import capi
+
+    planes, h, w = shape
+    x = torch.randn(planes, h, w, generator=torch.Generator().manual_seed(9)).to(cuda)
+    out = torch.empty(planes, 2 * h, 2 * w, device=cuda)
+    capi.check(capi.lib().yb200_upsample_bilinear2x_f32(capi.ptr(x), capi.ptr(out), ctypes.c_int64(planes), h, w, capi.stream_ptr()), "bilinear")
+    ref = F.interpolate(x[None], scale_factor=2, mode="bilinear", align_corners=False)[0]
+    assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6), float((out - ref).abs().max())

@@ -24,6 +24,9 @@ class Yb200Error(RuntimeError):
     pass
 
 
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = -1, -2, -3  # yb200_status (include/yb200.h)
+
+
 class Act(ctypes.Structure):
     """mirror of `yb200_act` (include/yb200.h)"""
 

@@ -581,7 +581,8 @@ extern "C" int yb200_attention_fwd(const yb200_act* q, const yb200_act* k, const
   p.out = static_cast<__nv_bfloat16*>(out->ptr);
   p.out_pitch = out->c_pitch; p.out_coff = out->c_off;
   p.lse = lse;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev(false);
+  bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
     attr_set = true;
@@ -626,7 +627,8 @@ extern "C" int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const
   p.dq = static_cast<__nv_bfloat16*>(dq->ptr); p.dq_pitch = dq->c_pitch; p.dq_coff = dq->c_off;
   p.dk = static_cast<__nv_bfloat16*>(dk->ptr); p.dk_pitch = dk->c_pitch; p.dk_coff = dk->c_off;
   p.dv = static_cast<__nv_bfloat16*>(dv->ptr); p.dv_pitch = dv->c_pitch; p.dv_coff = dv->c_off;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev(false);
+  bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemKV));
     YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemQ));

@@ -75,7 +75,8 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     }
   }
   if (use_v1_kernel() && p.num_bnseg == 0) {  // one tile per CTA (kept for A/B comparison)
-    static int max_set = 0;
+    static PerDevice<int> max_set_dev(0);
+  int& max_set = max_set_dev.cur();
     const int smem = stages * Cfg::kStageBytes + 1024;
     if (smem > max_set) {
       YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -93,7 +94,8 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
       int pst = (212 * 1024) / stage_bytes;
       if (pst > kMaxStagesP) pst = kMaxStagesP;
       const int smem = pst * stage_bytes + 1024;
-      static int max_set_pair = 0;
+      static PerDevice<int> max_set_pair_dev(0);
+  int& max_set_pair = max_set_pair_dev.cur();
       if (smem > max_set_pair) {
         YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -131,7 +133,8 @@ static int launch_conv_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   if (pst > kMaxStagesP) pst = kMaxStagesP;
   if (pst < 2) pst = 2;
   const int smem = pst * kbs * Cfg::kStageBytes + 1024 + (xpose ? kXposeBytes : 0);
-  static int max_set_p = 0;
+  static PerDevice<int> max_set_p_dev(0);
+  int& max_set_p = max_set_p_dev.cur();
   if (smem > max_set_p) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     YB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, BK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -567,6 +570,43 @@ extern "C" int yb200_conv1x1_nchw_f32(const yb200_act* x, const void* w_fwd, con
   return conv_fwd_common(x, w_fwd, cout, 1, 1, p, as_stream(stream));
 }
 
+// the same with one weight matrix PER IMAGE (w_fwd: [n][cout][cin] bf16, i.e. n * cout rows): torch.bmm(pred_kernel, mask_features) of a whole batch
+// in one launch.  Pixel tiles must not span images (h * w a multiple of the 128-pixel tile: choose_tile then keeps tiles inside one image).
+extern "C" int yb200_conv1x1_nchw_f32_batched(const yb200_act* x, const void* w_fwd, int cout, float* out_nchw, void* stream) {
+  int rc;
+  if ((rc = check_act(x, "conv1x1_nchw_f32_batched x"))) return rc;
+  YB_REQUIRE(out_nchw && cout > 0 && cout <= 128, YB200_ERR_INVALID, "conv1x1_nchw_f32_batched: bad arguments (cout=%d)", cout);
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const long long hw = 1LL * x->h * x->w;
+  p.out = out_nchw;
+  p.out_sn = 1LL * cout * hw;
+  p.out_sh = x->w;
+  p.out_sw = 1;
+  YB_REQUIRE(hw < (1LL << 31), YB200_ERR_UNSUPPORTED, "conv1x1_nchw_f32_batched: plane too large");
+  p.out_sc = static_cast<int>(hw);
+  p.out_mh = 1; p.out_mw = 1;
+  p.epi_mode = EPI_F32_BIAS;
+  p.b_img_rows = cout;
+  set_tiles(p, x->n, x->h, x->w);
+  YB_REQUIRE(p.log_tw + p.log_th == 7, YB200_ERR_UNSUPPORTED,
+             "conv1x1_nchw_f32_batched: a 128-pixel tile would span images at %dx%d (use yb200_conv1x1_nchw_f32 per image)", x->h, x->w);
+  YB_REQUIRE(pick_block_n(cout) <= 128 && !use_v1_kernel(), YB200_ERR_UNSUPPORTED, "conv1x1_nchw_f32_batched: needs the persistent kernel");
+  // conv_fwd_common, with the weight matrix map covering all images' rows
+  const int bk = pick_block_k(x->c);
+  YB_REQUIRE(bk != 0, YB200_ERR_UNSUPPORTED, "conv1x1_nchw_f32_batched: input channels %d must be a multiple of 16", x->c);
+  const int bn = pick_block_n(cout);
+  p.num_taps = fill_fwd_taps(p.taps, *x, 1, 1, x->c);
+  p.cin_blocks = x->c / bk;
+  p.cout = cout;
+  const int tw = 1 << p.log_tw, th = 1 << p.log_th;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_act_map(&tmA, *x, false, bk, tw, th, 1))) return rc;
+  if ((rc = make_mat_map(&tmB, w_fwd, 1LL * x->n * cout, x->c, bn, bk))) return rc;
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(cout, bn));
+  return launch_conv(bn, bk, tmA, tmB, p, grid, pick_stages(bn, bk, p.cin_blocks), as_stream(stream));
+}
+
 extern "C" int yb200_linear_gelu_fwd(const yb200_act* x, const void* w_fwd, const float* bias, const yb200_act* u_out, const yb200_act* h_out,
                                      void* stream) {
   int rc;
@@ -914,7 +954,8 @@ extern "C" int64_t yb200_conv2d_wgrad_workspace(const yb200_act* x, const yb200_
 
 template <int TC>
 static int launch_wgrad_inst(const CUtensorMap& tmDz, const CUtensorMap& tmX, const WgradPlan& pl, dim3 grid, cudaStream_t st) {
-  static int max_set = 0;
+  static PerDevice<int> max_set_dev(0);
+  int& max_set = max_set_dev.cur();
   if (pl.smem > max_set) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     max_set = pl.smem;

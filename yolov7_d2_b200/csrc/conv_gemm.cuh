@@ -111,6 +111,7 @@ struct ConvGemmParams {
   // launches read the whole tensor four times).
   int num_phases;
   int phase_tap[5];
+  int b_img_rows; // > 0: per-image weights -- the tile of image n reads weight rows n * b_img_rows + column (tiles must not span images)
   int xpose;      // EPI_F32_BIAS with channel-contiguous rows: transpose each 32 x 32 chunk through shared memory (kXposeBytes behind the ring)
   const __nv_bfloat16* aux_in;  // EPI_BF16_GELU_BWD: pre-activation u, same geometry as `out`
   __nv_bfloat16* aux_out;       // EPI_BF16_BIAS_GELU: where u is stored (may be null), same geometry as `out`
@@ -675,7 +676,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             const uint32_t sa = smem_base + (stage * kb_per_slot + j) * Cfg::kStageBytes;
             const ConvTap& tp = p.taps[tap];
             tma_load_5d(sa, &tmA, full, tp.c0 + cb * BLOCK_K, w0 + tp.dw, tp.p, h0 + tp.dh, n0);
-            tma_load_2d(sa + Cfg::kABytes, &tmB, full, tp.kb + cb * BLOCK_K, col0);
+            tma_load_2d(sa + Cfg::kABytes, &tmB, full, tp.kb + cb * BLOCK_K, col0 + n0 * p.b_img_rows);
             if (++cb == p.cin_blocks) { cb = 0; ++tap; }
           }
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }

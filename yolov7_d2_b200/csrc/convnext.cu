@@ -618,7 +618,8 @@ extern "C" int yb200_dwconv7_wgrad(const yb200_act* x, const yb200_act* dy, floa
   const int slices = x->c / kDwC;
   cudaStream_t st = as_stream(stream);
   constexpr int kSmem = (kDwHH * kDwRow + kDwTH * kDwTW) * kDwPixWords * 4;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev(false);
+  bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
@@ -671,7 +672,8 @@ extern "C" int yb200_layernorm_bwd(const yb200_act* dy, const yb200_act* x, cons
   __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx->ptr) + dx->c_off;
   rc = dispatch_steps(x->c, [&](auto steps) {
     constexpr int S = decltype(steps)::value;
-    static bool attr_set = false;  // per instantiation
+    static PerDevice<bool> attr_set_dev(false);
+  bool& attr_set = attr_set_dev.cur();  // per instantiation
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnWarps * 2 * S * 128 * 4);
       if (e != cudaSuccess) return fail(YB200_ERR_CUDA, "layernorm_bwd: %s", cudaGetErrorString(e));

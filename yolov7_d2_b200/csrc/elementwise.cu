@@ -890,7 +890,8 @@ extern "C" int yb200_spp_pool(const yb200_act* x, const yb200_act* o5, const yb2
   constexpr int kCg = 16;
   const size_t tiled_smem = static_cast<size_t>(x->h) * x->w * kCg * 2 * sizeof(uint32_t);
   if (x->c % kCg == 0 && tiled_smem <= 200 * 1024) {
-    static size_t smem_set = 48 * 1024;
+    static PerDevice<size_t> smem_set_dev(48 * 1024);
+    size_t& smem_set = smem_set_dev.cur();
     if (tiled_smem > smem_set) {
       YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_tiled_kernel<kCg>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tiled_smem)));
       smem_set = tiled_smem;
@@ -918,7 +919,8 @@ extern "C" int yb200_spp_pool_bwd(const yb200_act* d0, const yb200_act* d5, cons
   constexpr int kCg = 16;
   const size_t tiled_smem = static_cast<size_t>(dx->h) * dx->w * kCg * sizeof(float);
   if (dx->c % kCg == 0 && tiled_smem <= 200 * 1024) {  // same condition as the forward: the argmax codes stay inside the map
-    static size_t smem_set = 48 * 1024;
+    static PerDevice<size_t> smem_set_dev(48 * 1024);
+    size_t& smem_set = smem_set_dev.cur();
     if (tiled_smem > smem_set) {
       YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_bwd_tiled_kernel<kCg>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tiled_smem)));
       smem_set = tiled_smem;
@@ -941,6 +943,48 @@ extern "C" int yb200_copy_view(const yb200_act* src, const yb200_act* dst, void*
   YB_REQUIRE(same_shape(src, dst), YB200_ERR_INVALID, "copy_view: shape mismatch");
   const long long total = 1LL * src->n * src->h * src->w * (src->c / 8);
   launch_k(copy_view_kernel, grid_for(total, 256), 256, 0, as_stream(stream), mk(src), mk(dst));
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) on fp32 planes [planes][h][w] -> [planes][2h][2w]
+// (SparseInst mask logits, decoder_sparseinst.py:148-153).  Source coordinate (dst + 0.5) / 2 - 0.5, negative values clamped to 0, the upper
+// neighbour clamped to the last row / column; the four products are combined in ATen's order.  One thread per INPUT pixel writes its 2 x 2 outputs.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void upsample_bilinear2x_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int h, int w) {
+  pdl_sync();
+  const long long total = planes * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    const int y = static_cast<int>((i / w) % h);
+    const long long pl = i / (1LL * w * h);
+    const float* src = in + pl * h * w;
+    float* dst = out + pl * 4LL * h * w;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      // output row 2y + dy: source y - 0.25 (dy = 0) or y + 0.25 (dy = 1)
+      const int y0 = dy == 0 ? max(y - 1, 0) : y;
+      const int y1 = min(y0 + 1, h - 1);
+      const float ly = dy == 0 ? (y == 0 ? 0.f : 0.75f) : 0.25f;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int x0 = dx == 0 ? max(x - 1, 0) : x;
+        const int x1 = min(x0 + 1, w - 1);
+        const float lx = dx == 0 ? (x == 0 ? 0.f : 0.75f) : 0.25f;
+        const float v = (1.f - ly) * ((1.f - lx) * src[y0 * w + x0] + lx * src[y0 * w + x1]) + ly * ((1.f - lx) * src[y1 * w + x0] + lx * src[y1 * w + x1]);
+        dst[(2LL * y + dy) * (2 * w) + 2 * x + dx] = v;
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int yb200_upsample_bilinear2x_f32(const float* in, float* out, int64_t planes, int h, int w, void* stream) {
+  YB_REQUIRE(in && out && planes > 0 && h > 0 && w > 0, YB200_ERR_INVALID, "upsample_bilinear2x_f32: bad arguments");
+  const long long total = planes * h * w;
+  launch_k(upsample_bilinear2x_kernel, grid_for(total, 256), 256, 0, as_stream(stream), in, out, static_cast<long long>(planes), h, w);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,7 +15,21 @@ namespace yb {
 
 char* err_buf();
 int fail(int code, const char* fmt, ...);
-int sm_count();
+int sm_count();  // of the CURRENT device
+int current_device();
+// function attributes (dynamic shared memory limits) are per device: caches of "already raised to N bytes" must be too
+template <typename T>
+struct PerDevice {
+  T v[64];
+  T init;
+  bool used[64];
+  explicit PerDevice(T init_value) : init(init_value) { memset(used, 0, sizeof(used)); }
+  T& cur() {
+    const int d = current_device() & 63;
+    if (!used[d]) { v[d] = init; used[d] = true; }
+    return v[d];
+  }
+};
 
 #define YB_CHECK_CUDA(expr)                                                                      \
   do {                                                                                           \

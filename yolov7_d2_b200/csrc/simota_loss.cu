@@ -627,7 +627,8 @@ extern "C" int yb200_simota_assign(const float* outputs, const float* labels, in
   launch_k(simota_count_gt_kernel, ceil_div(batch, 64), 64, 0, st, labels, batch, max_gt, num_gt, totals);
   YB_CHECK_CUDA(cudaGetLastError());
   const size_t tile = static_cast<size_t>(kPrepAnchors) * channels * sizeof(float);
-  static size_t prep_smem = 0;
+  static PerDevice<size_t> prep_smem_dev(0);
+  size_t& prep_smem = prep_smem_dev.cur();
   if (tile > prep_smem) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile)));
     prep_smem = tile;
@@ -671,7 +672,8 @@ extern "C" int yb200_yolox_loss(const float* outputs, const float* labels, int b
   out.bias_acc = want_grad ? bias_acc : nullptr;
   cudaStream_t st = as_stream(stream);
   const size_t tile = static_cast<size_t>(kLossAnchors) * channels * sizeof(float);
-  static size_t loss_smem = 0;
+  static PerDevice<size_t> loss_smem_dev(0);
+  size_t& loss_smem = loss_smem_dev.cur();
   if (tile > loss_smem) {
     YB_CHECK_CUDA(cudaFuncSetAttribute(yolox_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile)));
     loss_smem = tile;

@@ -11,7 +11,7 @@ Kernel sequence (NHWC bf16 inside):
   UMMA descriptors straight on the NHWC tiles), normaliser = column sums, inst = raw / max(norm, 1e-6)
   heads: three small GEMMs with fp32 output (`yb200_conv1x1_bias_f32`)  |  mask projection 1x1
   pred_masks = per-image 1x1 convolution of the mask features with pred_kernel[b] as weights, fp32 NCHW written by the GEMM epilogue
-The final bilinear x2 up-sampling (decoder_sparseinst.py:148-153) is torch's F.interpolate on that output.
+The final bilinear x2 up-sampling (decoder_sparseinst.py:148-153) is `yb200_upsample_bilinear2x_f32` (other scale factors: F.interpolate).
 Round-1 scope: forward (inference; the loss / Hungarian matching of sparseinst_loss.py and the backward are not built): runs under no_grad.
 Instance / kernel counts are padded to multiples of 16 internally (100 -> 112: padded IAM channels get bias -30, i.e. probability 0).
 """
@@ -184,10 +184,22 @@ class BaseIAMDecoder(nn.Module):
         capi.check(L.yb200_conv2d_affine_fwd(ctypes.byref(ma), capi.ptr(self._pack(proj.weight, self.kernel_dim, self.mask_dim)), None, capi.ptr(proj.bias.detach()), None,
                                              ctypes.byref(mfa), 1, 1, sp), "projection")
         masks = torch.empty(b, npad, h, w, device=dev)
-        for i in range(b):  # torch.bmm(pred_kernel, mask_features) (:143-146): the image's kernels are the weights of a 1x1 convolution
-            mi = capi.act(mf[i:i + 1])
-            capi.check(L.yb200_conv1x1_nchw_f32(ctypes.byref(mi), capi.ptr(self._pack(kernel[i], npad, self.kernel_dim)), None, npad, capi.ptr(masks[i]), sp), "mask bmm")
-        pred_masks = F.interpolate(masks[:, :n], scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
+        # torch.bmm(pred_kernel, mask_features) (:143-146): an image's predicted kernels are the weights of a 1x1 convolution over its mask features.
+        # One launch for the batch when a 128-pixel tile stays inside one image (the [B * Npad, kernel_dim] kernels are packed to bf16 by one launch too)
+        rc = L.yb200_conv1x1_nchw_f32_batched(ctypes.byref(mfa), capi.ptr(self._pack(kernel.reshape(b * npad, self.kernel_dim), b * npad, self.kernel_dim)), npad,
+                                              capi.ptr(masks), sp)
+        if rc == capi.ERR_UNSUPPORTED:  # small maps (tiles would span images): one launch per image
+            for i in range(b):
+                mi = capi.act(mf[i:i + 1])
+                capi.check(L.yb200_conv1x1_nchw_f32(ctypes.byref(mi), capi.ptr(self._pack(kernel[i], npad, self.kernel_dim)), None, npad, capi.ptr(masks[i]), sp), "mask bmm")
+        else:
+            capi.check(rc, "mask bmm (batched)")
+        if self.scale_factor == 2:  # bilinear x2 (:148-153) on the device kernel; other factors keep torch's interpolate
+            m_lo = masks[:, :n].contiguous()
+            pred_masks = torch.empty(b, n, 2 * h, 2 * w, device=dev)
+            capi.check(L.yb200_upsample_bilinear2x_f32(capi.ptr(m_lo), capi.ptr(pred_masks), ctypes.c_int64(b * n), h, w, sp), "bilinear x2")
+        else:
+            pred_masks = F.interpolate(masks[:, :n], scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
         out = {"pred_logits": logits, "pred_masks": pred_masks, "pred_scores": scores}
         if self.output_iam:
             out["pred_iam"] = F.interpolate(iam.permute(0, 3, 1, 2).float(), scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
