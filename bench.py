@@ -532,9 +532,15 @@ def main():
     if not args.no_e2e:
         # two pinned host batches used alternately; the next step's batch is handed to model.prefetch() right after this step's forward
         # was launched, so its host->device copy (inside the timed region, every step) overlaps this step's backward
-        host = [images.pin_memory(), images.flip(0).contiguous().pin_memory()]
-        batches = [batched_inputs_from(host[0], labels), batched_inputs_from(host[1], labels.flip(0).contiguous())]
-        h2d = world * (host[0].numel() + labels.numel() * 4 + B * 8)
+        # as a detectron2 dataloader delivers them: every image its own pageable host tensor (no collated / pinned batch tensor): the model
+        # gathers them into its pinned staging buffer and issues one DMA per batch
+        def as_list(imgs, labs):
+            b = batched_inputs_from(imgs, labs)
+            for x in b:
+                x["image"] = x["image"].clone()
+            return b
+        batches = [as_list(images, labels), as_list(images.flip(0), labels.flip(0).contiguous())]
+        h2d = world * (images.numel() + labels.numel() * 4 + B * 8)
         api_i = [0]
         def api_step():
             if opt is not None:
@@ -542,13 +548,13 @@ def main():
             cur, nxt = batches[api_i[0] & 1], batches[(api_i[0] + 1) & 1]
             api_i[0] += 1
             losses = model(cur)
-            if not args.no_prefetch:
-                model.prefetch(nxt)
             sum(losses.values()).backward()
             if world > 1:
                 dist.all_reduce(flat_grad)
             if opt is not None:
                 opt.step()
+            if not args.no_prefetch:
+                model.prefetch(nxt)  # host gather + DMA of the next batch while this step's graphs run on the device
             return float(losses["total_loss"].detach())  # device -> host read of the step's result
 
         for _ in range(max(3, args.warmup)):  # call 1 eager, call 2 captures the forward / backward graphs, then replays
@@ -567,7 +573,7 @@ def main():
         e2e = {"value": world * B * args.steps / (ms2 / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * world,
                "api": ("optimizer.zero_grad() + " if opt is not None else "") + "YOLOX.forward(batched_inputs) + sum(loss_dict.values()).backward()"
                       + (" + optimizer.step()" if opt is not None else "") + " + loss.item()"
-                      + ("" if args.no_prefetch else "; model.prefetch(next batch) after forward: each step's pinned-host -> device copy overlaps the previous step's backward")}
+                      + ("" if args.no_prefetch else "; inputs = a list of separately allocated pageable uint8 images (as a detectron2 dataloader delivers them); model.prefetch(next batch) after the step's launches: the host gather into pinned memory and the host -> device copy overlap this step's device work")}
 
     # ---- NMS boxes/s (second half of the BASELINE metric) ----
     nms = None

@@ -169,7 +169,8 @@ def test_every_pdl_launched_kernel_waits_for_its_predecessor():
     names = set()
     for s in src.values():
         names.update(m.group(1) for m in re.finditer(r"launch_k\(\s*([A-Za-z_]\w*)", s))
-    names.discard("void")  # the declaration of launch_k itself
+        names.update(m.group(1) for m in re.finditer(r"launch_k_opt\([^,]+,\s*([A-Za-z_]\w*)", s))
+    names -= {"void", "kernel"}  # the declarations of launch_k / launch_k_opt themselves
     assert len(names) >= 50
     for n in sorted(names):
         bodies = []

@@ -960,7 +960,7 @@ static int launch_wgrad_inst(const CUtensorMap& tmDz, const CUtensorMap& tmX, co
     YB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
     max_set = pl.smem;
   }
-  launch_k(wgrad_gemm_kernel<TC>, grid, kConvThreads, pl.smem, st, tmDz, tmX, pl.p);
+  launch_k_opt(use_pdl_wgrad(), wgrad_gemm_kernel<TC>, grid, kConvThreads, pl.smem, st, tmDz, tmX, pl.p);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -992,7 +992,7 @@ extern "C" int yb200_conv2d_wgrad(const yb200_act* x, const yb200_act* dz, int k
   if (rc) return rc;
   const long long total = 1LL * pl.p.cout * pl.p.num_taps * pl.p.cin;
   const int blocks = static_cast<int>(std::min<long long>((total + 31) / 32, 16 * sm_count()));
-  launch_k(wgrad_reduce_kernel, blocks, 256, 0, st, pl.p.ws, grad_oihw, pl.splits, pl.p.cout, pl.p.num_taps, pl.p.cin, cin_real, accumulate);
+  launch_k_opt(use_pdl_wgrad(), wgrad_reduce_kernel, blocks, 256, 0, st, pl.p.ws, grad_oihw, pl.splits, pl.p.cout, pl.p.num_taps, pl.p.cin, cin_real, accumulate);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -27,6 +27,15 @@ bool use_pdl() {
   return v == 1;
 }
 
+bool use_pdl_wgrad() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YB200_PDL_WGRAD");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int current_device() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -202,7 +202,7 @@ simota_prep_kernel(const float* __restrict__ outputs, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // kernel 2: one block per (gt, image): dynamic k from the 10 largest IoUs, then the k cheapest candidates
 // ------------------------------------------------------------------------------------------------
-constexpr int kMatchThreads = 256;
+constexpr int kMatchThreads = 512;  // candidates per thread bound the scan (dependent loads per candidate): 512 threads halve it; the tournament rounds grow by 8 warp heads
 
 struct CostIdx {
   float c;

@@ -562,18 +562,20 @@ class YOLOX(nn.Module):
             base = imgs[0]
             contiguous_run = base.is_pinned() and all(i.is_contiguous() and i.data_ptr() == base.data_ptr() + k * nbytes for k, i in enumerate(imgs))
             if contiguous_run:
-                src = torch.as_strided(base, (len(imgs), 3, hp, wp), (nbytes, hp * wp, wp, 1))
+                images_dst.copy_(torch.as_strided(base, (len(imgs), 3, hp, wp), (nbytes, hp * wp, wp, 1)), non_blocking=True)
+            elif all(i.is_pinned() and i.is_contiguous() for i in imgs):
+                for k, im in enumerate(imgs):  # separately allocated pinned images: one asynchronous DMA each, no host-side gather
+                    images_dst[k].copy_(im, non_blocking=True)
             else:
+                # what a detectron2 dataloader hands over: a list of separately allocated pageable tensors.  Gather them into a persistent
+                # pinned staging buffer (one multi-threaded torch.stack), then one DMA.
                 if getattr(eng, "_stage", None) is None:
                     eng._stage = torch.empty(images_dst.shape, dtype=torch.uint8).pin_memory()
                     eng._stage_evt = torch.cuda.Event()
                 else:
                     eng._stage_evt.synchronize()  # the previous DMA out of the staging buffer has finished
-                for k, im in enumerate(imgs):
-                    eng._stage[k].copy_(im)
-                src = eng._stage
-            images_dst.copy_(src, non_blocking=True)
-            if not contiguous_run:
+                torch.stack(imgs, out=eng._stage)
+                images_dst.copy_(eng._stage, non_blocking=True)
                 eng._stage_evt.record()
         else:
             if not getattr(eng, "device_pad", True):  # a plan that reads images_u8 as is: the padding value goes in here
@@ -618,18 +620,20 @@ class YOLOX(nn.Module):
 
     def prefetch(self, batched_inputs):
         """Input-side pipelining: start the host->device copies of the NEXT batch on a copy stream while the
-        current step is still running; the following `forward(batched_inputs)` with this same list only swaps buffers.  The copies go
-        into the plan's alternate buffers, after everything already enqueued on the compute stream (so the step that last used them has
-        finished).  Optional: forward() alone behaves exactly like the reference (copy, then compute)."""
+        current step is still running; the following `forward(batched_inputs)` with this same list only copies device-to-device into the plan's
+        static buffers.  The copies go into the plan's alternate buffers as soon as their previous contents have been consumed.  Optional: forward() alone behaves exactly like the reference (copy, then compute)."""
         eng, imgs, hp, wp = self._plan_for(batched_inputs)
         if getattr(eng, "_alt", None) is None:
             eng._alt = (torch.empty_like(eng.images_u8), torch.empty_like(eng.labels), torch.empty_like(eng.hw_valid))
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._copy_fence, self._copy_done = torch.cuda.Event(), torch.cuda.Event()
-        self._copy_fence.record(torch.cuda.current_stream())
+            self._copy_done = torch.cuda.Event()
         with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._copy_fence)
+            # the alternate buffers were last READ by the device-to-device copy at the head of the step that consumed the previous prefetch
+            # (preprocess_image records `_alt_free` there): wait for that, not for the whole step in flight -- the DMA overlaps its kernels
+            free = getattr(eng, "_alt_free", None)
+            if free is not None:
+                self._copy_stream.wait_event(free)
             self._stage_batch(batched_inputs, self.training, eng, imgs, hp, wp, *eng._alt)
             self._copy_done.record(self._copy_stream)
         self._prefetched = (batched_inputs, eng)
@@ -646,6 +650,9 @@ class YOLOX(nn.Module):
             eng.images_u8.copy_(alt[0], non_blocking=True)
             eng.labels.copy_(alt[1], non_blocking=True)
             eng.hw_valid.copy_(alt[2], non_blocking=True)
+            if getattr(eng, "_alt_free", None) is None:
+                eng._alt_free = torch.cuda.Event()
+            eng._alt_free.record(torch.cuda.current_stream())
             self._prefetched = None
             return eng, image_sizes
         self._stage_batch(batched_inputs, training, eng, imgs, hp, wp, eng.images_u8, eng.labels, eng.hw_valid)
