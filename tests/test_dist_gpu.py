@@ -1,5 +1,7 @@
-"""Two-GPU correctness of the data-parallel exchange (needs 2 CUDA devices; NCCL): the bucketed, backward-overlapped all-reduce of
-yolov7_d2_b200.dist.GradientBuckets leaves in every rank's flat gradient buffer the sum of the two ranks' single-GPU gradients."""
+"""Two-rank correctness of the data-parallel exchange: the bucketed, backward-overlapped all-reduce of yolov7_d2_b200.dist.GradientBuckets
+leaves in every rank's flat gradient buffer the sum of the two ranks' single-GPU gradients.  With two or more CUDA devices: one rank per GPU over
+NCCL (what `bench.py --gpus N` and the driver's scaling run use).  On a one-GPU box the two ranks share cuda:0 and exchange through gloo (NCCL
+refuses two ranks on one device): the same engine kernels, range-by-range backward, communication stream and event ordering, without NVLink."""
 import os
 import socket
 
@@ -17,14 +19,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, backend):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dev = torch.device("cuda", rank if backend == "nccl" else 0)
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     from yolov7_d2_b200 import synth
     from yolov7_d2_b200.dist import GradientBuckets
     from yolov7_d2_b200.engine import YoloxEngine
@@ -61,14 +66,14 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs: NCCL refuses two ranks on one device, and two gloo ranks sharing one GPU hang in its CUDA path; the host logic is covered by tests/test_dist_cpu.py (gloo), this test by `gpurun --gpus 2` (profiles/r2_bench_2gpu.json comes from the same call)")
 def test_bucketed_allreduce_equals_sum_of_single_gpu_gradients(cuda):
     import torch.multiprocessing as mp
 
     world = 2
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, backend), nprocs=world, join=True)
     for r in range(world):
         layout_ok, cos, rel = out[r]
         assert layout_ok, "a parameter lies outside every gradient bucket"

@@ -31,7 +31,7 @@ bool use_pdl_wgrad() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("YB200_PDL_WGRAD");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;  // default off: measured +1 % step throughput (profiles/r2_ab_runs.md)
   }
   return v == 1;
 }

@@ -58,7 +58,8 @@ void choose_tile(int n, int h, int w, int npix, int* log_tw, int* log_th);
 // then scheduled while this one drains: its CTAs take the SM slots that free up and park at their own griddepcontrol.wait until this grid has
 // completed and flushed -- launch latency and block scheduling of ~540 launches per step leave the critical path.  YB200_PDL=0 launches plainly.
 bool use_pdl();
-bool use_pdl_wgrad();  // YB200_PDL_WGRAD=0: the weight-gradient kernels (side stream, up to 160 KB of shared memory per parked CTA) launch plainly
+bool use_pdl_wgrad();  // the weight-gradient kernels (side stream) launch plainly unless YB200_PDL_WGRAD=1: a parked CTA of theirs holds up to 160 KB of
+                       // shared memory that the main stream's kernels then cannot use
 template <typename... K, typename... A>
 inline cudaError_t launch_k_opt(bool pdl, void (*kernel)(K...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
   cudaLaunchConfig_t cfg = {};
