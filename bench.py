@@ -541,7 +541,7 @@ def main():
             return b
         batches = [as_list(images, labels), as_list(images.flip(0), labels.flip(0).contiguous())]
         h2d = world * (images.numel() + labels.numel() * 4 + B * 8)
-        api_i = [0]
+        api_i, api_cpu = [0], [0.0]
         def api_step():
             if opt is not None:
                 opt.zero_grad()
@@ -554,12 +554,15 @@ def main():
             if opt is not None:
                 opt.step()
             if not args.no_prefetch:
+                t0 = time.perf_counter()
                 model.prefetch(nxt)  # host gather + DMA of the next batch while this step's graphs run on the device
+                api_cpu[0] += time.perf_counter() - t0
             return float(losses["total_loss"].detach())  # device -> host read of the step's result
 
         for _ in range(max(3, args.warmup)):  # call 1 eager, call 2 captures the forward / backward graphs, then replays
             api_step()
         barrier()
+        api_cpu[0] = 0.0
         e0.record()
         for _ in range(args.steps):
             api_step()
@@ -571,6 +574,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t)
         e2e = {"value": world * B * args.steps / (ms2 / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * world,
+               "prefetch_host_ms_per_step": round(api_cpu[0] / args.steps * 1e3, 3),
                "api": ("optimizer.zero_grad() + " if opt is not None else "") + "YOLOX.forward(batched_inputs) + sum(loss_dict.values()).backward()"
                       + (" + optimizer.step()" if opt is not None else "") + " + loss.item()"
                       + ("" if args.no_prefetch else "; inputs = a list of separately allocated pageable uint8 images (as a detectron2 dataloader delivers them); model.prefetch(next batch) after the step's launches: the host gather into pinned memory and the host -> device copy overlap this step's device work")}

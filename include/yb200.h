@@ -171,6 +171,10 @@ int yb200_copy_view(const yb200_act* src, const yb200_act* dst, void* stream);
  * obj / cls (yolox_head.py:209-211, 247-272).                                                                  */
 int yb200_yolox_decode(float* outputs, int batch, int num_anchors, int channels, const int32_t* level_hw_stride,
                        int num_levels, int eval_mode, void* stream);
+/* Training decode that also keeps the RAW regression outputs: raw_reg [batch][num_anchors][4] fp32 (16-byte aligned) = `origin_preds` of the
+ * L1 branch (`use_l1`, yolox_head.py:186-195).                                                                                           */
+int yb200_yolox_decode_keep_raw(float* outputs, int batch, int num_anchors, int channels, const int32_t* level_hw_stride,
+                                int num_levels, float* raw_reg, void* stream);
 /* SimOTA dynamic-k assignment for the whole batch (get_assignments + get_in_boxes_info + dynamic_k_matching,
  * yolox_head.py:450-669) on DECODED outputs and labels [batch][max_gt][5] = (cls, cx, cy, w, h), zero padded.
  * Per anchor: fg_mask (u8), matched_gt (-1 when background), matched_iou, matched_cls; per image num_gt / num_fg;
@@ -192,6 +196,14 @@ int yb200_yolox_loss(const float* outputs, const float* labels, int batch, int n
                      const float* matched_iou, const int32_t* matched_cls, const int32_t* totals, const float* weights3,
                      double* loss_acc3, float* losses6, void* const* d_cls, void* const* d_regobj, float* d_dense,
                      double* bias_acc, void* stream);
+/* The same with the L1 branch (`use_l1`, yolox_head.py:389-429, 443-448): loss_l1 = sum |raw_reg[fg] - l1_target| / num_fg with
+ * l1_target = (gt_xy / stride - grid, log(gt_wh / stride + 1e-8)); total = 5*iou + obj + cls + l1, losses6[4] = l1; weights4[3] = d objective /
+ * d loss_l1; the gradient sign(raw - target) * weight / num_fg is added to the regression gradients.  loss_acc4: fp64 scratch [4].          */
+int yb200_yolox_loss_l1(const float* outputs, const float* raw_reg, const float* labels, int batch, int num_anchors, int channels,
+                        int max_gt, const int32_t* level_hw_stride, int num_levels, const uint8_t* fg_mask,
+                        const int32_t* matched_gt, const float* matched_iou, const int32_t* matched_cls, const int32_t* totals,
+                        const float* weights4, double* loss_acc4, float* losses6, void* const* d_cls, void* const* d_regobj,
+                        float* d_dense, double* bias_acc, void* stream);
 /* bias gradients of reg_preds / obj_preds / cls_preds of one level out of bias_acc (which is re-zeroed).          */
 int yb200_head_bias_grad(double* bias_acc, int num_levels, int channels, int level, float* grad_reg_bias4,
                          float* grad_obj_bias1, float* grad_cls_bias, int accumulate, void* stream);

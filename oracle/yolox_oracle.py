@@ -284,13 +284,19 @@ def simota_assign(gt_boxes, gt_classes, boxes, cls_logits, obj_logits, x_shifts,
     return fg_mask, matched_gt, gt_classes[matched_gt], (matching * ious).sum(0)[fg_in]
 
 
-def yolox_losses(outputs, labels, x_shifts, y_shifts, strides, num_classes=80, loss_type="iou", return_assign=False):
-    """YOLOXHead.get_losses without L1   (yolox_head.py:274-441).
+def l1_target(gt, stride, x_shifts, y_shifts, eps=1e-8):
+    """get_l1_target (yolox_head.py:443-448): the matched gt box in the RAW parametrisation of the regression outputs"""
+    return torch.stack([gt[:, 0] / stride - x_shifts, gt[:, 1] / stride - y_shifts, torch.log(gt[:, 2] / stride + eps), torch.log(gt[:, 3] / stride + eps)], 1)
+
+
+def yolox_losses(outputs, labels, x_shifts, y_shifts, strides, num_classes=80, loss_type="iou", return_assign=False, origin_preds=None):
+    """YOLOXHead.get_losses   (yolox_head.py:274-441).
     outputs [B,A,5+C] (decoded boxes + raw logits), labels [B,G,5] = (cls,cx,cy,w,h) zero padded.
-    Returns (total, 5*iou, obj, cls, num_fg/num_gt)."""
+    Returns (total, 5*iou, obj, cls, num_fg/num_gt).  origin_preds [B,A,4] (the raw regression outputs, `use_l1`, :186-195, :389-429) adds the
+    L1 term to the total and makes the result (total, 5*iou, obj, cls, l1, num_fg/num_gt)."""
     bsz, num_anchors = outputs.shape[:2]
     nlabel = (labels.sum(2) > 0).sum(1)
-    fg_masks, cls_t, reg_t, assigns = [], [], [], []
+    fg_masks, cls_t, reg_t, assigns, l1_t = [], [], [], [], []
     num_fg, num_gts = 0.0, 0.0
     for b in range(bsz):
         g = int(nlabel[b])
@@ -309,6 +315,8 @@ def yolox_losses(outputs, labels, x_shifts, y_shifts, strides, num_classes=80, l
             cls_t.append(F.one_hot(mcls.to(torch.int64), num_classes) * miou[:, None])
             reg_t.append(gtb[mgt])
             assigns.append((fg, mgt, mcls, miou))
+            if origin_preds is not None:
+                l1_t.append(l1_target(gtb[mgt], strides[fg], x_shifts[fg], y_shifts[fg]))
         fg_masks.append(fg)
     fg_all = torch.cat(fg_masks)
     cls_t, reg_t = torch.cat(cls_t), torch.cat(reg_t)
@@ -318,7 +326,12 @@ def yolox_losses(outputs, labels, x_shifts, y_shifts, strides, num_classes=80, l
     l_obj = F.binary_cross_entropy_with_logits(outputs[..., 4].reshape(-1, 1), obj_t, reduction="none").sum() / num_fg
     l_cls = F.binary_cross_entropy_with_logits(outputs[..., 5:].reshape(-1, num_classes)[fg_all], cls_t, reduction="none").sum() / num_fg
     total = 5.0 * l_iou + l_obj + l_cls
-    res = (total, 5.0 * l_iou, l_obj, l_cls, num_fg / max(num_gts, 1))
+    if origin_preds is not None:
+        tgt = torch.cat(l1_t) if l1_t else outputs.new_zeros((0, 4))
+        l_l1 = (origin_preds.reshape(-1, 4)[fg_all] - tgt).abs().sum() / num_fg
+        res = (total + l_l1, 5.0 * l_iou, l_obj, l_cls, l_l1, num_fg / max(num_gts, 1))
+    else:
+        res = (total, 5.0 * l_iou, l_obj, l_cls, num_fg / max(num_gts, 1))
     return res + (assigns,) if return_assign else res
 
 

@@ -105,6 +105,25 @@ def test_simota_and_losses(case):
         assert torch.equal(miou, T(g[f"{case}.b{b}.matched_iou"])), f"matched_iou image {b}"
 
 
+@pytest.mark.parametrize("case", ["trained", "init"])
+def test_l1_branch(case):
+    """`use_l1` (yolox_head.py:389-429, 443-448): fixture from the reference head with origin_preds (oracle/gen_golden_l1.py); the leaf is the RAW head
+    output, from which both the decoded boxes and origin_preds derive"""
+    g = load("simota_l1.npz")
+    size = int(g["size"])
+    raw = T(g[f"{case}.raw"]).clone().requires_grad_(True)
+    labels = T(g[f"{case}.labels"])
+    xs, ys, ss = orc.anchor_grid([(size // s, size // s) for s in orc.STRIDES])
+    grid = torch.stack((xs, ys), 1)[None]
+    out = torch.cat([(raw[..., :2] + grid) * ss[None, :, None], torch.exp(raw[..., 2:4]) * ss[None, :, None], raw[..., 4:]], -1)
+    total, iou5, lobj, lcls, l1, ratio = orc.yolox_losses(out, labels, xs, ys, ss, origin_preds=raw[..., :4])
+    total.backward()
+    got = np.array([float(total), float(iou5), float(lobj), float(lcls), float(l1), float(ratio)])
+    assert np.allclose(got, g[f"{case}.losses"], rtol=1e-6, atol=1e-6), (got, g[f"{case}.losses"])
+    assert float(l1) > 0.1
+    assert torch.allclose(raw.grad, T(g[f"{case}.grad"]), rtol=1e-5, atol=1e-8)
+
+
 def test_simota_exercises_hard_branches():
     """the fixtures cover dynamic k > 1 and anchors contested by several ground truths"""
     g = load("simota.npz")

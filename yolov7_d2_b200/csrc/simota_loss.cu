@@ -52,13 +52,14 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // decode (in place on [B, A, 5+C] fp32): xy = (xy + grid) * s, wh = exp(wh) * s; eval additionally sigmoid(obj, cls)
 //   yolox_head.py:226-245 (train), 197-224 + 247-272 (eval)
 // ------------------------------------------------------------------------------------------------
-__global__ void decode_kernel(float* __restrict__ out, int batch, int num_anchors, int ch, Levels L, int eval_mode) {
+__global__ void decode_kernel(float* __restrict__ out, int batch, int num_anchors, int ch, Levels L, int eval_mode, float4* __restrict__ raw_reg) {
   pdl_sync();
   const long long total = 1LL * batch * num_anchors;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int a = static_cast<int>(i % num_anchors);
     const Anchor an = anchor_of(L, a);
     float* o = out + i * ch;
+    if (raw_reg) raw_reg[i] = make_float4(o[0], o[1], o[2], o[3]);  // origin_preds (yolox_head.py:195): the L1 branch compares the RAW outputs
     o[0] = __fmul_rn(__fadd_rn(o[0], an.gx), an.s);
     o[1] = __fmul_rn(__fadd_rn(o[1], an.gy), an.s);
     o[2] = __fmul_rn(expf(o[2]), an.s);
@@ -202,7 +203,7 @@ simota_prep_kernel(const float* __restrict__ outputs, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // kernel 2: one block per (gt, image): dynamic k from the 10 largest IoUs, then the k cheapest candidates
 // ------------------------------------------------------------------------------------------------
-constexpr int kMatchThreads = 512;  // candidates per thread bound the scan (dependent loads per candidate): 512 threads halve it; the tournament rounds grow by 8 warp heads
+constexpr int kMatchThreads = 256;  // (512 threads measured slower: 0.44 vs 0.35 ms for the four SimOTA kernels -- the tournament rounds, not the scan, dominate)
 
 struct CostIdx {
   float c;
@@ -411,7 +412,8 @@ struct LossOut {
   __nv_bfloat16* d_cls[kMaxLevels];
   __nv_bfloat16* d_ro[kMaxLevels];
   float* d_dense;    // optional fp32 [B, A, 5+C] gradient w.r.t. the raw outputs (tests)
-  double* loss_acc;  // [3] sums of iou / obj / cls losses (un-normalised)
+  double* loss_acc;  // [3] sums of iou / obj / cls losses (un-normalised); [4] with the L1 branch
+  const float4* raw_reg;  // use_l1: the raw regression outputs [B][A] (origin_preds), else null
   double* bias_acc;  // [levels][5+C] sums of the raw-output gradients (prediction-conv bias gradients), may be null
 };
 
@@ -426,7 +428,7 @@ yolox_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ l
                   int want_loss, int want_grad) {
   pdl_sync();
   extern __shared__ __align__(16) float tile[];  // [kLossAnchors][ch] outputs, reused for gradients
-  __shared__ double s_loss[3];
+  __shared__ double s_loss[4];
   const int b = blockIdx.y;
   int lvl = 0;  // blocks never straddle levels: each level is cut into its own 128-anchor blocks
 #pragma unroll
@@ -437,12 +439,13 @@ yolox_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ l
   const int nc = ch - 5;
   const float nfg = fmaxf(static_cast<float>(totals[0]), 1.f);
   const float w_iou = want_grad ? weights[0] / nfg : 0.f, w_obj = want_grad ? weights[1] / nfg : 0.f, w_cls = want_grad ? weights[2] / nfg : 0.f;
+  const float w_l1 = (want_grad && out.raw_reg) ? weights[3] / nfg : 0.f;
   const float* src = outputs + (1LL * b * num_anchors + a0) * ch;
   load_tile_f32(tile, src, na * ch);
-  if (threadIdx.x < 3) s_loss[threadIdx.x] = 0.0;
+  if (threadIdx.x < 4) s_loss[threadIdx.x] = 0.0;
   __syncthreads();
 
-  float l_iou = 0.f, l_obj = 0.f, l_cls = 0.f;
+  float l_iou = 0.f, l_obj = 0.f, l_cls = 0.f, l_l1 = 0.f;
   if (threadIdx.x < na) {
     const int a = a0 + threadIdx.x;
     const long long ia = 1LL * b * num_anchors + a;
@@ -490,6 +493,18 @@ yolox_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ l
       row[1] = dpy * an.s;
       row[2] = dpw * pw;    // w = exp(raw) * s
       row[3] = dph * ph;
+      if (out.raw_reg) {
+        // L1 branch (yolox_head.py:389-429, 443-448): |raw - target| with target = (gt_xy / s - grid, log(gt_wh / s + 1e-8)); d|x| = sign(x)
+        const float4 r = out.raw_reg[ia];
+        const float t0 = __fsub_rn(__fdiv_rn(gt.cx, an.s), an.gx), t1 = __fsub_rn(__fdiv_rn(gt.cy, an.s), an.gy);
+        const float t2 = logf(__fadd_rn(__fdiv_rn(gt.w, an.s), 1e-8f)), t3 = logf(__fadd_rn(__fdiv_rn(gt.h, an.s), 1e-8f));
+        const float e0 = r.x - t0, e1 = r.y - t1, e2 = r.z - t2, e3 = r.w - t3;
+        l_l1 = (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3));
+        row[0] += w_l1 * ((e0 > 0.f) - (e0 < 0.f));
+        row[1] += w_l1 * ((e1 > 0.f) - (e1 < 0.f));
+        row[2] += w_l1 * ((e2 > 0.f) - (e2 < 0.f));
+        row[3] += w_l1 * ((e3 > 0.f) - (e3 < 0.f));
+      }
     } else {
       row[0] = row[1] = row[2] = row[3] = 0.f;
       for (int c = 0; c < nc; ++c) row[5 + c] = 0.f;
@@ -499,9 +514,10 @@ yolox_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ l
     atomicAdd(&s_loss[0], static_cast<double>(l_iou));
     atomicAdd(&s_loss[1], static_cast<double>(l_obj));
     atomicAdd(&s_loss[2], static_cast<double>(l_cls));
+    if (out.raw_reg) atomicAdd(&s_loss[3], static_cast<double>(l_l1));
   }
   __syncthreads();
-  if (want_loss && threadIdx.x < 3) atomicAdd(out.loss_acc + threadIdx.x, s_loss[threadIdx.x]);
+  if (want_loss && threadIdx.x < (out.raw_reg ? 4 : 3)) atomicAdd(out.loss_acc + threadIdx.x, s_loss[threadIdx.x]);
   if (!want_grad) return;
 
   // ---- gradient tile -> global (coalesced) ----
@@ -543,17 +559,19 @@ yolox_loss_kernel(const float* __restrict__ outputs, const float* __restrict__ l
 }
 
 // (total, 5*iou, obj, cls, l1 = 0, num_fg / max(num_gts, 1))  --  the 6-tuple get_losses returns (yolox_head.py:433-441)
-__global__ void yolox_loss_finish_kernel(double* __restrict__ loss_acc, const int* __restrict__ totals, float* __restrict__ out6) {
+__global__ void yolox_loss_finish_kernel(double* __restrict__ loss_acc, const int* __restrict__ totals, float* __restrict__ out6, int with_l1) {
   pdl_sync();
   const float nfg = fmaxf(static_cast<float>(totals[0]), 1.f);
   const float li = static_cast<float>(loss_acc[0]) / nfg, lo = static_cast<float>(loss_acc[1]) / nfg, lc = static_cast<float>(loss_acc[2]) / nfg;
-  out6[0] = 5.f * li + lo + lc;
+  const float l1 = with_l1 ? static_cast<float>(loss_acc[3]) / nfg : 0.f;
+  out6[0] = 5.f * li + lo + lc + l1;  // reg_weight * loss_iou + loss_obj + loss_cls + loss_l1 (yolox_head.py:431-432)
   out6[1] = 5.f * li;
   out6[2] = lo;
   out6[3] = lc;
-  out6[4] = 0.f;
+  out6[4] = l1;
   out6[5] = nfg / fmaxf(static_cast<float>(totals[1]), 1.f);
   loss_acc[0] = loss_acc[1] = loss_acc[2] = 0.0;
+  if (with_l1) loss_acc[3] = 0.0;
 }
 
 int make_levels(const int32_t* level_hw_stride, int num_levels, int num_anchors, Levels* L) {
@@ -584,15 +602,26 @@ int make_levels(const int32_t* level_hw_stride, int num_levels, int num_anchors,
 // ================================================================================================
 // C ABI
 // ================================================================================================
+static int decode_impl(float* outputs, int batch, int num_anchors, int channels, const int32_t* level_hw_stride, int num_levels, int eval_mode,
+                       float* raw_reg, void* stream);
 extern "C" int yb200_yolox_decode(float* outputs, int batch, int num_anchors, int channels, const int32_t* level_hw_stride, int num_levels,
                                   int eval_mode, void* stream) {
+  return decode_impl(outputs, batch, num_anchors, channels, level_hw_stride, num_levels, eval_mode, nullptr, stream);
+}
+extern "C" int yb200_yolox_decode_keep_raw(float* outputs, int batch, int num_anchors, int channels, const int32_t* level_hw_stride, int num_levels,
+                                           float* raw_reg, void* stream) {
+  YB_REQUIRE(raw_reg != nullptr && (reinterpret_cast<uintptr_t>(raw_reg) & 15) == 0, YB200_ERR_INVALID, "yolox_decode_keep_raw: raw_reg must be a 16-byte aligned [B][A][4] buffer");
+  return decode_impl(outputs, batch, num_anchors, channels, level_hw_stride, num_levels, 0, raw_reg, stream);
+}
+static int decode_impl(float* outputs, int batch, int num_anchors, int channels, const int32_t* level_hw_stride, int num_levels, int eval_mode,
+                       float* raw_reg, void* stream) {
   YB_REQUIRE(outputs && batch > 0 && num_anchors > 0 && channels > 5, YB200_ERR_INVALID, "yolox_decode: bad arguments");
   Levels L;
   int rc = make_levels(level_hw_stride, num_levels, num_anchors, &L);
   if (rc) return rc;
   const long long total = 1LL * batch * num_anchors;
   const int blocks = static_cast<int>(std::min<long long>((total + 127) / 128, 16LL * sm_count()));
-  launch_k(decode_kernel, blocks, 128, 0, as_stream(stream), outputs, batch, num_anchors, channels, L, eval_mode);
+  launch_k(decode_kernel, blocks, 128, 0, as_stream(stream), outputs, batch, num_anchors, channels, L, eval_mode, reinterpret_cast<float4*>(raw_reg));
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -646,11 +675,33 @@ extern "C" int yb200_simota_assign(const float* outputs, const float* labels, in
   return 0;
 }
 
+static int yolox_loss_impl(const float* outputs, const float* labels, int batch, int num_anchors, int channels, int max_gt,
+                           const int32_t* level_hw_stride, int num_levels, const uint8_t* fg_mask, const int32_t* matched_gt,
+                           const float* matched_iou, const int32_t* matched_cls, const int32_t* totals, const float* weights3,
+                           double* loss_acc3, float* losses6, void* const* d_cls, void* const* d_regobj, float* d_dense, double* bias_acc,
+                           const float* raw_reg, void* stream);
 extern "C" int yb200_yolox_loss(const float* outputs, const float* labels, int batch, int num_anchors, int channels, int max_gt,
                                 const int32_t* level_hw_stride, int num_levels, const uint8_t* fg_mask, const int32_t* matched_gt,
                                 const float* matched_iou, const int32_t* matched_cls, const int32_t* totals, const float* weights3,
                                 double* loss_acc3, float* losses6, void* const* d_cls, void* const* d_regobj, float* d_dense, double* bias_acc,
                                 void* stream) {
+  return yolox_loss_impl(outputs, labels, batch, num_anchors, channels, max_gt, level_hw_stride, num_levels, fg_mask, matched_gt, matched_iou, matched_cls,
+                         totals, weights3, loss_acc3, losses6, d_cls, d_regobj, d_dense, bias_acc, nullptr, stream);
+}
+extern "C" int yb200_yolox_loss_l1(const float* outputs, const float* raw_reg, const float* labels, int batch, int num_anchors, int channels, int max_gt,
+                                   const int32_t* level_hw_stride, int num_levels, const uint8_t* fg_mask, const int32_t* matched_gt,
+                                   const float* matched_iou, const int32_t* matched_cls, const int32_t* totals, const float* weights4,
+                                   double* loss_acc4, float* losses6, void* const* d_cls, void* const* d_regobj, float* d_dense, double* bias_acc,
+                                   void* stream) {
+  YB_REQUIRE(raw_reg != nullptr && (reinterpret_cast<uintptr_t>(raw_reg) & 15) == 0, YB200_ERR_INVALID, "yolox_loss_l1: raw_reg must be a 16-byte aligned [B][A][4] buffer");
+  return yolox_loss_impl(outputs, labels, batch, num_anchors, channels, max_gt, level_hw_stride, num_levels, fg_mask, matched_gt, matched_iou, matched_cls,
+                         totals, weights4, loss_acc4, losses6, d_cls, d_regobj, d_dense, bias_acc, raw_reg, stream);
+}
+static int yolox_loss_impl(const float* outputs, const float* labels, int batch, int num_anchors, int channels, int max_gt,
+                           const int32_t* level_hw_stride, int num_levels, const uint8_t* fg_mask, const int32_t* matched_gt,
+                           const float* matched_iou, const int32_t* matched_cls, const int32_t* totals, const float* weights3,
+                           double* loss_acc3, float* losses6, void* const* d_cls, void* const* d_regobj, float* d_dense, double* bias_acc,
+                           const float* raw_reg, void* stream) {
   YB_REQUIRE(outputs && labels && fg_mask && matched_gt && matched_iou && matched_cls && totals && loss_acc3, YB200_ERR_INVALID,
              "yolox_loss: null pointer");
   const bool want_loss = losses6 != nullptr;
@@ -669,6 +720,7 @@ extern "C" int yb200_yolox_loss(const float* outputs, const float* labels, int b
   }
   out.d_dense = want_grad ? d_dense : nullptr;
   out.loss_acc = loss_acc3;
+  out.raw_reg = reinterpret_cast<const float4*>(raw_reg);
   out.bias_acc = want_grad ? bias_acc : nullptr;
   cudaStream_t st = as_stream(stream);
   const size_t tile = static_cast<size_t>(kLossAnchors) * channels * sizeof(float);
@@ -683,7 +735,7 @@ extern "C" int yb200_yolox_loss(const float* outputs, const float* labels, int b
       outputs, labels, num_anchors, channels, max_gt, L, fg_mask, matched_gt, matched_iou, matched_cls, totals, weights3, out, want_loss, want_grad);
   YB_CHECK_CUDA(cudaGetLastError());
   if (want_loss) {
-    launch_k(yolox_loss_finish_kernel, 1, 1, 0, st, loss_acc3, totals, losses6);
+    launch_k(yolox_loss_finish_kernel, 1, 1, 0, st, loss_acc3, totals, losses6, raw_reg != nullptr ? 1 : 0);
     YB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;

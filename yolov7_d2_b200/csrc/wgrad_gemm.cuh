@@ -193,8 +193,20 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad_oihw,
   for (unsigned base = blockIdx.x * 32u; base < total; base += gridDim.x * 32u) {
     const unsigned i = base + ox;
     float acc = 0.f;
-    if (i < total)
-      for (int s = sl; s < splits; s += 8) acc += ws[static_cast<size_t>(s) * total + i];
+    if (i < total) {
+      // four independent loads in flight per thread (the kernel is latency bound: one 4-byte load per thread and iteration otherwise);
+      // fixed association order, so the result does not depend on the launch
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int s = sl;
+      for (; s + 24 < splits; s += 32) {
+        a0 += ws[static_cast<size_t>(s) * total + i];
+        a1 += ws[static_cast<size_t>(s + 8) * total + i];
+        a2 += ws[static_cast<size_t>(s + 16) * total + i];
+        a3 += ws[static_cast<size_t>(s + 24) * total + i];
+      }
+      for (; s < splits; s += 8) a0 += ws[static_cast<size_t>(s) * total + i];
+      acc = (a0 + a1) + (a2 + a3);
+    }
     part[sl][ox] = acc;
     __syncthreads();
     if (sl == 0 && i < total) {

@@ -12,6 +12,8 @@ own parameters (views into the engine's flat fp32 buffers) and marshal tensors.
 import ctypes
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -567,16 +569,25 @@ class YOLOX(nn.Module):
                 for k, im in enumerate(imgs):  # separately allocated pinned images: one asynchronous DMA each, no host-side gather
                     images_dst[k].copy_(im, non_blocking=True)
             else:
-                # what a detectron2 dataloader hands over: a list of separately allocated pageable tensors.  Gather them into a persistent
-                # pinned staging buffer (one multi-threaded torch.stack), then one DMA.
-                if getattr(eng, "_stage", None) is None:
-                    eng._stage = torch.empty(images_dst.shape, dtype=torch.uint8).pin_memory()
-                    eng._stage_evt = torch.cuda.Event()
+                # what a detectron2 dataloader hands over: a list of separately allocated pageable tensors.  Measured on the B200 box (2 x Xeon 8562Y+,
+                # profiles/r2_ab_runs.md): one asynchronous copy per image straight from pageable memory (the driver stages it) gives the best
+                # end-to-end rate; gathering into a pinned staging buffer costs less host time with a thread pool but not with torch.stack.
+                mode = os.environ.get("YB200_GATHER", "direct")  # direct | threads | stack (A/B knob, profiles/r2_ab_runs.md)
+                if mode == "direct":  # one cudaMemcpyAsync per pageable image: the driver stages each through its own pinned buffers
+                    for k, im in enumerate(imgs):
+                        images_dst[k].copy_(im, non_blocking=True)
                 else:
-                    eng._stage_evt.synchronize()  # the previous DMA out of the staging buffer has finished
-                torch.stack(imgs, out=eng._stage)
-                images_dst.copy_(eng._stage, non_blocking=True)
-                eng._stage_evt.record()
+                    if getattr(eng, "_stage", None) is None:
+                        eng._stage = torch.empty(images_dst.shape, dtype=torch.uint8).pin_memory()
+                        eng._stage_evt = torch.cuda.Event()
+                    else:
+                        eng._stage_evt.synchronize()  # the previous DMA out of the staging buffer has finished
+                    if mode == "threads":
+                        self._gather(imgs, eng._stage)
+                    else:
+                        torch.stack(imgs, out=eng._stage)
+                    images_dst.copy_(eng._stage, non_blocking=True)
+                    eng._stage_evt.record()
         else:
             if not getattr(eng, "device_pad", True):  # a plan that reads images_u8 as is: the padding value goes in here
                 images_dst.fill_(int(round(self.padded_value)))
@@ -585,6 +596,21 @@ class YOLOX(nn.Module):
         hw_dst.copy_(torch.tensor([[i.shape[-2], i.shape[-1]] for i in imgs], dtype=torch.int32), non_blocking=True)
         if training:
             self._stage_labels(batched_inputs, labels_dst)
+
+    def _gather(self, imgs, stage):
+        """stage[k] = imgs[k] on a small thread pool (Tensor.copy_ releases the GIL: the memcpys run in parallel)"""
+        pool = getattr(self, "_gather_pool", None)
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._gather_pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1), thread_name_prefix="yb200-gather")
+        n = len(imgs)
+        chunk = max(1, (n + 7) // 8)
+
+        def work(lo):
+            for k in range(lo, min(lo + chunk, n)):
+                stage[k].copy_(imgs[k])
+
+        list(pool.map(work, range(0, n, chunk)))
 
     def _stage_labels(self, batched_inputs, labels_dst):
         """[B, max_boxes, 5] = (cls, cx, cy, w, h), zero padded (yolox.py:150-162, BoxModeMy XYXY_ABS -> cxcywh boxes.py:547-551).
