@@ -234,3 +234,39 @@ def test_api_cuda_graphs_reproduce_eager_training(cuda, monkeypatch):
     (la, pa), (lb, pb) = results
     assert np.allclose(la, lb, rtol=2e-3), (la, lb)
     assert float((pa - pb).abs().max()) <= 1e-3 * float(pb.abs().max())
+
+
+@pytest.mark.gpu
+def test_l1_loss_switches_on_after_the_augmentation_phase(cuda):
+    """yolox.py:105-121, 207-208 + yolox_head.py:186-195, 389-429: once `iter > INPUT.MOSAIC_AND_MIXUP.DISABLE_AT_ITER` the loss dict gains `l1_loss`
+    (L1 on the raw regression outputs), the total includes it, and it trains (eager launch, graph capture and replay)"""
+    import bench
+    from yolov7_d2_b200 import optim
+    from yolov7_d2_b200.modeling import YOLOX
+
+    cfg = bench.yolox_s_cfg("cuda")
+    m = YOLOX(cfg)
+    m.load_state_dict(orc.yolox_state_dict(6), strict=True)
+    m.train()
+    images, labels = orc.synthetic_batch(2, 128, 71, max_gt=4)
+    bi = bench.batched_inputs_from(images, labels)
+    assert "l1_loss" not in m(bi) and not m.use_l1
+    m.update_iter(m.enable_l1_loss_at + 1)
+    out = m(bi)
+    assert m.use_l1 and m.head.use_l1 and set(out.keys()) == {"total_loss", "iou_loss", "conf_loss", "cls_loss", "l1_loss"}
+    eng = m._plan(2, 128, 128)
+    xs, ys, ss = orc.anchor_grid([(h, w) for h, w, _, _ in eng.levels])
+    ref = orc.yolox_losses(eng.outputs.cpu(), labels, xs, ys, ss, origin_preds=eng.raw_reg.cpu())
+    got = [float(out[k]) for k in ("total_loss", "iou_loss", "conf_loss", "cls_loss", "l1_loss")]
+    assert np.allclose(got, [float(v) for v in ref[:5]], rtol=1e-4, atol=1e-5), (got, ref[:5])
+    assert got[4] > 0.1
+    cfg.SOLVER.BASE_LR = 1e-3
+    opt = optim.build_optimizer_mapper(cfg, m)
+    losses = []
+    for _ in range(4):  # eager, capture, replay, replay
+        opt.zero_grad()
+        o = m(bi)
+        sum(o.values()).backward()
+        opt.step()
+        losses.append(float(o["l1_loss"].detach()))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses

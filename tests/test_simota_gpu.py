@@ -101,6 +101,48 @@ def test_simota_loss_vs_reference_golden(cuda, case):
     assert (r["acc"] == 0).all()
 
 
+@pytest.mark.parametrize("case", ["trained", "init"])
+def test_l1_branch_vs_reference_golden(cuda, case):
+    """`use_l1` (yolox_head.py:186-195, 389-429, 443-448): yb200_yolox_decode_keep_raw + yb200_yolox_loss_l1 on the RAW head outputs of the fixture
+    tests/golden/simota_l1.npz (reference head with origin_preds): the six losses to 1e-4, the gradient w.r.t. the raw outputs to 1e-4 of its max"""
+    from yolov7_d2_b200 import capi
+
+    L = capi.lib()
+    g = np.load(os.path.join(GOLD, "simota_l1.npz"))
+    size = int(g["size"])
+    hw = [(size // s, size // s, s) for s in orc.STRIDES]
+    raw = torch.from_numpy(g[f"{case}.raw"])
+    labels = torch.from_numpy(g[f"{case}.labels"]).to(cuda).contiguous()
+    b, a, ch = raw.shape
+    out = raw.to(cuda).contiguous()
+    lv = (ctypes.c_int32 * (3 * len(hw)))(*[v for t in hw for v in t])
+    raw_reg = torch.full((b, a, 4), float("nan"), device=cuda)
+    capi.check(L.yb200_yolox_decode_keep_raw(capi.ptr(out), b, a, ch, lv, len(hw), capi.ptr(raw_reg), capi.stream_ptr()), "decode_keep_raw")
+    assert torch.equal(raw_reg.cpu(), raw[..., :4])
+    ws = torch.empty(L.yb200_simota_workspace(b, a), dtype=torch.uint8, device=cuda)
+    i32 = lambda *shape: torch.empty(*shape, dtype=torch.int32, device=cuda)
+    num_gt, mgt, mcls, nfg, totals = i32(b), i32(b, a), i32(b, a), i32(b), i32(2)
+    fg = torch.empty(b, a, dtype=torch.uint8, device=cuda)
+    miou = torch.empty(b, a, device=cuda)
+    capi.check(L.yb200_simota_assign(capi.ptr(out), capi.ptr(labels), b, a, ch, labels.shape[1], lv, len(hw), capi.ptr(ws), capi.ptr(num_gt), capi.ptr(fg),
+                                     capi.ptr(mgt), capi.ptr(miou), capi.ptr(mcls), capi.ptr(nfg), capi.ptr(totals), capi.stream_ptr()), "simota_assign")
+    w4 = torch.tensor([5.0, 1.0, 1.0, 1.0], device=cuda)
+    acc = torch.zeros(4, dtype=torch.float64, device=cuda)
+    losses = torch.empty(6, device=cuda)
+    dense = torch.full((b, a, ch), float("nan"), device=cuda)
+    capi.check(L.yb200_yolox_loss_l1(capi.ptr(out), capi.ptr(raw_reg), capi.ptr(labels), b, a, ch, labels.shape[1], lv, len(hw), capi.ptr(fg), capi.ptr(mgt),
+                                     capi.ptr(miou), capi.ptr(mcls), capi.ptr(totals), capi.ptr(w4), capi.ptr(acc), capi.ptr(losses), None, None,
+                                     capi.ptr(dense), None, capi.stream_ptr()), "yolox_loss_l1")
+    torch.cuda.synchronize()
+    got, ref = losses.cpu().double().numpy(), g[f"{case}.losses"]
+    assert np.allclose(got, ref, rtol=1e-4, atol=1e-5), (got, ref)
+    assert got[4] > 0.1 and abs(got[0] - (got[1] + got[2] + got[3] + got[4])) <= 1e-4 * got[0]
+    ref_grad = torch.from_numpy(g[f"{case}.grad"])
+    err = (dense.cpu() - ref_grad).abs().max().item()
+    assert err <= 1e-4 * ref_grad.abs().max().item() + 1e-7, err
+    assert (acc.cpu() == 0).all()
+
+
 def test_simota_full_size_vs_oracle(cuda):
     """640x640 (8400 anchors), batch 4 incl. an empty image and a crowded one: exact indices vs the CPU oracle"""
     from oracle.gen_golden import trained_like_outputs

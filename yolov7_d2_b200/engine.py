@@ -404,9 +404,11 @@ class YoloxEngine:
         self.matched_cls = torch.zeros(n, a, dtype=torch.int32, device=dev)
         self.num_fg_img = torch.zeros(n, dtype=torch.int32, device=dev)
         self.totals = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.loss_acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self.losses = torch.zeros(6, device=dev)
-        self.loss_weights = torch.tensor([5.0, 1.0, 1.0], device=dev)
+        self.loss_weights = torch.tensor([5.0, 1.0, 1.0, 1.0], device=dev)  # d objective / d (loss_iou, loss_obj, loss_cls, loss_l1)
+        self.use_l1 = False       # YOLOXHead.use_l1 (yolox_head.py:131): the L1 term on the raw regression outputs, switched on late in training
+        self.raw_reg = None       # [B, A, 4] fp32 `origin_preds`, allocated on first use
         self.bias_acc = torch.zeros(len(self.levels), ch, dtype=torch.float64, device=dev)
         self.d_cls = [torch.zeros(n, h, w, self.nc, dtype=torch.bfloat16, device=dev) for (h, w, _, _) in self.levels]
         self.d_ro = [torch.zeros(n, h, w, 16, dtype=torch.bfloat16, device=dev) for (h, w, _, _) in self.levels]
@@ -580,8 +582,7 @@ class YoloxEngine:
                 self._count(2, "strict pred convs level %d" % op.level)
         if training:
             self.flat_nbt += 1
-        capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
-                                        0 if training else 1, sp), "decode")
+        self._decode(training)
         self._count(1, "decode")
 
     def forward_features(self, training=True, op_range=None):
@@ -671,9 +672,19 @@ class YoloxEngine:
             self._count(1, "num_batches_tracked += 1 (torch)")
         if hi_i < len(self.ops):
             return
-        capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
-                                        0 if training else 1, sp), "decode")
+        self._decode(training)
         self._count(1, "decode", "decode", 8.0 * self.n * self.num_anchors * 4)
+
+    def _decode(self, training):
+        L, sp = self.L, capi.stream_ptr()
+        if training and self.use_l1:
+            if self.raw_reg is None:
+                self.raw_reg = torch.zeros(self.n, self.num_anchors, 4, device=self.dev)
+            capi.check(L.yb200_yolox_decode_keep_raw(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
+                                                     capi.ptr(self.raw_reg), sp), "decode (+ origin_preds)")
+        else:
+            capi.check(L.yb200_yolox_decode(capi.ptr(self.outputs), self.n, self.num_anchors, 5 + self.nc, self.lv, len(self.levels),
+                                            0 if training else 1, sp), "decode")
 
     def assign_and_loss(self, with_grad=True):
         L, sp = self.L, capi.stream_ptr()
@@ -683,22 +694,31 @@ class YoloxEngine:
                                          capi.ptr(self.matched_iou), capi.ptr(self.matched_cls), capi.ptr(self.num_fg_img), capi.ptr(self.totals), sp),
                    "simota_assign")
         self._count(4, "simota (count_gt, prep, match, resolve)", "simota_assign", 4.0 * n * a * ch)
-        capi.check(L.yb200_yolox_loss(capi.ptr(self.outputs), capi.ptr(self.labels), n, a, ch, self.max_gt, self.lv, len(self.levels),
-                                      capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls),
-                                      capi.ptr(self.totals), capi.ptr(self.loss_weights) if with_grad else None, capi.ptr(self.loss_acc),
-                                      capi.ptr(self.losses), self.p_dcls if with_grad else None, self.p_dro if with_grad else None, None,
-                                      capi.ptr(self.bias_acc) if with_grad else None, sp), "yolox_loss")
+        self._loss(capi.ptr(self.loss_weights) if with_grad else None, capi.ptr(self.losses), self.p_dcls if with_grad else None,
+                   self.p_dro if with_grad else None, capi.ptr(self.bias_acc) if with_grad else None, "yolox_loss")
         self._count(2, "yolox_loss + finish", "yolox_loss", n * a * ch * (4.0 + (2.0 if with_grad else 0.0)))
 
     def loss_grad_only(self):
         """recompute d loss / d head outputs with the current loss_weights (autograd path: upstream gradients arrive late)"""
         L, sp = self.L, capi.stream_ptr()
         n, a, ch = self.n, self.num_anchors, 5 + self.nc
-        capi.check(L.yb200_yolox_loss(capi.ptr(self.outputs), capi.ptr(self.labels), n, a, ch, self.max_gt, self.lv, len(self.levels),
-                                      capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls),
-                                      capi.ptr(self.totals), capi.ptr(self.loss_weights), capi.ptr(self.loss_acc), None, self.p_dcls, self.p_dro, None,
-                                      capi.ptr(self.bias_acc), sp), "yolox_loss grad")
+        self._loss(capi.ptr(self.loss_weights), None, self.p_dcls, self.p_dro, capi.ptr(self.bias_acc), "yolox_loss grad")
         self._count(1, "yolox_loss grad")
+
+    def _loss(self, weights, losses, p_dcls, p_dro, bias_acc, what):
+        """get_losses (yolox_head.py:412-441), with the L1 term when `use_l1` (the decode of this step kept the raw regression outputs)"""
+        L, sp = self.L, capi.stream_ptr()
+        n, a, ch = self.n, self.num_anchors, 5 + self.nc
+        lab, fg, mgt, miou, mcls = capi.ptr(self.labels), capi.ptr(self.fg_mask), capi.ptr(self.matched_gt), capi.ptr(self.matched_iou), capi.ptr(self.matched_cls)
+        tot, acc, nl = capi.ptr(self.totals), capi.ptr(self.loss_acc), len(self.levels)
+        if self.use_l1:
+            if self.raw_reg is None:
+                raise capi.Yb200Error("use_l1 was switched on after this step's forward: run the forward pass again")
+            capi.check(L.yb200_yolox_loss_l1(capi.ptr(self.outputs), capi.ptr(self.raw_reg), lab, n, a, ch, self.max_gt, self.lv, nl, fg, mgt, miou, mcls, tot,
+                                             weights, acc, losses, p_dcls, p_dro, None, bias_acc, sp), what + " (+ L1)")
+        else:
+            capi.check(L.yb200_yolox_loss(capi.ptr(self.outputs), lab, n, a, ch, self.max_gt, self.lv, nl, fg, mgt, miou, mcls, tot, weights, acc, losses,
+                                          p_dcls, p_dro, None, bias_acc, sp), what)
 
     # ------------------------------------------------------------------ backward
     def _plan_bn_fusion(self):

@@ -389,16 +389,18 @@ class _TrainStep(torch.autograd.Function):
             engine.forward_features(True)
             engine.assign_and_loss(with_grad=False)
 
-        _run_graphed(engine, "forward", fwd)
+        l1 = bool(getattr(getattr(engine, "yx", engine), "use_l1", False))  # the captured graphs differ (decode keeps the raw outputs, the loss has a fourth term)
+        ctx.graph_tag = "+l1" if l1 else ""
+        _run_graphed(engine, "forward" + ctx.graph_tag, fwd)
         ctx.engine = engine
         l = engine.losses
-        return l[0].clone(), l[1].clone(), l[2].clone(), l[3].clone()
+        return l[0].clone(), l[1].clone(), l[2].clone(), l[3].clone(), l[4].clone()
 
     @staticmethod
-    def backward(ctx, g_total, g_iou, g_obj, g_cls):
+    def backward(ctx, g_total, g_iou, g_obj, g_cls, g_l1):
         eng = ctx.engine
-        # outputs: total = 5*iou + obj + cls, iou_loss = 5*iou, conf_loss = obj, cls_loss = cls   (yolox.py:201-206)
-        eng.loss_weights.copy_(torch.stack([5.0 * (g_total + g_iou), g_total + g_obj, g_total + g_cls]).float())
+        # outputs: total = 5*iou + obj + cls [+ l1], iou_loss = 5*iou, conf_loss = obj, cls_loss = cls, l1_loss = l1   (yolox.py:201-208)
+        eng.loss_weights.copy_(torch.stack([5.0 * (g_total + g_iou), g_total + g_obj, g_total + g_cls, g_total + g_l1]).float())
         if ctx.flat_grads:
             # every parameter's .grad already is its slice of the flat gradient buffer (YOLOX.attach_flat_grads): accumulate in place
             gb = getattr(eng, "_grad_buckets", None)
@@ -411,7 +413,7 @@ class _TrainStep(torch.autograd.Function):
                     eng.loss_grad_only()
                     eng.backward(accumulate=True)
 
-                _run_graphed(eng, "backward", bwd)
+                _run_graphed(eng, "backward" + ctx.graph_tag, bwd)
             return (None, None) + (None,) * len(eng.param_names)
         eng.loss_grad_only()
         eng.backward()
@@ -522,6 +524,13 @@ class YOLOX(nn.Module):
 
     def update_iter(self, i):
         self.iter = i
+
+    def _maybe_enable_l1(self):
+        """yolox.py:105-121: past `INPUT.MOSAIC_AND_MIXUP.DISABLE_AT_ITER` (the last, augmentation-free iterations) the head adds the L1 term.  The
+        reference broadcasts rank 0's decision; every rank evaluates the same `iter > enable_l1_loss_at`, so the flag is set locally."""
+        if self.training and not self.use_l1 and self.iter > self.enable_l1_loss_at:
+            self.use_l1 = True
+            self.head.use_l1 = True
 
     # -- helpers ---------------------------------------------------------------------------------
     def _plan(self, batch, h, w):
@@ -690,8 +699,14 @@ class YOLOX(nn.Module):
         if self.training:
             if self._flat_grads:
                 self._ensure_flat_grads()
-            total, iou, conf, cls = _TrainStep.apply(eng, self._flat_grads, *self._params_in_engine_order())
-            return {"total_loss": total, "iou_loss": iou, "conf_loss": conf, "cls_loss": cls}
+            self._maybe_enable_l1()
+            target = getattr(eng, "yx", eng)  # the YOLOX-ConvNeXt composite keeps the head in its YoloxEngine
+            target.use_l1 = bool(self.use_l1)
+            total, iou, conf, cls, l1 = _TrainStep.apply(eng, self._flat_grads, *self._params_in_engine_order())
+            out = {"total_loss": total, "iou_loss": iou, "conf_loss": conf, "cls_loss": cls}
+            if self.use_l1:
+                out["l1_loss"] = l1  # yolox.py:207-208
+            return out
         with torch.no_grad():
             outputs = eng.eval_forward()
             detections = postprocess(outputs, self.num_classes, self.conf_threshold, self.nms_threshold)
