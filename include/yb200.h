@@ -101,6 +101,11 @@ int yb200_conv2d_dgrad_bnbwd(const yb200_act* dz, const void* w_dgrad, const yb2
 int64_t yb200_conv2d_wgrad_workspace(const yb200_act* x, const yb200_act* dz, int ksize, int stride);
 int yb200_conv2d_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real,
                        float* grad_oihw, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same for the PIXEL-GROUPED stem (x, dz = the grouped views of yb200_conv2d_fwd_fold, `group` pixels per group): grad_oihw is the gradient of
+ * the EXPANDED weight matrix, valid at the positions the expansion fills (the caller folds them onto the [cout, cin, 3, 3] parameter); positions
+ * that the expansion leaves zero are not computed (side taps multiply one neighbour pixel instead of the whole group).                      */
+int yb200_conv2d_wgrad_grouped(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real, int group,
+                               float* grad_oihw, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- preprocessing ------------------------------------------------------------------------------- */
 /* uint8 NCHW images -> Focus (space-to-depth) NHWC bf16 [n, h/2, w/2, 16]: channel = patch*3 + rgb with patch order

@@ -889,7 +889,7 @@ struct WgradPlan {
   int tw, th, tn;
 };
 
-int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, WgradPlan* pl) {
+int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, WgradPlan* pl, int group = 0) {
   int rc;
   if ((rc = check_act(x, "conv2d_wgrad x"))) return rc;
   if ((rc = check_act(dz, "conv2d_wgrad dz"))) return rc;
@@ -915,6 +915,25 @@ int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, W
   p.nb = p.bn / p.kc_b;
   p.cin_tiles = x->c / p.bn;
   p.num_taps = fill_fwd_taps(p.taps, *x, ksize, stride, 0);
+  if (group > 1) {
+    // pixel-grouped 3x3 convolution (the stem): the expanded weight matrix is non-zero for the left / right neighbour group only at its last /
+    // first pixel, and only those entries are folded back onto the parameter.  The side taps therefore load and multiply cpp = C / group channels.
+    const int cpp = x->c / group;
+    YB_REQUIRE(ksize == 3 && stride == 1 && x->c % group == 0 && cpp % 16 == 0 && x->c_off == 0 && x->c == x->c_pitch && p.cin_tiles == 1 && p.nb == 1,
+               YB200_ERR_UNSUPPORTED, "conv2d_wgrad_grouped: needs a 3x3 stride-1 convolution on a whole [.., %d x 16k]-channel grouped tensor of <= 64 channels (got c=%d pitch=%d group=%d)",
+               group, x->c, x->c_pitch, group);
+    static int sparse = -1;
+    if (sparse < 0) {
+      const char* e = getenv("YB200_STEM_SPARSE");
+      sparse = (e && e[0] == '0') ? 0 : 1;
+    }
+    for (int t = 0; t < p.num_taps && sparse; ++t) {
+      ConvTap& tp = p.taps[t];
+      tp.kb = 0;
+      if (tp.dw == -1) { tp.c0 += (group - 1) * cpp; tp.kb = (group - 1) * cpp; tp.ks = cpp / 16; }
+      if (tp.dw == 1) tp.ks = cpp / 16;
+    }
+  }
   p.tpc = p.num_taps == 1 ? 1 : 3;  // (9 taps per CTA for narrow layers was measured slower: many 2 KB TMA boxes per stage)
   p.tap_groups = ceil_div(p.num_taps, p.tpc);
   p.dz_c0 = dz->c_off;
@@ -965,10 +984,21 @@ static int launch_wgrad_inst(const CUtensorMap& tmDz, const CUtensorMap& tmX, co
   return 0;
 }
 
+static int wgrad_impl(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real, int group, float* grad_oihw, int accumulate,
+                      void* workspace, int64_t workspace_bytes, void* stream);
 extern "C" int yb200_conv2d_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real, float* grad_oihw,
                                   int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+  return wgrad_impl(x, dz, ksize, stride, cin_real, 0, grad_oihw, accumulate, workspace, workspace_bytes, stream);
+}
+extern "C" int yb200_conv2d_wgrad_grouped(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real, int group, float* grad_oihw,
+                                          int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+  YB_REQUIRE(group > 1, YB200_ERR_INVALID, "conv2d_wgrad_grouped: group %d (use yb200_conv2d_wgrad)", group);
+  return wgrad_impl(x, dz, ksize, stride, cin_real, group, grad_oihw, accumulate, workspace, workspace_bytes, stream);
+}
+static int wgrad_impl(const yb200_act* x, const yb200_act* dz, int ksize, int stride, int cin_real, int group, float* grad_oihw, int accumulate,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
   WgradPlan pl;
-  int rc = plan_wgrad(x, dz, ksize, stride, &pl);
+  int rc = plan_wgrad(x, dz, ksize, stride, &pl, group);
   if (rc) return rc;
   YB_REQUIRE(grad_oihw && workspace, YB200_ERR_INVALID, "conv2d_wgrad: null pointer");
   YB_REQUIRE(cin_real > 0 && cin_real <= x->c, YB200_ERR_INVALID, "conv2d_wgrad: cin_real %d vs padded %d", cin_real, x->c);

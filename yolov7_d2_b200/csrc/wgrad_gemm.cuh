@@ -31,7 +31,9 @@ struct WgradParams {
   int cin_tiles, cout_tiles;
   int dz_c0;                      // channel offset of dz slice inside its buffer
   float* ws;                      // [split][cout][num_taps][cin] fp32
-  ConvTap taps[kMaxTaps];         // x taps (c0, dw, p, dh); kb unused
+  ConvTap taps[kMaxTaps];         // x taps (c0, dw, p, dh).  ks > 0 (pixel-grouped stem, yb200_conv2d_wgrad_grouped): only the first 16 * ks channels
+                                  // of this tap's x box are real (the box starts at the one neighbour pixel that matters, the rest is TMA zero fill):
+                                  // the MMA runs with N = 16 * ks and the epilogue stores those columns at input channel kb, zeros elsewhere
 };
 
 template <int TMEM_COLS>
@@ -114,7 +116,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.bn, 1, 1);
+      const uint32_t idesc_full = umma_idesc_bf16(128, p.bn, 1, 1);
       const uint32_t lcode_a = umma_layout_code(p.kc_a * 2);
       const uint32_t lcode_b = umma_layout_code(p.kc_b * 2);
       const uint32_t row_a = p.kc_a * 2, row_b = p.kc_b * 2;
@@ -131,6 +133,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
         const uint32_t sa = smem_base + stage * stage_bytes;
         for (int ti = 0; ti < ntap; ++ti) {
           const uint32_t sb = sa + a_bytes + ti * b_tap_bytes;
+          const int ks = p.taps[tap0 + ti].ks;
+          const uint32_t idesc = ks > 0 ? umma_idesc_bf16(128, 16 * ks, 1, 1) : idesc_full;
 #pragma unroll
           for (int k = 0; k < kWgPix / 16; ++k) {
             const uint64_t da = umma_smem_desc(sa + k * 16 * row_a, lbo_a, 8 * row_a, lcode_a);
@@ -155,10 +159,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
     float* wsb = p.ws + (long long)split * p.cout * p.num_taps * p.cin;
     for (int ti = 0; ti < ntap; ++ti) {
       float* dst = wsb + ((long long)co * p.num_taps + tap0 + ti) * p.cin + cin_tile * p.bn;
+      const int ks = p.taps[tap0 + ti].ks, shift = p.taps[tap0 + ti].kb;
       for (int c = 0; c < p.bn; c += 16) {
         uint32_t r[16];
-        if (nblk > 0) {
-          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ti * p.bn + c, r);
+        const int src = ks > 0 ? c - shift : c;  // accumulator column of output column c (sparse taps: only [shift, shift + 16 ks) exist)
+        if (nblk > 0 && (ks == 0 || (src >= 0 && src < 16 * ks))) {
+          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ti * p.bn + src, r);
           tmem_ld_wait();
         } else {
 #pragma unroll

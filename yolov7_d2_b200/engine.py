@@ -829,8 +829,8 @@ class YoloxEngine:
         self._ensure_ws(need)
 
         def run():
-            capi.check(L.yb200_conv2d_wgrad(ctypes.byref(xg), ctypes.byref(dzg), 3, 1, 4 * op.cin_pad, capi.ptr(op.g_exp), 0, capi.ptr(self.ws),
-                                            ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad stem (grouped)")
+            capi.check(L.yb200_conv2d_wgrad_grouped(ctypes.byref(xg), ctypes.byref(dzg), 3, 1, 4 * op.cin_pad, 4, capi.ptr(op.g_exp), 0, capi.ptr(self.ws),
+                                                    ctypes.c_int64(self.ws_bytes), capi.stream_ptr()), "wgrad stem (grouped)")
             g = op.g_dst.reshape(-1)
             if not acc:
                 g.zero_()
