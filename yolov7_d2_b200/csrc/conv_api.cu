@@ -947,7 +947,18 @@ int plan_wgrad(const yb200_act* x, const yb200_act* dz, int ksize, int stride, W
   while (tc < cols) tc <<= 1;
   pl->tmem_cols = tc;
   const int stage = kWgPix * 2 * (p.kc_a * p.ma + p.kc_b * p.nb * p.tpc);
-  pl->smem = stage * kWgStages + 1024;
+  p.stages = kWgStages;
+  if (std::min(512 / tc, (220 * 1024) / (stage * kWgStages + 1024)) <= 1) {  // one CTA per SM anyway: deepen the ring (YB200_WGRAD_STAGES caps it, A/B)
+    static int cap = -1;
+    if (cap < 0) {
+      const char* e = getenv("YB200_WGRAD_STAGES");
+      cap = e ? atoi(e) : kWgMaxStages;
+      if (cap < kWgStages) cap = kWgStages;
+      if (cap > kWgMaxStages) cap = kWgMaxStages;
+    }
+    p.stages = std::max(kWgStages, std::min(cap, (220 * 1024 - 1024) / stage));
+  }
+  pl->smem = stage * p.stages + 1024;
   // Split the pixel range so that ONE wave of CTAs covers the machine (every CTA pays TMEM allocation, pipeline fill and
   // a full accumulator write-back, so extra waves are pure overhead); occupancy is bounded by TMEM columns and shared memory.
   int occ = std::min(std::min(512 / tc, (220 * 1024) / pl->smem), 8);

@@ -16,7 +16,8 @@ namespace yb {
 
 constexpr int kWgPix = 64;      // pixels per K block (4 UMMA K-steps)
 constexpr int kWgMaxTpc = 9;    // taps per CTA (9 when the cin tile is narrow enough for 9 accumulators in TMEM, else 3)
-constexpr int kWgStages = 3;
+constexpr int kWgStages = 3;     // default ring depth (keeps two or more CTAs per SM on the small layers)
+constexpr int kWgMaxStages = 6;  // one-CTA-per-SM plans (the pixel-grouped stem: 40 KB stages) take as many as fit: the kernel is latency bound otherwise
 
 struct WgradParams {
   int tiles_w, tiles_h, tiles_n;  // 64-pixel tiles over the dz pixel grid
@@ -28,6 +29,7 @@ struct WgradParams {
   int kc_b, nb;                   // x channel box width (<=64) and boxes per BN tile
   int bn;                         // cin tile width = kc_b*nb
   int tpc, tap_groups, num_taps;  // taps per CTA, groups, total taps
+  int stages;                     // ring depth (kWgStages .. kWgMaxStages)
   int cin_tiles, cout_tiles;
   int dz_c0;                      // channel offset of dz slice inside its buffer
   float* ws;                      // [split][cout][num_taps][cin] fp32
@@ -42,15 +44,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
                   const __grid_constant__ WgradParams p) {
   pdl_sync();
   extern __shared__ uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t s_bar[2 * kWgStages + 1];
+  __shared__ __align__(8) uint64_t s_bar[2 * kWgMaxStages + 1];
+  const int num_stages = p.stages;
   __shared__ uint32_t s_tmem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t bar_full = smem_u32(&s_bar[0]);
-  const uint32_t bar_empty = smem_u32(&s_bar[kWgStages]);
-  const uint32_t bar_acc = smem_u32(&s_bar[2 * kWgStages]);
+  const uint32_t bar_empty = smem_u32(&s_bar[kWgMaxStages]);
+  const uint32_t bar_acc = smem_u32(&s_bar[2 * kWgMaxStages]);
 
   // work decomposition: blockIdx.x = ((cout_tile * cin_tiles + cin_tile) * tap_groups + group), blockIdx.y = split
   int w = blockIdx.x;
@@ -72,7 +75,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
   const uint32_t stage_bytes = a_bytes + b_tap_bytes * p.tpc;  // constant stride even for a short last group
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) {
+    for (int s = 0; s < num_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -111,7 +114,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
             tma_load_5d(sb + j * b_box_bytes, &tmX, full, tp.c0 + cin_tile * p.bn + j * p.kc_b, w0 + tp.dw, tp.p,
                         h0 + tp.dh, n0);
         }
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -143,7 +146,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
           }
         }
         umma_commit(bar_empty + 8 * stage);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(bar_acc);
     }
