@@ -124,22 +124,28 @@ nms_suppress_kernel(const unsigned long long* __restrict__ keys_in, const float4
     }
   }
   __syncthreads();
-  // survivors: re-key by (score descending, anchor ascending), everything else to the end
+  // survivors: re-key by (score descending, anchor ascending) and COMPACT them to the front, so that the second sort runs over the next power
+  // of two above their number (a few hundred to a few thousand) instead of the whole padded array.  All reads of sk complete before the first write.
+  unsigned long long mine[16];  // apad <= 16384 = 16 x kNmsThreads
   int kept = 0;
-  for (int i = threadIdx.x; i < apad; i += blockDim.x) {
-    unsigned long long k = sk[i];
-    if (i < n && !sup[i]) {
-      k &= (1ull << (32 + kIdxBits)) - 1;  // drop the class field
-      ++kept;
-    } else {
-      k = kEmpty;
-    }
-    sk[i] = k;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int i = threadIdx.x + u * kNmsThreads;
+    if (i < n && !sup[i]) mine[kept++] = sk[i] & ((1ull << (32 + kIdxBits)) - 1);  // drop the class field
   }
-  atomicAdd(&s_keep, kept);
+  __syncthreads();
+  const int pos = atomicAdd(&s_keep, kept);  // the order inside the compacted range is irrelevant: it is sorted next
+#pragma unroll
+  for (int u = 0; u < 16; ++u)
+    if (u < kept) sk[pos + u] = mine[u];
   __syncthreads();
   const int nk = s_keep;
-  bitonic_sort_smem(sk, apad);
+  int npad = 1;
+  while (npad < nk) npad <<= 1;
+  if (npad > apad) npad = apad;
+  for (int i = nk + threadIdx.x; i < npad; i += blockDim.x) sk[i] = kEmpty;
+  __syncthreads();
+  bitonic_sort_smem(sk, npad);
   if (threadIdx.x == 0) det_count[b] = nk;
   const float4* mt = meta + 1LL * b * num_anchors;
   float* d = det + 1LL * b * num_anchors * 7;
