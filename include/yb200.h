@@ -383,6 +383,22 @@ int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const yb200_act*
                         const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
                         const yb200_act* dv, void* workspace, void* stream);
 
+/* Dropout of the transformer layers (detr_backbone.py:132-152, 200-214).  The masks are a counter-based hash of (seed, element index) evaluated
+ * inside the kernels -- keep(element) with probability 1 - p_drop, kept values scaled by 1 / (1 - p_drop) -- so the backward calls regenerate the
+ * mask of the forward from the same seed; p_drop = 0 is exactly the dropout-free kernel.  (Not torch's Philox stream: same distribution, different
+ * bits; oracle/detr_oracle.py restates the hash for the parity tests.)
+ *   yb200_attention_fwd_dropout / _bwd_dropout: nn.MultiheadAttention(dropout = p) -- the mask multiplies the softmax probabilities (index: image, head,
+ *     query, key); lse stays the log-sum-exp of the undropped scores.
+ *   yb200_dropout: out = residual + x * mask(seed) / (1 - p) * extra_scale on [B][1][L][C] bf16 views (index: logical element ((b L + l) C + c));
+ *     residual may be NULL; the backward of nn.Dropout is the same call on the gradient.                                                          */
+int yb200_attention_fwd_dropout(const yb200_act* q, const yb200_act* k, const yb200_act* v, const uint8_t* key_padding_mask, float scale,
+                                const yb200_act* out, float* lse, float p_drop, uint32_t seed, void* stream);
+int yb200_attention_bwd_dropout(const yb200_act* q, const yb200_act* k, const yb200_act* v, const yb200_act* out, const yb200_act* dout,
+                                const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
+                                const yb200_act* dv, void* workspace, float p_drop, uint32_t seed, void* stream);
+int yb200_dropout(const yb200_act* x, const yb200_act* residual, const yb200_act* out, float p_drop, uint32_t seed, float extra_scale,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

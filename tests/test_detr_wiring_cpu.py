@@ -71,20 +71,33 @@ class TorchKernels:
         b, _, l, e = t.shape
         return t.view(b, l, heads, e // heads).permute(0, 2, 1, 3)
 
-    def attention_train(self, q, k, v, mask, heads):
-        qt = _sl(q)
+    @staticmethod
+    def _attn_drop(qt, kt, heads, p_drop, seed):
+        if p_drop <= 0:
+            return None
+        return dto.attention_dropout_multiplier(seed, qt.shape[0], heads, qt.shape[2], kt.shape[2], p_drop)
+
+    def attention_train(self, q, k, v, mask, heads, p_drop=0.0, seed=0):
+        qt, kt = _sl(q), _sl(k)
         b, _, lq, e = qt.shape
-        o = dto.attention_core(self._heads(qt, heads), self._heads(_sl(k), heads), self._heads(_sl(v), heads), mask.bool() if mask is not None else None)
+        o = dto.attention_core(self._heads(qt, heads), self._heads(kt, heads), self._heads(_sl(v), heads), mask.bool() if mask is not None else None,
+                               attn_drop=self._attn_drop(qt, kt, heads, p_drop, seed))
         return o.permute(0, 2, 1, 3).reshape(b, 1, lq, e), None
 
-    def attention_bwd(self, q, k, v, out, dout, mask, heads, lse, dq, dk, dv):
+    def attention_bwd(self, q, k, v, out, dout, mask, heads, lse, dq, dk, dv, p_drop=0.0, seed=0):
         with torch.enable_grad():
             qt, kt, vt = (_sl(t).clone().requires_grad_(True) for t in (q, k, v))
             b, _, lq, e = qt.shape
-            o = dto.attention_core(self._heads(qt, heads), self._heads(kt, heads), self._heads(vt, heads), mask.bool() if mask is not None else None)
+            o = dto.attention_core(self._heads(qt, heads), self._heads(kt, heads), self._heads(vt, heads), mask.bool() if mask is not None else None,
+                                   attn_drop=self._attn_drop(qt, kt, heads, p_drop, seed))
             o.permute(0, 2, 1, 3).reshape(b, 1, lq, e).backward(dout)
         for (t, off, c), g in zip((dq, dk, dv), (qt.grad, kt.grad, vt.grad)):
             t[..., off:off + c] = g
+
+    def dropout(self, x, p_drop, seed, residual=None, scale=1.0):
+        b, _, l, c = x.shape
+        y = x * dto.dropout_multiplier(seed, (b, l, c), p_drop).view(b, 1, l, c) * scale
+        return y + residual if residual is not None else y
 
 
 @pytest.fixture()
@@ -104,6 +117,7 @@ def test_encoder_layer_training_wiring(detr_fp32):
     d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
     layer = type("Layer", (), {})()
     layer.k, layer.d_model, layer.nhead = TorchKernels(), d, nhead
+    layer._dropout_state = lambda n: (0.0, (0,) * n)
     sd = dto.layer_state_dict("encoder", d, ffn, seed=2)
     params = [sd[n].clone().requires_grad_(True) for n in detr._EncoderLayerFn.NAMES]
     src = torch.tensor(gold["enc_src"]).requires_grad_(True)
@@ -134,6 +148,7 @@ def test_decoder_layer_training_wiring(detr_fp32):
     d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
     layer = type("Layer", (), {})()
     layer.k, layer.d_model, layer.nhead = TorchKernels(), d, nhead
+    layer._dropout_state = lambda n: (0.0, (0,) * n)
     sd = dto.layer_state_dict("decoder", d, ffn, seed=3)
     params = [sd[n].clone().requires_grad_(True) for n in detr._DecoderLayerFn.NAMES]
     names = ("dec_tgt", "dec_mem", "enc_pos", "dec_qpos")
@@ -160,6 +175,84 @@ def test_decoder_layer_training_wiring(detr_fp32):
         assert err <= 2e-5 * ref.abs().max().item(), f"{what}: {err:.3e}"
 
     close(out.detach(), ref_out.detach(), "output")
+    for k, a, r in zip(names, ours, refs):
+        close(a.grad, r.grad, k + " gradient")
+    for n, p in zip(detr._DecoderLayerFn.NAMES, params):
+        close(p.grad, sdr["l." + n].grad, n)
+
+
+P_DROP = 0.1
+
+
+def test_encoder_layer_training_wiring_with_dropout(detr_fp32):
+    """dropout = 0.1 (the reference's default, detr_backbone.py:132,140-152): the four masks of one step (attention probabilities, dropout1, FFN
+    dropout, dropout2) enter the forward and are re-applied in the right places of the backward -- against the autograd of the oracle layer with the
+    same explicit masks (oracle.detr_oracle: the kernels' counter-based hash restated in torch)"""
+    detr = detr_fp32
+    gold = np.load(GOLD, allow_pickle=False)
+    d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
+    seeds = (11, 22, 33, 44)
+    layer = type("Layer", (), {})()
+    layer.k, layer.d_model, layer.nhead = TorchKernels(), d, nhead
+    layer._dropout_state = lambda n: (P_DROP, seeds)
+    sd = dto.layer_state_dict("encoder", d, ffn, seed=2)
+    params = [sd[n].clone().requires_grad_(True) for n in detr._EncoderLayerFn.NAMES]
+    src = torch.tensor(gold["enc_src"]).requires_grad_(True)
+    pos = torch.tensor(gold["enc_pos"]).requires_grad_(True)
+    mask = torch.tensor(gold["enc_mask"])
+    out = detr._EncoderLayerFn.apply(layer, src, pos, mask.to(torch.uint8), *params)
+    gout = torch.tensor(gold["enc_gout"])
+    out.backward(gout)
+    drop = (dto.attention_dropout_multiplier(seeds[0], b, nhead, L, L, P_DROP), dto.dropout_multiplier(seeds[1], (b, L, d), P_DROP),
+            dto.dropout_multiplier(seeds[2], (b, L, ffn), P_DROP), dto.dropout_multiplier(seeds[3], (b, L, d), P_DROP))
+    sdr = {"l." + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    s2, p2 = torch.tensor(gold["enc_src"]).requires_grad_(True), torch.tensor(gold["enc_pos"]).requires_grad_(True)
+    ref = dto.encoder_layer_post(s2, sdr, "l.", nhead, mask, p2, drop=drop)
+    ref.backward(gout)
+    plain = dto.encoder_layer_post(torch.tensor(gold["enc_src"]), {k: v.detach() for k, v in sdr.items()}, "l.", nhead, mask, torch.tensor(gold["enc_pos"]))
+    assert (ref.detach() - plain).abs().max() > 1e-2, "the masks must change the result"
+
+    def close(a, r, what):
+        err = (a - r).abs().max().item()
+        assert err <= 2e-5 * r.abs().max().item() + 1e-7, f"{what}: {err:.3e}"
+
+    close(out.detach(), ref.detach(), "output")
+    close(src.grad, s2.grad, "src gradient")
+    close(pos.grad, p2.grad, "pos gradient")
+    for n, p in zip(detr._EncoderLayerFn.NAMES, params):
+        close(p.grad, sdr["l." + n].grad, n)
+
+
+def test_decoder_layer_training_wiring_with_dropout(detr_fp32):
+    detr = detr_fp32
+    gold = np.load(GOLD, allow_pickle=False)
+    d, nhead, ffn, b, L = (int(v) for v in gold["dims"])
+    seeds = (5, 6, 7, 8, 9, 10)
+    layer = type("Layer", (), {})()
+    layer.k, layer.d_model, layer.nhead = TorchKernels(), d, nhead
+    layer._dropout_state = lambda n: (P_DROP, seeds)
+    sd = dto.layer_state_dict("decoder", d, ffn, seed=3)
+    params = [sd[n].clone().requires_grad_(True) for n in detr._DecoderLayerFn.NAMES]
+    names = ("dec_tgt", "dec_mem", "enc_pos", "dec_qpos")
+    ours = [torch.tensor(gold[k]).requires_grad_(True) for k in names]
+    mem_mask = torch.tensor(gold["enc_mask"])
+    out = detr._DecoderLayerFn.apply(layer, ours[0], ours[1], ours[2], ours[3], None, mem_mask.to(torch.uint8), *params)
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+    out.backward(gout)
+    lq, lk = ours[0].shape[0], ours[1].shape[0]
+    drop = (dto.attention_dropout_multiplier(seeds[0], b, nhead, lq, lq, P_DROP), dto.dropout_multiplier(seeds[1], (b, lq, d), P_DROP),
+            dto.attention_dropout_multiplier(seeds[2], b, nhead, lq, lk, P_DROP), dto.dropout_multiplier(seeds[3], (b, lq, d), P_DROP),
+            dto.dropout_multiplier(seeds[4], (b, lq, ffn), P_DROP), dto.dropout_multiplier(seeds[5], (b, lq, d), P_DROP))
+    refs = [torch.tensor(gold[k]).requires_grad_(True) for k in names]
+    sdr = {"l." + k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = dto.decoder_layer_post(refs[0], refs[1], sdr, "l.", nhead, mem_mask, refs[2], refs[3], drop=drop)
+    ref.backward(gout)
+
+    def close(a, r, what):
+        err = (a - r).abs().max().item()
+        assert err <= 2e-5 * r.abs().max().item() + 1e-7, f"{what}: {err:.3e}"
+
+    close(out.detach(), ref.detach(), "output")
     for k, a, r in zip(names, ours, refs):
         close(a.grad, r.grad, k + " gradient")
     for n, p in zip(detr._DecoderLayerFn.NAMES, params):

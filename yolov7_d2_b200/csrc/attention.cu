@@ -34,7 +34,25 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Dropout (nn.MultiheadAttention(dropout=p) on the attention probabilities, nn.Dropout on the residual branches / the FFN, detr_backbone.py:140-152,
+// 200-214): a counter-based hash instead of torch's Philox stream -- keep(element) = (mix32(seed-derived key ^ index * golden) >> 8) >= p * 2^24 -- so the
+// backward kernels regenerate the mask of the forward from (seed, indices) alone.  thr24 == 0 disables it (p = 0 / eval: not a single extra instruction).
+struct DropParams {
+  uint32_t seed, thr24;
+  float inv_keep;
+};
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+// per-row key of the attention mask: (seed, image * heads + head, query index)
+__device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, uint32_t bh, uint32_t q) { return mix32(seed ^ mix32(bh * 0x9E3779B1u + q + 0x7F4A7C15u)); }
+__device__ __forceinline__ float drop_factor(uint32_t row_key, uint32_t col, const DropParams& d) {
+  return (mix32(row_key ^ (col * 0x9E3779B1u)) >> 8) >= d.thr24 ? d.inv_keep : 0.f;
+}
+
 struct AttnParams {
+  DropParams drop;
   int lq, lk, heads;
   int q_coff, k_coff, v_coff;   // channel offsets of head 0 inside the q / k / v buffers
   float scale_log2;             // softmax scale * log2(e)
@@ -125,6 +143,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int tid = threadIdx.x - 64;     // 0..127 among the softmax threads
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     float m = -INFINITY, l = 0.f;
+    const uint32_t drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(q0 + row));
     float acc[kAttD];
 #pragma unroll
     for (int i = 0; i < kAttD; ++i) acc[i] = 0.f;
@@ -182,9 +201,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, bb.y - m_safe));
           const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), p.scale_log2, bb.z - m_safe));
           const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), p.scale_log2, bb.w - m_safe));
-          rowsum += (p0 + p1) + (p2 + p3);
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          rowsum += (p0 + p1) + (p2 + p3);  // the normaliser is the sum of the UNDROPPED probabilities: dropout(softmax(S)) V
+          if (p.drop.thr24 != 0) {
+            const uint32_t col = static_cast<uint32_t>(j * kAttTile + c + i);
+            pk[i >> 1] = pack_bf16x2(p0 * drop_factor(drop_key, col, p.drop), p1 * drop_factor(drop_key, col + 1, p.drop));
+            pk[(i >> 1) + 1] = pack_bf16x2(p2 * drop_factor(drop_key, col + 2, p.drop), p3 * drop_factor(drop_key, col + 3, p.drop));
+          } else {
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
         }
         const uint32_t blk = sP + (c >> 6) * (kAttTile * 128) + row * 128;
 #pragma unroll
@@ -244,6 +269,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 // straight from their token-major tiles.
 // ================================================================================================================================
 struct AttnBwdParams {
+  DropParams drop;
   int lq, lk, heads;
   int q_coff, k_coff, v_coff, do_coff;
   float scale, scale_log2;
@@ -279,8 +305,11 @@ __global__ void attention_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, i
 }
 
 // one 32-column chunk of P and dS for the thread's query row: reads S and dP from TMEM, writes both bf16 tiles ([query][key], swizzle 128)
+// With dropout D (0 or 1/(1-p) per element): O = (D o P) V, so the tile written for dV = (D o P)^T dO is the dropped one, dP = D o (dO V^T) and
+// dS = P o (dP - <dO, O>) -- the row term <dO, O> (attention_bwd_prep_kernel) already contains D through O.
 __device__ __forceinline__ void bwd_chunk(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_base, int c, int row, const float* bias, float lse_log2, float dsum,
-                                          float scale, float scale_log2, uint32_t sP, uint32_t sDS, bool write_p) {
+                                          float scale, float scale_log2, uint32_t sP, uint32_t sDS, bool write_p, const DropParams& drop, uint32_t drop_key,
+                                          int key0) {
   uint32_t r[32], g[32];
   tmem_ld_32x32(tmem_s + lane_base + c, r);
   tmem_ld_32x32(tmem_dp + lane_base + c, g);
@@ -293,10 +322,16 @@ __device__ __forceinline__ void bwd_chunk(uint32_t tmem_s, uint32_t tmem_dp, uin
     const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), scale_log2, bb.y - lse_log2));
     const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), scale_log2, bb.z - lse_log2));
     const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), scale_log2, bb.w - lse_log2));
-    pk[i >> 1] = pack_bf16x2(p0, p1);
-    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-    dk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(g[i]) - dsum) * scale, p1 * (__uint_as_float(g[i + 1]) - dsum) * scale);
-    dk[(i >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(g[i + 2]) - dsum) * scale, p3 * (__uint_as_float(g[i + 3]) - dsum) * scale);
+    float f0 = 1.f, f1 = 1.f, f2 = 1.f, f3 = 1.f;
+    if (drop.thr24 != 0) {
+      const uint32_t col = static_cast<uint32_t>(key0 + c + i);
+      f0 = drop_factor(drop_key, col, drop); f1 = drop_factor(drop_key, col + 1, drop);
+      f2 = drop_factor(drop_key, col + 2, drop); f3 = drop_factor(drop_key, col + 3, drop);
+    }
+    pk[i >> 1] = pack_bf16x2(p0 * f0, p1 * f1);
+    pk[(i >> 1) + 1] = pack_bf16x2(p2 * f2, p3 * f3);
+    dk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(g[i]) * f0 - dsum) * scale, p1 * (__uint_as_float(g[i + 1]) * f1 - dsum) * scale);
+    dk[(i >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(g[i + 2]) * f2 - dsum) * scale, p3 * (__uint_as_float(g[i + 3]) * f3 - dsum) * scale);
   }
   const uint32_t off = (c >> 6) * (kAttTile * 128) + row * 128;
 #pragma unroll
@@ -416,8 +451,10 @@ attention_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_wait(bar_sdp, i & 1);
       tc_fence_after();
       if (i > 0) mbar_wait(bar_done, (i - 1) & 1);  // the previous tile's P / dS have been consumed
+      const uint32_t drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(qi));
 #pragma unroll 1
-      for (int c = 0; c < kAttTile; c += 32) bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias, lse_log2, dsum, p.scale, p.scale_log2, sP, sDS, true);
+      for (int c = 0; c < kAttTile; c += 32)
+        bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias, lse_log2, dsum, p.scale, p.scale_log2, sP, sDS, true, p.drop, drop_key, k0);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_pds);
@@ -521,6 +558,7 @@ attention_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float lse_log2 = qi < p.lq ? p.lse[stat] * 1.4426950408889634f : INFINITY;
     if (lse_log2 == -INFINITY) lse_log2 = INFINITY;
     const float dsum = qi < p.lq ? p.dsum[stat] : 0.f;
+    const uint32_t drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(qi));
     for (int j = 0; j < ntiles; ++j) {
       {
         const int key = j * kAttTile + tid;
@@ -532,7 +570,8 @@ attention_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_after();
       if (j > 0) mbar_wait(bar_done, (j - 1) & 1);
 #pragma unroll 1
-      for (int c = 0; c < kAttTile; c += 32) bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias[j & 1], lse_log2, dsum, p.scale, p.scale_log2, sDS, sDS, false);
+      for (int c = 0; c < kAttTile; c += 32)
+        bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias[j & 1], lse_log2, dsum, p.scale, p.scale_log2, sDS, sDS, false, p.drop, drop_key, j * kAttTile);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_ds);
@@ -559,8 +598,25 @@ int check_seq(const yb200_act* a, const char* name) {
 
 }  // namespace
 
+static int make_drop(float p_drop, uint32_t seed, DropParams* d, const char* who) {
+  YB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, YB200_ERR_INVALID, "%s: dropout probability %g outside [0, 1)", who, p_drop);
+  d->seed = seed;
+  d->thr24 = static_cast<uint32_t>(static_cast<double>(p_drop) * 16777216.0);
+  d->inv_keep = 1.f / (1.f - p_drop);
+  return 0;
+}
+static int attention_fwd_impl(const yb200_act* q, const yb200_act* k, const yb200_act* v, const uint8_t* key_padding_mask, float scale,
+                              const yb200_act* out, float* lse, float p_drop, uint32_t seed, void* stream);
 extern "C" int yb200_attention_fwd(const yb200_act* q, const yb200_act* k, const yb200_act* v, const uint8_t* key_padding_mask, float scale,
                                    const yb200_act* out, float* lse, void* stream) {
+  return attention_fwd_impl(q, k, v, key_padding_mask, scale, out, lse, 0.f, 0u, stream);
+}
+extern "C" int yb200_attention_fwd_dropout(const yb200_act* q, const yb200_act* k, const yb200_act* v, const uint8_t* key_padding_mask, float scale,
+                                           const yb200_act* out, float* lse, float p_drop, uint32_t seed, void* stream) {
+  return attention_fwd_impl(q, k, v, key_padding_mask, scale, out, lse, p_drop, seed, stream);
+}
+static int attention_fwd_impl(const yb200_act* q, const yb200_act* k, const yb200_act* v, const uint8_t* key_padding_mask, float scale,
+                              const yb200_act* out, float* lse, float p_drop, uint32_t seed, void* stream) {
   int rc;
   if ((rc = check_seq(q, "attention_fwd q"))) return rc;
   if ((rc = check_seq(k, "attention_fwd k"))) return rc;
@@ -574,6 +630,7 @@ extern "C" int yb200_attention_fwd(const yb200_act* q, const yb200_act* k, const
   if ((rc = make_act_map(&tmK, *k, false, kAttD, kAttTile, 1, 1))) return rc;
   if ((rc = make_act_map(&tmV, *v, false, kAttD, kAttTile, 1, 1))) return rc;
   AttnParams p;
+  if ((rc = make_drop(p_drop, seed, &p.drop, "attention_fwd"))) return rc;
   p.lq = q->w; p.lk = k->w; p.heads = q->c / kAttD;
   p.q_coff = q->c_off; p.k_coff = k->c_off; p.v_coff = v->c_off;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -598,9 +655,22 @@ extern "C" int64_t yb200_attention_bwd_workspace(const yb200_act* q) {
   return 4LL * q->n * (q->c / kAttD) * q->w;
 }
 
+static int attention_bwd_impl(const yb200_act* q, const yb200_act* k, const yb200_act* v, const yb200_act* out, const yb200_act* dout,
+                              const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
+                              const yb200_act* dv, void* workspace, float p_drop, uint32_t seed, void* stream);
 extern "C" int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const yb200_act* v, const yb200_act* out, const yb200_act* dout,
                                    const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
                                    const yb200_act* dv, void* workspace, void* stream) {
+  return attention_bwd_impl(q, k, v, out, dout, key_padding_mask, scale, lse, dq, dk, dv, workspace, 0.f, 0u, stream);
+}
+extern "C" int yb200_attention_bwd_dropout(const yb200_act* q, const yb200_act* k, const yb200_act* v, const yb200_act* out, const yb200_act* dout,
+                                           const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
+                                           const yb200_act* dv, void* workspace, float p_drop, uint32_t seed, void* stream) {
+  return attention_bwd_impl(q, k, v, out, dout, key_padding_mask, scale, lse, dq, dk, dv, workspace, p_drop, seed, stream);
+}
+static int attention_bwd_impl(const yb200_act* q, const yb200_act* k, const yb200_act* v, const yb200_act* out, const yb200_act* dout,
+                              const uint8_t* key_padding_mask, float scale, const float* lse, const yb200_act* dq, const yb200_act* dk,
+                              const yb200_act* dv, void* workspace, float p_drop, uint32_t seed, void* stream) {
   int rc;
   const yb200_act* all[8] = {q, k, v, out, dout, dq, dk, dv};
   const char* names[8] = {"attention_bwd q", "attention_bwd k", "attention_bwd v", "attention_bwd out", "attention_bwd dout", "attention_bwd dq", "attention_bwd dk",
@@ -618,6 +688,7 @@ extern "C" int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const
   if ((rc = make_act_map(&tmV, *v, false, kAttD, kAttTile, 1, 1))) return rc;
   if ((rc = make_act_map(&tmDO, *dout, false, kAttD, kAttTile, 1, 1))) return rc;
   AttnBwdParams p;
+  if ((rc = make_drop(p_drop, seed, &p.drop, "attention_bwd"))) return rc;
   p.lq = q->w; p.lk = k->w; p.heads = q->c / kAttD;
   p.q_coff = q->c_off; p.k_coff = k->c_off; p.v_coff = v->c_off; p.do_coff = dout->c_off;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
@@ -641,6 +712,60 @@ extern "C" int yb200_attention_bwd(const yb200_act* q, const yb200_act* k, const
                                                                                   q->w, p.heads, static_cast<float*>(workspace));
   launch_k(attention_bwd_kv_kernel, dim3(ceil_div(p.lk, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemKV, st, tmQ, tmK, tmV, tmDO, p);
   launch_k(attention_bwd_q_kernel, dim3(ceil_div(p.lq, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemQ, st, tmQ, tmK, tmV, tmDO, p);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// nn.Dropout on a [B][1][L][C] bf16 activation (dropout / dropout1 / dropout2 / dropout3 of the transformer layers, detr_backbone.py:147-152, 207-214):
+//   out = residual + x * keep(seed, element) / (1 - p) * extra_scale        (residual may be null; extra_scale = 1 except in the FFN backward)
+// with the same counter-based hash as the attention kernels; `element` is the logical index ((b * L + l) * C + c), so views with different channel
+// pitches share a mask and the backward pass (the same call on the gradient, same seed) regenerates it.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const __nv_bfloat16* __restrict__ res, int res_pitch,
+                                    __nv_bfloat16* __restrict__ out, int out_pitch, long long rows, int c, DropParams d, float extra_scale) {
+  pdl_sync();
+  const int cv = c / 8;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cv;
+    const int c8 = static_cast<int>(i - r * cv) * 8;
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + r * x_pitch + c8);
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+    if (res) rv = *reinterpret_cast<const uint4*>(res + r * res_pitch + c8);
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, rs[4] = {rv.x, rv.y, rv.z, rv.w};
+    uint32_t o[4];
+    const uint32_t e0 = static_cast<uint32_t>(r * c + c8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float f0 = (mix32(d.seed ^ ((e0 + 2 * k) * 0x9E3779B1u)) >> 8) >= d.thr24 ? d.inv_keep * extra_scale : 0.f;
+      const float f1 = (mix32(d.seed ^ ((e0 + 2 * k + 1) * 0x9E3779B1u)) >> 8) >= d.thr24 ? d.inv_keep * extra_scale : 0.f;
+      o[k] = pack_bf16x2(fmaf(bf16_lo(xs[k]), f0, bf16_lo(rs[k])), fmaf(bf16_hi(xs[k]), f1, bf16_hi(rs[k])));
+    }
+    *reinterpret_cast<uint4*>(out + r * out_pitch + c8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+}  // namespace
+
+extern "C" int yb200_dropout(const yb200_act* x, const yb200_act* residual, const yb200_act* out, float p_drop, uint32_t seed, float extra_scale,
+                             void* stream) {
+  int rc;
+  if ((rc = check_seq(x, "dropout x"))) return rc;
+  if ((rc = check_seq(out, "dropout out"))) return rc;
+  if (residual && (rc = check_seq(residual, "dropout residual"))) return rc;
+  YB_REQUIRE(out->n == x->n && out->w == x->w && out->c == x->c && (!residual || (residual->n == x->n && residual->w == x->w && residual->c == x->c)),
+             YB200_ERR_INVALID, "dropout: shapes differ");
+  YB_REQUIRE(1LL * x->n * x->w * x->c < (1LL << 32), YB200_ERR_UNSUPPORTED, "dropout: more than 2^32 elements");
+  DropParams d;
+  if ((rc = make_drop(p_drop, seed, &d, "dropout"))) return rc;
+  const long long rows = 1LL * x->n * x->w;
+  const long long total = rows * (x->c / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16LL * sm_count()));
+  launch_k(dropout_bf16_kernel, blocks, 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(x->ptr) + x->c_off, x->c_pitch,
+           residual ? static_cast<const __nv_bfloat16*>(residual->ptr) + residual->c_off : nullptr, residual ? residual->c_pitch : 0,
+           static_cast<__nv_bfloat16*>(out->ptr) + out->c_off, out->c_pitch, rows, x->c, d, extra_scale);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -11,7 +11,10 @@ constructor arguments, parameter names / shapes (`self_attn.in_proj_weight` [3E,
 Internally tokens are batch-first bf16 `[B, 1, L, E]` views (yb200_act).  Forward and backward: with gradients enabled the layers run as one autograd node each
 (`_EncoderLayerFn` / `_DecoderLayerFn`: attention backward, data / weight gradients and LayerNorm backward on the same kernels), validated on
 hardware against the reference layer's autograd (tests/test_detr_gpu.py, round 2: 6 passed); YB200_DETR_TRAINING=0 forces the inference path.
-Dropout (p = 0.1 in the reference) is identity here: parity runs use eval mode / p = 0.  `attn_mask` (never passed by the
+Dropout (p = 0.1 in the reference: on the attention probabilities inside nn.MultiheadAttention and nn.Dropout on the residual branches / in the FFN) is
+active in training mode: the masks are a counter-based hash of (seed, element index) evaluated inside the kernels (yb200_attention_*_dropout,
+yb200_dropout), regenerated in the backward from the same seeds; seeds come from torch's CPU generator.  Same distribution as torch's Philox masks, not
+the same bits: parity = the same computation given the same mask (tests/test_detr_dropout_gpu.py, oracle/detr_oracle.py).  `attn_mask` (never passed by the
 reference's DETR) and `normalize_before=True` are not supported.  There is no CPU implementation.
 """
 import ctypes
@@ -154,24 +157,35 @@ class _Kernels:
         ws = self._ws(self.L.yb200_colsum_workspace(ctypes.byref(da)), dt.device)
         capi.check(self.L.yb200_colsum(ctypes.byref(da), ctypes.c_float(1.0), capi.ptr(out), 0, capi.ptr(ws), capi.stream_ptr()), "colsum")
 
-    def attention_train(self, q, k, v, mask, heads):
+    def attention_train(self, q, k, v, mask, heads, p_drop=0.0, seed=0):
+        """p_drop > 0: dropout on the attention probabilities (nn.MultiheadAttention(dropout=p), detr_backbone.py:140), mask = f(seed, b, h, q, k)"""
         qt, _, e = q
         b, _, lq, _ = qt.shape
         out = torch.empty(b, 1, lq, e, dtype=torch.bfloat16, device=qt.device)
         lse = torch.empty(b, heads, lq, device=qt.device)
         qa, ka, va, oa = self._a(*q), self._a(*k), self._a(*v), self._a(out)
-        capi.check(self.L.yb200_attention_fwd(ctypes.byref(qa), ctypes.byref(ka), ctypes.byref(va), capi.ptr(mask), ctypes.c_float((e // heads) ** -0.5),
-                                              ctypes.byref(oa), capi.ptr(lse), capi.stream_ptr()), "attention")
+        capi.check(self.L.yb200_attention_fwd_dropout(ctypes.byref(qa), ctypes.byref(ka), ctypes.byref(va), capi.ptr(mask), ctypes.c_float((e // heads) ** -0.5),
+                                                      ctypes.byref(oa), capi.ptr(lse), ctypes.c_float(p_drop), ctypes.c_uint32(seed), capi.stream_ptr()), "attention")
         return out, lse
 
-    def attention_bwd(self, q, k, v, out, dout, mask, heads, lse, dq, dk, dv):
+    def attention_bwd(self, q, k, v, out, dout, mask, heads, lse, dq, dk, dv, p_drop=0.0, seed=0):
         e = q[2]
         qa, ka, va, oa, da = self._a(*q), self._a(*k), self._a(*v), self._a(out), self._a(dout)
         dqa, dka, dva = self._a(*dq), self._a(*dk), self._a(*dv)
         ws = self._ws(self.L.yb200_attention_bwd_workspace(ctypes.byref(qa)), out.device)
-        capi.check(self.L.yb200_attention_bwd(ctypes.byref(qa), ctypes.byref(ka), ctypes.byref(va), ctypes.byref(oa), ctypes.byref(da), capi.ptr(mask),
-                                              ctypes.c_float((e // heads) ** -0.5), capi.ptr(lse), ctypes.byref(dqa), ctypes.byref(dka), ctypes.byref(dva), capi.ptr(ws),
-                                              capi.stream_ptr()), "attention bwd")
+        capi.check(self.L.yb200_attention_bwd_dropout(ctypes.byref(qa), ctypes.byref(ka), ctypes.byref(va), ctypes.byref(oa), ctypes.byref(da), capi.ptr(mask),
+                                                      ctypes.c_float((e // heads) ** -0.5), capi.ptr(lse), ctypes.byref(dqa), ctypes.byref(dka), ctypes.byref(dva),
+                                                      capi.ptr(ws), ctypes.c_float(p_drop), ctypes.c_uint32(seed), capi.stream_ptr()), "attention bwd")
+
+    def dropout(self, x, p_drop, seed, residual=None, scale=1.0):
+        """residual + x * keep(seed, element) / (1 - p) * scale  (nn.Dropout of the residual branches / the FFN, detr_backbone.py:147-152);
+        the backward is the same call on the gradient with the same seed"""
+        out = torch.empty_like(x)
+        xa, oa = self._a(x), self._a(out)
+        ra = self._a(residual) if residual is not None else None
+        capi.check(self.L.yb200_dropout(ctypes.byref(xa), ctypes.byref(ra) if ra is not None else None, ctypes.byref(oa), ctypes.c_float(p_drop), ctypes.c_uint32(seed),
+                                        ctypes.c_float(scale), capi.stream_ptr()), "dropout")
+        return out
 
     def attention(self, q, k, v, mask, heads):
         """q, k, v: (tensor, channel offset, E) slices of [B,1,L,*] buffers; mask: uint8 [B, Lk] or None"""
@@ -237,10 +251,20 @@ class _LayerBase(nn.Module):
         if normalize_before:
             raise capi.Yb200Error("normalize_before=True (forward_pre) is not implemented")
         self.d_model, self.nhead = d_model, nhead
+        self.dropout_p = float(dropout)
         self._ctor = (d_model, nhead, dim_feedforward, dropout, activation, normalize_before, device)
         self.linear1 = _Lin(d_model, dim_feedforward, device)
         self.linear2 = _Lin(dim_feedforward, d_model, device)
         self.k = _Kernels()
+
+    def _dropout_state(self, n):
+        """(p, n seeds) of one training forward.  p = 0 in eval mode / with dropout=0 (every kernel then takes its dropout-free path).  The seeds come
+        from torch's CPU generator (torch.manual_seed reproduces a run; no device synchronisation); the masks themselves are a counter-based hash of
+        (seed, element index) evaluated inside the kernels (csrc/attention.cu) -- not torch's Philox stream: same distribution, different bits."""
+        p = self.dropout_p if self.training else 0.0
+        if p <= 0.0:
+            return 0.0, (0,) * n
+        return p, tuple(int(v) for v in torch.randint(0, 2 ** 31 - 1, (n,)))
 
     def _self_attention(self, x, qk, att, mask):
         """x: value source, qk: query/key source ([B,1,L,E] bf16); returns x + out_proj(attention)"""
@@ -277,12 +301,21 @@ class _EncoderLayerFn(torch.autograd.Function):
         qkv = torch.empty(b, 1, l, 3 * e, dtype=torch.bfloat16, device=x.device)
         kn.linear(qk, w_in[:2 * e], b_in[:2 * e], out=qkv, out_off=0)
         kn.linear(x, w_in[2 * e:], b_in[2 * e:], out=qkv, out_off=2 * e)
-        att, lse = kn.attention_train((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), mask, heads)
-        y1 = kn.linear(att, w_o, b_o, residual=x)
+        pd, sd = layer._dropout_state(4)  # (p, seeds): attention probabilities, dropout1, FFN dropout, dropout2 (detr_backbone.py:157-170)
+        att, lse = kn.attention_train((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), mask, heads, pd, sd[0])
+        if pd > 0:
+            y1 = kn.dropout(kn.linear(att, w_o, b_o), pd, sd[1], residual=x)
+        else:
+            y1 = kn.linear(att, w_o, b_o, residual=x)
         x1, st1 = kn.layernorm_train(y1, g1, be1)
         h = kn.linear(x1, w1, b1, relu=True)
-        y2 = kn.linear(h, w2, b2, residual=x1)
+        if pd > 0:
+            h = kn.dropout(h, pd, sd[2])  # the dropped activation is what linear2 sees and what the backward needs (h > 0 and kept)
+            y2 = kn.dropout(kn.linear(h, w2, b2), pd, sd[3], residual=x1)
+        else:
+            y2 = kn.linear(h, w2, b2, residual=x1)
         out, st2 = kn.layernorm_train(y2, g2, be2)
+        ctx.drop = (pd, sd)
         ctx.layer, ctx.mask, ctx.has_pos = layer, mask, pos is not None
         ctx.saved = (x, qk, qkv, att, lse, y1, st1, x1, h, y2, st2)
         ctx.params = params
@@ -298,14 +331,20 @@ class _EncoderLayerFn(torch.autograd.Function):
         ff = w1.shape[0]
         g = _bl(g_out)
         # LayerNorm 2
+        pd, sd = ctx.drop
         g_y2, gg2, gb2 = kn.layernorm_bwd(g, y2, st2, g2)
-        # linear2 (+ residual to x1) and the ReLU in front of it
+        # linear2 (+ residual to x1) and the ReLU in front of it; with dropout: g_t = dropout2's mask on the branch gradient, and the saved h is the
+        # dropped activation (positive <=> positive and kept), so the ReLU mask also applies the FFN dropout mask -- its 1 / (1 - p) follows
+        g_t = kn.dropout(g_y2, pd, sd[3]) if pd > 0 else g_y2
         _, w2d = kn.pack2(w2)
-        du, gb1 = kn.dgrad_relu(g_y2, w2d, h)
+        du, gb1 = kn.dgrad_relu(g_t, w2d, h)
+        if pd > 0:
+            du = kn.dropout(du, pd, sd[2])
+            gb1 = gb1 / (1.0 - pd)
         gw2 = torch.empty(e, ff, device=dev)
-        kn.wgrad(h, g_y2, gw2)
+        kn.wgrad(h, g_t, gw2)
         gb2_lin = torch.empty(e, device=dev)
-        kn.colsum(g_y2, gb2_lin)
+        kn.colsum(g_t, gb2_lin)
         # linear1; the residual branch of x1 joins through the addend
         _, w1d = kn.pack2(w1)
         g_x1 = kn.dgrad(du, w1d, e, addend=g_y2)
@@ -314,15 +353,16 @@ class _EncoderLayerFn(torch.autograd.Function):
         # LayerNorm 1
         g_y1, gg1, gb1n = kn.layernorm_bwd(g_x1, y1, st1, g1)
         # out_proj (+ residual to x)
+        g_o = kn.dropout(g_y1, pd, sd[1]) if pd > 0 else g_y1
         _, wod = kn.pack2(w_o)
-        g_att = kn.dgrad(g_y1, wod, e)
+        g_att = kn.dgrad(g_o, wod, e)
         gwo = torch.empty(e, e, device=dev)
-        kn.wgrad(att, g_y1, gwo)
+        kn.wgrad(att, g_o, gwo)
         gbo = torch.empty(e, device=dev)
-        kn.colsum(g_y1, gbo)
+        kn.colsum(g_o, gbo)
         # attention core
         dqkv = torch.empty_like(qkv)
-        kn.attention_bwd((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), att, g_att, ctx.mask, heads, lse, (dqkv, 0, e), (dqkv, e, e), (dqkv, 2 * e, e))
+        kn.attention_bwd((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), att, g_att, ctx.mask, heads, lse, (dqkv, 0, e), (dqkv, e, e), (dqkv, 2 * e, e), pd, sd[0])
         # in_proj: q, k from qk = x + pos; v from x
         _, wqkd = kn.pack2(w_in[:2 * e])
         _, wvd = kn.pack2(w_in[2 * e:])
@@ -357,8 +397,9 @@ class _DecoderLayerFn(torch.autograd.Function):
         qkv = torch.empty(b, 1, lq, 3 * e, dtype=torch.bfloat16, device=x.device)
         kn.linear(qk, ws[:2 * e], bs[:2 * e], out=qkv, out_off=0)
         kn.linear(x, ws[2 * e:], bs[2 * e:], out=qkv, out_off=2 * e)
-        att1, lse1 = kn.attention_train((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), tgt_mask, heads)
-        y1 = kn.linear(att1, wso, bso, residual=x)
+        pd, sd = layer._dropout_state(6)  # self-attention probabilities, dropout1, cross-attention probabilities, dropout2, FFN dropout, dropout3
+        att1, lse1 = kn.attention_train((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), tgt_mask, heads, pd, sd[0])
+        y1 = kn.dropout(kn.linear(att1, wso, bso), pd, sd[1], residual=x) if pd > 0 else kn.linear(att1, wso, bso, residual=x)
         x1, st1 = kn.layernorm_train(y1, g1, be1)
         mem = _bl(memory)
         memk = mem if pos is None else kn.add(mem, _bl(pos))
@@ -368,12 +409,17 @@ class _DecoderLayerFn(torch.autograd.Function):
         kv = torch.empty(b, 1, lk, 2 * e, dtype=torch.bfloat16, device=x.device)
         kn.linear(memk, wc[e:2 * e], bc[e:2 * e], out=kv, out_off=0)
         kn.linear(mem, wc[2 * e:], bc[2 * e:], out=kv, out_off=e)
-        att2, lse2 = kn.attention_train((qc, 0, e), (kv, 0, e), (kv, e, e), mem_mask, heads)
-        y2 = kn.linear(att2, wco, bco, residual=x1)
+        att2, lse2 = kn.attention_train((qc, 0, e), (kv, 0, e), (kv, e, e), mem_mask, heads, pd, sd[2])
+        y2 = kn.dropout(kn.linear(att2, wco, bco), pd, sd[3], residual=x1) if pd > 0 else kn.linear(att2, wco, bco, residual=x1)
         x2, st2 = kn.layernorm_train(y2, g2, be2)
         h = kn.linear(x2, w1, b1, relu=True)
-        y3 = kn.linear(h, w2, b2, residual=x2)
+        if pd > 0:
+            h = kn.dropout(h, pd, sd[4])
+            y3 = kn.dropout(kn.linear(h, w2, b2), pd, sd[5], residual=x2)
+        else:
+            y3 = kn.linear(h, w2, b2, residual=x2)
         out, st3 = kn.layernorm_train(y3, g3, be3)
+        ctx.drop = (pd, sd)
         ctx.layer, ctx.masks, ctx.has = layer, (tgt_mask, mem_mask), (pos is not None, query_pos is not None)
         ctx.saved = (x, qk, qkv, att1, lse1, y1, st1, x1, mem, memk, q2, qc, kv, att2, lse2, y2, st2, x2, h, y3, st3)
         ctx.params = params
@@ -391,22 +437,28 @@ class _DecoderLayerFn(torch.autograd.Function):
         f32 = lambda *shape: torch.empty(*shape, device=dev)
         g = _bl(g_out)
         # FFN block
+        pd, sd = ctx.drop
         g_y3, gg3, gbn3 = kn.layernorm_bwd(g, y3, st3, g3)
-        du, gb1 = kn.dgrad_relu(g_y3, kn.pack2(w2)[1], h)
+        g_t = kn.dropout(g_y3, pd, sd[5]) if pd > 0 else g_y3
+        du, gb1 = kn.dgrad_relu(g_t, kn.pack2(w2)[1], h)
+        if pd > 0:
+            du = kn.dropout(du, pd, sd[4])
+            gb1 = gb1 / (1.0 - pd)
         gw2, gb2 = f32(e, ff), f32(e)
-        kn.wgrad(h, g_y3, gw2)
-        kn.colsum(g_y3, gb2)
+        kn.wgrad(h, g_t, gw2)
+        kn.colsum(g_t, gb2)
         g_x2 = kn.dgrad(du, kn.pack2(w1)[1], e, addend=g_y3)
         gw1 = f32(ff, e)
         kn.wgrad(x2, du, gw1)
         # cross-attention block
         g_y2, gg2, gbn2 = kn.layernorm_bwd(g_x2, y2, st2, g2)
-        g_att2 = kn.dgrad(g_y2, kn.pack2(wco)[1], e)
+        g_o2 = kn.dropout(g_y2, pd, sd[3]) if pd > 0 else g_y2
+        g_att2 = kn.dgrad(g_o2, kn.pack2(wco)[1], e)
         gwco, gbco = f32(e, e), f32(e)
-        kn.wgrad(att2, g_y2, gwco)
-        kn.colsum(g_y2, gbco)
+        kn.wgrad(att2, g_o2, gwco)
+        kn.colsum(g_o2, gbco)
         dqc, dkv = torch.empty_like(qc), torch.empty_like(kv)
-        kn.attention_bwd((qc, 0, e), (kv, 0, e), (kv, e, e), att2, g_att2, mem_mask, heads, lse2, (dqc, 0, e), (dkv, 0, e), (dkv, e, e))
+        kn.attention_bwd((qc, 0, e), (kv, 0, e), (kv, e, e), att2, g_att2, mem_mask, heads, lse2, (dqc, 0, e), (dkv, 0, e), (dkv, e, e), pd, sd[2])
         g_q2 = kn.dgrad(dqc, kn.pack2(wc[:e])[1], e)
         g_memk = kn.dgrad((dkv, 0, e), kn.pack2(wc[e:2 * e])[1], e)
         g_mem = kn.dgrad((dkv, e, e), kn.pack2(wc[2 * e:])[1], e, addend=g_memk)  # memory feeds keys (through + pos) and values
@@ -419,12 +471,13 @@ class _DecoderLayerFn(torch.autograd.Function):
         g_x1 = kn.add(g_y2, g_q2)  # residual branch + query path
         # self-attention block
         g_y1, gg1, gbn1 = kn.layernorm_bwd(g_x1, y1, st1, g1)
-        g_att1 = kn.dgrad(g_y1, kn.pack2(wso)[1], e)
+        g_o1 = kn.dropout(g_y1, pd, sd[1]) if pd > 0 else g_y1
+        g_att1 = kn.dgrad(g_o1, kn.pack2(wso)[1], e)
         gwso, gbso = f32(e, e), f32(e)
-        kn.wgrad(att1, g_y1, gwso)
-        kn.colsum(g_y1, gbso)
+        kn.wgrad(att1, g_o1, gwso)
+        kn.colsum(g_o1, gbso)
         dqkv = torch.empty_like(qkv)
-        kn.attention_bwd((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), att1, g_att1, tgt_mask, heads, lse1, (dqkv, 0, e), (dqkv, e, e), (dqkv, 2 * e, e))
+        kn.attention_bwd((qkv, 0, e), (qkv, e, e), (qkv, 2 * e, e), att1, g_att1, tgt_mask, heads, lse1, (dqkv, 0, e), (dqkv, e, e), (dqkv, 2 * e, e), pd, sd[0])
         g_qk = kn.dgrad((dqkv, 0, 2 * e), kn.pack2(ws[:2 * e])[1], e)
         g_x = kn.dgrad((dqkv, 2 * e, e), kn.pack2(ws[2 * e:])[1], e, addend=g_y1)
         g_tgt = kn.add(g_x, g_qk)
@@ -602,7 +655,7 @@ class TransformerDecoder(nn.Module):
 class Transformer(nn.Module):
     """detr_backbone.py:25-66: encoder stack over the flattened feature map, decoder stack over the object queries.
     forward(src [B,C,H,W], mask [B,H,W] bool, query_embed [Q,C], pos_embed [B,C,H,W]) -> (hs [layers or 1, B, Q, C], memory [B,C,H,W]).
-    Dropout (0.1 in the reference) is the identity in these layers (module docstring); normalize_before is not supported."""
+    Dropout (0.1 in the reference) is active in training mode (`_LayerBase._dropout_state`); normalize_before is not supported."""
 
     def __init__(self, d_model=512, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048, dropout=0.1, activation="relu",
                  normalize_before=False, return_intermediate_dec=False, device="cuda"):
