@@ -62,6 +62,8 @@ struct AttnParams {
   float* lse;                   // [B][heads][lq] natural-log sum-exp of the scaled scores, may be null
 };
 
+template <bool DROP>  // the dropout-free instantiation is the kernel as it was (the extra integer work and registers cost the p = 0 path 35 % when the
+                      // choice was a run-time branch inside the softmax loop)
 __global__ void __launch_bounds__(kAttThreads)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ AttnParams p) {
@@ -143,7 +145,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int tid = threadIdx.x - 64;     // 0..127 among the softmax threads
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     float m = -INFINITY, l = 0.f;
-    const uint32_t drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(q0 + row));
+    uint32_t drop_key = 0;
+    if constexpr (DROP) drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(q0 + row));
     float acc[kAttD];
 #pragma unroll
     for (int i = 0; i < kAttD; ++i) acc[i] = 0.f;
@@ -202,7 +205,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), p.scale_log2, bb.z - m_safe));
           const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), p.scale_log2, bb.w - m_safe));
           rowsum += (p0 + p1) + (p2 + p3);  // the normaliser is the sum of the UNDROPPED probabilities: dropout(softmax(S)) V
-          if (p.drop.thr24 != 0) {
+          if constexpr (DROP) {
             const uint32_t col = static_cast<uint32_t>(j * kAttTile + c + i);
             pk[i >> 1] = pack_bf16x2(p0 * drop_factor(drop_key, col, p.drop), p1 * drop_factor(drop_key, col + 1, p.drop));
             pk[(i >> 1) + 1] = pack_bf16x2(p2 * drop_factor(drop_key, col + 2, p.drop), p3 * drop_factor(drop_key, col + 3, p.drop));
@@ -307,6 +310,7 @@ __global__ void attention_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, i
 // one 32-column chunk of P and dS for the thread's query row: reads S and dP from TMEM, writes both bf16 tiles ([query][key], swizzle 128)
 // With dropout D (0 or 1/(1-p) per element): O = (D o P) V, so the tile written for dV = (D o P)^T dO is the dropped one, dP = D o (dO V^T) and
 // dS = P o (dP - <dO, O>) -- the row term <dO, O> (attention_bwd_prep_kernel) already contains D through O.
+template <bool DROP>
 __device__ __forceinline__ void bwd_chunk(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_base, int c, int row, const float* bias, float lse_log2, float dsum,
                                           float scale, float scale_log2, uint32_t sP, uint32_t sDS, bool write_p, const DropParams& drop, uint32_t drop_key,
                                           int key0) {
@@ -323,7 +327,7 @@ __device__ __forceinline__ void bwd_chunk(uint32_t tmem_s, uint32_t tmem_dp, uin
     const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), scale_log2, bb.z - lse_log2));
     const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), scale_log2, bb.w - lse_log2));
     float f0 = 1.f, f1 = 1.f, f2 = 1.f, f3 = 1.f;
-    if (drop.thr24 != 0) {
+    if constexpr (DROP) {
       const uint32_t col = static_cast<uint32_t>(key0 + c + i);
       f0 = drop_factor(drop_key, col, drop); f1 = drop_factor(drop_key, col + 1, drop);
       f2 = drop_factor(drop_key, col + 2, drop); f3 = drop_factor(drop_key, col + 3, drop);
@@ -356,6 +360,7 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (
   }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kAttThreads)
 attention_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ AttnBwdParams p) {
@@ -451,10 +456,11 @@ attention_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_wait(bar_sdp, i & 1);
       tc_fence_after();
       if (i > 0) mbar_wait(bar_done, (i - 1) & 1);  // the previous tile's P / dS have been consumed
-      const uint32_t drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(qi));
+      uint32_t drop_key = 0;
+      if constexpr (DROP) drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(qi));
 #pragma unroll 1
       for (int c = 0; c < kAttTile; c += 32)
-        bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias, lse_log2, dsum, p.scale, p.scale_log2, sP, sDS, true, p.drop, drop_key, k0);
+        bwd_chunk<DROP>(tmem_s, tmem_dp, lane_base, c, row, s_bias, lse_log2, dsum, p.scale, p.scale_log2, sP, sDS, true, p.drop, drop_key, k0);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_pds);
@@ -475,6 +481,7 @@ attention_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   if (warp == 1) tmem_dealloc<512>(s_tmem);
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kAttThreads)
 attention_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ AttnBwdParams p) {
@@ -558,7 +565,8 @@ attention_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float lse_log2 = qi < p.lq ? p.lse[stat] * 1.4426950408889634f : INFINITY;
     if (lse_log2 == -INFINITY) lse_log2 = INFINITY;
     const float dsum = qi < p.lq ? p.dsum[stat] : 0.f;
-    const uint32_t drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(qi));
+    uint32_t drop_key = 0;
+    if constexpr (DROP) drop_key = drop_row_key(p.drop.seed, static_cast<uint32_t>(b * p.heads + h), static_cast<uint32_t>(qi));
     for (int j = 0; j < ntiles; ++j) {
       {
         const int key = j * kAttTile + tid;
@@ -571,7 +579,7 @@ attention_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (j > 0) mbar_wait(bar_done, (j - 1) & 1);
 #pragma unroll 1
       for (int c = 0; c < kAttTile; c += 32)
-        bwd_chunk(tmem_s, tmem_dp, lane_base, c, row, s_bias[j & 1], lse_log2, dsum, p.scale, p.scale_log2, sDS, sDS, false, p.drop, drop_key, j * kAttTile);
+        bwd_chunk<DROP>(tmem_s, tmem_dp, lane_base, c, row, s_bias[j & 1], lse_log2, dsum, p.scale, p.scale_log2, sDS, sDS, false, p.drop, drop_key, j * kAttTile);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_ds);
@@ -641,11 +649,15 @@ static int attention_fwd_impl(const yb200_act* q, const yb200_act* k, const yb20
   static PerDevice<bool> attr_set_dev(false);
   bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
     attr_set = true;
   }
   dim3 grid(ceil_div(p.lq, kAttTile), p.heads, q->n);
-  launch_k(attention_fwd_kernel, grid, kAttThreads, kAttSmem, as_stream(stream), tmQ, tmK, tmV, p);
+  if (p.drop.thr24 != 0)
+    launch_k(attention_fwd_kernel<true>, grid, kAttThreads, kAttSmem, as_stream(stream), tmQ, tmK, tmV, p);
+  else
+    launch_k(attention_fwd_kernel<false>, grid, kAttThreads, kAttSmem, as_stream(stream), tmQ, tmK, tmV, p);
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -701,8 +713,10 @@ static int attention_bwd_impl(const yb200_act* q, const yb200_act* k, const yb20
   static PerDevice<bool> attr_set_dev(false);
   bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemKV));
-    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemQ));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemKV));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemQ));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemKV));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemQ));
     attr_set = true;
   }
   cudaStream_t st = as_stream(stream);
@@ -710,8 +724,13 @@ static int attention_bwd_impl(const yb200_act* q, const yb200_act* k, const yb20
   launch_k(attention_bwd_prep_kernel, static_cast<int>((rows + 255) / 256), 256, 0, st, static_cast<const __nv_bfloat16*>(out->ptr), out->c_pitch, out->c_off,
                                                                                   static_cast<const __nv_bfloat16*>(dout->ptr), dout->c_pitch, dout->c_off, q->n,
                                                                                   q->w, p.heads, static_cast<float*>(workspace));
-  launch_k(attention_bwd_kv_kernel, dim3(ceil_div(p.lk, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemKV, st, tmQ, tmK, tmV, tmDO, p);
-  launch_k(attention_bwd_q_kernel, dim3(ceil_div(p.lq, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemQ, st, tmQ, tmK, tmV, tmDO, p);
+  if (p.drop.thr24 != 0) {
+    launch_k(attention_bwd_kv_kernel<true>, dim3(ceil_div(p.lk, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemKV, st, tmQ, tmK, tmV, tmDO, p);
+    launch_k(attention_bwd_q_kernel<true>, dim3(ceil_div(p.lq, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemQ, st, tmQ, tmK, tmV, tmDO, p);
+  } else {
+    launch_k(attention_bwd_kv_kernel<false>, dim3(ceil_div(p.lk, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemKV, st, tmQ, tmK, tmV, tmDO, p);
+    launch_k(attention_bwd_q_kernel<false>, dim3(ceil_div(p.lq, kAttTile), p.heads, q->n), kAttThreads, kBwdSmemQ, st, tmQ, tmK, tmV, tmDO, p);
+  }
   YB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
