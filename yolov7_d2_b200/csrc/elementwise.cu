@@ -800,7 +800,8 @@ static int bn_silu_bwd_impl(const yb200_act* z, const yb200_act* da, const yb200
   const int red_rows = red_shuffle ? static_cast<int>(block.x * block.y) / 32 : static_cast<int>(block.y);
   const size_t red_smem = static_cast<size_t>(red_rows) * 2 * z->c * sizeof(float);
   // tuning knob (tools/bench_bn.py): YB200_BN_RED = "U:MINB:ITERS" -- loads in flight per thread, resident blocks per SM, pixels per thread
-  static int red_u = -1, red_minb = 4, red_it = 0;  // measured best of the sweep in profiles/r2_bn_backward_sweep.md: U=2, 4 blocks / SM
+  static int red_u = -1, red_minb = 3, red_it = 0;  // U = 2 loads in flight, 3 blocks / SM: best INSIDE the step (17.21 vs 17.43 ms per step with 4 blocks / SM,
+                                                     // which wins the stand-alone sweep of profiles/r2_bn_backward_sweep.md by 4 %)
   if (red_u < 0) {
     red_u = 2;
     const char* e = getenv("YB200_BN_RED");
