@@ -257,3 +257,17 @@ def test_decoder_layer_training_wiring_with_dropout(detr_fp32):
         close(a.grad, r.grad, k + " gradient")
     for n, p in zip(detr._DecoderLayerFn.NAMES, params):
         close(p.grad, sdr["l." + n].grad, n)
+
+
+def test_restated_dropout_hash_properties():
+    """oracle.detr_oracle.{dropout_multiplier, attention_dropout_multiplier}: deterministic in the seed, keep rate 1 - p, kept values 1 / (1 - p),
+    different seeds / heads / rows give different masks (the kernels' own masks are compared with these bit for bit on the GPU)"""
+    m1, m2, m3 = dto.dropout_multiplier(9, (4, 64, 256), 0.1), dto.dropout_multiplier(9, (4, 64, 256), 0.1), dto.dropout_multiplier(10, (4, 64, 256), 0.1)
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    assert abs(float((m1 > 0).float().mean()) - 0.9) < 0.01
+    assert set(m1.unique().tolist()) == {0.0, float(torch.tensor(1.0) / (torch.tensor(1.0) - torch.tensor(0.1)))}
+    a = dto.attention_dropout_multiplier(3, 2, 8, 100, 120, 0.1)
+    assert abs(float((a > 0).float().mean()) - 0.9) < 0.01
+    assert not torch.equal(a[0, 0], a[0, 1]) and not torch.equal(a[0, 0], a[1, 0]) and not torch.equal(a[0, 0, 0], a[0, 0, 1])
+    # p = 0.5: threshold exactly half of the 24-bit range
+    assert abs(float((dto.dropout_multiplier(1, (1, 1000, 64), 0.5) > 0).float().mean()) - 0.5) < 0.01
